@@ -1,0 +1,408 @@
+// bf16 GEMM on the sm_100a 5th-gen tensor cores: TMA-staged 128B-swizzled tiles -> tcgen05.mma
+// (accumulator in TMEM, double buffered) -> tcgen05.ld epilogue with fused bias / scale / GELU /
+// SwiGLU / residual.  Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer
+// (+ TMEM allocator), warps 2..5 = epilogue (one TMEM lane quadrant each).
+//
+// Replaces, on the hot path, every nn.Linear of fair-esm ESM2 (q/k/v/out_proj, fc1, fc2 — reached via
+// procyon/model/esm.py:536), of HF LlamaDecoderLayer (q/k/v/o_proj, gate/up/down_proj — reached via
+// procyon/model/pmc_llama.py:571) and of create_mlp (procyon/model/model_utils.py:13-41).
+#include <mutex>
+#include <unordered_map>
+
+#include "common.cuh"
+#include "ops.h"
+
+namespace pcy {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle span
+constexpr int UMMA_K = 16;
+constexpr int NUM_EPI_WARPS = 4;
+constexpr int NUM_THREADS = 64 + NUM_EPI_WARPS * 32;
+
+template <int BN>
+struct TileCfg {
+  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int TMEM_COLS = 2 * BN;  // two accumulator buffers (256 or 512 columns: powers of two)
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+struct EpiParams {
+  void* C;
+  int64_t ldc;
+  const float* bias;
+  const bf16* residual;
+  int64_t ldr;
+  int M, N, K;
+  int c_fp32;
+  int act;
+  float scale;
+  int scale_ncols;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                         const EpiParams p) {
+  using Cfg = TileCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B tiles need 1024-byte alignment
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
+  // barrier layout (8 bytes each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], then tmem ptr
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::STAGES + 2 + s); };
+  const uint32_t tmem_ptr_smem = bar_base + 8u * (2 * Cfg::STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int m_blocks = (p.M + BM - 1) / BM;
+  const int n_blocks = (p.N + BN - 1) / BN;
+  const int num_tiles = m_blocks * n_blocks;
+  const int k_blocks = (p.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), NUM_EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile % m_blocks;
+        const int n_blk = tile / m_blocks;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+          const uint32_t sb = sa + Cfg::A_BYTES;
+          mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+          tma_load_2d(sa, &tmap_a, full_bar(stage), kb * BK, m_blk * BM);
+          tma_load_2d(sb, &tmap_b, full_bar(stage), kb * BK, n_blk * BN);
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1);  // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+          const uint32_t sb = sa + Cfg::A_BYTES;
+          const uint64_t a_desc = make_desc_kmajor_sw128(sa);
+          const uint64_t b_desc = make_desc_kmajor_sw128(sb);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // advance 32 bytes (16 bf16) along K inside the swizzle atom: +2 in the (addr >> 4) field
+            tc_mma_bf16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
+                        (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          tc_commit(empty_bar(stage));  // frees the smem slot once these MMAs retire
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const bool swiglu = (p.act == ACT_SWIGLU);
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile % m_blocks;
+      const int n_blk = tile / m_blocks;
+      const int row = m_blk * BM + quad * 32 + lane;
+      const bool row_ok = row < p.M;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int col0 = n_blk * BN + c * 32;
+        if (col0 >= p.N) break;  // warp-uniform
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(t_addr + (uint32_t)(c * 32), r);
+        tc_wait_ld();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        const bool full_cols = (col0 + 32 <= p.N);
+        if (p.bias != nullptr) {
+          if (full_cols) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+              v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);
+          }
+        }
+        if (col0 < p.scale_ncols) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < p.scale_ncols) v[j] *= p.scale;
+        }
+        if (!swiglu) {
+          if (p.act == ACT_GELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+          }
+          if (row_ok) {
+            if (p.residual != nullptr) {
+              const bf16* rp = p.residual + (int64_t)row * p.ldr + col0;
+              if (full_cols && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                  const uint4 u = *reinterpret_cast<const uint4*>(rp + j);
+                  const float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z),
+                               f3 = unpack_bf16x2(u.w);
+                  v[j] += f0.x; v[j + 1] += f0.y; v[j + 2] += f1.x; v[j + 3] += f1.y;
+                  v[j + 4] += f2.x; v[j + 5] += f2.y; v[j + 6] += f3.x; v[j + 7] += f3.y;
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (col0 + j < p.N) v[j] += __bfloat162float(rp[j]);
+              }
+            }
+            if (p.c_fp32) {
+              float* cp = reinterpret_cast<float*>(p.C) + (int64_t)row * p.ldc + col0;
+              if (full_cols && ((reinterpret_cast<uintptr_t>(cp) & 15) == 0)) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                  *reinterpret_cast<float4*>(cp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (col0 + j < p.N) cp[j] = v[j];
+              }
+            } else {
+              bf16* cp = reinterpret_cast<bf16*>(p.C) + (int64_t)row * p.ldc + col0;
+              if (full_cols && ((reinterpret_cast<uintptr_t>(cp) & 15) == 0)) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                  uint4 u;
+                  u.x = pack_bf16x2(v[j], v[j + 1]);
+                  u.y = pack_bf16x2(v[j + 2], v[j + 3]);
+                  u.z = pack_bf16x2(v[j + 4], v[j + 5]);
+                  u.w = pack_bf16x2(v[j + 6], v[j + 7]);
+                  *reinterpret_cast<uint4*>(cp + j) = u;
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (col0 + j < p.N) cp[j] = __float2bfloat16_rn(v[j]);
+              }
+            }
+          }
+        } else {
+          // SwiGLU: columns [0,16) of the chunk are gate, [16,32) are up -> 16 outputs at col0/2.
+          // N is a multiple of 32 in this mode (checked on the host).
+          if (row_ok) {
+            const int ocol0 = col0 >> 1;
+            float o[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) o[j] = silu(v[j]) * v[16 + j];
+            if (p.residual != nullptr) {
+              const bf16* rp = p.residual + (int64_t)row * p.ldr + ocol0;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) o[j] += __bfloat162float(rp[j]);
+            }
+            bf16* cp = reinterpret_cast<bf16*>(p.C) + (int64_t)row * p.ldc + ocol0;
+            if ((reinterpret_cast<uintptr_t>(cp) & 15) == 0) {
+#pragma unroll
+              for (int j = 0; j < 16; j += 8) {
+                uint4 u;
+                u.x = pack_bf16x2(o[j], o[j + 1]);
+                u.y = pack_bf16x2(o[j + 2], o[j + 3]);
+                u.z = pack_bf16x2(o[j + 4], o[j + 5]);
+                u.w = pack_bf16x2(o[j + 6], o[j + 7]);
+                *reinterpret_cast<uint4*>(cp + j) = u;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) cp[j] = __float2bfloat16_rn(o[j]);
+            }
+          }
+        }
+      }
+      // all TMEM reads of this warp are complete (wait::ld above) -> release the accumulator
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host side: tensor-map cache + launch
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+struct MapKey {
+  const void* ptr;
+  int64_t rows, cols, ld;
+  int box_rows;
+  bool operator==(const MapKey& o) const {
+    return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows;
+  }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    size_t h = reinterpret_cast<size_t>(k.ptr);
+    h = h * 1000003u ^ (size_t)k.rows;
+    h = h * 1000003u ^ (size_t)k.cols;
+    h = h * 1000003u ^ (size_t)k.ld;
+    h = h * 1000003u ^ (size_t)k.box_rows;
+    return h;
+  }
+};
+
+// 2-D bf16 tensor map: inner dim = cols (K), outer = rows; box = {64, box_rows}; 128B swizzle; OOB -> 0.
+int get_tensor_map(const bf16* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows, CUtensorMap* out) {
+  static std::mutex mu;
+  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  MapKey key{ptr, rows, cols, ld, box_rows};
+  {
+    std::lock_guard<std::mutex> g(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) {
+      *out = it->second;
+      return 0;
+    }
+  }
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return set_error(PCY_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<bf16*>(ptr), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(PCY_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) ptr=%p rows=%lld cols=%lld ld=%lld", (int)r,
+                     (const void*)ptr, (long long)rows, (long long)cols, (long long)ld);
+  {
+    std::lock_guard<std::mutex> g(mu);
+    if (cache.size() > 4096) cache.clear();
+    cache.emplace(key, *out);
+  }
+  return 0;
+}
+
+template <int BN>
+int launch(const GemmArgs& a, cudaStream_t stream) {
+  using Cfg = TileCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    PCY_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  CUtensorMap ta, tb;
+  PCY_TRY(get_tensor_map(a.A, a.M, a.K, a.lda, BM, &ta));
+  PCY_TRY(get_tensor_map(a.W, a.N, a.K, a.ldw, BN, &tb));
+  EpiParams p;
+  p.C = a.C; p.ldc = a.ldc; p.bias = a.bias; p.residual = a.residual; p.ldr = a.ldr;
+  p.M = a.M; p.N = a.N; p.K = a.K; p.c_fp32 = a.c_fp32; p.act = a.act; p.scale = a.scale;
+  p.scale_ncols = a.scale_ncols;
+  const int tiles = ceil_div(a.M, BM) * ceil_div(a.N, BN);
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  gemm_bf16_tcgen05_kernel<BN><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
+  PCY_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace
+
+int gemm_bf16_tc(const GemmArgs& a, cudaStream_t stream) {
+  PCY_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0, "gemm: empty problem M=%d N=%d K=%d", a.M, a.N, a.K);
+  PCY_REQUIRE(a.K % 8 == 0 && a.lda % 8 == 0 && a.ldw % 8 == 0, "gemm: K/lda/ldw must be multiples of 8");
+  PCY_REQUIRE((reinterpret_cast<uintptr_t>(a.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.W) & 15) == 0,
+              "gemm: A and W must be 16-byte aligned");
+  if (a.act == ACT_SWIGLU) {
+    PCY_REQUIRE(a.N % 32 == 0 && !a.c_fp32, "gemm: SwiGLU needs N %% 32 == 0 and bf16 output");
+  }
+  // Tile choice: 128x256 unless that leaves most SMs idle / wastes a wide tail.
+  const int sms = num_sms();
+  const int tiles256 = ceil_div(a.M, BM) * ceil_div(a.N, 256);
+  const int tiles128 = ceil_div(a.M, BM) * ceil_div(a.N, 128);
+  bool use128 = (a.N <= 128) || (tiles256 < sms && tiles128 > tiles256);
+  if (!use128) {
+    // wave quantisation: prefer the tile size with the better SM-time efficiency
+    const double w256 = (double)tiles256 / (double)(ceil_div(tiles256, sms) * sms);
+    const double w128 = (double)tiles128 / (double)(ceil_div(tiles128, sms) * sms);
+    if (w128 > w256 * 1.15) use128 = true;
+  }
+  return use128 ? launch<128>(a, stream) : launch<256>(a, stream);
+}
+
+}  // namespace pcy
