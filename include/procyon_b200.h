@@ -52,6 +52,68 @@ int pcy_linear_bf16_ex(const void* A, int64_t lda, const void* W, int64_t ldw, v
  * rows [32g, 32g+16) = gate rows [16g, 16g+16), rows [32g+16, 32g+32) = up rows [16g, 16g+16). F % 16 == 0. */
 int pcy_pack_gate_up(const void* gate, const void* up, void* packed, int F, int K, void* stream);
 
+/* ---- row kernels (exposed for parity tests and for host code that composes ops) ---------------------------
+ * LayerNorm = torch.nn.LayerNorm (fair-esm ESM1bLayerNorm); RMSNorm = HF LlamaRMSNorm. bf16 in/out. */
+int pcy_layernorm_bf16(const void* x, const void* gamma, const void* beta, void* y, int64_t rows, int d, float eps,
+                       void* stream);
+int pcy_rmsnorm_bf16(const void* x, const void* weight, void* y, int64_t rows, int d, float eps, void* stream);
+/* rotate-half RoPE in place on n_heads heads from column col0; position = pos0 + row % T;
+ * cos_sin fp32 [n_pos][head_dim/2][2] (fair-esm RotaryEmbedding / HF apply_rotary_pos_emb). */
+int pcy_rope_inplace(void* x, int64_t rows, int T, int n_heads, int head_dim, int64_t ld, int col0,
+                     const float* cos_sin, int pos0, void* stream);
+/* softmax(scale * q k^T + mask) v without materialising scores. Strides in elements (batch, row, head).
+ * key_valid: uint8 [B,Tk] (1 = attend) or NULL; causal: key j visible to query i iff j <= i + Tk - Tq.
+ * fair-esm MultiheadAttention (procyon/model/esm.py:536), HF LlamaAttention (procyon/model/pmc_llama.py:221-247). */
+int pcy_attention_bf16(const void* q, const void* k, const void* v, void* o, int64_t q_bs, int64_t q_rs, int q_hs,
+                       int64_t k_bs, int64_t k_rs, int k_hs, int64_t v_bs, int64_t v_rs, int v_hs, int64_t o_bs,
+                       int64_t o_rs, int o_hs, int B, int H, int KVH, int Tq, int Tk, int head_dim,
+                       const uint8_t* key_valid, int64_t key_valid_bs, float scale, int causal, void* stream);
+
+/* ---- ESM2 encoder -------------------------------------------------------------------------------------------
+ * Replaces fair-esm `ESM2.forward(tokens, repr_layers=[L])` as called by ESM_PLM.forward
+ * (procyon/model/esm.py:504-541): returns representations[L] (after emb_layer_norm_after), bf16 [B*T, d]. */
+typedef struct {
+  int n_layers, d_model, n_heads, ffn_dim, vocab;
+  int pad_idx, mask_idx, token_dropout;
+  float ln_eps;
+} pcy_esm_config;
+
+enum {
+  PCY_ESM_EMBED = 0, /* bf16 [vocab,d]        embed_tokens.weight */
+  PCY_ESM_LNF_G = 1, /* bf16 [d]              emb_layer_norm_after.weight */
+  PCY_ESM_LNF_B = 2,
+  PCY_ESM_LN1_G = 3, /* bf16 [d]              layers.N.self_attn_layer_norm */
+  PCY_ESM_LN1_B = 4,
+  PCY_ESM_WQKV = 5,  /* bf16 [3d,d]           cat(q_proj, k_proj, v_proj).weight */
+  PCY_ESM_BQKV = 6,  /* fp32 [3d] */
+  PCY_ESM_WO = 7,    /* bf16 [d,d]            out_proj */
+  PCY_ESM_BO = 8,    /* fp32 [d] */
+  PCY_ESM_LN2_G = 9, /* bf16 [d]              final_layer_norm */
+  PCY_ESM_LN2_B = 10,
+  PCY_ESM_W1 = 11,   /* bf16 [ffn,d]          fc1 */
+  PCY_ESM_B1 = 12,   /* fp32 [ffn] */
+  PCY_ESM_W2 = 13,   /* bf16 [d,ffn]          fc2 */
+  PCY_ESM_B2 = 14    /* fp32 [d] */
+};
+
+int pcy_esm_create(const pcy_esm_config* cfg, void** handle);
+int pcy_esm_destroy(void* handle);
+/* src may be a host or a device pointer; the library keeps its own packed copy */
+int pcy_esm_load_tensor(void* handle, int kind, int layer, const void* src, int64_t nbytes);
+/* cos/sin table fp32 [n_pos][head_dim/2][2] (host or device pointer); n_pos >= the longest T encoded */
+int pcy_esm_set_rope_table(void* handle, const float* cos_sin, int n_pos);
+int64_t pcy_esm_workspace_bytes(void* handle, int B, int T);
+/* tokens int32 [B,T] (device) -> out_states bf16 [B*T, d] (device) */
+int pcy_esm_encode(void* handle, const int32_t* tokens, int B, int T, void* out_states, void* workspace,
+                   int64_t workspace_bytes, void* stream);
+/* ProteinPooler.forward (procyon/model/esm.py:154-217): out[o] = mean|max over the non-pad token rows of the chunk
+ * rows seg_rows[seg_ptr[o] : seg_ptr[o+1]] (concatenated in that order). mode 0 = mean (nanmean), 1 = max;
+ * correction = protein_pooling_correction_option (drop first and last non-pad row, mean only).
+ * states bf16 [n_rows*T, d]; tokens int32 [n_rows, T]; out bf16 or fp32 [n_out, d]. */
+int pcy_pool_segments(const void* states, const int32_t* tokens, const int32_t* seg_ptr, const int32_t* seg_rows,
+                      void* out, int out_fp32, int T, int d, int n_out, int pad_idx, int mode, int correction,
+                      void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -69,4 +69,29 @@ int pcy_pack_gate_up(const void* gate, const void* up, void* packed, int F, int 
   return 0;
 }
 
+int pcy_layernorm_bf16(const void* x, const void* gamma, const void* beta, void* y, int64_t rows, int d, float eps,
+                       void* stream) {
+  return layernorm_bf16((const bf16*)x, (const bf16*)gamma, (const bf16*)beta, (bf16*)y, rows, d, eps,
+                        (cudaStream_t)stream);
+}
+int pcy_rmsnorm_bf16(const void* x, const void* weight, void* y, int64_t rows, int d, float eps, void* stream) {
+  return rmsnorm_bf16((const bf16*)x, (const bf16*)weight, (bf16*)y, rows, d, eps, (cudaStream_t)stream);
+}
+int pcy_rope_inplace(void* x, int64_t rows, int T, int n_heads, int head_dim, int64_t ld, int col0,
+                     const float* cos_sin, int pos0, void* stream) {
+  return rope_inplace((bf16*)x, rows, T, n_heads, head_dim, ld, col0, cos_sin, nullptr, pos0, (cudaStream_t)stream);
+}
+int pcy_attention_bf16(const void* q, const void* k, const void* v, void* o, int64_t q_bs, int64_t q_rs, int q_hs,
+                       int64_t k_bs, int64_t k_rs, int k_hs, int64_t v_bs, int64_t v_rs, int v_hs, int64_t o_bs,
+                       int64_t o_rs, int o_hs, int B, int H, int KVH, int Tq, int Tk, int head_dim,
+                       const uint8_t* key_valid, int64_t key_valid_bs, float scale, int causal, void* stream) {
+  AttnArgs a;
+  a.q = (const bf16*)q; a.k = (const bf16*)k; a.v = (const bf16*)v; a.o = (bf16*)o;
+  a.q_bs = q_bs; a.q_rs = q_rs; a.q_hs = q_hs; a.k_bs = k_bs; a.k_rs = k_rs; a.k_hs = k_hs;
+  a.v_bs = v_bs; a.v_rs = v_rs; a.v_hs = v_hs; a.o_bs = o_bs; a.o_rs = o_rs; a.o_hs = o_hs;
+  a.B = B; a.H = H; a.KVH = KVH; a.Tq = Tq; a.Tk = Tk; a.head_dim = head_dim;
+  a.key_valid = key_valid; a.key_valid_bs = key_valid_bs; a.scale = scale; a.causal = causal;
+  return flash_attention(a, (cudaStream_t)stream);
+}
+
 }  // extern "C"

@@ -299,6 +299,12 @@ pool_kernel(const bf16* __restrict__ x, const int32_t* __restrict__ tokens, cons
   }
 }
 
+__global__ void key_valid_kernel(const int32_t* __restrict__ tokens, uint8_t* __restrict__ valid, int64_t n,
+                                 int pad_idx) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    valid[i] = tokens[i] != pad_idx;
+}
+
 __global__ void rope_table_kernel(float* __restrict__ cos_sin, int P, int half, float theta, int head_dim) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= P * half) return;
@@ -354,6 +360,15 @@ int rope_inplace(bf16* x, int64_t rows, int T, int n_heads, int head_dim, int64_
 int rope_table(float* cos_sin, int P, int head_dim, float theta, cudaStream_t stream) {
   const int half = head_dim / 2;
   rope_table_kernel<<<ceil_div((int64_t)P * half, 256), 256, 0, stream>>>(cos_sin, P, half, theta, head_dim);
+  PCY_LAUNCH_CHECK();
+  return 0;
+}
+
+int make_key_valid(const int32_t* tokens, uint8_t* valid, int64_t n, int pad_idx, cudaStream_t stream) {
+  if (n == 0) return 0;
+  int grid = ceil_div(n, 256);
+  if (grid > 4096) grid = 4096;
+  key_valid_kernel<<<grid, 256, 0, stream>>>(tokens, valid, n, pad_idx);
   PCY_LAUNCH_CHECK();
   return 0;
 }

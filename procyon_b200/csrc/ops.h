@@ -45,25 +45,39 @@ int layernorm_bf16(const bf16* x, const bf16* gamma, const bf16* beta, bf16* y, 
                    cudaStream_t stream);
 int rmsnorm_bf16(const bf16* x, const bf16* weight, bf16* y, int64_t rows, int d, float eps, cudaStream_t stream);
 
-// ---- ESM2 pieces -------------------------------------------------------------------------------
+// ---- embeddings / rotary / pooling -------------------------------------------------------------
 // x[b,t,:] = E[tok] * (1-0.12)/(1-mask_ratio_b); mask tokens -> 0; pad rows -> 0  (fair-esm ESM2.forward)
 int esm_embed(const int32_t* tokens, const bf16* table, bf16* x, int B, int T, int d, int pad_idx, int mask_idx,
               int token_dropout, cudaStream_t stream);
-// rotate-half RoPE on q and k inside a fused [rows, 3*d] qkv buffer; position = row % T.
-int rope_qk_inplace(bf16* qkv, int64_t rows, int T, int n_heads, int head_dim, int64_t ld, const float* cos_sin,
-                    cudaStream_t stream);
-// fills cos_sin[T][head_dim/2][2] fp32
-int rope_table(float* cos_sin, int T, int head_dim, float theta, int pos0, cudaStream_t stream);
-// bidirectional attention with key-padding mask. qkv [B*T, 3d] (q pre-scaled), out [B*T, d].
-int esm_attention(const bf16* qkv, const int32_t* tokens, bf16* out, int B, int T, int n_heads, int head_dim,
-                  int pad_idx, cudaStream_t stream);
-// ProteinPooler: segmented mean/max over non-pad rows grouped by batch_keys.
-int pool_segments(const bf16* x, const int32_t* tokens, const int32_t* batch_keys, void* out, int out_fp32,
-                  int n_rows, int T, int d, int n_out, int pad_idx, int mode /*0 mean,1 max*/, int correction,
-                  cudaStream_t stream);
-
-// ---- Llama pieces -------------------------------------------------------------------------------
 int llama_embed_splice(const int32_t* ids, const bf16* table, const bf16* soft_tokens, const int32_t* soft_index,
                        bf16* x, int64_t n_tok, int d, cudaStream_t stream);
+// rotate-half RoPE, in place, on n_heads heads starting at column col0 of each row; position =
+// (pos_ptr ? *pos_ptr : pos0) + row % T; cos_sin fp32 [P][head_dim/2][2].
+int rope_inplace(bf16* x, int64_t rows, int T, int n_heads, int head_dim, int64_t ld, int col0,
+                 const float* cos_sin, const int32_t* pos_ptr, int pos0, cudaStream_t stream);
+int rope_table(float* cos_sin, int P, int head_dim, float theta, cudaStream_t stream);
+// ProteinPooler: segmented mean/max over non-pad rows. seg_ptr [n_out+1], seg_rows = chunk rows per output.
+int pool_segments(const bf16* x, const int32_t* tokens, const int32_t* seg_ptr, const int32_t* seg_rows, void* out,
+                  int out_fp32, int T, int d, int n_out, int pad_idx, int mode /*0 mean,1 max*/, int correction,
+                  cudaStream_t stream);
+// key_valid[i] = tokens[i] != pad_idx
+int make_key_valid(const int32_t* tokens, uint8_t* valid, int64_t n, int pad_idx, cudaStream_t stream);
+
+// ---- attention ------------------------------------------------------------------------------------
+struct AttnArgs {
+  const bf16* q = nullptr;
+  const bf16* k = nullptr;
+  const bf16* v = nullptr;
+  bf16* o = nullptr;
+  // element strides: batch, row (token), head
+  int64_t q_bs = 0, q_rs = 0, k_bs = 0, k_rs = 0, v_bs = 0, v_rs = 0, o_bs = 0, o_rs = 0;
+  int q_hs = 0, k_hs = 0, v_hs = 0, o_hs = 0;
+  int B = 0, H = 0, KVH = 0, Tq = 0, Tk = 0, head_dim = 0;
+  const uint8_t* key_valid = nullptr;  // [B, Tk] 1 = attend; may be null
+  int64_t key_valid_bs = 0;
+  float scale = 1.0f;  // multiplies q.k before softmax
+  int causal = 0;      // key j visible to query i iff j <= i + (Tk - Tq)
+};
+int flash_attention(const AttnArgs& a, cudaStream_t stream);
 
 }  // namespace pcy

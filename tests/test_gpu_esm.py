@@ -1,0 +1,87 @@
+"""ESM2 encoder + pooler on the GPU vs the CPU oracle (same seeded weights and tokens)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _build(num_params, sd, pooling="mean", correction=False, custom=None, max_len=1024):
+    from procyon_b200.model.esm import ESM_PLM
+
+    m = ESM_PLM(num_params=num_params, pooling_method=pooling, protein_pooling_correction_option=correction,
+                custom_config=custom, max_protein_len=max_len)
+    missing = m.model.load_state_dict(sd, strict=True)
+    return m.cuda()
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(name="tiny16", custom=(2, 64, 4), lengths=[20, 9, 31, 1]),        # head_dim 16
+    dict(name="tiny24", custom=(2, 96, 4), lengths=[50, 70, 3]),           # head_dim 24 (ESM2-35M style)
+    dict(name="tiny64", custom=(3, 256, 4), lengths=[130, 64, 100, 129]),  # head_dim 64 (650M style)
+])
+def test_esm_states_and_pool(cuda_device, cfg):
+    from oracle import esm2 as O
+
+    L, d, H = cfg["custom"]
+    sd = O.random_esm_state_dict(L, d, seed=7)
+    toks = O.random_protein_tokens(len(cfg["lengths"]), 0, seed=3, lengths=cfg["lengths"])
+    toks[0, 3] = O.MASK_IDX  # exercise the mask-dropout rescale
+    ref = O.esm2_forward(sd, toks, L, H, act_round="bf16")
+    m = _build("custom", sd, custom=cfg["custom"])
+    got = m.encode_tokens(toks.cuda()).float().cpu()
+    nonpad = toks != O.PAD_IDX
+    # bf16 activations through L layers: tolerance = a few bf16 ulps of O(1) LayerNorm outputs
+    torch.testing.assert_close(got[nonpad], ref[nonpad], rtol=3e-2, atol=3e-2)
+    for pooling, corr in (("mean", False), ("mean", True), ("max", False)):
+        m.pooler.pooling_method = pooling
+        m.pooler.protein_pooling_correction_option = corr
+        z, logits = m(toks.cuda())
+        assert logits is None
+        refp = O.protein_pooler(ref, torch.arange(toks.shape[0]), ~nonpad, pooling, corr)
+        torch.testing.assert_close(z.float().cpu(), refp, rtol=3e-2, atol=3e-2)
+
+
+def test_esm_config1_35m(cuda_device):
+    """BASELINE config 1: ESM2-35M encode of 16 synthetic 256-residue proteins, pooled (mean)."""
+    from oracle import esm2 as O
+
+    L, d, H = O.ESM_SIZES["35m"]
+    sd = O.random_esm_state_dict(L, d, seed=0)
+    toks = O.random_protein_tokens(16, 256, seed=1234)
+    ref = O.esm_plm_forward(sd, toks, L, H, pooling="mean", act_round="bf16")
+    m = _build("35m", sd, pooling="mean")
+    z, _ = m(toks.cuda())
+    assert z.shape == (16, d)
+    torch.testing.assert_close(z.float().cpu(), ref, rtol=3e-2, atol=2e-2)
+    # determinism + micro-batching invariance: pooled rows do not depend on the pass they were encoded in
+    m.max_tokens_per_pass = 3 * toks.shape[1]
+    z2, _ = m(toks.cuda())
+    assert torch.equal(z, z2)
+
+
+def test_esm_long_protein_split(cuda_device):
+    """Proteins longer than max_protein_len are chunked into extra rows and re-pooled across chunks."""
+    from oracle import esm2 as O
+
+    L, d, H = 2, 64, 4
+    sd = O.random_esm_state_dict(L, d, seed=11)
+    toks = O.random_protein_tokens(3, 0, seed=5, lengths=[100, 30, 75])
+    for pooling in ("mean", "max"):
+        ref = O.esm_plm_forward(sd, toks, L, H, pooling=pooling, max_protein_len=32, act_round="bf16")
+        m = _build("custom", sd, pooling=pooling, custom=(L, d, H), max_len=32)
+        z, _ = m(toks.cuda())
+        assert z.shape == ref.shape == (3, d)
+        torch.testing.assert_close(z.float().cpu(), ref, rtol=3e-2, atol=2e-2)
+        zs, _ = m(toks.cuda(), aggregate=False)
+        refs = O.esm_plm_forward(sd, toks, L, H, max_protein_len=32, act_round="bf16", aggregate=False)
+        assert zs.shape == refs.shape
+        keep = (toks != O.PAD_IDX)[:, : refs.shape[1]]
+        torch.testing.assert_close(zs.float().cpu()[keep], refs[keep], rtol=3e-2, atol=3e-2)
+
+
+def test_esm_empty_batch(cuda_device):
+    from procyon_b200.model.esm import ESM_PLM
+
+    m = ESM_PLM(num_params="custom", custom_config=(1, 64, 4), pooling_method="mean").cuda()
+    out = m.encode_tokens(torch.zeros((0, 10), dtype=torch.int64, device="cuda"))
+    assert out.shape == (0, 10, 64)

@@ -1,0 +1,158 @@
+"""Parity of the op-level C ABI (called through ctypes) against the CPU oracle / plain fp32 torch on CPU."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _cpu_linear(a, w, bias=None, residual=None, act=0, scale=1.0, scale_ncols=0):
+    v = a.float() @ w.float().t()
+    if bias is not None:
+        v = v + bias
+    if scale_ncols:
+        v[:, :scale_ncols] *= scale
+    if act == 1:
+        v = F.gelu(v)
+    elif act == 2:
+        M, N = v.shape
+        v = v.view(M, N // 32, 2, 16)
+        v = (F.silu(v[:, :, 0]) * v[:, :, 1]).reshape(M, N // 2)
+    if residual is not None:
+        v = v + residual.float()
+    return v
+
+
+@pytest.mark.parametrize("M,N,K,force", [
+    (128, 256, 64, "tc"), (300, 1000, 200, "tc"), (17, 264, 72, "tc"), (514, 3840, 1280, "tc"),
+    (1, 4096, 4096, "skinny"), (3, 1000, 512, "skinny"), (10, 2560, 1280, "skinny"), (16, 520, 264, "skinny"),
+    (5, 4096, 14336, "skinny"),
+])
+@pytest.mark.parametrize("epi", ["plain", "bias_gelu", "bias_res_scale"])
+def test_linear_parity(cuda_device, M, N, K, force, epi):
+    from procyon_b200 import ops
+
+    g = torch.Generator().manual_seed(M + 13 * N + 7 * K)
+    a = (torch.randn(M, K, generator=g) * 0.5).bfloat16()
+    w = (torch.randn(N, K, generator=g) / math.sqrt(K)).bfloat16()
+    bias = torch.randn(N, generator=g) if epi != "plain" else None
+    res = torch.randn(M, N, generator=g).bfloat16() if epi == "bias_res_scale" else None
+    act = 1 if epi == "bias_gelu" else 0
+    sc = 64 if epi == "bias_res_scale" else 0
+    ref = _cpu_linear(a, w, bias, res, act, 0.125, sc)
+    out = ops.linear(a.cuda(), w.cuda(), bias.cuda() if bias is not None else None,
+                     residual=res.cuda() if res is not None else None, act=act, scale=0.125, scale_ncols=sc,
+                     force=force)
+    # tolerance: one bf16 rounding of the output (2^-8 relative) + fp32 accumulation-order noise
+    torch.testing.assert_close(out.float().cpu(), ref, rtol=1e-2, atol=1e-2 * ref.abs().max().item())
+    out32 = ops.linear(a.cuda(), w.cuda(), bias.cuda() if bias is not None else None,
+                       residual=res.cuda() if res is not None else None, act=act, scale=0.125, scale_ncols=sc,
+                       force=force, out_fp32=True)
+    torch.testing.assert_close(out32.cpu(), ref, rtol=2e-4, atol=2e-4 * ref.abs().max().item())
+
+
+@pytest.mark.parametrize("M,force", [(1, "skinny"), (4, "skinny"), (9, "skinny"), (200, "tc")])
+def test_swiglu_parity(cuda_device, M, force):
+    from procyon_b200 import ops
+
+    g = torch.Generator().manual_seed(M)
+    Fdim, K = 1024, 512
+    a = (torch.randn(M, K, generator=g) * 0.5).bfloat16()
+    gate = (torch.randn(Fdim, K, generator=g) / math.sqrt(K)).bfloat16()
+    up = (torch.randn(Fdim, K, generator=g) / math.sqrt(K)).bfloat16()
+    ref = F.silu(a.float() @ gate.float().t()) * (a.float() @ up.float().t())
+    packed = ops.pack_gate_up(gate.cuda(), up.cuda())
+    out = ops.linear(a.cuda(), packed, act=ops.ACT_SWIGLU, force=force)
+    torch.testing.assert_close(out.float().cpu(), ref, rtol=1e-2, atol=1e-2 * ref.abs().max().item())
+
+
+def test_linear_is_linear_at_full_size(cuda_device):
+    """size-independent property at Llama shapes: f(a1 + a2) == f(a1) + f(a2) in fp32 output."""
+    from procyon_b200 import ops
+
+    torch.manual_seed(0)
+    w = (torch.randn(6144, 4096, device="cuda") / 64).bfloat16()
+    a1 = torch.randn(1024, 4096, device="cuda").bfloat16()
+    a2 = (torch.randn(1024, 4096, device="cuda") * 2 ** -9).bfloat16()
+    s = (a1.float() + a2.float()).bfloat16()
+    exact = (s.float() == a1.float() + a2.float())
+    o1 = ops.linear(a1, w, out_fp32=True, force="tc")
+    o2 = ops.linear(a2, w, out_fp32=True, force="tc")
+    os_ = ops.linear(s, w, out_fp32=True, force="tc")
+    rows = exact.all(dim=1)
+    assert rows.any()
+    torch.testing.assert_close(os_[rows], (o1 + o2)[rows], rtol=1e-3, atol=1e-3)
+    # tensor-core and weight-streaming kernels agree on the same rows
+    o_sk = ops.linear(a1[:8], w, out_fp32=True, force="skinny")
+    torch.testing.assert_close(o_sk, o1[:8], rtol=1e-4, atol=1e-3)
+
+
+@pytest.mark.parametrize("d", [320, 480, 1280, 2560, 4096, 5120])
+def test_norms(cuda_device, d):
+    from procyon_b200 import _lib
+    from procyon_b200._lib import c_float, c_i64, c_int, check, ptr, stream_ptr
+
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(d)
+    x = (torch.randn(37, d, generator=g) * 2 + 0.3).bfloat16()
+    w = (1 + 0.1 * torch.randn(d, generator=g)).bfloat16()
+    b = (0.1 * torch.randn(d, generator=g)).bfloat16()
+    xc, wc, bc = x.cuda(), w.cuda(), b.cuda()
+    y = torch.empty_like(xc)
+    check(lib.pcy_layernorm_bf16(ptr(xc), ptr(wc), ptr(bc), ptr(y), c_i64(37), c_int(d), c_float(1e-5), stream_ptr()))
+    ref = F.layer_norm(x.float(), (d,), w.float(), b.float(), 1e-5)
+    torch.testing.assert_close(y.float().cpu(), ref.bfloat16().float(), rtol=1.6e-2, atol=1e-2)
+    check(lib.pcy_rmsnorm_bf16(ptr(xc), ptr(wc), ptr(y), c_i64(37), c_int(d), c_float(1e-5), stream_ptr()))
+    xf = x.float()
+    ref = (w.float() * (xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-5)).bfloat16().float()).bfloat16()
+    torch.testing.assert_close(y.float().cpu(), ref.float(), rtol=1.6e-2, atol=1e-2)
+
+
+@pytest.mark.parametrize("hd,H,KVH,Tq,Tk,causal,masked", [
+    (64, 4, 4, 70, 70, 0, True), (24, 5, 5, 33, 33, 0, True), (16, 4, 4, 130, 130, 0, False),
+    (128, 8, 2, 200, 200, 1, True), (128, 4, 1, 64, 64, 1, False), (64, 2, 2, 514, 514, 0, True),
+    (128, 8, 2, 5, 133, 1, False),
+])
+def test_attention_parity(cuda_device, hd, H, KVH, Tq, Tk, causal, masked):
+    from procyon_b200 import _lib
+    from procyon_b200._lib import c_float, c_i64, c_int, check, ptr, stream_ptr
+
+    lib = _lib.load()
+    B = 2
+    g = torch.Generator().manual_seed(hd + Tq)
+    q = torch.randn(B, Tq, H, hd, generator=g).bfloat16()
+    k = torch.randn(B, Tk, KVH, hd, generator=g).bfloat16()
+    v = torch.randn(B, Tk, KVH, hd, generator=g).bfloat16()
+    valid = torch.ones(B, Tk, dtype=torch.uint8)
+    if masked:
+        if causal:
+            valid[1, :7] = 0  # left padding
+        else:
+            valid[1, Tk - 9:] = 0  # right padding
+    scale = 1.0 / math.sqrt(hd)
+    # oracle: eager attention in fp32 (pmc_llama.py:221-247 / fair-esm MultiheadAttention)
+    rep = H // KVH
+    kk = k.float().repeat_interleave(rep, dim=2).permute(0, 2, 1, 3)
+    vv = v.float().repeat_interleave(rep, dim=2).permute(0, 2, 1, 3)
+    s = (q.float().permute(0, 2, 1, 3) @ kk.transpose(-1, -2)) * scale
+    mask = (valid == 0)[:, None, None, :].expand(B, H, Tq, Tk).clone()
+    if causal:
+        i = torch.arange(Tq)[:, None] + (Tk - Tq)
+        j = torch.arange(Tk)[None, :]
+        mask |= (j > i)[None, None]
+    s = s.masked_fill(mask, float("-inf"))
+    pr = torch.softmax(s, dim=-1)
+    pr = torch.nan_to_num(pr, nan=0.0)
+    ref = (pr @ vv).permute(0, 2, 1, 3)  # B,Tq,H,hd
+    qc, kc, vc, vm = q.cuda(), k.cuda(), v.cuda(), valid.cuda()
+    o = torch.zeros(B, Tq, H, hd, device="cuda", dtype=torch.bfloat16)
+    check(lib.pcy_attention_bf16(ptr(qc), ptr(kc), ptr(vc), ptr(o), c_i64(Tq * H * hd), c_i64(H * hd), c_int(hd),
+                                 c_i64(Tk * KVH * hd), c_i64(KVH * hd), c_int(hd), c_i64(Tk * KVH * hd),
+                                 c_i64(KVH * hd), c_int(hd), c_i64(Tq * H * hd), c_i64(H * hd), c_int(hd), c_int(B),
+                                 c_int(H), c_int(KVH), c_int(Tq), c_int(Tk), c_int(hd), ptr(vm), c_i64(Tk),
+                                 c_float(scale), c_int(causal), stream_ptr()))
+    got = o.float().cpu()
+    rows_ok = ~mask.all(dim=-1).permute(0, 2, 1)  # fully masked query rows are undefined in the reference
+    torch.testing.assert_close(got[rows_ok], ref[rows_ok], rtol=2e-2, atol=2e-2)
