@@ -114,6 +114,84 @@ int pcy_pool_segments(const void* states, const int32_t* tokens, const int32_t* 
                       void* out, int out_fp32, int T, int d, int n_out, int pad_idx, int mode, int correction,
                       void* stream);
 
+/* ---- Llama decoder ------------------------------------------------------------------------------------------
+ * Replaces LlamaPostTokenization.forward -> HF LlamaForCausalLM.forward (procyon/model/pmc_llama.py:546-596),
+ * the prefill / decode calls of UnifiedProCyon._generate_beam_search and _generate_sampling
+ * (procyon/model/model_unified.py:762-769, :885-887) and their token selection (:782-833, :891-911). */
+typedef struct {
+  int n_layers, d_model, n_heads, n_kv_heads, head_dim, ffn_dim, vocab;
+  float rms_eps;
+} pcy_llama_config;
+
+enum {
+  PCY_LLAMA_EMBED = 0,   /* bf16 [V,d]            model.embed_tokens.weight */
+  PCY_LLAMA_LM_HEAD = 1, /* bf16 [V,d]            lm_head.weight */
+  PCY_LLAMA_NORM = 2,    /* bf16 [d]              model.norm.weight */
+  PCY_LLAMA_LN1 = 3,     /* bf16 [d]              layers.N.input_layernorm.weight */
+  PCY_LLAMA_LN2 = 4,     /* bf16 [d]              layers.N.post_attention_layernorm.weight */
+  PCY_LLAMA_WQKV = 5,    /* bf16 [(H+2KVH)hd,d]   cat(q_proj, k_proj, v_proj).weight */
+  PCY_LLAMA_WO = 6,      /* bf16 [d,H*hd]         o_proj.weight */
+  PCY_LLAMA_WGATEUP = 7, /* bf16 [2F,d]           pcy_pack_gate_up(gate_proj.weight, up_proj.weight) */
+  PCY_LLAMA_WDOWN = 8    /* bf16 [d,F]            down_proj.weight */
+};
+
+int pcy_llama_create(const pcy_llama_config* cfg, void** handle);
+int pcy_llama_destroy(void* handle);
+int pcy_llama_load_tensor(void* handle, int kind, int layer, const void* src, int64_t nbytes);
+/* cos/sin fp32 [n_pos][head_dim/2][2] (host or device); n_pos >= prompt length + generated length */
+int pcy_llama_set_rope_table(void* handle, const float* cos_sin, int n_pos);
+int64_t pcy_llama_prefill_workspace_bytes(void* handle, int B, int S);
+/* Full-sequence forward over B sequences of S positions (left- or right-padded; key_valid uint8 [B,S], 1 = attend,
+ * NULL = no padding). input_embeds bf16 [B*S,d]. Optional outputs: kv_prompt bf16 [L][2][B][S][KVH*hd] (the KV
+ * cache, one copy per input), hidden_out bf16 [B*S,d] (= hidden_states[-1], after the final RMSNorm),
+ * sel_logits fp32 [n_sel,V] = LM-head logits of the flat rows sel_rows[0..n_sel). */
+int pcy_llama_prefill(void* handle, const void* input_embeds, const uint8_t* key_valid, int B, int S, void* kv_prompt,
+                      void* hidden_out, const int32_t* sel_rows, int n_sel, float* sel_logits, void* workspace,
+                      int64_t workspace_bytes, void* stream);
+
+/* Device-resident state of one generate() call. rows = n_inputs * beams (<= 16). All pointers are device memory
+ * owned by the caller. state[0] = t (tokens generated so far), state[2] = 1 once every beam of every input holds an
+ * EOS (beam mode with stop_on_all_eos), state[3] = the step at which that happened. */
+typedef struct {
+  int n_inputs, beams, S, max_gen;
+  const void* kv_prompt;       /* bf16 [L][2][n_inputs][S][KVH*hd], from pcy_llama_prefill */
+  const uint8_t* prompt_valid; /* uint8 [n_inputs][S] or NULL */
+  void* kv_gen;                /* bf16 [L][2][rows][max_gen][KVH*hd] */
+  int32_t* tokens;             /* [rows][max_gen] generated token ids */
+  int32_t* slots;              /* [rows][max_gen] physical KV row of every generated position (beam ancestry) */
+  float* logprobs;             /* [rows] running log-probabilities */
+  float* logits_cur;           /* fp32 [rows][V] logits of the current step */
+  float* logits_hist;          /* fp32 [max_gen][rows][V] per-step logits (physical rows) or NULL */
+  int32_t* state;              /* int32 [8] */
+  void* workspace;
+  int64_t workspace_bytes;
+} pcy_decode_buffers;
+
+#define PCY_SELECT_GREEDY 0
+#define PCY_SELECT_BEAM 1
+
+int64_t pcy_llama_decode_workspace_bytes(void* handle, int rows, int S, int max_gen);
+/* clears state/tokens/slots/log-probs/workspace; copies prefill_logits fp32 [n_inputs,V] to every beam row */
+int pcy_decode_reset(void* handle, const pcy_decode_buffers* b, const float* prefill_logits, void* stream);
+/* one model step on token t-1 of every row (KV-cache append + attention through `slots`) -> logits_cur */
+int pcy_llama_decode_forward(void* handle, const pcy_decode_buffers* b, void* stream);
+/* token selection from logits_cur: greedy arg-max, or diverse beam search (Hamming penalty across groups) with
+ * beam reorder of tokens / log-probs / KV ancestry; appends logits to logits_hist; t += 1 */
+int pcy_decode_select(void* handle, const pcy_decode_buffers* b, int mode, int group_size, float diversity_penalty,
+                      int eos_id, int stop_on_all_eos, void* stream);
+
+/* ---- losses and retrieval scoring -------------------------------------------------------------------------
+ * Row-wise cross-entropy of fp32 logits [rows, V] (row stride ld) against int32 labels: acc[0] += sum_i
+ * (logsumexp(x_i) - x_i[label_i]), acc[1] += rows. HF LlamaForCausalLM loss (procyon/model/pmc_llama.py:576) is
+ * acc[0]/acc[1] over the shifted, non-ignored positions. */
+int pcy_cross_entropy_rows(const float* logits, const int32_t* labels, int rows, int V, int64_t ld, float* acc,
+                           void* stream);
+/* out[q][n] = cos(queries[q], db[n]) with F.normalize semantics (eps 1e-12): get_proteins_from_embedding
+ * (procyon/data/inference_utils.py:955-961), ProcyonRetrievalEval cosine sims
+ * (procyon/evaluate/framework/procyon.py:400-406). queries fp32 [nq,d]; db fp32 or bf16 [n_db,d]. */
+int pcy_cosine_scores(const float* queries, const void* db, int db_is_bf16, float* out, int n_queries, int n_db,
+                      int d, int64_t ld_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

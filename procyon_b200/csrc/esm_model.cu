@@ -149,6 +149,7 @@ int64_t pcy_esm_workspace_bytes(void* handle, int B, int T) {
 
 int pcy_esm_encode(void* handle, const int32_t* tokens, int B, int T, void* out_states, void* workspace,
                    int64_t workspace_bytes, void* stream_) {
+  if (B == 0 || T == 0) return 0;
   PCY_REQUIRE(handle && tokens && out_states && workspace, "esm_encode: null argument");
   EsmModel* m = reinterpret_cast<EsmModel*>(handle);
   cudaStream_t stream = (cudaStream_t)stream_;

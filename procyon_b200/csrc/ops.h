@@ -80,4 +80,48 @@ struct AttnArgs {
 };
 int flash_attention(const AttnArgs& a, cudaStream_t stream);
 
+// ---- decode-step attention (RoPE + KV append + split-KV attention + combine, one launch) ------------
+struct DecodeAttnArgs {
+  const bf16* qkv = nullptr;  // [rows, (H + 2 KVH) * head_dim], un-roped output of the fused QKV projection
+  int64_t qkv_ld = 0;
+  const float* cos_sin = nullptr;
+  const bf16* k_prompt = nullptr;  // [n_inputs][S][KVH*head_dim]
+  const bf16* v_prompt = nullptr;
+  bf16* k_gen = nullptr;  // [rows][max_gen][KVH*head_dim]
+  bf16* v_gen = nullptr;
+  const int32_t* slots = nullptr;         // [rows][max_gen]
+  const uint8_t* prompt_valid = nullptr;  // [n_inputs][S] or null
+  const int32_t* state = nullptr;         // device: state[0] = t
+  float* partials = nullptr;
+  int32_t* tickets = nullptr;  // [rows*KVH], zero-initialised once
+  bf16* out = nullptr;         // [rows, H*head_dim]
+  int rows = 0, beams = 1, H = 0, KVH = 0, head_dim = 0, S = 0, max_gen = 0;
+};
+int decode_attention(const DecodeAttnArgs& a, cudaStream_t stream);
+int decode_attention_splits(int S, int max_gen);
+int64_t decode_attention_partial_floats(int rows, int H, int KVH, int S, int max_gen);
+
+// ---- decode-step token selection ---------------------------------------------------------------------
+struct DecodeSelectArgs {
+  const float* logits = nullptr;  // [rows][vocab]
+  float* logits_hist = nullptr;   // [max_gen][rows][vocab] or null
+  int32_t* tokens = nullptr;      // [rows][max_gen]
+  int32_t* slots = nullptr;       // [rows][max_gen]
+  float* logprobs = nullptr;      // [rows]
+  int32_t* state = nullptr;       // [8]: t, -, finished, finish_step, scratch
+  float* workspace = nullptr;     // topk_workspace_floats(rows)
+  int n_inputs = 0, beams = 1, group = 1, max_gen = 0, vocab = 0, eos_id = -1;
+  float diversity_penalty = 0.f;
+  int greedy = 0;
+  int stop_on_all_eos = 0;
+};
+int decode_select(const DecodeSelectArgs& a, cudaStream_t stream);
+int topk_workspace_floats(int rows);
+
+// ---- losses / scoring -----------------------------------------------------------------------------------
+int cross_entropy_rows(const float* logits, const int32_t* labels, int rows, int V, int64_t ld, float* acc,
+                       cudaStream_t stream);
+int cosine_scores(const float* Q, const void* D, int db_bf16, float* out, int nq, int N, int d, int64_t ldo,
+                  cudaStream_t stream);
+
 }  // namespace pcy
