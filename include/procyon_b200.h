@@ -192,6 +192,22 @@ int pcy_cross_entropy_rows(const float* logits, const int32_t* labels, int rows,
 int pcy_cosine_scores(const float* queries, const void* db, int db_is_bf16, float* out, int n_queries, int n_db,
                       int d, int64_t ld_out, void* stream);
 
+/* F.normalize(x, dim=-1) on fp32 rows */
+int pcy_normalize_rows(const float* x, float* out, int rows, int d, void* stream);
+/* InfoNCEInBatch.forward (procyon/model/contrastive.py:120-204) on L2-normalised fp32 embeddings:
+ * sim_st = zs @ all_t^T / tau, sim_ts = zt @ all_s^T / tau, logits multiplied by mask[rank_off+i][j] (uint8 [G,G] or
+ * NULL), targets rank_off + i, loss = (CE_st + CE_ts) / 2 -> loss[0]. sims_scratch: fp32 [2*b*G]. Without gathering,
+ * pass all_s = zs, all_t = zt, G = b, rank_off = 0. */
+int pcy_infonce_loss(const float* zs, const float* zt, const float* all_s, const float* all_t, const uint8_t* mask,
+                     float* sims_scratch, float* loss, int b, int G, int d, int rank_off, float temperature,
+                     void* stream);
+
+/* Token embedding + soft-token splice: UnifiedProCyon._prepare_input_embeddings
+ * (procyon/model/model_unified.py:1147-1167). out[i] = soft_tokens[soft_index[i]] if soft_index[i] >= 0 else
+ * table[ids[i]]; ids/soft_index int32 [n_tok] (soft_index may be NULL), table/soft/out bf16 rows of width d. */
+int pcy_embed_splice(const int32_t* ids, const void* table, const void* soft_tokens, const int32_t* soft_index,
+                     void* out, int64_t n_tok, int d, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -94,4 +94,10 @@ int pcy_attention_bf16(const void* q, const void* k, const void* v, void* o, int
   return flash_attention(a, (cudaStream_t)stream);
 }
 
+int pcy_embed_splice(const int32_t* ids, const void* table, const void* soft_tokens, const int32_t* soft_index,
+                     void* out, int64_t n_tok, int d, void* stream) {
+  return llama_embed_splice(ids, (const bf16*)table, (const bf16*)soft_tokens, soft_index, (bf16*)out, n_tok, d,
+                            (cudaStream_t)stream);
+}
+
 }  // extern "C"

@@ -121,6 +121,10 @@ int topk_workspace_floats(int rows);
 // ---- losses / scoring -----------------------------------------------------------------------------------
 int cross_entropy_rows(const float* logits, const int32_t* labels, int rows, int V, int64_t ld, float* acc,
                        cudaStream_t stream);
+int normalize_rows(const float* x, float* out, int rows, int d, cudaStream_t stream);
+int infonce_loss(const float* zs, const float* zt, const float* all_s, const float* all_t, const uint8_t* mask,
+                 float* sims_scratch, float* loss, int b, int G, int d, int rank_off, float temperature,
+                 cudaStream_t stream);
 int cosine_scores(const float* Q, const void* D, int db_bf16, float* out, int nq, int N, int d, int64_t ldo,
                   cudaStream_t stream);
 

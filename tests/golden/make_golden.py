@@ -1,0 +1,296 @@
+"""Generates the golden vectors under tests/golden/ (run in the build container, where /root/reference exists):
+
+    python tests/golden/make_golden.py
+
+Two sources, both seeded and small:
+  (1) the UNMODIFIED reference code, imported from /root/reference through ref_import.py (third-party packages that
+      are absent here are stubbed; the functions executed below do not touch them);
+  (2) the installed HuggingFace classes (transformers 5.5.0: EsmForMaskedLM, LlamaForCausalLM, eager attention) for
+      the two transformer stacks whose arithmetic lives in un-vendored dependencies of the reference.
+The files are committed; tests read only the .pt files (the GPU box has no /root/reference).
+"""
+import os
+import sys
+import types
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+import ref_import  # noqa: E402
+
+ref_import.install()
+ref_esm = ref_import.import_reference("procyon.model.esm")
+ref_mu = ref_import.import_reference("procyon.model.model_unified")
+import procyon.model.contrastive as ref_con  # noqa: E402
+import procyon.model.model_utils as ref_utils  # noqa: E402
+import procyon.training.train_utils as ref_tu  # noqa: E402
+
+from oracle import esm2 as OE  # noqa: E402
+from oracle import llama as OL  # noqa: E402
+from procyon_b200.data.simple_tokenizer import SimpleTokenizer  # noqa: E402
+
+
+def save(name, obj):
+    path = os.path.join(HERE, name)
+    torch.save(obj, path)
+    print(f"wrote {name}: {os.path.getsize(path) / 1024:.1f} KiB")
+
+
+# ------------------------------------------------------------------------------------------------ (1) reference
+def golden_pooler():
+    g = torch.Generator().manual_seed(0)
+    cases = []
+    for T, d, keys, lens in [(12, 16, [0, 1, 2, 0, 2], [10, 5, 10, 3, 7]), (9, 8, [0, 1, 3], [7, 1, 4])]:
+        z = torch.randn(len(keys), T, d, generator=g)
+        toks = torch.full((len(keys), T), 1, dtype=torch.int64)
+        for i, L in enumerate(lens):
+            toks[i, 0] = 0
+            toks[i, 1 : L + 1] = torch.randint(4, 24, (L,), generator=g)
+            toks[i, L + 1] = 2
+        pad = toks == 1
+        bk = torch.tensor(keys)
+        for method in ("mean", "max"):
+            for corr in (False, True):
+                pooler = ref_esm.ProteinPooler(pooling_method=method, protein_pooling_correction_option=corr)
+                out = pooler(z.clone(), batch_keys=bk, padding_mask=pad)
+                cases.append(dict(z=z, tokens=toks, batch_keys=bk, method=method, correction=corr, out=out))
+    save("pooler.pt", cases)
+
+
+def golden_split():
+    cases = []
+    for lens, max_len in [([100, 30, 75], 32), ([10, 20], 32), ([65, 64, 33, 32], 32), ([200], 50)]:
+        toks = OE.random_protein_tokens(len(lens), 0, seed=sum(lens), lengths=lens)
+        new_toks, keys, eos = ref_tu.batched_split_long_seq(toks.clone(), padding_idx=1, eos_idx=2,
+                                                            long_protein_strategy="split", max_protein_len=max_len)
+        eos = [int(e) for e in eos]
+        g = torch.Generator().manual_seed(1)
+        z = torch.randn(new_toks.shape[0], new_toks.shape[1], 4, generator=g)
+        rev = ref_tu.reverse_batched_split(z, keys, eos_locs=eos)
+        cases.append(dict(tokens=toks, max_len=max_len, new_toks=new_toks, batch_keys=keys, eos_loc=eos, z=z, rev=rev))
+    save("split.pt", cases)
+
+
+def golden_mlp():
+    cases = []
+    for n_layers, i, o, h in [(1, 24, 40, 16), (3, 24, 40, 32), (2, 32, 16, 64)]:
+        torch.manual_seed(n_layers)
+        mlp = ref_utils.create_mlp(n_layers, i, o, h).eval()
+        x = torch.randn(5, i)
+        with torch.no_grad():
+            y = mlp(x)
+        cases.append(dict(n_layers=n_layers, in_f=i, out_f=o, hidden=h, state_dict=mlp.state_dict(), x=x, y=y,
+                          keys=list(mlp.state_dict().keys())))
+    save("mlp.pt", cases)
+
+
+def golden_infonce():
+    cases = []
+    for b, d in [(8, 32), (3, 16)]:
+        torch.manual_seed(b)
+        head = ref_con.InfoNCEInBatch(input_embed_dim=d, use_projection=False, all_gather_version=False)
+        zs, zt = torch.randn(b, d), torch.randn(b, d)
+        with torch.no_grad():
+            loss = head({"positive": {"sequence": zs, "text": zt}})
+        cases.append(dict(zs=zs, zt=zt, loss=loss, temperature=float(head.temperature)))
+    save("infonce.pt", cases)
+
+
+def golden_host_utils():
+    out = {}
+    ids1, ids2 = torch.tensor([3, 3, 5, 7, 5]), torch.tensor([1, 2, 2, 4, 4])
+    out["conflict"] = dict(id1=ids1, id2=ids2, out=ref_utils.compute_conflict_matrix(ids1, ids2))
+    tens = [torch.tensor([5, 6, 7]), torch.tensor([1]), torch.tensor([2, 3, 4, 5, 6])]
+    pt, am = ref_utils.left_pad_tensors(tens, pad_value=9)
+    out["left_pad"] = dict(tensors=tens, padded=pt, mask=am)
+    lab = torch.tensor([[1, 50, 3, 50, 4, 5], [50, 2, 3, 4, 5, 6]])
+    out["mask_before"] = dict(labels=lab, answer_idx=50, out=ref_mu.mask_before(lab, 50, before_last_answer=True))
+    a = [1, 99, 2, 3, 99, 4]
+    out["multi_replace"] = dict(a=a, b=[[7, 8], [9]], tok=99, out=ref_mu.multi_replace_tokens(a, [[7, 8], [9]], 99))
+    probs = torch.softmax(torch.randn(3, 11, generator=torch.Generator().manual_seed(5)), -1)
+    out["nucleus"] = dict(probs=probs, p=0.8, mask=ref_mu.UnifiedProCyon._get_nucleus_mask(None, probs.clone(), 0.8))
+    save("host_utils.pt", out)
+
+
+class _FakeSelf:
+    """Just enough of UnifiedProCyon for its unbound methods to run."""
+
+
+def _fake_model(tokenizer, max_text_len=48, roll_num=0):
+    f = _FakeSelf()
+    f.tokenizer = tokenizer
+    f.config = types.SimpleNamespace(max_text_len=max_text_len, roll_num=roll_num)
+    f.training = False
+    f.context_crop_sampling = False
+    # reproduce _init_tokenizer's additions in order (model_unified.py:1100-1133)
+    ref_mu.UnifiedProCyon._init_tokenizer  # (needs LLAMA3 files; inline the additions instead)
+    tk = tokenizer
+
+    def first(s):
+        return tk(s, add_special_tokens=False).input_ids[0]
+
+    tk.add_tokens("[CLS]"); tk.sep_token = "[CLS]"; tk.sep_token_id = first("[CLS]")
+    tk.add_tokens("[PAD]"); tk.pad_token = "[PAD]"; tk.pad_token_id = first("[PAD]")
+    for name, attr in [("<|protein|>", "prot_replacement_idx"), ("[PROT]", "prot_retrieval_idx"),
+                       ("[ANSWER]", "answer_idx"), ("<|struct|>", "struct_idx"), ("<|drug|>", "drug_idx"),
+                       ("[EXT]", "ext_idx")]:
+        tk.add_tokens(name)
+        setattr(f, attr, first(name))
+    f.use_llama_tokenizer = True
+    f.train_qa_full_lm = False
+    return f
+
+
+def golden_prompt_and_labels():
+    tk = SimpleTokenizer(base_vocab=500)
+    f = _fake_model(tk, max_text_len=48)
+    instructions = [
+        "Describe protein <|protein|> given context [EXT] and also [EXT] . [ANSWER]",
+        "Is <|protein|> related to [EXT] ? [ANSWER] yes . Is <|protein|> related to [EXT] ? [ANSWER]",
+    ]
+    texts = [["alpha beta gamma delta epsilon zeta eta theta", "one two three"],
+             ["kinase activity regulator", "membrane transport protein complex subunit"]]
+    out = {}
+    for name, kw in [("train", dict()), ("gen", dict(no_pad=True, left_pad=True, crop_off=True))]:
+        ids, am = ref_mu.UnifiedProCyon._prepare_text_inputs_and_tokenize(f, list(instructions),
+                                                                          [list(t) for t in texts], **kw)
+        out[name] = dict(input_ids=ids, attn_masks=am)
+    # labels (forward, model_unified.py:521-538) through the real forward with stubbed neighbours
+    ids = out["train"]["input_ids"]
+    f._preprocessing = lambda inputs, **kw: (torch.zeros(ids.shape[0], ids.shape[1], 4), ids, out["train"]["attn_masks"],
+                                            ids == f.prot_retrieval_idx, None, None)
+    f.text_encoder = lambda **kw: types.SimpleNamespace(hidden_states=None)
+    res = ref_mu.UnifiedProCyon.forward(f, {"target": {"seq": None, "text": None}}, get_full_labels=True)
+    out["labels"] = res["full_labels"]
+    out["instructions"], out["texts"], out["max_text_len"], out["base_vocab"] = instructions, texts, 48, 500
+    # splice (_prepare_input_embeddings, model_unified.py:1135-1175)
+    torch.manual_seed(3)
+    f.input_embeddings = torch.nn.Embedding(len(tk) - 1, 8)
+    soft = torch.randn(int((ids == f.prot_replacement_idx).sum()), 8)
+    with torch.no_grad():
+        z, ret = ref_mu.UnifiedProCyon._prepare_input_embeddings(f, ids, protein_soft_tokens=soft)
+    out["splice"] = dict(table=f.input_embeddings.weight.detach().clone(), soft=soft, z=z, ret=ret)
+    save("prompt_labels_splice.pt", out)
+
+
+def golden_beam_search():
+    """The reference's own _generate_beam_search loop driven by the oracle Llama as `text_encoder`."""
+    cfg = OL.LlamaCfg(d_model=128, n_layers=2, n_heads=1, n_kv_heads=1, ffn_dim=256, vocab=211, max_pos=128)
+    sd = OL.random_llama_state_dict(cfg, seed=5, dtype=torch.float32)
+    cases = []
+    for n, S, beams, group, pen, max_len, eos in [(2, 9, 4, 2, 0.8, 7, -1), (1, 6, 5, 5, 0.8, 6, -1),
+                                                   (2, 5, 6, 1, 0.5, 5, -1), (1, 7, 2, 2, 0.8, 12, None)]:
+        g = torch.Generator().manual_seed(n * 100 + beams)
+        emb = torch.randn(n, S, cfg.d_model, generator=g) * 0.5
+        mask = torch.ones(n, S)
+
+        f = _FakeSelf()
+        f.text_encoder = _OracleTextEncoder(sd, cfg)
+        f.tokenizer = types.SimpleNamespace(eos_token_id=eos if eos is not None else -1)
+        if eos is None:
+            # pick an EOS id that the run actually produces, so the early-exit branch (:833) is exercised
+            o0, _, _ = ref_mu.UnifiedProCyon._generate_beam_search(f, emb, mask, max_len=max_len, beam_size=beams,
+                                                                    beam_group_size=group, diversity_penalty=pen)
+            f.tokenizer.eos_token_id = int(o0[0, 0, 2])
+            f.text_encoder = _OracleTextEncoder(sd, cfg)
+        out, lp, logits = ref_mu.UnifiedProCyon._generate_beam_search(f, emb, mask, max_len=max_len, beam_size=beams,
+                                                                       beam_group_size=group, diversity_penalty=pen)
+        cases.append(dict(cfg=cfg.__dict__, seed=5, emb=emb, beams=beams, group=group, penalty=pen, max_len=max_len,
+                          eos=f.tokenizer.eos_token_id, out=out, log_probs=lp, logits=logits))
+    save("beam_search.pt", cases)
+
+
+class _OracleTextEncoder:
+    """LlamaPostTokenization look-alike on top of oracle.llama (fp32), with HF-style tuple KV cache."""
+
+    def __init__(self, sd, cfg):
+        self.sd, self.cfg = sd, cfg
+        self.model = types.SimpleNamespace(vocab_size=cfg.vocab)
+
+    def __call__(self, input_embeds=None, input_ids=None, attn_masks=None, use_cache=True, past_key_values=None, **kw):
+        past = None if past_key_values is None else [(k, v) for k, v in past_key_values]
+        r = OL.llama_forward(self.sd, self.cfg, inputs_embeds=input_embeds, input_ids=input_ids,
+                             attention_mask=attn_masks if past is None else None, past=past)
+        pkv = [[k.clone(), v.clone()] for k, v in r["past"]]  # mutable, like HF 4.31's tuple-of-tensors in-place use
+        return types.SimpleNamespace(logits=r["logits"], past_key_values=pkv)
+
+
+# ------------------------------------------------------------------------------------------------ (2) HF classes
+def golden_hf_esm():
+    from transformers import EsmConfig, EsmForMaskedLM
+
+    torch.manual_seed(0)
+    cases = []
+    for L, d, H, lens in [(2, 64, 4, [20, 9, 31]), (2, 96, 4, [14, 30])]:
+        cfg = EsmConfig(vocab_size=33, mask_token_id=32, pad_token_id=1, hidden_size=d, num_hidden_layers=L,
+                        num_attention_heads=H, intermediate_size=4 * d, position_embedding_type="rotary",
+                        token_dropout=True, emb_layer_norm_before=False, layer_norm_eps=1e-5,
+                        attn_implementation="eager", hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+        m = EsmForMaskedLM(cfg).eval()
+        for p in m.parameters():
+            torch.nn.init.normal_(p, std=0.1)
+        hsd = m.state_dict()
+        sd = {"embed_tokens.weight": hsd["esm.embeddings.word_embeddings.weight"]}
+        for l in range(L):
+            h, p = f"esm.encoder.layer.{l}.", f"layers.{l}."
+            for a, b in (("query", "q_proj"), ("key", "k_proj"), ("value", "v_proj")):
+                sd[p + f"self_attn.{b}.weight"] = hsd[h + f"attention.self.{a}.weight"]
+                sd[p + f"self_attn.{b}.bias"] = hsd[h + f"attention.self.{a}.bias"]
+            sd[p + "self_attn.out_proj.weight"] = hsd[h + "attention.output.dense.weight"]
+            sd[p + "self_attn.out_proj.bias"] = hsd[h + "attention.output.dense.bias"]
+            sd[p + "self_attn_layer_norm.weight"] = hsd[h + "attention.LayerNorm.weight"]
+            sd[p + "self_attn_layer_norm.bias"] = hsd[h + "attention.LayerNorm.bias"]
+            sd[p + "fc1.weight"], sd[p + "fc1.bias"] = hsd[h + "intermediate.dense.weight"], hsd[h + "intermediate.dense.bias"]
+            sd[p + "fc2.weight"], sd[p + "fc2.bias"] = hsd[h + "output.dense.weight"], hsd[h + "output.dense.bias"]
+            sd[p + "final_layer_norm.weight"], sd[p + "final_layer_norm.bias"] = hsd[h + "LayerNorm.weight"], hsd[h + "LayerNorm.bias"]
+        sd["emb_layer_norm_after.weight"] = hsd["esm.encoder.emb_layer_norm_after.weight"]
+        sd["emb_layer_norm_after.bias"] = hsd["esm.encoder.emb_layer_norm_after.bias"]
+        toks = OE.random_protein_tokens(len(lens), 0, seed=3, lengths=lens)
+        toks[0, 3] = 32
+        with torch.no_grad():
+            out = m(input_ids=toks, attention_mask=(toks != 1).long(), output_hidden_states=True)
+        cases.append(dict(n_layers=L, d=d, n_heads=H, state_dict={k: v.clone() for k, v in sd.items()}, tokens=toks,
+                          states=out.hidden_states[-1]))
+    save("hf_esm.pt", cases)
+
+
+def golden_hf_llama():
+    from transformers import LlamaConfig, LlamaForCausalLM
+
+    torch.manual_seed(0)
+    c = OL.LlamaCfg(d_model=128, n_layers=2, n_heads=4, n_kv_heads=2, ffn_dim=256, vocab=300, max_pos=256)
+    hc = LlamaConfig(vocab_size=c.vocab, hidden_size=c.d_model, intermediate_size=c.ffn_dim,
+                     num_hidden_layers=c.n_layers, num_attention_heads=c.n_heads, num_key_value_heads=c.n_kv_heads,
+                     rms_norm_eps=1e-5, max_position_embeddings=256,
+                     rope_parameters={"rope_type": "default", "rope_theta": 10000.0}, attn_implementation="eager",
+                     tie_word_embeddings=False)
+    hm = LlamaForCausalLM(hc).eval()
+    for p in hm.parameters():
+        torch.nn.init.normal_(p, std=0.1)
+    sd = {k: v.clone() for k, v in hm.state_dict().items()}
+    ids = torch.randint(0, 300, (2, 17))
+    emb = sd["model.embed_tokens.weight"][ids]
+    lab = ids.clone()
+    lab[:, :5] = -100
+    nxt = torch.randint(0, 300, (2, 1))
+    with torch.no_grad():
+        o = hm(inputs_embeds=emb, output_hidden_states=True, use_cache=True, labels=lab)
+        o2 = hm(input_ids=nxt, past_key_values=o.past_key_values, use_cache=True)
+    save("hf_llama.pt", dict(cfg=c.__dict__, state_dict=sd, ids=ids, labels=lab, next_ids=nxt, logits=o.logits,
+                             hidden_last=o.hidden_states[-1], loss=o.loss, decode_logits=o2.logits))
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(4)
+    golden_pooler()
+    golden_split()
+    golden_mlp()
+    golden_infonce()
+    golden_host_utils()
+    golden_prompt_and_labels()
+    golden_beam_search()
+    golden_hf_esm()
+    golden_hf_llama()

@@ -69,21 +69,19 @@ def test_swiglu_parity(cuda_device, M, force):
 
 
 def test_linear_is_linear_at_full_size(cuda_device):
-    """size-independent property at Llama shapes: f(a1 + a2) == f(a1) + f(a2) in fp32 output."""
+    """size-independent property at Llama shapes: f(a1 + a2) == f(a1) + f(a2) (inputs chosen so a1 + a2 is exact)."""
     from procyon_b200 import ops
 
     torch.manual_seed(0)
     w = (torch.randn(6144, 4096, device="cuda") / 64).bfloat16()
-    a1 = torch.randn(1024, 4096, device="cuda").bfloat16()
-    a2 = (torch.randn(1024, 4096, device="cuda") * 2 ** -9).bfloat16()
+    a1 = (torch.randint(-8, 9, (1024, 4096), device="cuda").float() / 8).bfloat16()
+    a2 = (torch.randint(-8, 9, (1024, 4096), device="cuda").float() / 8).bfloat16()
     s = (a1.float() + a2.float()).bfloat16()
-    exact = (s.float() == a1.float() + a2.float())
+    assert torch.equal(s.float(), a1.float() + a2.float())
     o1 = ops.linear(a1, w, out_fp32=True, force="tc")
     o2 = ops.linear(a2, w, out_fp32=True, force="tc")
     os_ = ops.linear(s, w, out_fp32=True, force="tc")
-    rows = exact.all(dim=1)
-    assert rows.any()
-    torch.testing.assert_close(os_[rows], (o1 + o2)[rows], rtol=1e-3, atol=1e-3)
+    torch.testing.assert_close(os_, o1 + o2, rtol=1e-3, atol=2e-3)
     # tensor-core and weight-streaming kernels agree on the same rows
     o_sk = ops.linear(a1[:8], w, out_fp32=True, force="skinny")
     torch.testing.assert_close(o_sk, o1[:8], rtol=1e-4, atol=1e-3)
