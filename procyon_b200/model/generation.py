@@ -17,17 +17,20 @@ import torch
 
 from .pmc_llama import SELECT_BEAM, SELECT_GREEDY, DecodeSession, LlamaPostTokenization
 
+# kernels launched through CUDA-graph replays (the library's own counter only sees direct launches)
+GRAPH_REPLAY_LAUNCHES = 0
+
 
 def _run(text_encoder: LlamaPostTokenization, input_embeds, attn_mask, max_len, beams, mode, group, penalty, eos_id,
          stop_on_all_eos, return_logits, use_graph=True):
     n, S, _ = input_embeds.shape
     dev = input_embeds.device
     sel = torch.arange(n, device=dev, dtype=torch.int32) * S + (S - 1)
-    kv, _, prefill_logits, valid = text_encoder.prefill(input_embeds, attn_mask, want_cache=True, want_hidden=False,
-                                                         sel_rows=sel)
-    if attn_mask is None:
-        valid = None
-    sess = text_encoder.new_session(n, beams, S, max_len, kv, valid, keep_logits=return_logits)
+    sess = text_encoder.get_session(n, beams, S, max_len, dev, attn_mask is not None, return_logits)
+    _, _, prefill_logits, valid = text_encoder.prefill(input_embeds, attn_mask, want_cache=True, want_hidden=False,
+                                                        sel_rows=sel, kv_out=sess.kv_prompt)
+    if attn_mask is not None:
+        sess.prompt_valid.copy_(valid)
     sess.reset(prefill_logits)
     sess.select(mode, group, penalty, eos_id, stop_on_all_eos)  # step 0: tokens from the prefill logits
     steps_left = max_len - 1
@@ -44,6 +47,8 @@ def _run(text_encoder: LlamaPostTokenization, input_embeds, attn_mask, max_len, 
                     burst = min(16, steps_left - done) if stop_on_all_eos else steps_left - done
                     for _ in range(burst):
                         g.replay()
+                    global GRAPH_REPLAY_LAUNCHES
+                    GRAPH_REPLAY_LAUNCHES += burst * sess.graph_launches
                     done += burst
                     if stop_on_all_eos and done < steps_left and int(sess.state[2].item()) != 0:
                         break

@@ -537,8 +537,11 @@ class UnifiedProCyon(nn.Module):
             raise _lib.ProcyonB200Error("sampling supports at most 16 inputs per call")
         dev = input_embeds.device
         sel = torch.arange(n, device=dev, dtype=torch.int32) * S + (S - 1)
-        kv, _, logits, valid = te.prefill(input_embeds, attn_masks, want_cache=True, want_hidden=False, sel_rows=sel)
-        sess = te.new_session(n, 1, S, max_len, kv, valid if attn_masks is not None else None, keep_logits=False)
+        sess = te.get_session(n, 1, S, max_len, dev, attn_masks is not None, False)
+        _, _, logits, valid = te.prefill(input_embeds, attn_masks, want_cache=True, want_hidden=False, sel_rows=sel,
+                                         kv_out=sess.kv_prompt)
+        if attn_masks is not None:
+            sess.prompt_valid.copy_(valid)
         sess.reset(logits)
         total = torch.zeros(n, device=dev)
         all_logits, toks = [], []

@@ -202,18 +202,20 @@ class DecodeSession:
     """Device-resident generation state (KV caches, token / ancestry tables, logits) for one generate() call."""
 
     def __init__(self, owner: "LlamaPostTokenization", n_inputs: int, beams: int, S: int, max_gen: int,
-                 kv_prompt: torch.Tensor, prompt_valid: Optional[torch.Tensor], keep_logits: bool):
+                 device, masked: bool, keep_logits: bool):
         lib = _lib.load()
         self.owner = owner
         c = owner.model.config
-        dev = kv_prompt.device
+        dev = torch.device(device)
         rows = n_inputs * beams
         if rows > 16:
             raise _lib.ProcyonB200Error(f"n_inputs*beams = {rows} > 16 rows per decode session; split the batch")
         kvd = c.num_key_value_heads * c.head_dim
         V = owner.model.vocab_size
         self.n_inputs, self.beams, self.S, self.max_gen, self.rows, self.V = n_inputs, beams, S, max_gen, rows, V
-        self.kv_prompt, self.prompt_valid = kv_prompt, prompt_valid
+        self.kv_prompt = torch.empty((c.num_hidden_layers, 2, n_inputs, S, kvd), device=dev, dtype=torch.bfloat16)
+        self.prompt_valid = torch.ones((n_inputs, S), device=dev, dtype=torch.uint8) if masked else None
+        kv_prompt, prompt_valid = self.kv_prompt, self.prompt_valid
         self.kv_gen = torch.empty((c.num_hidden_layers, 2, rows, max_gen, kvd), device=dev, dtype=torch.bfloat16)
         self.tokens = torch.zeros((rows, max_gen), device=dev, dtype=torch.int32)
         self.slots = torch.zeros((rows, max_gen), device=dev, dtype=torch.int32)
@@ -234,6 +236,7 @@ class DecodeSession:
         self.device = dev
         self._graph = None
         self._graph_key = None
+        self.graph_launches = 0
 
     def reset(self, prefill_logits: Optional[torch.Tensor]):
         check(_lib.load().pcy_decode_reset(self.owner._handle, ctypes.byref(self.c), ptr(prefill_logits),
@@ -253,14 +256,17 @@ class DecodeSession:
         key = (mode, group, float(penalty), eos_id, bool(stop_on_all_eos))
         if self._graph is not None and self._graph_key == key:
             return self._graph
+        lib = _lib.load()
         g = torch.cuda.CUDAGraph()
         side = torch.cuda.Stream(self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
+        n0 = lib.pcy_launch_count()
         with torch.cuda.stream(side):
             with torch.cuda.graph(g, stream=side):
                 self.forward()
                 self.select(mode, group, penalty, eos_id, stop_on_all_eos)
         torch.cuda.current_stream(self.device).wait_stream(side)
+        self.graph_launches = lib.pcy_launch_count() - n0  # kernels replayed by every g.replay()
         self._graph, self._graph_key = g, key
         return g
 
@@ -367,6 +373,7 @@ class LlamaPostTokenization(nn.Module):
             _lib.load().pcy_llama_destroy(self._handle)
             self._handle = None
             self._ws = None
+            self.__dict__.pop("_sessions", None)
 
     def __del__(self):
         try:
@@ -381,7 +388,7 @@ class LlamaPostTokenization(nn.Module):
 
     # ---- kernels-level entry points ---------------------------------------------------------------------------
     def prefill(self, input_embeds: torch.Tensor, attn_masks: Optional[torch.Tensor], *, want_cache: bool,
-                want_hidden: bool, sel_rows: Optional[torch.Tensor] = None):
+                want_hidden: bool, sel_rows: Optional[torch.Tensor] = None, kv_out: Optional[torch.Tensor] = None):
         """input_embeds bf16 [B,S,d] on CUDA. Returns (kv_prompt | None, hidden [B,S,d] | None, sel_logits | None)."""
         lib = _lib.load()
         _lib.require_cuda(input_embeds)
@@ -395,7 +402,10 @@ class LlamaPostTokenization(nn.Module):
         if attn_masks is not None:
             valid = (attn_masks.to(dev) != 0).to(torch.uint8).contiguous()
         kvd = c.num_key_value_heads * c.head_dim
-        kv = torch.empty((c.num_hidden_layers, 2, B, S, kvd), device=dev, dtype=torch.bfloat16) if want_cache else None
+        kv = None
+        if want_cache:
+            kv = kv_out if kv_out is not None else torch.empty((c.num_hidden_layers, 2, B, S, kvd), device=dev,
+                                                               dtype=torch.bfloat16)
         hidden = torch.empty((B, S, d), device=dev, dtype=torch.bfloat16) if want_hidden else None
         n_sel, logits = 0, None
         if sel_rows is not None and sel_rows.numel() > 0:
@@ -427,9 +437,17 @@ class LlamaPostTokenization(nn.Module):
             self._lm_cache_key = key
         return self._lm_cache
 
-    def new_session(self, n_inputs, beams, S, max_gen, kv_prompt, prompt_valid, keep_logits) -> DecodeSession:
-        self._ensure_rope(S + max_gen, kv_prompt.device)
-        return DecodeSession(self, n_inputs, beams, S, max_gen, kv_prompt, prompt_valid, keep_logits)
+    def get_session(self, n_inputs, beams, S, max_gen, device, masked, keep_logits) -> DecodeSession:
+        """Decode sessions (KV caches, tables, captured step graph) are cached per shape and reused across calls."""
+        self._ensure_packed(torch.device(device))
+        self._ensure_rope(S + max_gen, device)
+        key = (n_inputs, beams, S, max_gen, str(device), bool(masked), bool(keep_logits), id(self._handle))
+        cache = self.__dict__.setdefault("_sessions", {})
+        if key not in cache:
+            if len(cache) >= 4:  # bound the memory held by cached sessions
+                cache.pop(next(iter(cache)))
+            cache[key] = DecodeSession(self, n_inputs, beams, S, max_gen, device, masked, keep_logits)
+        return cache[key]
 
     # ---- reference-facing forward -------------------------------------------------------------------------------
     def forward(self, input_embeds=None, input_ids=None, attn_masks=None, full_labels=None, past_key_values=None,
@@ -466,7 +484,11 @@ class LlamaPostTokenization(nn.Module):
             loss = lm_loss(self, hidden, full_labels)
         past = None
         if use_cache:
-            past = self.new_session(B, 1, S, 256, kv, valid, keep_logits=False)
+            past = DecodeSession(self, B, 1, S, 256, dev, attn_masks is not None, keep_logits=False)
+            self._ensure_rope(S + 256, dev)
+            past.kv_prompt.copy_(kv)
+            if attn_masks is not None:
+                past.prompt_valid.copy_(valid)
             past.reset(sel_logits)
         out = CausalLMOutput(self, hidden, n_layers, loss=loss, past=past)
         return out

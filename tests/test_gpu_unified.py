@@ -1,0 +1,217 @@
+"""UnifiedProCyon (ESM2 -> pool -> projector -> splice -> Llama -> retrieval head / generation) on the GPU vs the
+CPU oracle composed from oracle.esm2 / oracle.fusion / oracle.llama / oracle.generate, on a tiny seeded model."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _tiny_model(pooling="mean", n_proj=3):
+    from procyon_b200.data.simple_tokenizer import SimpleTokenizer
+    from procyon_b200.model.model_unified import UnifiedProCyon
+    from procyon_b200.model.pmc_llama import LlamaConfig
+    from procyon_b200.training.training_args_IT import ModelArgs
+
+    torch.manual_seed(0)
+    cfg = ModelArgs(protein_encoder_num_params="custom", protein_pooling_opt=pooling, max_text_len=64,
+                    num_layers_token_projector=n_proj, num_layers_shared_projector=n_proj,
+                    num_layers_lm_projector=n_proj, hidden_size_token_projector=96, hidden_size_shared_projector=96,
+                    hidden_size_lm_projector=96, ret_token_access="last", roll_num=0, train_qa_full_lm=False)
+    lc = LlamaConfig(hidden_size=512, intermediate_size=1024, num_hidden_layers=2, num_attention_heads=4,
+                     num_key_value_heads=2, vocab_size=997, max_position_embeddings=512)
+    m = UnifiedProCyon(cfg, tokenizer=SimpleTokenizer(base_vocab=997), llama_config=lc, esm_custom_config=(2, 64, 4))
+    for n, p in m.named_parameters():
+        if p.dim() > 1 and "projector" in n:
+            torch.nn.init.normal_(p, std=p.shape[1] ** -0.5)
+        if "protein_seq_encoder" in n and p.dim() > 1:
+            torch.nn.init.normal_(p, std=0.12)
+    m.text_encoder.model.lm_head.weight.data.normal_(std=512 ** -0.5)
+    for l in m.text_encoder.model.model.layers:
+        for w in (l.self_attn.q_proj, l.self_attn.k_proj, l.self_attn.v_proj, l.self_attn.o_proj, l.mlp.gate_proj,
+                  l.mlp.up_proj):
+            w.weight.data.normal_(std=512 ** -0.5)
+        l.mlp.down_proj.weight.data.normal_(std=1024 ** -0.5)
+    m.text_encoder.model.model.embed_tokens.weight.data.normal_(std=0.5)
+    return m.bfloat16().eval().cuda()
+
+
+def _inputs(n=2):
+    from oracle.esm2 import random_protein_tokens
+
+    toks = random_protein_tokens(3, 0, seed=8, lengths=[30, 12, 21])
+    return {
+        "data": {"seq": toks, "seq_idx": torch.tensor([11, 12, 13]), "text": ["binds atp and magnesium ions",
+                 "membrane transport complex subunit"], "text_idx": [4, 9], "drug": None},
+        "input": {"seq": [[0], [2]], "text": [[0], [1]], "drug": None},
+        "target": {"seq": None, "text": None, "drug": None},
+        "instructions": ["Protein : <|protein|> Context : [EXT] Describe the function . [ANSWER] it works [PROT]",
+                         "Protein : <|protein|> Context : [EXT] What does it do ? [ANSWER] nothing much here [PROT]"],
+        "reference_indices": {"input": {"seq": [[5], [7]]}, "target": {"text": [0, 1]}},
+    }
+
+
+def _oracle_embeds(m, inputs, ids):
+    """ESM -> pool -> token projector -> splice, all in the oracle, from the model's own (bf16) weights."""
+    from oracle import esm2 as OE
+    from oracle.fusion import mlp_forward, splice
+
+    sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    esd = {k[len("protein_seq_encoder.model."):]: v for k, v in sd.items() if k.startswith("protein_seq_encoder.model.")}
+    pooled = OE.esm_plm_forward(esd, inputs["data"]["seq"], 2, 4, pooling=m.config.protein_pooling_opt,
+                                act_round="bf16").to(torch.bfloat16).float()
+    tok_sd = {k[len("token_projectors.aaseq."):]: v for k, v in sd.items() if k.startswith("token_projectors.aaseq.")}
+    flat = [i for row in inputs["input"]["seq"] for i in row]
+    soft = mlp_forward(tok_sd, pooled[flat], act_round="bf16")
+    table = sd["input_embeddings.weight"].float()
+    z, ret = splice(ids.cpu(), table, m.prot_replacement_idx, soft, m.prot_retrieval_idx, m.config.roll_num)
+    return sd, pooled, z, ret
+
+
+def _llama_cfg_sd(m, sd):
+    from oracle.llama import LlamaCfg
+
+    c = m.text_encoder.model.config
+    oc = LlamaCfg(d_model=c.hidden_size, n_layers=c.num_hidden_layers, n_heads=c.num_attention_heads,
+                  n_kv_heads=c.num_key_value_heads, ffn_dim=c.intermediate_size, vocab=m.text_encoder.model.vocab_size,
+                  max_pos=512)
+    lsd = {k[len("text_encoder.model."):]: v for k, v in sd.items() if k.startswith("text_encoder.model.")}
+    return oc, lsd
+
+
+def test_state_dict_keys_follow_reference_layout(cuda_device):
+    m = _tiny_model()
+    keys = set(m.state_dict().keys())
+    for k in ["text_encoder.model.model.embed_tokens.weight", "text_encoder.model.model.layers.0.self_attn.q_proj.weight",
+              "text_encoder.model.model.layers.1.mlp.down_proj.weight", "text_encoder.model.model.norm.weight",
+              "text_encoder.model.lm_head.weight", "input_embeddings.weight",
+              "protein_seq_encoder.model.embed_tokens.weight",
+              "protein_seq_encoder.model.layers.0.self_attn.out_proj.bias",
+              "protein_seq_encoder.model.emb_layer_norm_after.weight", "token_projectors.aaseq.0.weight",
+              "token_projectors.aaseq.3.bias", "token_projectors.aaseq.6.weight", "aaseq_shared_projector.6.bias",
+              "aaseq_lm_projector.0.weight", "contrastive_head.temperature"]:
+        assert k in keys, k
+    # vocab = len(tokenizer) - 1: the [EXT] row is dropped (model_unified.py:166)
+    assert m.input_embeddings.weight.shape[0] == 997 + 8 - 1
+
+
+def test_forward_lm_loss_and_retrieval_head(cuda_device):
+    from oracle.fusion import make_labels, mlp_forward
+    from oracle.llama import llama_forward
+
+    m = _tiny_model()
+    inputs = _inputs()
+    out = m(inputs, retrieval=False, get_full_labels=True)
+    ids = out["text_toks"]
+    sd, pooled, z, ret = _oracle_embeds(m, inputs, ids)
+    oc, lsd = _llama_cfg_sd(m, sd)
+    labels = make_labels(ids.cpu(), m.tokenizer.pad_token_id, [m.prot_replacement_idx, m.prot_retrieval_idx,
+                                                             m.drug_idx, m.struct_idx], m.answer_idx, False)
+    assert torch.equal(out["full_labels"].cpu(), labels)
+    mask = (ids.cpu() != m.tokenizer.pad_token_id).float()
+    ref = llama_forward(lsd, oc, inputs_embeds=z, attention_mask=mask, labels=labels, act_round="bf16")
+    assert abs(out["outputs"].loss.item() - ref["loss"].item()) < 3e-2
+    keep = mask.bool()
+    torch.testing.assert_close(out["outputs"].hidden_states[-1].float().cpu()[keep], ref["hidden_states"][-1][keep],
+                               rtol=4e-2, atol=4e-2)
+    # retrieval head: hidden_states[-1] at [PROT] -> aaseq_lm_projector
+    out_r = m(inputs, retrieval=True)
+    lm_sd = {k[len("aaseq_lm_projector."):]: v for k, v in sd.items() if k.startswith("aaseq_lm_projector.")}
+    ref_q = mlp_forward(lm_sd, ref["hidden_states"][-1][ret].to(torch.bfloat16).float(), act_round="bf16")
+    got_q = out_r["contrastive_out"]["positive"]["text"].float().cpu()
+    assert got_q.shape == ref_q.shape == (2, 64)
+    torch.testing.assert_close(got_q, ref_q, rtol=5e-2, atol=5e-2)
+    assert out_r["contrastive_loss"] is None and out_r["full_labels"] is None
+
+
+def test_forward_sequences_and_retrieval_scores(cuda_device):
+    from oracle.fusion import cosine_scores as o_cos, mlp_forward
+    from procyon_b200.data.inference_utils import get_proteins_from_batched_embeddings, get_proteins_from_embedding
+
+    m = _tiny_model(pooling="max")
+    inputs = _inputs()
+    fs = m.forward_sequences(inputs["data"]["seq"], get_soft_tokens=True)
+    sd, pooled, _, _ = _oracle_embeds(m, inputs, m(inputs, retrieval=True)["text_toks"])
+    torch.testing.assert_close(fs["original"].float().cpu(), pooled, rtol=3e-2, atol=3e-2)
+    sh_sd = {k[len("aaseq_shared_projector."):]: v for k, v in sd.items() if k.startswith("aaseq_shared_projector.")}
+    torch.testing.assert_close(fs["shared"].float().cpu(), mlp_forward(sh_sd, pooled, act_round="bf16"), rtol=5e-2,
+                               atol=5e-2)
+    assert fs["token"].shape == (3, 512)
+    # scoring over a synthetic database (fp32, as the reference keeps it) incl. a zero row (normalize eps)
+    g = torch.Generator().manual_seed(99)
+    db = torch.randn(1000, 64, generator=g)
+    db[17] = 0
+    q = torch.randn(5, 64, generator=g)
+    sims = get_proteins_from_batched_embeddings(db.cuda(), q)
+    torch.testing.assert_close(sims, o_cos(q, db), rtol=1e-4, atol=1e-5)
+    df = get_proteins_from_embedding(db.cuda(), query_embeddings=q[:1], top_k=7)
+    assert df["index"].tolist() == o_cos(q[:1], db)[0].argsort(descending=True)[:7].tolist()
+    sims_bf = get_proteins_from_batched_embeddings(db.bfloat16().cuda(), q)
+    torch.testing.assert_close(sims_bf, o_cos(q, db.bfloat16().float()), rtol=1e-3, atol=1e-4)
+
+
+def test_generate_beam_matches_oracle(cuda_device):
+    from oracle.generate import generate_beam_search as o_beam
+
+    m = _tiny_model()
+    inputs = _inputs()
+    toks, lp, logits, texts = m.generate(inputs, max_len=6, method="beam", beam_size=4, beam_group_size=2,
+                                         diversity_penalty=0.8)
+    assert toks.shape == (2, 4, 6) and len(texts) == 2 and len(texts[0]) == 4
+    # oracle on the same spliced, left-padded prompt
+    (_, ids, am, _, _, _) = m._preprocessing(inputs, crop_off=True, no_pad=True, left_pad=True)
+    sd, pooled, z, ret = _oracle_embeds(m, inputs, ids)
+    oc, lsd = _llama_cfg_sd(m, sd)
+    ro, rlp, rlogits = o_beam(lsd, oc, z, am.cpu(), max_len=6, beam_size=4, beam_group_size=2, diversity_penalty=0.8,
+                              eos_id=m.tokenizer.eos_token_id, act_round="bf16", mask_pads_in_decode=True)
+    steps = rlogits.shape[2]
+    same = (toks[..., :steps] == ro[..., :steps]).all(dim=-1)
+    assert same.float().mean() >= 0.5
+    torch.testing.assert_close(lp[same], rlp[same], rtol=2e-2, atol=8e-2)
+
+
+def test_generate_greedy_and_sampling_run(cuda_device):
+    m = _tiny_model()
+    inputs = _inputs()
+    t1, lp1, lg1, tx1 = m.generate(inputs, max_len=5, method="greedy")
+    t2, lp2, lg2, tx2 = m.generate(inputs, max_len=5, method="greedy")
+    assert t1.shape == (2, 1, 5) and torch.equal(t1, t2) and torch.equal(lp1, lp2)  # deterministic
+    assert torch.equal(lg1.argmax(-1).cpu(), t1)
+    t3, lp3, lg3, _ = m.generate(inputs, max_len=4, method="nucleus", nucleus_prob=0.9, num_text_per_instance=2)
+    assert t3.shape == (2, 2, 4) and lg3.shape[:3] == (2, 2, 4) and bool(torch.isfinite(lp3).all())
+    torch.manual_seed(1)
+    t4, _, _, _ = m.generate(inputs, max_len=4, method="sampling", temperature=1.0)
+    assert t4.shape == (2, 1, 4)
+
+
+def test_infonce_matches_reference_golden(cuda_device):
+    import os
+
+    from procyon_b200.model.contrastive import InfoNCEInBatch
+
+    for c in torch.load(os.path.join(os.path.dirname(__file__), "golden", "infonce.pt"), weights_only=False):
+        head = InfoNCEInBatch(c["zs"].shape[1], use_projection=False).cuda()
+        loss = head({"positive": {"sequence": c["zs"].cuda(), "text": c["zt"].cuda()}})
+        torch.testing.assert_close(loss.cpu(), c["loss"], rtol=1e-4, atol=1e-5)
+
+
+def test_pooler_and_mlp_match_reference_goldens(cuda_device):
+    import os
+
+    from procyon_b200.model.esm import ProteinPooler
+    from procyon_b200.model.model_utils import create_mlp
+
+    G = os.path.join(os.path.dirname(__file__), "golden")
+    for c in torch.load(os.path.join(G, "pooler.pt"), weights_only=False):
+        p = ProteinPooler(c["method"], c["correction"])
+        z = c["z"].bfloat16()
+        out = p(z.cuda(), batch_keys=c["batch_keys"], tokens=c["tokens"].cuda(), out_fp32=True)
+        from oracle.esm2 import protein_pooler
+
+        ref = protein_pooler(z.float(), c["batch_keys"], c["tokens"] == 1, c["method"], c["correction"])
+        torch.testing.assert_close(out.cpu(), ref, rtol=1e-5, atol=1e-5, equal_nan=True)
+        torch.testing.assert_close(out.cpu(), c["out"], rtol=2e-2, atol=2e-2, equal_nan=True)  # bf16 input rounding
+    for c in torch.load(os.path.join(G, "mlp.pt"), weights_only=False):
+        mlp = create_mlp(c["n_layers"], c["in_f"], c["out_f"], c["hidden"])
+        mlp.load_state_dict(c["state_dict"])
+        y = mlp.cuda()(c["x"].cuda())
+        torch.testing.assert_close(y.float().cpu(), c["y"], rtol=3e-2, atol=3e-2)
