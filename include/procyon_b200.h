@@ -170,6 +170,8 @@ typedef struct {
 #define PCY_SELECT_GREEDY 0
 #define PCY_SELECT_BEAM 1
 
+/* rows <= 4 use one persistent kernel per decode step by default; 0 selects the one-launch-per-op path (tests) */
+int pcy_set_decode_megakernel(int enabled);
 int64_t pcy_llama_decode_workspace_bytes(void* handle, int rows, int S, int max_gen);
 /* clears state/tokens/slots/log-probs/workspace; copies prefill_logits fp32 [n_inputs,V] to every beam row */
 int pcy_decode_reset(void* handle, const pcy_decode_buffers* b, const float* prefill_logits, void* stream);

@@ -10,6 +10,7 @@
 //            as a CUDA graph.
 // Semantics: HF transformers 4.31 LlamaForCausalLM as wrapped by LlamaPostTokenization.forward
 // (procyon/model/pmc_llama.py:546-596, :287-406): positions arange(past, past+S), fp32 softmax, RMSNorm in fp32.
+#include <cstdlib>
 #include <vector>
 
 #include "common.cuh"
@@ -28,6 +29,7 @@ struct LlamaModel {
   std::vector<void*> slabs;
   float* rope = nullptr;
   int rope_pos = 0;
+  LlamaLayerPtrs* layers_dev = nullptr;
   int qkv_dim() const { return (cfg.n_heads + 2 * cfg.n_kv_heads) * cfg.head_dim; }
   int kv_dim() const { return cfg.n_kv_heads * cfg.head_dim; }
 };
@@ -83,7 +85,14 @@ __global__ void broadcast_rows_kernel(const float* __restrict__ in, float* __res
 
 using namespace pcy;
 
+static bool g_use_megakernel = true;
+
 extern "C" {
+
+int pcy_set_decode_megakernel(int enabled) {
+  g_use_megakernel = enabled != 0;
+  return 0;
+}
 
 int pcy_llama_create(const pcy_llama_config* cfg, void** handle) {
   PCY_REQUIRE(cfg && handle, "llama_create: null argument");
@@ -111,6 +120,18 @@ int pcy_llama_create(const pcy_llama_config* cfg, void** handle) {
     for (void* p : m->slabs) cudaFree(p);
     delete m;
     return PCY_ERR_CUDA;
+  }
+  {
+    std::vector<LlamaLayerPtrs> host(cfg->n_layers);
+    for (int l = 0; l < cfg->n_layers; ++l) {
+      const LlamaLayer& y = m->layers[l];
+      host[l] = LlamaLayerPtrs{y.ln1, y.ln2, y.wqkv, y.wo, y.wgu, y.wdown};
+    }
+    void* p = nullptr;
+    PCY_CUDA(cudaMalloc(&p, sizeof(LlamaLayerPtrs) * cfg->n_layers));
+    m->slabs.push_back(p);
+    PCY_CUDA(cudaMemcpy(p, host.data(), sizeof(LlamaLayerPtrs) * cfg->n_layers, cudaMemcpyHostToDevice));
+    m->layers_dev = reinterpret_cast<LlamaLayerPtrs*>(p);
   }
   *handle = m;
   return 0;
@@ -265,6 +286,7 @@ int64_t pcy_llama_decode_workspace_bytes(void* handle, int rows, int S, int max_
   b += round_up(decode_attention_partial_floats(rows, m->cfg.n_heads, m->cfg.n_kv_heads, S, max_gen) * 4, 256);
   b += round_up((int64_t)rows * m->cfg.n_kv_heads * 4, 256);
   b += round_up((int64_t)topk_workspace_floats(rows) * 4, 256);
+  if (decode_megakernel_supported(m->cfg, rows)) b += decode_megakernel_scratch_bytes(m->cfg, rows, S, max_gen) + 256;
   return b + 4096;
 }
 
@@ -282,12 +304,18 @@ int pcy_llama_decode_forward(void* handle, const pcy_decode_buffers* b, void* st
   if (b->workspace_bytes < pcy_llama_decode_workspace_bytes(handle, rows, b->S, b->max_gen))
     return set_error(PCY_ERR_WORKSPACE, "llama_decode_forward: workspace too small");
   uint8_t* p = reinterpret_cast<uint8_t*>(round_up(reinterpret_cast<int64_t>(b->workspace), 256));
+  carve<float>(p, topk_workspace_floats(rows));  // selection scratch comes first (see pcy_decode_select)
   bf16* x = carve<bf16>(p, (int64_t)rows * d);
   bf16* attn = carve<bf16>(p, (int64_t)rows * d);
   bf16* qkv = carve<bf16>(p, (int64_t)rows * qkv_dim);
   bf16* act = carve<bf16>(p, (int64_t)rows * f);
   float* partials = carve<float>(p, decode_attention_partial_floats(rows, H, KVH, b->S, b->max_gen));
   int32_t* tickets = carve<int32_t>(p, (int64_t)rows * KVH);  // zeroed by pcy_decode_reset
+  static const bool force_multi = getenv("PCY_DECODE_MULTIKERNEL") != nullptr;
+  if (!force_multi && g_use_megakernel && decode_megakernel_supported(c, rows)) {
+    // persistent single-launch step (rows <= 4): see decode_megakernel.cu
+    return decode_megakernel(c, m->layers_dev, m->embed, m->lm_head, m->norm, m->rope, b, p, stream);
+  }
 
   embed_last_token_kernel<<<rows, 128, 0, stream>>>(b->tokens, b->state, m->embed, x, b->max_gen, d);
   PCY_LAUNCH_CHECK();
@@ -356,12 +384,6 @@ int pcy_decode_select(void* handle, const pcy_decode_buffers* b, int mode, int g
   const int H = m->cfg.n_heads, KVH = m->cfg.n_kv_heads, d = m->cfg.d_model;
   // the top-k scratch sits after the forward-pass buffers in the shared workspace
   uint8_t* p = reinterpret_cast<uint8_t*>(round_up(reinterpret_cast<int64_t>(b->workspace), 256));
-  carve<bf16>(p, (int64_t)rows * d);
-  carve<bf16>(p, (int64_t)rows * d);
-  carve<bf16>(p, (int64_t)rows * m->qkv_dim());
-  carve<bf16>(p, (int64_t)rows * m->cfg.ffn_dim);
-  carve<float>(p, decode_attention_partial_floats(rows, H, KVH, b->S, b->max_gen));
-  carve<int32_t>(p, (int64_t)rows * KVH);
   float* tk = carve<float>(p, topk_workspace_floats(rows));
   DecodeSelectArgs a;
   a.logits = b->logits_cur; a.logits_hist = b->logits_hist; a.tokens = b->tokens; a.slots = b->slots;

@@ -118,6 +118,19 @@ struct DecodeSelectArgs {
 int decode_select(const DecodeSelectArgs& a, cudaStream_t stream);
 int topk_workspace_floats(int rows);
 
+// ---- persistent decode-step kernel (rows <= 4) --------------------------------------------------------------
+struct LlamaLayerPtrs {
+  const bf16 *ln1, *ln2, *wqkv, *wo, *wgu, *wdown;
+};
+}  // namespace pcy
+#include "../../include/procyon_b200.h"
+namespace pcy {
+bool decode_megakernel_supported(const pcy_llama_config& c, int rows);
+int64_t decode_megakernel_scratch_bytes(const pcy_llama_config& c, int rows, int S, int max_gen);
+int decode_megakernel(const pcy_llama_config& c, const LlamaLayerPtrs* layers_dev, const bf16* embed,
+                      const bf16* lm_head, const bf16* norm, const float* rope, const pcy_decode_buffers* b,
+                      void* scratch, cudaStream_t stream);
+
 // ---- losses / scoring -----------------------------------------------------------------------------------
 int cross_entropy_rows(const float* logits, const int32_t* labels, int rows, int V, int64_t ld, float* acc,
                        cudaStream_t stream);

@@ -5,12 +5,15 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def _cfgs():
+def _cfgs(kind="gq2"):
     from oracle.llama import LlamaCfg
     from procyon_b200.model.pmc_llama import LlamaConfig
 
-    oc = LlamaCfg(d_model=512, n_layers=2, n_heads=4, n_kv_heads=2, ffn_dim=1024, vocab=1003, max_pos=512)
-    pc = LlamaConfig(hidden_size=512, intermediate_size=1024, num_hidden_layers=2, num_attention_heads=4,
+    # gq2: 4 query / 2 kv heads -> one-launch-per-op decode path; gq4: 8 / 2 heads (Llama-3's ratio) -> rows <= 4 take
+    # the persistent decode kernel
+    H, d = (4, 512) if kind == "gq2" else (8, 1024)
+    oc = LlamaCfg(d_model=d, n_layers=2, n_heads=H, n_kv_heads=2, ffn_dim=1024, vocab=1003, max_pos=512)
+    pc = LlamaConfig(hidden_size=d, intermediate_size=1024, num_hidden_layers=2, num_attention_heads=H,
                      num_key_value_heads=2, vocab_size=1003, max_position_embeddings=512)
     return oc, pc
 
@@ -23,11 +26,11 @@ def _build(sd, pc):
     return m.cuda()
 
 
-@pytest.fixture(scope="module")
-def llama(cuda_device):
+@pytest.fixture(scope="module", params=["gq2", "gq4"])
+def llama(cuda_device, request):
     from oracle.llama import random_llama_state_dict
 
-    oc, pc = _cfgs()
+    oc, pc = _cfgs(request.param)
     sd = random_llama_state_dict(oc, seed=3)
     return oc, sd, _build(sd, pc)
 
@@ -109,13 +112,14 @@ def test_greedy_generation(llama):
                 torch.testing.assert_close(logits[b].cpu(), rlogits[b], rtol=3e-2, atol=5e-2)
 
 
-@pytest.mark.parametrize("beams,group,pad", [(4, 2, 0), (4, 4, 0), (6, 1, 0), (4, 2, 5)])
-def test_beam_search(llama, beams, group, pad):
+@pytest.mark.parametrize("n,beams,group,pad", [(2, 4, 2, 0), (2, 4, 4, 0), (2, 6, 1, 0), (2, 4, 2, 5), (1, 4, 2, 0),
+                                                (2, 2, 1, 3)])
+def test_beam_search(llama, n, beams, group, pad):
     from oracle.generate import generate_beam_search as oracle_beam
     from procyon_b200.model.generation import generate_beam_search
 
     oc, sd, m = llama
-    ids, emb, mask = _inputs(oc, sd, 2, 24, seed=beams * 10 + group, pad_left=pad)
+    ids, emb, mask = _inputs(oc, sd, n, 24, seed=beams * 10 + group, pad_left=pad)
     am = mask if pad else None
     ro, rlp, rlogits = oracle_beam(sd, oc, emb.float(), mask if pad else torch.ones_like(mask), max_len=8,
                                    beam_size=beams, beam_group_size=group, diversity_penalty=0.8, eos_id=-5,
@@ -123,7 +127,7 @@ def test_beam_search(llama, beams, group, pad):
     out, lp, logits = generate_beam_search(m, emb.cuda(), am.cuda() if am is not None else None, max_len=8,
                                            beam_size=beams, beam_group_size=group, diversity_penalty=0.8,
                                            eos_token_id=-5)
-    assert out.shape == ro.shape == (2, beams, 8)
+    assert out.shape == ro.shape == (n, beams, 8)
     same = (out == ro).all(dim=-1)
     # beams whose whole token history agrees must agree on score and on the gathered per-step logits
     assert same.float().mean() >= 0.5, f"only {same.float().mean():.2f} of beams match the oracle"
@@ -150,3 +154,26 @@ def test_beam_search_stops_on_eos(llama):
         assert logits2.shape[2] == steps_ref
         assert int(out2[..., steps_ref:].abs().sum()) == 0
         torch.testing.assert_close(lp2, rlp, rtol=1e-2, atol=6e-2)
+
+
+def test_persistent_and_per_op_decode_agree(cuda_device):
+    """The single-launch decode step and the one-launch-per-op path implement the same math."""
+    from oracle.llama import random_llama_state_dict
+    from procyon_b200 import _lib
+    from procyon_b200.model.generation import generate_greedy
+
+    oc, pc = _cfgs("gq4")
+    sd = random_llama_state_dict(oc, seed=3)
+    m = _build(sd, pc)
+    ids, emb, mask = _inputs(oc, sd, 3, 50, seed=7, pad_left=4)
+    lib = _lib.load()
+    try:
+        lib.pcy_set_decode_megakernel(1)
+        o1, lp1, lg1 = generate_greedy(m, emb.cuda(), mask.cuda(), max_len=10)
+        lib.pcy_set_decode_megakernel(0)
+        o2, lp2, lg2 = generate_greedy(m, emb.cuda(), mask.cuda(), max_len=10, use_graph=False)
+    finally:
+        lib.pcy_set_decode_megakernel(1)
+    torch.testing.assert_close(lg1[:, 1], lg2[:, 1], rtol=2e-2, atol=3e-2)  # first decode step: same inputs
+    agree = (o1 == o2).float().mean().item()
+    assert agree > 0.7, agree
