@@ -17,7 +17,8 @@ namespace {
 
 constexpr int MK_THREADS = 512;
 constexpr int MK_WARPS = MK_THREADS / 32;
-constexpr int KCH = 2048;  // K elements per work unit (8 x 16-byte loads per lane)
+constexpr int KCH = 1024;  // K elements per work unit (UL x 16-byte loads per lane)
+constexpr int UL = KCH / 256;
 constexpr int HD = 128;
 constexpr int ATT_CHUNK = 64;  // keys per attention work item
 constexpr int MAX_OUT_PER_CTA = 1024;
@@ -88,22 +89,25 @@ __device__ __forceinline__ int weight_row(int epi, int o_lo, int r) {
   return (j >> 4) * 32 + (j & 15) + ((r & 1) ? 16 : 0);
 }
 
-template <int MT>
-__device__ void prefetch_phase(const bf16* W, int64_t ldw, int n_out, int K, int epi) {
+// L2 prefetch of this CTA's slice of a coming phase: lines [line0, line0 + n_lines) of the slice, issued before the
+// grid barrier so that HBM keeps streaming while CTAs wait and stage activations.
+__device__ void prefetch_phase(const bf16* W, int64_t ldw, int n_out, int K, int epi, int line0, int n_lines) {
   int lo, hi;
   cta_range(n_out, lo, hi);
   const int rpo = (epi == EPI_SWIGLU) ? 2 : 1;
   const int n_rows = (hi - lo) * rpo;
-  // first ~64 KB of this CTA's slice: thread t prefetches one 128-byte line
   const int lines_per_row = (K * 2) / 128;
-  const int t = threadIdx.x;
-  const int r = t / lines_per_row, l = t % lines_per_row;
-  if (r < n_rows) prefetch_l2(W + (int64_t)weight_row(epi, lo, r) * ldw + l * 64);
+  const int total = n_rows * lines_per_row;
+  const int end = min(total, line0 + n_lines);
+  for (int i = line0 + threadIdx.x; i < end; i += MK_THREADS) {
+    const int r = i / lines_per_row, l = i % lines_per_row;
+    prefetch_l2(W + (int64_t)weight_row(epi, lo, r) * ldw + l * 64);
+  }
 }
 
 // out = epi(W[n_out(x2), K] . A[MT, K]);  A is read through L2 (written by other CTAs earlier in this kernel)
 template <int MT>
-__device__ void gemv_phase(const Smem& sm, const bf16* __restrict__ W, int64_t ldw, int n_out, int K,
+__device__ __noinline__ void gemv_phase(const Smem& sm, const bf16* __restrict__ W, int64_t ldw, int n_out, int K,
                            const bf16* A, int64_t lda, int rows, const bf16* __restrict__ rms_w, float eps, int epi,
                            void* out, int64_t ldo, bf16* copy_a_to /* or null: mirror the A rows to global */) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -167,21 +171,24 @@ __device__ void gemv_phase(const Smem& sm, const bf16* __restrict__ W, int64_t l
   // ---- stream the weights: unit = (local row, K chunk of 2048) ----
   const int kc_per_row = (K + KCH - 1) / KCH;
   const int n_units = n_rows * kc_per_row;
-  for (int u = warp; u < n_units; u += MK_WARPS) {
+  auto load_unit = [&](int u, uint4 (&w)[UL]) {
     const int r = u / kc_per_row, kc = u % kc_per_row;
     const bf16* wrow = W + (int64_t)weight_row(epi, o_lo, r) * ldw + kc * KCH;
-    const int k_rem = K - kc * KCH;  // elements left in this row from the chunk start
-    uint4 w[8];
+    const int k_rem = K - kc * KCH;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < UL; ++j) {
       const int k = j * 256 + lane * 8;
       w[j] = (k < k_rem) ? ldg_nc_v4(wrow + k) : make_uint4(0, 0, 0, 0);
     }
+  };
+  auto consume_unit = [&](int u, const uint4 (&w)[UL]) {
+    const int r = u / kc_per_row, kc = u % kc_per_row;
+    const int k_rem = K - kc * KCH;
     float acc[MT];
 #pragma unroll
     for (int m = 0; m < MT; ++m) acc[m] = 0.f;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < UL; ++j) {
       const int k = j * 256 + lane * 8;
       if (k < k_rem) {
 #pragma unroll
@@ -196,6 +203,20 @@ __device__ void gemv_phase(const Smem& sm, const bf16* __restrict__ W, int64_t l
       const float v = warp_sum(acc[m]);
       if (lane == 0) atomicAdd(&sm.out[r * MT + m], v);
     }
+  };
+  // two units in flight per warp: the loads of unit u+16 are issued before unit u is reduced
+  uint4 w0[UL], w1[UL];
+  int u = warp;
+  if (u < n_units) load_unit(u, w0);
+  while (u < n_units) {
+    const int u1 = u + MK_WARPS;
+    if (u1 < n_units) load_unit(u1, w1);
+    consume_unit(u, w0);
+    if (u1 >= n_units) break;
+    const int u2 = u1 + MK_WARPS;
+    if (u2 < n_units) load_unit(u2, w0);
+    consume_unit(u1, w1);
+    u = u2;
   }
   __syncthreads();
 
@@ -244,12 +265,14 @@ struct MegaParams {
   bf16* act;    // [rows][ffn]
   float* part;  // [rows][KVH][max_splits][GQ][HD+2]
   int max_splits;
+  int* tickets;  // [rows][KVH], zero between launches
   unsigned int* barrier;
+  unsigned long long* timing;  // optional: globaltimer at every phase boundary (CTA 0), for profiling
 };
 
 // P2: one work item = (row, kv head, split of 64 keys): RoPE(q, k_new), KV append, scores, softmax stats, P.V
 template <int GQ>
-__device__ void attention_items(const MegaParams& p, uint8_t* smem_raw, int layer) {
+__device__ __noinline__ void attention_items(const MegaParams& p, uint8_t* smem_raw, int layer) {
   float* s_q = reinterpret_cast<float*>(smem_raw);  // [GQ][HD]
   float* s_knew = s_q + GQ * HD;                    // [HD]
   float* s_vnew = s_knew + HD;                      // [HD]
@@ -409,6 +432,35 @@ __device__ void attention_items(const MegaParams& p, uint8_t* smem_raw, int laye
         part[tid * (HD + 2) + HD + 1] = s_ml[tid * 2 + 1];
       }
     }
+    // the last split to finish for this (row, kv head) merges all of them (no extra grid barrier)
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+      const int ticket = atomicAdd(&p.tickets[row * KVH + kvh], 1);
+      s_last = (ticket == n_splits - 1);
+      if (s_last) p.tickets[row * KVH + kvh] = 0;
+    }
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      const int hq = tid / HD, dim = tid % HD;  // 512 threads = 4 heads x 128 dims
+      for (int hh = hq; hh < GQ; hh += MK_THREADS / HD) {
+        const float* ps = p.part + (((int64_t)row * KVH + kvh) * p.max_splits) * GQ * (HD + 2) + hh * (HD + 2);
+        const int64_t stride = (int64_t)GQ * (HD + 2);
+        float m = -INFINITY;
+        for (int sp = 0; sp < n_splits; ++sp) m = fmaxf(m, __ldcg(ps + sp * stride + HD));
+        float l = 0.f, acc = 0.f;
+        for (int sp = 0; sp < n_splits; ++sp) {
+          const float ms = __ldcg(ps + sp * stride + HD);
+          if (ms == -INFINITY) continue;
+          const float w = exp2f(ms - m);
+          l += w * __ldcg(ps + sp * stride + HD + 1);
+          acc += w * __ldcg(ps + sp * stride + dim);
+        }
+        p.attn[(int64_t)row * (H * HD) + (kvh * GQ + hh) * HD + dim] = __float2bfloat16_rn(l > 0.f ? acc / l : 0.f);
+      }
+    }
   }
 }
 
@@ -458,6 +510,12 @@ llama_decode_megakernel(const MegaParams p) {
 
   GridBarrier bar{p.barrier, 0u, gridDim.x};
   const int t = p.state[0];
+  int tix = 0;
+  auto stamp = [&]() {
+    if (p.timing != nullptr && blockIdx.x == 0 && threadIdx.x == 0) p.timing[tix] = globaltimer_ns();
+    ++tix;
+  };
+  stamp();
 
   for (int l = 0; l < c.n_layers; ++l) {
     const LlamaLayerPtrs& y = p.layers[l];
@@ -485,39 +543,49 @@ llama_decode_megakernel(const MegaParams p) {
     } else {
       gemv_phase<MT>(sm, y.wqkv, d, qkv_dim, d, p.x, d, p.rows, y.ln1, c.rms_eps, EPI_BF16, p.qkv, qkv_dim, nullptr);
     }
-    prefetch_phase<MT>(y.wo, H * HD, d, H * HD, EPI_RESIDUAL);
+    prefetch_phase(y.wo, H * HD, d, H * HD, EPI_RESIDUAL, 0, 1 << 20);   // all of Wo: lands during attention
+    prefetch_phase(y.wgu, d, f, d, EPI_SWIGLU, 0, 2400);                    // + the first ~300 KB/CTA of gate/up
     bar.sync();
+    stamp();
     // ---- P2: attention partials ----
     attention_items<GQ>(p, att_smem, l);
     bar.sync();
-    attention_combine<GQ>(p);
-    bar.sync();
+    stamp();
     // ---- P3: x += Wo . attn ----
     gemv_phase<MT>(sm, y.wo, H * HD, d, H * HD, p.attn, H * HD, p.rows, nullptr, 0.f, EPI_RESIDUAL, p.x, d, nullptr);
-    prefetch_phase<MT>(y.wgu, d, f, d, EPI_SWIGLU);
+    prefetch_phase(y.wgu, d, f, d, EPI_SWIGLU, 2400, 800);
     bar.sync();
+    stamp();
     // ---- P4: act = silu(Wg . rms(x)) * (Wu . rms(x)) ----
     gemv_phase<MT>(sm, y.wgu, d, f, d, p.x, d, p.rows, y.ln2, c.rms_eps, EPI_SWIGLU, p.act, f, nullptr);
-    prefetch_phase<MT>(y.wdown, f, d, f, EPI_RESIDUAL);
+    prefetch_phase(y.wdown, f, d, f, EPI_RESIDUAL, 0, 1600);
     bar.sync();
+    stamp();
     // ---- P5: x += Wdown . act ----
     gemv_phase<MT>(sm, y.wdown, f, d, f, p.act, f, p.rows, nullptr, 0.f, EPI_RESIDUAL, p.x, d, nullptr);
-    if (l + 1 < c.n_layers) prefetch_phase<MT>(p.layers[l + 1].wqkv, d, qkv_dim, d, EPI_BF16);
-    else prefetch_phase<MT>(p.lm_head, d, c.vocab, d, EPI_FP32);
+    if (l + 1 < c.n_layers) prefetch_phase(p.layers[l + 1].wqkv, d, qkv_dim, d, EPI_BF16, 0, 1 << 20);
+    else prefetch_phase(p.lm_head, d, c.vocab, d, EPI_FP32, 0, 1600);
     bar.sync();
+    stamp();
   }
   // ---- logits = Wlm . rms(x) ----
   gemv_phase<MT>(sm, p.lm_head, d, c.vocab, d, p.x, d, p.rows, p.norm, c.rms_eps, EPI_FP32, p.logits, c.vocab, nullptr);
+  __syncthreads();
+  stamp();
 }
 
+unsigned long long* g_timing = nullptr;
+
 }  // namespace
+
+void decode_megakernel_set_timing(unsigned long long* dev_buf) { g_timing = dev_buf; }
 
 int64_t decode_megakernel_scratch_bytes(const pcy_llama_config& c, int rows, int S, int max_gen) {
   const int64_t d = c.d_model, qkv = (int64_t)(c.n_heads + 2 * c.n_kv_heads) * HD;
   const int max_splits = ceil_div(S + max_gen, ATT_CHUNK);
   int64_t b = round_up(rows * d * 2, 256) * 2 + round_up(rows * qkv * 2, 256) + round_up((int64_t)rows * c.ffn_dim * 2, 256);
   b += round_up((int64_t)rows * c.n_kv_heads * max_splits * (c.n_heads / c.n_kv_heads) * (HD + 2) * 4, 256);
-  b += 256;
+  b += 1024;
   return b;
 }
 
@@ -546,13 +614,15 @@ int decode_megakernel(const pcy_llama_config& c, const LlamaLayerPtrs* layers_de
   uint8_t* s = reinterpret_cast<uint8_t*>(round_up(reinterpret_cast<int64_t>(scratch), 256));
   auto carve = [&](int64_t bytes) { uint8_t* r = s; s += round_up(bytes, 256); return r; };
   p.barrier = reinterpret_cast<unsigned int*>(carve(256));
+  p.tickets = reinterpret_cast<int*>(carve(256));
   p.x = reinterpret_cast<bf16*>(carve(rows * d * 2));
   p.attn = reinterpret_cast<bf16*>(carve(rows * d * 2));
   p.qkv = reinterpret_cast<bf16*>(carve(rows * qkv * 2));
   p.act = reinterpret_cast<bf16*>(carve((int64_t)rows * c.ffn_dim * 2));
   p.max_splits = ceil_div(b->S + b->max_gen, ATT_CHUNK);
   p.part = reinterpret_cast<float*>(s);
-  PCY_CUDA(cudaMemsetAsync(p.barrier, 0, sizeof(unsigned int), stream));
+  p.timing = g_timing;
+  PCY_CUDA(cudaMemsetAsync(p.barrier, 0, 512, stream));  // barrier counter + tickets
 
   const int mt = rows <= 1 ? 1 : rows <= 2 ? 2 : 4;
   const int kmax = c.ffn_dim > c.d_model ? c.ffn_dim : c.d_model;

@@ -89,6 +89,11 @@ static bool g_use_megakernel = true;
 
 extern "C" {
 
+int pcy_set_decode_timing_buffer(void* dev_u64) {
+  decode_megakernel_set_timing(reinterpret_cast<unsigned long long*>(dev_u64));
+  return 0;
+}
+
 int pcy_set_decode_megakernel(int enabled) {
   g_use_megakernel = enabled != 0;
   return 0;
