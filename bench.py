@@ -161,50 +161,33 @@ def device_generate(model, esm_tokens_dev, ids_dev):
     return _run(model.text_encoder, x, None, GEN_LEN, 1, SELECT_GREEDY, 1, 0.0, -1, False, False)
 
 
-def time_decode_gemvs(model, device, iters=3):
-    """CUDA-event time of the dominant kernel (weight-streaming GEMV) over the launches of one decode step."""
-    from procyon_b200 import ops
+def time_decode_kernel(model, sess, device, iters=20):
+    """CUDA-event time of the dominant kernel: the persistent Llama decode-step kernel (one launch per token).
+    Algorithmic bytes per launch = every weight matrix once (15.01 GB) + the KV rows of the context."""
+    from procyon_b200.model.pmc_llama import SELECT_GREEDY
 
     c = model.text_encoder.model.config
     d, f, V = c.hidden_size, c.intermediate_size, model.text_encoder.model.vocab_size
     qkv = (c.num_attention_heads + 2 * c.num_key_value_heads) * c.head_dim
-    # two distinct layers' worth of weights, alternated, so nothing is served from the 126 MB L2
-    sets = []
-    for _ in range(2):
-        sets.append(dict(wqkv=torch.randn(qkv, d, device=device).bfloat16(), wo=torch.randn(d, d, device=device).bfloat16(),
-                         wgu=torch.randn(2 * f, d, device=device).bfloat16(),
-                         wdn=torch.randn(d, f, device=device).bfloat16()))
-    lm = model.text_encoder._lm_head_bf16(device)
-    ln = torch.ones(d, device=device, dtype=torch.bfloat16)
-    x = torch.randn(1, d, device=device).bfloat16()
-    att = torch.randn(1, d, device=device).bfloat16()
-    o_qkv = torch.empty(1, qkv, device=device, dtype=torch.bfloat16)
-    o_act = torch.empty(1, f, device=device, dtype=torch.bfloat16)
-    o_x = torch.empty(1, d, device=device, dtype=torch.bfloat16)
-    o_lm = torch.empty(1, V, device=device, dtype=torch.float32)
-
-    def one_step():
-        for l in range(c.num_hidden_layers):
-            w = sets[l & 1]
-            ops.linear(x, w["wqkv"], out=o_qkv, force="skinny", rms_weight=ln)
-            ops.linear(att, w["wo"], residual=x, out=o_x, force="skinny")
-            ops.linear(x, w["wgu"], act=ops.ACT_SWIGLU, out=o_act, force="skinny", rms_weight=ln)
-            ops.linear(o_act, w["wdn"], residual=x, out=o_x, force="skinny")
-        ops.linear(x, lm, out=o_lm, force="skinny", rms_weight=ln)
-
-    one_step()
+    kvd = c.num_key_value_heads * c.head_dim
+    # put the session at mid-generation: context = S + GEN_LEN/2
+    t_mid = GEN_LEN // 2
+    sess.state[0] = t_mid
+    for _ in range(3):
+        sess.forward()
     torch.cuda.synchronize(device)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(iters):
-        one_step()
+        sess.forward()  # state[0] is not advanced (no select): every launch does identical work
     e1.record()
     torch.cuda.synchronize(device)
-    launches = 4 * c.num_hidden_layers + 1
     ms = e0.elapsed_time(e1) / iters
-    bytes_step = 2.0 * (c.num_hidden_layers * (qkv * d + d * d + 2 * f * d + d * f) + V * d)
-    return {"ms_per_step": ms, "launches": launches, "bytes_per_launch": bytes_step / launches,
-            "us_per_launch": ms * 1e3 / launches, "gbs": bytes_step / ms / 1e6}
+    weight_bytes = 2.0 * (c.num_hidden_layers * (qkv * d + d * d + 2 * f * d + d * f) + V * d)
+    kv_bytes = 2.0 * c.num_hidden_layers * 2 * (sess.S + t_mid) * kvd
+    total = weight_bytes + kv_bytes
+    return {"ms_per_launch": ms, "bytes_per_launch": total, "weight_bytes": weight_bytes, "kv_bytes": kv_bytes,
+            "gbs": total / ms / 1e6}
 
 
 def time_esm_encode(model, device, world, rank, steps, warmup):
@@ -340,11 +323,11 @@ def run_ours(args):
               "decode_ms_per_token": (ms_per_step - ms_esm - ms_prefill) / (GEN_LEN - 1)}
 
     # ---- roofline of the dominant kernel (weight-streaming GEMV of the decode step) ----
-    gemv = time_decode_gemvs(model, device)
-    roofline = {"kernel": "gemm_skinny_kernel (Llama decode GEMV)", "bound": "hbm", "achieved": gemv["gbs"],
-                "peak": hbm_peak, "unit": "GB/s", "frac": gemv["gbs"] / hbm_peak, "peak_source": peak_src,
-                "traffic": None, "bytes_per_launch": gemv["bytes_per_launch"], "us_per_launch": gemv["us_per_launch"],
-                "launches_per_decode_step": gemv["launches"]}
+    dk = time_decode_kernel(model, sess, device)
+    roofline = {"kernel": "llama_decode_megakernel<1,4> (one launch per generated token)", "bound": "hbm",
+                "achieved": dk["gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": dk["gbs"] / hbm_peak,
+                "peak_source": peak_src, "traffic": None, "bytes_per_launch": dk["bytes_per_launch"],
+                "ms_per_launch": dk["ms_per_launch"], "weight_bytes": dk["weight_bytes"], "kv_bytes": dk["kv_bytes"]}
     esm = time_esm_encode(model, device, world, rank, steps=max(2, K // 2), warmup=2)
     esm["frac_of_bf16_peak"] = esm["tflops_per_gpu"] / tf_peak
     esm["frac_of_bf16_sustained"] = esm["tflops_per_gpu"] / tf_sus

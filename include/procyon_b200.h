@@ -172,7 +172,7 @@ typedef struct {
 
 /* rows <= 4 use one persistent kernel per decode step by default; 0 selects the one-launch-per-op path (tests) */
 int pcy_set_decode_megakernel(int enabled);
-/* profiling aid: device uint64 buffer [5*L + 2] that receives %globaltimer at every phase boundary of the persistent
+/* profiling aid: device uint64 buffer [18*L + 12] that receives %globaltimer at every phase boundary of the persistent
  * decode kernel (NULL disables) */
 int pcy_set_decode_timing_buffer(void* dev_u64);
 int64_t pcy_llama_decode_workspace_bytes(void* handle, int rows, int S, int max_gen);

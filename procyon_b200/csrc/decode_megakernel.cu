@@ -17,10 +17,10 @@ namespace {
 
 constexpr int MK_THREADS = 512;
 constexpr int MK_WARPS = MK_THREADS / 32;
-constexpr int KCH = 1024;  // K elements per work unit (UL x 16-byte loads per lane)
-constexpr int UL = KCH / 256;
+constexpr int UL = 8;          // 512-byte weight segments in flight per warp (one 16-byte load per lane each)
 constexpr int HD = 128;
-constexpr int ATT_CHUNK = 64;  // keys per attention work item
+constexpr int ATT_CHUNK = 128;  // keys per attention work item (8 per warp)
+constexpr int PSTR = HD + 4;    // floats per (split, head) attention partial: 128 outputs, max, sum (16-byte rows)
 constexpr int MAX_OUT_PER_CTA = 1024;
 
 __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
@@ -69,11 +69,18 @@ __device__ __forceinline__ float dot8f(const uint4& a, const uint4& w, float s) 
 }
 
 enum : int { EPI_BF16 = 0, EPI_RESIDUAL = 1, EPI_SWIGLU = 2, EPI_FP32 = 3 };
+enum : int { STAGE_PLAIN = 0, STAGE_RMS = 1, STAGE_ATTN = 2 };
 
 struct Smem {
   bf16* a;       // [MT][K] staged activations
   float* out;    // [MAX_OUT_PER_CTA * 2][MT] partial sums
   float* red;    // [MK_WARPS * 4] scratch
+  unsigned long long* tbuf;  // profiling stamps (CTA 0, thread 0) or null
+  int* tix;
+  __device__ __forceinline__ void stamp() const {
+    if (tbuf != nullptr && blockIdx.x == 0 && threadIdx.x == 0) tbuf[*tix] = globaltimer_ns();
+    if (tbuf != nullptr) ++*tix;
+  }
 };
 
 // balanced contiguous range of `n` items for this CTA
@@ -105,84 +112,126 @@ __device__ void prefetch_phase(const bf16* W, int64_t ldw, int n_out, int K, int
   }
 }
 
-// out = epi(W[n_out(x2), K] . A[MT, K]);  A is read through L2 (written by other CTAs earlier in this kernel)
+struct AttnSrc {  // STAGE_ATTN: A[m][head*128 + dim] = merge over splits of the attention partials
+  const float* part;
+  int n_splits, max_splits, KVH, GQ;
+};
+
+// out = epi(W[n_out(x2), K] . A[MT, K]).  The CTA's slice of W is treated as a flat list of 512-byte segments that is
+// divided evenly among the 16 warps (a warp's range may start and end inside a row); the first batch of weight loads
+// is issued before the activations are staged, so its latency overlaps the staging.
 template <int MT>
-__device__ __noinline__ void gemv_phase(const Smem& sm, const bf16* __restrict__ W, int64_t ldw, int n_out, int K,
-                           const bf16* A, int64_t lda, int rows, const bf16* __restrict__ rms_w, float eps, int epi,
-                           void* out, int64_t ldo, bf16* copy_a_to /* or null: mirror the A rows to global */) {
+__device__ void gemv_phase(const Smem& sm, const bf16* __restrict__ W, int64_t ldw, int n_out, int K, int stage,
+                           const bf16* A, int64_t lda, const AttnSrc& asrc, int rows, const bf16* __restrict__ rms_w,
+                           float eps, int epi, void* out, int64_t ldo) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  // ---- stage A (optionally RMS-normalised, HF semantics) ----
-  for (int m = 0; m < MT; ++m) {
-    bf16* dst = sm.a + (int64_t)m * K;
-    if (m < rows) {
-      const bf16* src = A + (int64_t)m * lda;
-      float rstd = 1.f;
-      if (rms_w != nullptr) {
-        float ss = 0.f;
-        for (int k = tid * 8; k < K; k += MK_THREADS * 8) {
-          const uint4 u = __ldcg(reinterpret_cast<const uint4*>(src + k));
-          const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
-          ss += a.x * a.x + a.y * a.y + b.x * b.x + b.y * b.y + c.x * c.x + c.y * c.y + d.x * d.x + d.y * d.y;
-        }
-        ss = warp_sum(ss);
-        if (lane == 0) sm.red[warp] = ss;
-        __syncthreads();
-        float tot = 0.f;
-#pragma unroll
-        for (int w = 0; w < MK_WARPS; ++w) tot += sm.red[w];
-        rstd = rsqrtf(tot / (float)K + eps);
-        __syncthreads();
-      }
-      for (int k = tid * 8; k < K; k += MK_THREADS * 8) {
-        const uint4 u = __ldcg(reinterpret_cast<const uint4*>(src + k));
-        if (copy_a_to != nullptr) {
-          // every CTA mirrors its own column slice of the un-normalised rows (used to seed the residual stream)
-          int clo, chi;
-          cta_range(K / 8, clo, chi);
-          if (k / 8 >= clo && k / 8 < chi) *reinterpret_cast<uint4*>(copy_a_to + (int64_t)m * K + k) = u;
-        }
-        if (rms_w != nullptr) {
-          const uint4 g = *reinterpret_cast<const uint4*>(rms_w + k);
-          const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
-          const uint32_t gg[4] = {g.x, g.y, g.z, g.w};
-          uint32_t oo[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float2 x = unpack_bf16x2(uu[i]);
-            const float2 w = unpack_bf16x2(gg[i]);
-            oo[i] = pack_bf16x2(w.x * bf16_round(x.x * rstd), w.y * bf16_round(x.y * rstd));
-          }
-          *reinterpret_cast<uint4*>(dst + k) = make_uint4(oo[0], oo[1], oo[2], oo[3]);
-        } else {
-          *reinterpret_cast<uint4*>(dst + k) = u;
-        }
-      }
-    } else {
-      for (int k = tid * 8; k < K; k += MK_THREADS * 8) *reinterpret_cast<uint4*>(dst + k) = make_uint4(0, 0, 0, 0);
-    }
-  }
   int o_lo, o_hi;
   cta_range(n_out, o_lo, o_hi);
   const int rpo = (epi == EPI_SWIGLU) ? 2 : 1;
   const int n_rows = (o_hi - o_lo) * rpo;
-  for (int i = tid; i < n_rows * MT; i += MK_THREADS) sm.out[i] = 0.f;
-  __syncthreads();
-
-  // ---- stream the weights: unit = (local row, K chunk of 2048) ----
+  // work unit = (local row, K chunk of 2048 elements): 8 x 16-byte loads per lane; units go round-robin to warps
+  constexpr int KCH = UL * 256;
   const int kc_per_row = (K + KCH - 1) / KCH;
   const int n_units = n_rows * kc_per_row;
-  auto load_unit = [&](int u, uint4 (&w)[UL]) {
-    const int r = u / kc_per_row, kc = u % kc_per_row;
-    const bf16* wrow = W + (int64_t)weight_row(epi, o_lo, r) * ldw + kc * KCH;
-    const int k_rem = K - kc * KCH;
-#pragma unroll
-    for (int j = 0; j < UL; ++j) {
-      const int k = j * 256 + lane * 8;
-      w[j] = (k < k_rem) ? ldg_nc_v4(wrow + k) : make_uint4(0, 0, 0, 0);
+  uint4 wb[UL];
+#define PCY_LOAD_UNIT(U)                                                                     \
+  {                                                                                          \
+    const int r_ = (U) / kc_per_row, kc_ = (U) - r_ * kc_per_row;                            \
+    const bf16* wrow_ = W + (int64_t)weight_row(epi, o_lo, r_) * ldw + kc_ * KCH;            \
+    const int k_rem_ = K - kc_ * KCH;                                                        \
+    _Pragma("unroll") for (int j = 0; j < UL; ++j) {                                         \
+      const int k_ = j * 256 + lane * 8;                                                     \
+      wb[j] = (k_ < k_rem_) ? ldg_nc_v4(wrow_ + k_) : make_uint4(0, 0, 0, 0);                \
+    }                                                                                        \
+  }
+
+  // ---- stage A (plain | RMS-normalised with HF rounding | merged attention partials) ----
+  for (int m = 0; m < MT; ++m) {
+    bf16* dst = sm.a + (int64_t)m * K;
+    if (m >= rows) {
+      for (int k = tid * 8; k < K; k += MK_THREADS * 8) *reinterpret_cast<uint4*>(dst + k) = make_uint4(0, 0, 0, 0);
+      continue;
     }
-  };
-  auto consume_unit = [&](int u, const uint4 (&w)[UL]) {
-    const int r = u / kc_per_row, kc = u % kc_per_row;
+    if (stage == STAGE_ATTN) {
+      for (int k = tid * 8; k < K; k += MK_THREADS * 8) {
+        const int head = k / HD, dim = k % HD;
+        const int kvh = head / asrc.GQ, hq = head % asrc.GQ;
+        const float* ps = asrc.part + (((int64_t)m * asrc.KVH + kvh) * asrc.max_splits) * asrc.GQ * PSTR + hq * PSTR;
+        const int64_t stride = (int64_t)asrc.GQ * PSTR;
+        float mx = -INFINITY;
+        for (int sp = 0; sp < asrc.n_splits; ++sp) mx = fmaxf(mx, __ldcg(ps + sp * stride + HD));
+        float l = 0.f, acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+        for (int sp = 0; sp < asrc.n_splits; ++sp) {
+          const float ms = __ldcg(ps + sp * stride + HD);
+          if (ms == -INFINITY) continue;
+          const float w = exp2f(ms - mx);
+          l += w * __ldcg(ps + sp * stride + HD + 1);
+          const float4 v0 = __ldcg(reinterpret_cast<const float4*>(ps + sp * stride + dim));
+          const float4 v1 = __ldcg(reinterpret_cast<const float4*>(ps + sp * stride + dim + 4));
+          acc[0] += w * v0.x; acc[1] += w * v0.y; acc[2] += w * v0.z; acc[3] += w * v0.w;
+          acc[4] += w * v1.x; acc[5] += w * v1.y; acc[6] += w * v1.z; acc[7] += w * v1.w;
+        }
+        const float inv = l > 0.f ? 1.f / l : 0.f;
+        *reinterpret_cast<uint4*>(dst + k) =
+            make_uint4(pack_bf16x2(acc[0] * inv, acc[1] * inv), pack_bf16x2(acc[2] * inv, acc[3] * inv),
+                       pack_bf16x2(acc[4] * inv, acc[5] * inv), pack_bf16x2(acc[6] * inv, acc[7] * inv));
+      }
+      continue;
+    }
+    const bf16* src = A + (int64_t)m * lda;
+    float rstd = 1.f;
+    if (stage == STAGE_RMS) {
+      float ss = 0.f;
+      for (int k = tid * 8; k < K; k += MK_THREADS * 8) {
+        const uint4 u = __ldcg(reinterpret_cast<const uint4*>(src + k));
+        const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+        ss += a.x * a.x + a.y * a.y + b.x * b.x + b.y * b.y + c.x * c.x + c.y * c.y + d.x * d.x + d.y * d.y;
+      }
+      ss = warp_sum(ss);
+      if (lane == 0) sm.red[warp] = ss;
+      __syncthreads();
+      float tot = 0.f;
+#pragma unroll
+      for (int w = 0; w < MK_WARPS; ++w) tot += sm.red[w];
+      rstd = rsqrtf(tot / (float)K + eps);
+      __syncthreads();
+    }
+    for (int k = tid * 8; k < K; k += MK_THREADS * 8) {
+      const uint4 u = __ldcg(reinterpret_cast<const uint4*>(src + k));
+      if (stage == STAGE_RMS) {
+        const uint4 g = *reinterpret_cast<const uint4*>(rms_w + k);
+        const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+        const uint32_t gg[4] = {g.x, g.y, g.z, g.w};
+        uint32_t oo[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 x = unpack_bf16x2(uu[i]);
+          const float2 w = unpack_bf16x2(gg[i]);
+          oo[i] = pack_bf16x2(w.x * bf16_round(x.x * rstd), w.y * bf16_round(x.y * rstd));  // HF LlamaRMSNorm
+        }
+        *reinterpret_cast<uint4*>(dst + k) = make_uint4(oo[0], oo[1], oo[2], oo[3]);
+      } else {
+        *reinterpret_cast<uint4*>(dst + k) = u;
+      }
+    }
+  }
+  for (int i = tid; i < n_rows * MT; i += MK_THREADS) sm.out[i] = 0.f;
+  // residual values are final since two phases ago: fetch them now, off the critical path
+  const int n_o = o_hi - o_lo;
+  float res_pre = 0.f;
+  if (epi == EPI_RESIDUAL && tid < n_o * MT) {
+    const int o = tid / MT, m = tid % MT;
+    if (m < rows) res_pre = ldcg_bf16(reinterpret_cast<const bf16*>(out) + (int64_t)m * ldo + o_lo + o);
+  }
+  __syncthreads();
+  sm.stamp();
+
+  // ---- stream the weights ----
+  for (int u = warp; u < n_units; u += MK_WARPS) {
+    PCY_LOAD_UNIT(u)
+    const int r = u / kc_per_row, kc = u - r * kc_per_row;
     const int k_rem = K - kc * KCH;
     float acc[MT];
 #pragma unroll
@@ -194,7 +243,7 @@ __device__ __noinline__ void gemv_phase(const Smem& sm, const bf16* __restrict__
 #pragma unroll
         for (int m = 0; m < MT; ++m) {
           const uint4 a = *reinterpret_cast<const uint4*>(sm.a + (int64_t)m * K + kc * KCH + k);
-          acc[m] = dot8f(a, w[j], acc[m]);
+          acc[m] = dot8f(a, wb[j], acc[m]);
         }
       }
     }
@@ -203,25 +252,12 @@ __device__ __noinline__ void gemv_phase(const Smem& sm, const bf16* __restrict__
       const float v = warp_sum(acc[m]);
       if (lane == 0) atomicAdd(&sm.out[r * MT + m], v);
     }
-  };
-  // two units in flight per warp: the loads of unit u+16 are issued before unit u is reduced
-  uint4 w0[UL], w1[UL];
-  int u = warp;
-  if (u < n_units) load_unit(u, w0);
-  while (u < n_units) {
-    const int u1 = u + MK_WARPS;
-    if (u1 < n_units) load_unit(u1, w1);
-    consume_unit(u, w0);
-    if (u1 >= n_units) break;
-    const int u2 = u1 + MK_WARPS;
-    if (u2 < n_units) load_unit(u2, w0);
-    consume_unit(u1, w1);
-    u = u2;
   }
+#undef PCY_LOAD_UNIT
   __syncthreads();
+  sm.stamp();
 
   // ---- epilogue ----
-  const int n_o = o_hi - o_lo;
   for (int i = tid; i < n_o * MT; i += MK_THREADS) {
     const int o = i / MT, m = i % MT;
     if (m >= rows) continue;
@@ -235,7 +271,7 @@ __device__ __noinline__ void gemv_phase(const Smem& sm, const bf16* __restrict__
         reinterpret_cast<float*>(out)[(int64_t)m * ldo + col] = v;
       } else {
         bf16* op = reinterpret_cast<bf16*>(out) + (int64_t)m * ldo + col;
-        if (epi == EPI_RESIDUAL) v += ldcg_bf16(op);
+        if (epi == EPI_RESIDUAL) v += (i == tid) ? res_pre : ldcg_bf16(op);
         *op = __float2bfloat16_rn(v);
       }
     }
@@ -261,18 +297,17 @@ struct MegaParams {
   // scratch (global)
   bf16* x;      // [rows][d]
   bf16* qkv;    // [rows][qkv_dim]
-  bf16* attn;   // [rows][d]
   bf16* act;    // [rows][ffn]
-  float* part;  // [rows][KVH][max_splits][GQ][HD+2]
+  float* part;  // [rows][KVH][max_splits][GQ][PSTR]
   int max_splits;
-  int* tickets;  // [rows][KVH], zero between launches
   unsigned int* barrier;
   unsigned long long* timing;  // optional: globaltimer at every phase boundary (CTA 0), for profiling
 };
 
-// P2: one work item = (row, kv head, split of 64 keys): RoPE(q, k_new), KV append, scores, softmax stats, P.V
+// P2: one work item = (row, kv head, split of 256 keys): RoPE(q, k_new), KV append, scores, softmax, P.V -> partial.
+// The partials are merged by the next phase while it stages its activations (no combine pass, no extra barrier).
 template <int GQ>
-__device__ __noinline__ void attention_items(const MegaParams& p, uint8_t* smem_raw, int layer) {
+__device__ void attention_items(const MegaParams& p, uint8_t* smem_raw, int layer) {
   float* s_q = reinterpret_cast<float*>(smem_raw);  // [GQ][HD]
   float* s_knew = s_q + GQ * HD;                    // [HD]
   float* s_vnew = s_knew + HD;                      // [HD]
@@ -292,12 +327,46 @@ __device__ __noinline__ void attention_items(const MegaParams& p, uint8_t* smem_
   const bf16* vp = p.kv_prompt + ((int64_t)layer * 2 + 1) * n_prompt * kvd;
   bf16* kg = p.kv_gen + ((int64_t)layer * 2 + 0) * n_gen * kvd;
   bf16* vg = p.kv_gen + ((int64_t)layer * 2 + 1) * n_gen * kvd;
+  const int sub = lane >> 3, l8 = lane & 7;  // 8 lanes per key, 16 dims per lane
+  constexpr int KPW = ATT_CHUNK / MK_WARPS / 4;  // key iterations per warp (4 keys each)
 
   for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
     const int split = item % n_splits, kvh = (item / n_splits) % KVH, row = item / (n_splits * KVH);
     const int input = row / p.beams;
     const bf16* qkv_row = p.qkv + (int64_t)row * qkv_dim;
-    __syncthreads();
+    const int k0 = split * ATT_CHUNK;
+    const int n_keys = min(ctx, k0 + ATT_CHUNK) - k0;
+    // K/V row pointers of this lane's keys (nullptr = the current token, held in smem; or out of range)
+    const bf16* kptr[KPW];
+    const bf16* vptr[KPW];
+    bool valid[KPW];
+    uint4 kreg[KPW][2];
+#pragma unroll
+    for (int it = 0; it < KPW; ++it) {
+      const int kk = (it * MK_WARPS + warp) * 4 + sub;
+      const int pos = k0 + kk;
+      kptr[it] = vptr[it] = nullptr;
+      valid[it] = kk < n_keys;
+      if (valid[it] && pos != pos_cur) {
+        if (pos < p.S) {
+          const int64_t base = ((int64_t)input * p.S + pos) * kvd + kvh * HD + l8 * 16;
+          kptr[it] = kp + base;
+          vptr[it] = vp + base;
+          if (p.prompt_valid) valid[it] = p.prompt_valid[(int64_t)input * p.S + pos] != 0;
+        } else {
+          const int g = pos - p.S;
+          const int prow = p.slots[(int64_t)row * p.max_gen + g];
+          const int64_t base = ((int64_t)prow * p.max_gen + g) * kvd + kvh * HD + l8 * 16;
+          kptr[it] = kg + base;
+          vptr[it] = vg + base;
+        }
+      }
+      if (kptr[it] != nullptr) {  // issue all K loads before touching shared memory
+        kreg[it][0] = __ldcg(reinterpret_cast<const uint4*>(kptr[it]));
+        kreg[it][1] = __ldcg(reinterpret_cast<const uint4*>(kptr[it] + 8));
+      }
+    }
+    __syncthreads();  // previous item done with the shared buffers
     {
       const float2* cs = reinterpret_cast<const float2*>(p.rope) + (int64_t)pos_cur * (HD / 2);
       for (int i = tid; i < (GQ + 1) * (HD / 2); i += MK_THREADS) {
@@ -317,180 +386,124 @@ __device__ __noinline__ void attention_items(const MegaParams& p, uint8_t* smem_
       if (tid < HD) s_vnew[tid] = ldcg_bf16(qkv_row + (H + KVH + kvh) * HD + tid);
     }
     __syncthreads();
-    const int k0 = split * ATT_CHUNK;
-    const int n_keys = min(ctx, k0 + ATT_CHUNK) - k0;
     if (pos_cur >= k0 && pos_cur < k0 + ATT_CHUNK && tid < HD) {
       const int64_t off = ((int64_t)row * p.max_gen + g_cur) * kvd + kvh * HD + tid;
       kg[off] = __float2bfloat16_rn(s_knew[tid]);
       vg[off] = __float2bfloat16_rn(s_vnew[tid]);
     }
-    // one key per 8 lanes (16 dims each); 16 warps x 4 keys = the whole 64-key chunk in one shot
-    const int sub = lane >> 3, l8 = lane & 7;
-    const int kk = warp * 4 + sub;
-    const int pos = k0 + kk;
-    bool valid = kk < n_keys;
-    const bf16* vptr = nullptr;
-    float kf[16];
-    if (valid) {
-      if (pos == pos_cur) {
+    // ---- scores ----
 #pragma unroll
-        for (int j = 0; j < 16; ++j) kf[j] = s_knew[l8 * 16 + j];
-      } else {
-        const bf16* kptr;
-        if (pos < p.S) {
-          const int64_t base = ((int64_t)input * p.S + pos) * kvd + kvh * HD;
-          kptr = kp + base;
-          vptr = vp + base;
-          if (p.prompt_valid) valid = p.prompt_valid[(int64_t)input * p.S + pos] != 0;
-        } else {
-          const int g = pos - p.S;
-          const int prow = p.slots[(int64_t)row * p.max_gen + g];
-          const int64_t base = ((int64_t)prow * p.max_gen + g) * kvd + kvh * HD;
-          kptr = kg + base;
-          vptr = vg + base;
-        }
-        const uint4 u0 = __ldcg(reinterpret_cast<const uint4*>(kptr + l8 * 16));
-        const uint4 u1 = __ldcg(reinterpret_cast<const uint4*>(kptr + l8 * 16 + 8));
-        const uint32_t w[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+    for (int it = 0; it < KPW; ++it) {
+      const int kk = (it * MK_WARPS + warp) * 4 + sub;
+      float kf[16];
+      if (kptr[it] != nullptr) {
+        const uint32_t w[8] = {kreg[it][0].x, kreg[it][0].y, kreg[it][0].z, kreg[it][0].w,
+                               kreg[it][1].x, kreg[it][1].y, kreg[it][1].z, kreg[it][1].w};
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float2 f = unpack_bf16x2(w[j]);
           kf[2 * j] = f.x;
           kf[2 * j + 1] = f.y;
         }
-      }
-    }
-    // issue the V loads now so they overlap the score / softmax work
-    float vf[16];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) vf[j] = 0.f;
-    if (kk < n_keys) {
-      if (pos == pos_cur) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) vf[j] = bf16_round(s_vnew[l8 * 16 + j]);
       } else {
-        const uint4 u0 = __ldcg(reinterpret_cast<const uint4*>(vptr + l8 * 16));
-        const uint4 u1 = __ldcg(reinterpret_cast<const uint4*>(vptr + l8 * 16 + 8));
-        const uint32_t w[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float2 f = unpack_bf16x2(w[j]);
-          vf[2 * j] = f.x;
-          vf[2 * j + 1] = f.y;
-        }
+        for (int j = 0; j < 16; ++j) kf[j] = s_knew[l8 * 16 + j];  // current token (or unused)
       }
-    }
 #pragma unroll
-    for (int h = 0; h < GQ; ++h) {
-      float a = 0.f;
-      if (valid) {
+      for (int h = 0; h < GQ; ++h) {
+        float a = 0.f;
 #pragma unroll
         for (int j = 0; j < 16; ++j) a = fmaf(kf[j], s_q[h * HD + l8 * 16 + j], a);
+        a += __shfl_xor_sync(0xffffffffu, a, 1);
+        a += __shfl_xor_sync(0xffffffffu, a, 2);
+        a += __shfl_xor_sync(0xffffffffu, a, 4);
+        if (l8 == 0) s_sc[h * ATT_CHUNK + kk] = valid[it] ? a : -INFINITY;
       }
-      a += __shfl_xor_sync(0xffffffffu, a, 1);
-      a += __shfl_xor_sync(0xffffffffu, a, 2);
-      a += __shfl_xor_sync(0xffffffffu, a, 4);
-      if (l8 == 0) s_sc[h * ATT_CHUNK + kk] = valid ? a : -INFINITY;
+    }
+    // V loads in flight while the softmax statistics are computed
+    uint4 vreg[KPW][2];
+#pragma unroll
+    for (int it = 0; it < KPW; ++it) {
+      if (vptr[it] != nullptr) {
+        vreg[it][0] = __ldcg(reinterpret_cast<const uint4*>(vptr[it]));
+        vreg[it][1] = __ldcg(reinterpret_cast<const uint4*>(vptr[it] + 8));
+      }
     }
     __syncthreads();
     if (warp < GQ) {
       const int h = warp;
-      float m = fmaxf(s_sc[h * ATT_CHUNK + lane], s_sc[h * ATT_CHUNK + lane + 32]);
+      float m = -INFINITY;
+      for (int k = lane; k < ATT_CHUNK; k += 32) m = fmaxf(m, s_sc[h * ATT_CHUNK + k]);
       m = warp_max(m);
-      const float p0 = (m == -INFINITY) ? 0.f : exp2f(s_sc[h * ATT_CHUNK + lane] - m);
-      const float p1 = (m == -INFINITY) ? 0.f : exp2f(s_sc[h * ATT_CHUNK + lane + 32] - m);
-      s_sc[h * ATT_CHUNK + lane] = p0;
-      s_sc[h * ATT_CHUNK + lane + 32] = p1;
-      const float l = warp_sum(p0 + p1);
+      float l = 0.f;
+      for (int k = lane; k < ATT_CHUNK; k += 32) {
+        const float pr = (m == -INFINITY) ? 0.f : exp2f(s_sc[h * ATT_CHUNK + k] - m);
+        s_sc[h * ATT_CHUNK + k] = pr;
+        l += pr;
+      }
+      l = warp_sum(l);
       if (lane == 0) { s_ml[h * 2] = m; s_ml[h * 2 + 1] = l; }
     }
     __syncthreads();
-    // P.V: each lane weights its 16 V dims by p[h][key]; reduce the warp's 4 keys by shuffles, warps via smem
+    // ---- P.V: two heads at a time to bound the accumulator registers ----
 #pragma unroll
-    for (int h = 0; h < GQ; ++h) {
-      const float pr = s_sc[h * ATT_CHUNK + kk];
+    for (int hp = 0; hp < GQ; hp += 2) {
+      float acc[2][16];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        float v = pr * vf[j];
-        v += __shfl_xor_sync(0xffffffffu, v, 8);
-        v += __shfl_xor_sync(0xffffffffu, v, 16);
-        if (sub == 0) s_po[(warp * GQ + h) * HD + l8 * 16 + j] = v;
+      for (int j = 0; j < 16; ++j) acc[0][j] = acc[1][j] = 0.f;
+#pragma unroll
+      for (int it = 0; it < KPW; ++it) {
+        const int kk = (it * MK_WARPS + warp) * 4 + sub;
+        float vf[16];
+        if (vptr[it] != nullptr) {
+          const uint32_t w[8] = {vreg[it][0].x, vreg[it][0].y, vreg[it][0].z, vreg[it][0].w,
+                                 vreg[it][1].x, vreg[it][1].y, vreg[it][1].z, vreg[it][1].w};
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float2 f = unpack_bf16x2(w[j]);
+            vf[2 * j] = f.x;
+            vf[2 * j + 1] = f.y;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) vf[j] = bf16_round(s_vnew[l8 * 16 + j]);
+        }
+        const float p0 = s_sc[hp * ATT_CHUNK + kk];
+        const float p1 = (hp + 1 < GQ) ? s_sc[(hp + 1) * ATT_CHUNK + kk] : 0.f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          acc[0][j] = fmaf(p0, vf[j], acc[0][j]);
+          acc[1][j] = fmaf(p1, vf[j], acc[1][j]);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        if (hp + q < GQ) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float v = acc[q][j];
+            v += __shfl_xor_sync(0xffffffffu, v, 8);
+            v += __shfl_xor_sync(0xffffffffu, v, 16);
+            if (sub == 0) s_po[(warp * GQ + hp + q) * HD + l8 * 16 + j] = v;
+          }
+        }
       }
     }
     __syncthreads();
-    float* part = p.part + (((int64_t)row * KVH + kvh) * p.max_splits + split) * GQ * (HD + 2);
+    float* part = p.part + (((int64_t)row * KVH + kvh) * p.max_splits + split) * GQ * PSTR;
     {
-      const int h = tid / HD, dim = tid % HD;  // 512 threads = GQ(4) x 128; loop for other GQ
+      const int h = tid / HD, dim = tid % HD;  // 512 threads = 4 heads x 128 dims
       for (int hh = h; hh < GQ; hh += MK_THREADS / HD) {
         float s = 0.f;
 #pragma unroll
         for (int w = 0; w < MK_WARPS; ++w) s += s_po[(w * GQ + hh) * HD + dim];
-        part[hh * (HD + 2) + dim] = s;
+        part[hh * PSTR + dim] = s;
       }
       if (tid < GQ) {
-        part[tid * (HD + 2) + HD] = s_ml[tid * 2];
-        part[tid * (HD + 2) + HD + 1] = s_ml[tid * 2 + 1];
+        part[tid * PSTR + HD] = s_ml[tid * 2];
+        part[tid * PSTR + HD + 1] = s_ml[tid * 2 + 1];
       }
     }
-    // the last split to finish for this (row, kv head) merges all of them (no extra grid barrier)
-    __shared__ int s_last;
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) {
-      const int ticket = atomicAdd(&p.tickets[row * KVH + kvh], 1);
-      s_last = (ticket == n_splits - 1);
-      if (s_last) p.tickets[row * KVH + kvh] = 0;
-    }
-    __syncthreads();
-    if (s_last) {
-      __threadfence();
-      const int hq = tid / HD, dim = tid % HD;  // 512 threads = 4 heads x 128 dims
-      for (int hh = hq; hh < GQ; hh += MK_THREADS / HD) {
-        const float* ps = p.part + (((int64_t)row * KVH + kvh) * p.max_splits) * GQ * (HD + 2) + hh * (HD + 2);
-        const int64_t stride = (int64_t)GQ * (HD + 2);
-        float m = -INFINITY;
-        for (int sp = 0; sp < n_splits; ++sp) m = fmaxf(m, __ldcg(ps + sp * stride + HD));
-        float l = 0.f, acc = 0.f;
-        for (int sp = 0; sp < n_splits; ++sp) {
-          const float ms = __ldcg(ps + sp * stride + HD);
-          if (ms == -INFINITY) continue;
-          const float w = exp2f(ms - m);
-          l += w * __ldcg(ps + sp * stride + HD + 1);
-          acc += w * __ldcg(ps + sp * stride + dim);
-        }
-        p.attn[(int64_t)row * (H * HD) + (kvh * GQ + hh) * HD + dim] = __float2bfloat16_rn(l > 0.f ? acc / l : 0.f);
-      }
-    }
-  }
-}
-
-// P2c: one work item = (row, q head): merge the split partials -> attn[row, head*128 ...]
-template <int GQ>
-__device__ void attention_combine(const MegaParams& p) {
-  const int tid = threadIdx.x;
-  const int H = p.cfg.n_heads, KVH = p.cfg.n_kv_heads;
-  const int t = p.state[0];
-  const int ctx = p.S + t;
-  const int n_splits = (ctx + ATT_CHUNK - 1) / ATT_CHUNK;
-  const int per_cta = MK_THREADS / HD;  // heads handled at once by a CTA
-  const int n_items = p.rows * H;
-  for (int base = blockIdx.x * per_cta; base < n_items; base += gridDim.x * per_cta) {
-    const int item = base + tid / HD, dim = tid % HD;
-    if (item >= n_items) continue;
-    const int row = item / H, head = item % H, kvh = head / GQ, hq = head % GQ;
-    const float* ps = p.part + (((int64_t)row * KVH + kvh) * p.max_splits) * GQ * (HD + 2) + hq * (HD + 2);
-    const int64_t stride = (int64_t)GQ * (HD + 2);
-    float m = -INFINITY;
-    for (int s = 0; s < n_splits; ++s) m = fmaxf(m, __ldcg(ps + s * stride + HD));
-    float l = 0.f, acc = 0.f;
-    for (int s = 0; s < n_splits; ++s) {
-      const float ms = __ldcg(ps + s * stride + HD);
-      if (ms == -INFINITY) continue;
-      const float w = exp2f(ms - m);
-      l += w * __ldcg(ps + s * stride + HD + 1);
-      acc += w * __ldcg(ps + s * stride + dim);
-    }
-    p.attn[(int64_t)row * (H * HD) + head * HD + dim] = __float2bfloat16_rn(l > 0.f ? acc / l : 0.f);
   }
 }
 
@@ -510,19 +523,21 @@ llama_decode_megakernel(const MegaParams p) {
 
   GridBarrier bar{p.barrier, 0u, gridDim.x};
   const int t = p.state[0];
+  const int n_splits = (p.S + t + ATT_CHUNK - 1) / ATT_CHUNK;
+  const AttnSrc no_attn{nullptr, 0, 0, 0, 0};
+  const AttnSrc attn_src{p.part, n_splits, p.max_splits, KVH, GQ};
   int tix = 0;
-  auto stamp = [&]() {
-    if (p.timing != nullptr && blockIdx.x == 0 && threadIdx.x == 0) p.timing[tix] = globaltimer_ns();
-    ++tix;
-  };
+  sm.tbuf = p.timing;
+  sm.tix = &tix;
+  auto stamp = [&]() { sm.stamp(); };
   stamp();
 
   for (int l = 0; l < c.n_layers; ++l) {
     const LlamaLayerPtrs& y = p.layers[l];
     // ---- P1: qkv = Wqkv . rms(x) ----
     if (l == 0) {
-      // the residual stream starts as the embedding of the last token of every row; each CTA stages it straight
-      // from the table (MT rows may differ) and mirrors its column slice to x
+      // the residual stream starts as the embedding of the last token of every row: each CTA mirrors its column
+      // slice of the rows into x
       for (int m = 0; m < p.rows; ++m) {
         const int tok = p.tokens[(int64_t)m * p.max_gen + (t - 1)];
         const bf16* src = p.embed + (int64_t)tok * d;
@@ -531,45 +546,48 @@ llama_decode_megakernel(const MegaParams p) {
         for (int k8 = clo + threadIdx.x; k8 < chi; k8 += MK_THREADS)
           *reinterpret_cast<uint4*>(p.x + (int64_t)m * d + k8 * 8) = *reinterpret_cast<const uint4*>(src + k8 * 8);
       }
-      // P1 of layer 0 reads the rows from the table directly (x is not globally visible yet)
-      if (p.rows == 1) {
-        const int tok = p.tokens[(int64_t)0 * p.max_gen + (t - 1)];
-        gemv_phase<MT>(sm, y.wqkv, d, qkv_dim, d, p.embed + (int64_t)tok * d, d, 1, y.ln1, c.rms_eps, EPI_BF16, p.qkv,
-                       qkv_dim, nullptr);
+      if (p.rows == 1) {  // read the row straight from the table (x is not globally visible yet)
+        const int tok = p.tokens[t - 1];
+        gemv_phase<MT>(sm, y.wqkv, d, qkv_dim, d, STAGE_RMS, p.embed + (int64_t)tok * d, d, no_attn, 1, y.ln1,
+                       c.rms_eps, EPI_BF16, p.qkv, qkv_dim);
       } else {
-        bar.sync();  // rows > 1: wait until x is complete, then read it like any other layer
-        gemv_phase<MT>(sm, y.wqkv, d, qkv_dim, d, p.x, d, p.rows, y.ln1, c.rms_eps, EPI_BF16, p.qkv, qkv_dim, nullptr);
+        bar.sync();
+        gemv_phase<MT>(sm, y.wqkv, d, qkv_dim, d, STAGE_RMS, p.x, d, no_attn, p.rows, y.ln1, c.rms_eps, EPI_BF16,
+                       p.qkv, qkv_dim);
       }
     } else {
-      gemv_phase<MT>(sm, y.wqkv, d, qkv_dim, d, p.x, d, p.rows, y.ln1, c.rms_eps, EPI_BF16, p.qkv, qkv_dim, nullptr);
+      gemv_phase<MT>(sm, y.wqkv, d, qkv_dim, d, STAGE_RMS, p.x, d, no_attn, p.rows, y.ln1, c.rms_eps, EPI_BF16, p.qkv,
+                     qkv_dim);
     }
-    prefetch_phase(y.wo, H * HD, d, H * HD, EPI_RESIDUAL, 0, 1 << 20);   // all of Wo: lands during attention
-    prefetch_phase(y.wgu, d, f, d, EPI_SWIGLU, 0, 2400);                    // + the first ~300 KB/CTA of gate/up
+    prefetch_phase(y.wo, H * HD, d, H * HD, EPI_RESIDUAL, 0, 512);
+    stamp();
     bar.sync();
     stamp();
     // ---- P2: attention partials ----
     attention_items<GQ>(p, att_smem, l);
+    stamp();
     bar.sync();
     stamp();
-    // ---- P3: x += Wo . attn ----
-    gemv_phase<MT>(sm, y.wo, H * HD, d, H * HD, p.attn, H * HD, p.rows, nullptr, 0.f, EPI_RESIDUAL, p.x, d, nullptr);
-    prefetch_phase(y.wgu, d, f, d, EPI_SWIGLU, 2400, 800);
+    // ---- P3: x += Wo . attn (the attention partials are merged while staging) ----
+    gemv_phase<MT>(sm, y.wo, H * HD, d, H * HD, STAGE_ATTN, nullptr, 0, attn_src, p.rows, nullptr, 0.f, EPI_RESIDUAL,
+                   p.x, d);
+    stamp();
     bar.sync();
     stamp();
     // ---- P4: act = silu(Wg . rms(x)) * (Wu . rms(x)) ----
-    gemv_phase<MT>(sm, y.wgu, d, f, d, p.x, d, p.rows, y.ln2, c.rms_eps, EPI_SWIGLU, p.act, f, nullptr);
-    prefetch_phase(y.wdown, f, d, f, EPI_RESIDUAL, 0, 1600);
+    gemv_phase<MT>(sm, y.wgu, d, f, d, STAGE_RMS, p.x, d, no_attn, p.rows, y.ln2, c.rms_eps, EPI_SWIGLU, p.act, f);
+    stamp();
     bar.sync();
     stamp();
     // ---- P5: x += Wdown . act ----
-    gemv_phase<MT>(sm, y.wdown, f, d, f, p.act, f, p.rows, nullptr, 0.f, EPI_RESIDUAL, p.x, d, nullptr);
-    if (l + 1 < c.n_layers) prefetch_phase(p.layers[l + 1].wqkv, d, qkv_dim, d, EPI_BF16, 0, 1 << 20);
-    else prefetch_phase(p.lm_head, d, c.vocab, d, EPI_FP32, 0, 1600);
+    gemv_phase<MT>(sm, y.wdown, f, d, f, STAGE_PLAIN, p.act, f, no_attn, p.rows, nullptr, 0.f, EPI_RESIDUAL, p.x, d);
+    stamp();
     bar.sync();
     stamp();
   }
   // ---- logits = Wlm . rms(x) ----
-  gemv_phase<MT>(sm, p.lm_head, d, c.vocab, d, p.x, d, p.rows, p.norm, c.rms_eps, EPI_FP32, p.logits, c.vocab, nullptr);
+  gemv_phase<MT>(sm, p.lm_head, d, c.vocab, d, STAGE_RMS, p.x, d, no_attn, p.rows, p.norm, c.rms_eps, EPI_FP32,
+                 p.logits, c.vocab);
   __syncthreads();
   stamp();
 }
@@ -584,7 +602,7 @@ int64_t decode_megakernel_scratch_bytes(const pcy_llama_config& c, int rows, int
   const int64_t d = c.d_model, qkv = (int64_t)(c.n_heads + 2 * c.n_kv_heads) * HD;
   const int max_splits = ceil_div(S + max_gen, ATT_CHUNK);
   int64_t b = round_up(rows * d * 2, 256) * 2 + round_up(rows * qkv * 2, 256) + round_up((int64_t)rows * c.ffn_dim * 2, 256);
-  b += round_up((int64_t)rows * c.n_kv_heads * max_splits * (c.n_heads / c.n_kv_heads) * (HD + 2) * 4, 256);
+  b += round_up((int64_t)rows * c.n_kv_heads * max_splits * (c.n_heads / c.n_kv_heads) * PSTR * 4, 256);
   b += 1024;
   return b;
 }
@@ -614,9 +632,9 @@ int decode_megakernel(const pcy_llama_config& c, const LlamaLayerPtrs* layers_de
   uint8_t* s = reinterpret_cast<uint8_t*>(round_up(reinterpret_cast<int64_t>(scratch), 256));
   auto carve = [&](int64_t bytes) { uint8_t* r = s; s += round_up(bytes, 256); return r; };
   p.barrier = reinterpret_cast<unsigned int*>(carve(256));
-  p.tickets = reinterpret_cast<int*>(carve(256));
+  carve(256);
   p.x = reinterpret_cast<bf16*>(carve(rows * d * 2));
-  p.attn = reinterpret_cast<bf16*>(carve(rows * d * 2));
+  carve(rows * d * 2);
   p.qkv = reinterpret_cast<bf16*>(carve(rows * qkv * 2));
   p.act = reinterpret_cast<bf16*>(carve((int64_t)rows * c.ffn_dim * 2));
   p.max_splits = ceil_div(b->S + b->max_gen, ATT_CHUNK);
@@ -627,7 +645,7 @@ int decode_megakernel(const pcy_llama_config& c, const LlamaLayerPtrs* layers_de
   const int mt = rows <= 1 ? 1 : rows <= 2 ? 2 : 4;
   const int kmax = c.ffn_dim > c.d_model ? c.ffn_dim : c.d_model;
   const size_t smem_gemv = (size_t)mt * kmax * 2 + (size_t)MAX_OUT_PER_CTA * 2 * mt * 4 + MK_WARPS * 4 * 4;
-  const size_t smem_att = (size_t)(4 * HD + 2 * HD + 4 * ATT_CHUNK + 8 + MK_WARPS * 4 * HD) * 4;
+  const size_t smem_att = (size_t)(4 * HD + 2 * HD + 4 * ATT_CHUNK + 8 + MK_WARPS * 4 * HD) * 4 + 64;
   const size_t smem = smem_gemv > smem_att ? smem_gemv : smem_att;
   PCY_REQUIRE(smem <= 220 * 1024, "decode megakernel: needs %zu bytes of shared memory", smem);
   void* fn = nullptr;

@@ -22,30 +22,34 @@ def main():
     sess.reset(logits)
     sess.select(SELECT_GREEDY, 1, 0.0, -1, False)
     L = te.model.config.num_hidden_layers
-    buf = torch.zeros(5 * L + 2, device=dev, dtype=torch.int64)
+    # stamps per layer: P1 [stage, stream, epi, bar], P2 [work, bar], P3 [4], P4 [4], P5 [4] = 18; + lm head [stage, stream, end]
+    per_layer = 18
+    n_stamps = 1 + per_layer * L + 3
+    buf = torch.zeros(n_stamps + 8, device=dev, dtype=torch.int64)
     lib = _lib.load()
     for _ in range(3):
         sess.forward()
         sess.select(SELECT_GREEDY, 1, 0.0, -1, False)
     lib.pcy_set_decode_timing_buffer(ctypes.c_void_p(buf.data_ptr()))
-    acc = torch.zeros(5 * L + 1, dtype=torch.float64)
+    acc = torch.zeros(n_stamps - 1, dtype=torch.float64)
     n = 10
     for _ in range(n):
         sess.forward()
         sess.select(SELECT_GREEDY, 1, 0.0, -1, False)
         torch.cuda.synchronize()
-        t = buf.cpu().double()
+        t = buf.cpu().double()[:n_stamps]
         acc += (t[1:] - t[:-1])
     lib.pcy_set_decode_timing_buffer(ctypes.c_void_p(0))
     acc /= n * 1e3  # us
-    names = ["P1 qkv", "P2 attention", "P3 o_proj", "P4 gate/up", "P5 down"]
-    per = acc[:-1].view(L, 5)
-    ideal = [50.3e6, 0, 33.6e6, 234.9e6, 117.4e6]
-    print("phase                mean us   min us   max us   ideal us @6.54TB/s")
-    for i, nm in enumerate(names):
-        print(f"{nm:18s} {per[:, i].mean():9.2f} {per[:, i].min():8.2f} {per[:, i].max():8.2f} {ideal[i] / 6538.9e3:9.2f}")
-    print(f"lm_head            {acc[-1]:9.2f}                    {128263 * 4096 * 2 / 6538.9e3:9.2f}")
-    print(f"total              {acc.sum():9.2f} us")
+    per = acc[: per_layer * L].view(L, per_layer)[1:].mean(0)  # skip layer 0 (different P1)
+    names = ["P1 stage", "P1 stream", "P1 epilogue", "P1 barrier", "P2 attention work", "P2 barrier", "P3 stage(+merge)",
+             "P3 stream", "P3 epilogue", "P3 barrier", "P4 stage", "P4 stream", "P4 epilogue", "P4 barrier", "P5 stage",
+             "P5 stream", "P5 epilogue", "P5 barrier"]
+    for nm, v in zip(names, per.tolist()):
+        print(f"{nm:22s} {v:8.2f} us")
+    print(f"layer total            {per.sum():8.2f} us   (ideal streaming 66.7 us)")
+    print("lm head [stage, stream, epilogue]", [round(x, 2) for x in acc[per_layer * L:].tolist()])
+    print(f"step total             {acc.sum():8.2f} us")
 
 
 if __name__ == "__main__":
