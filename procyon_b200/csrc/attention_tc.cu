@@ -1,0 +1,286 @@
+// Bidirectional (ESM2) attention on the sm_100a tensor cores: S = Q K^T and O_tile = P V are tcgen05.mma with
+// accumulators in TMEM, Q/K/V tiles arrive by TMA (128B swizzle), the softmax runs one query row per thread
+// straight out of TMEM (no shuffles), P goes back through shared memory as the A operand of the second MMA and
+// V is consumed in place as an MN-major B operand (no transpose).  128 queries x 128 keys per step, head_dim 64,
+// two CTAs per SM so one CTA's softmax overlaps the other's MMAs.
+//
+// Replaces fair-esm MultiheadAttention's bmm -> fp32 softmax -> bmm (reached via procyon/model/esm.py:536) for
+// the full 128-row query tiles; the ragged tail rows use the mma.sync kernel in attention.cu.
+#include <mutex>
+#include <unordered_map>
+
+#include "common.cuh"
+#include "ops.h"
+
+namespace pcy {
+
+namespace {
+
+constexpr int TBM = 128;  // queries per CTA
+constexpr int TBN = 128;  // keys per step
+constexpr int THD = 64;   // head dim
+constexpr int TC_THREADS = 160;  // warps 0-3: softmax rows; warp 4: TMA + MMA issue
+constexpr int Q_BYTES = TBM * THD * 2;
+constexpr int KV_BYTES = TBN * THD * 2;
+constexpr int P_BYTES = TBM * TBN * 2;
+constexpr int TC_SMEM = Q_BYTES + 2 * 2 * KV_BYTES + P_BYTES + TBN * 2 /*valid*/ + 256 /*barriers*/;
+constexpr int TMEM_COLS_ATT = 256;  // S: [0,128), O_tile: [128,192)
+
+struct TcAttnParams {
+  bf16* o;
+  int64_t o_rs;  // output row stride (elements)
+  const uint8_t* key_valid;  // [B][T] or null
+  int B, H, T, d;
+  int n_q_tiles;
+  float scale_log2;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 2)
+esm_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcAttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  // 128B-swizzled tiles need 1024-byte alignment; the dynamic window starts 1024-aligned when the kernel has no
+  // static shared memory (checked: a misaligned base would overrun the allocation)
+  const uint32_t base = smem_u32(smem_raw);
+  if ((base & 1023u) != 0u) __trap();
+  const uint32_t sQ = base;
+  const uint32_t sK = sQ + Q_BYTES;            // 2 stages
+  const uint32_t sV = sK + 2 * KV_BYTES;       // 2 stages
+  const uint32_t sP = sV + 2 * KV_BYTES;       // [2 blocks of 64 keys][128 rows][128 B]
+  const uint32_t sValid = sP + P_BYTES;        // 2 x 128 bytes
+  const uint32_t bars = sValid + 2 * TBN;
+  const uint32_t q_full = bars, kv_full0 = bars + 8, kv_empty0 = bars + 24, s_full = bars + 40, p_ready = bars + 48,
+                 o_full = bars + 56, tmem_slot = bars + 64;
+  uint8_t* valid_smem = smem_raw + (sValid - smem_u32(smem_raw));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q_tile = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int q0 = q_tile * TBM;
+  const int row_base = b * p.T;  // first row of this sequence in the [B*T, 3d] matrix
+  const int n_kv = (p.T + TBN - 1) / TBN;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmap);
+    mbar_init(q_full, 1);
+    mbar_init(kv_full0, 1);
+    mbar_init(kv_full0 + 8, 1);
+    mbar_init(kv_empty0, 1);
+    mbar_init(kv_empty0 + 8, 1);
+    mbar_init(s_full, 1);
+    mbar_init(p_ready, TBM);
+    mbar_init(o_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 4) {
+    tmem_alloc(tmem_slot, TMEM_COLS_ATT);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 4) {
+    if (lane == 0) {
+      // ---------------- TMA producer + MMA issuer (one thread) ----------------
+      mbar_arrive_expect_tx(q_full, Q_BYTES);
+      tma_load_2d(sQ, &tmap, q_full, h * THD, row_base + q0);
+      // prologue: first K/V stage
+      auto load_kv = [&](int j) {
+        const int st = j & 1;
+        mbar_arrive_expect_tx(kv_full0 + 8 * st, 2 * KV_BYTES);
+        tma_load_2d(sK + st * KV_BYTES, &tmap, kv_full0 + 8 * st, p.d + h * THD, row_base + j * TBN);
+        tma_load_2d(sV + st * KV_BYTES, &tmap, kv_full0 + 8 * st, 2 * p.d + h * THD, row_base + j * TBN);
+      };
+      load_kv(0);
+      mbar_wait(q_full, 0);
+      for (int j = 0; j < n_kv; ++j) {
+        const int st = j & 1;
+        mbar_wait(kv_full0 + 8 * st, (j >> 1) & 1);
+        tc_fence_after();
+        // S = Q K^T : M=128, N=keys in this tile rounded up to 16, K=64 (4 x UMMA_K)
+        const int keys = min(TBN, p.T - j * TBN);
+        const int n_mma = (keys + 15) & ~15;
+        const uint32_t idesc_s = make_idesc_bf16(TBM, n_mma);
+        const uint64_t qd = make_desc_kmajor_sw128(sQ);
+        const uint64_t kd = make_desc_kmajor_sw128(sK + st * KV_BYTES);
+#pragma unroll
+        for (int k = 0; k < THD / 16; ++k) tc_mma_bf16(tmem_base, qd + 2 * k, kd + 2 * k, idesc_s, k > 0 ? 1u : 0u);
+        tc_commit(s_full);
+        if (j + 1 < n_kv) {  // prefetch the next K/V tile into the other stage once its previous user (PV of j-1) is done
+          if (j + 1 >= 2) mbar_wait(kv_empty0 + 8 * ((j + 1) & 1), (((j + 1) >> 1) - 1) & 1);
+          load_kv(j + 1);
+        }
+        // O_tile = P V : M=128, N=64, K=n_mma keys; A = P (K-major, two 64-key blocks), B = V (MN-major)
+        mbar_wait(p_ready, j & 1);
+        tc_fence_after();
+        const uint32_t idesc_o = make_idesc_bf16(TBM, THD, 0, 1);
+        for (int k = 0; k < n_mma / 16; ++k) {
+          const uint64_t pd = make_desc_kmajor_sw128(sP + (k >> 2) * (TBM * 128) + (k & 3) * 32);
+          const uint64_t vd = make_desc_mnmajor_sw128(sV + st * KV_BYTES + k * 2048, 1024);
+          tc_mma_bf16(tmem_base + TBN, pd, vd, idesc_o, k > 0 ? 1u : 0u);
+        }
+        tc_commit(kv_empty0 + 8 * st);
+        tc_commit(o_full);
+      }
+    }
+  } else {
+    // ---------------- softmax / accumulate: thread = query row ----------------
+    const int r = threadIdx.x;  // 0..127, TMEM lane
+    const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
+    float o[THD];
+#pragma unroll
+    for (int i = 0; i < THD; ++i) o[i] = 0.f;
+    float m_run = -INFINITY, l_run = 0.f;
+    const uint8_t* valid_g = p.key_valid ? p.key_valid + (int64_t)b * p.T : nullptr;
+    for (int j = 0; j < n_kv; ++j) {
+      const int kbase = j * TBN;
+      // key validity bytes of this tile (double-buffered by tile parity)
+      uint8_t* vs = valid_smem + (j & 1) * TBN;
+      {
+        const int kidx = kbase + r;
+        uint8_t ok = kidx < p.T;
+        if (ok && valid_g) ok = valid_g[kidx];
+        vs[r] = ok;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // the 4 softmax warps only
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      const int keys = min(TBN, p.T - kbase);
+      const int n_mma = (keys + 15) & ~15;
+      float mx = -INFINITY;
+      // pass 1: row max over the valid keys
+#pragma unroll 1
+      for (int c = 0; c < n_mma; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(t_lane + c, v);
+        tc_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (c + i < n_mma && vs[c + i]) mx = fmaxf(mx, __uint_as_float(v[i]));
+      }
+      const float m_new = fmaxf(m_run, mx);
+      const float corr = (m_new == -INFINITY) ? 1.f : exp2f((m_run - m_new) * p.scale_log2);
+      const float moff = (m_new == -INFINITY) ? 0.f : m_new * p.scale_log2;
+      // pass 2: p = exp2(s*scale - moff) -> bf16 -> swizzled smem (A operand of the second MMA)
+      float lsum = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < n_mma; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(t_lane + c, v);
+        tc_wait_ld();
+        uint32_t packed[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float p0 = 0.f, p1 = 0.f;
+          if (c + i < n_mma && vs[c + i]) p0 = exp2f(__uint_as_float(v[i]) * p.scale_log2 - moff);
+          if (c + i + 1 < n_mma && vs[c + i + 1]) p1 = exp2f(__uint_as_float(v[i + 1]) * p.scale_log2 - moff);
+          lsum += p0 + p1;
+          packed[i >> 1] = pack_bf16x2(p0, p1);
+        }
+        // 32 keys = 4 chunks of 16 bytes; key c..c+31 lives in block c/64, chunks ((c%64)/8 .. +3)
+        const uint32_t blk = sP + (uint32_t)(c >> 6) * (TBM * 128) + (uint32_t)r * 128;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int chunk = ((c & 63) >> 3) + q;
+          const uint32_t addr = blk + (uint32_t)((chunk ^ (r & 7)) << 4);
+          asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(packed[4 * q]), "r"(packed[4 * q + 1]),
+                       "r"(packed[4 * q + 2]), "r"(packed[4 * q + 3])
+                       : "memory");
+        }
+      }
+      l_run = l_run * corr + lsum;
+      m_run = m_new;
+      // the previous O_tile has been consumed (below, previous iteration); publish P
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(p_ready);
+      // O += corr-scaled accumulate of this tile's P V
+      mbar_wait(o_full, j & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < THD; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(t_lane + TBN + c, v);
+        tc_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[c + i] = o[c + i] * corr + __uint_as_float(v[i]);
+      }
+      tc_fence_before();
+    }
+    // ---- finalize ----
+    const int qrow = q0 + r;
+    if (qrow < p.T) {
+      const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+      bf16* op = p.o + (int64_t)(row_base + qrow) * p.o_rs + h * THD;
+#pragma unroll
+      for (int c = 0; c < THD; c += 8) {
+        uint4 u;
+        u.x = pack_bf16x2(o[c] * inv, o[c + 1] * inv);
+        u.y = pack_bf16x2(o[c + 2] * inv, o[c + 3] * inv);
+        u.z = pack_bf16x2(o[c + 4] * inv, o[c + 5] * inv);
+        u.w = pack_bf16x2(o[c + 6] * inv, o[c + 7] * inv);
+        *reinterpret_cast<uint4*>(op + c) = u;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS_ATT);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int make_qkv_map(const bf16* qkv, int64_t rows, int64_t cols, int64_t ld, CUtensorMap* out) {
+  static EncodeTiledFn enc = nullptr;
+  if (!enc) {
+    void* fp = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return set_error(PCY_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+    enc = reinterpret_cast<EncodeTiledFn>(fp);
+  }
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)THD, (cuuint32_t)TBN};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<bf16*>(qkv), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(PCY_ERR_CUDA, "cuTensorMapEncodeTiled(qkv) failed (%d)", (int)r);
+  return 0;
+}
+
+}  // namespace
+
+// qkv bf16 [B*T, 3d] (q pre-scaled, RoPE applied), out bf16 [B*T, d]; handles query rows [0, floor(T/128)*128) of
+// every sequence and returns the number of rows covered in *rows_done.
+int esm_attention_tc(const bf16* qkv, const uint8_t* key_valid, bf16* out, int B, int T, int n_heads, int d,
+                     float scale, int* rows_done, cudaStream_t stream) {
+  *rows_done = 0;
+  const int n_q_tiles = T / TBM;
+  if (n_q_tiles == 0 || d / n_heads != THD) return 0;
+  static bool attr_set = false;
+  if (!attr_set) {
+    PCY_CUDA(cudaFuncSetAttribute(esm_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+    attr_set = true;
+  }
+  CUtensorMap tmap;
+  PCY_TRY(make_qkv_map(qkv, (int64_t)B * T, 3 * d, 3 * d, &tmap));
+  TcAttnParams p;
+  p.o = out; p.o_rs = d; p.key_valid = key_valid; p.B = B; p.H = n_heads; p.T = T; p.d = d; p.n_q_tiles = n_q_tiles;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  dim3 grid(n_q_tiles, n_heads, B);
+  esm_attention_tc_kernel<<<grid, TC_THREADS, TC_SMEM, stream>>>(tmap, p);
+  PCY_LAUNCH_CHECK();
+  *rows_done = n_q_tiles * TBM;
+  return 0;
+}
+
+}  // namespace pcy

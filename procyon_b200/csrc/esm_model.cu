@@ -39,7 +39,14 @@ T* carve(uint8_t*& p, int64_t n) {
 
 using namespace pcy;
 
+static bool g_esm_tc_attention = true;
+
 extern "C" {
+
+int pcy_set_esm_tc_attention(int enabled) {
+  g_esm_tc_attention = enabled != 0;
+  return 0;
+}
 
 int pcy_esm_create(const pcy_esm_config* cfg, void** handle) {
   PCY_REQUIRE(cfg && handle, "esm_create: null argument");
@@ -183,14 +190,16 @@ int pcy_esm_encode(void* handle, const int32_t* tokens, int B, int T, void* out_
     g.bias = y.bqkv; g.scale = q_scale; g.scale_ncols = d;  // q = (x Wq + bq) * head_dim^-0.5
     PCY_TRY(gemm_bf16(g, stream));
     PCY_TRY(rope_inplace(big, n, T, 2 * H, hd, 3 * d, 0, m->rope, nullptr, 0, stream));  // q and k heads
+    int rows_done = 0;
+    if (g_esm_tc_attention) PCY_TRY(esm_attention_tc(big, valid, h, B, T, H, d, 1.0f, &rows_done, stream));
     AttnArgs a;
-    a.q = big; a.k = big + d; a.v = big + 2 * d; a.o = h;
+    a.q = big + (int64_t)rows_done * 3 * d; a.k = big + d; a.v = big + 2 * d; a.o = h + (int64_t)rows_done * d;
     a.q_bs = a.k_bs = a.v_bs = (int64_t)T * 3 * d; a.q_rs = a.k_rs = a.v_rs = 3 * d;
     a.q_hs = a.k_hs = a.v_hs = hd;
     a.o_bs = (int64_t)T * d; a.o_rs = d; a.o_hs = hd;
-    a.B = B; a.H = H; a.KVH = H; a.Tq = T; a.Tk = T; a.head_dim = hd;
+    a.B = B; a.H = H; a.KVH = H; a.Tq = T - rows_done; a.Tk = T; a.head_dim = hd;
     a.key_valid = valid; a.key_valid_bs = T; a.scale = 1.0f; a.causal = 0;
-    PCY_TRY(flash_attention(a, stream));
+    if (rows_done < T) PCY_TRY(flash_attention(a, stream));  // ragged tail rows (or everything when hd != 64)
     GemmArgs o;
     o.A = h; o.lda = d; o.W = y.wo; o.ldw = d; o.C = x; o.ldc = d; o.M = (int)n; o.N = d; o.K = d;
     o.bias = y.bo; o.residual = x; o.ldr = d;

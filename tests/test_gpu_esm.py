@@ -85,3 +85,27 @@ def test_esm_empty_batch(cuda_device):
     m = ESM_PLM(num_params="custom", custom_config=(1, 64, 4), pooling_method="mean").cuda()
     out = m.encode_tokens(torch.zeros((0, 10), dtype=torch.int64, device="cuda"))
     assert out.shape == (0, 10, 64)
+
+
+def test_esm_tcgen05_attention_matches_mma_sync_and_oracle(cuda_device):
+    """head_dim 64: full 128-row query tiles run on tcgen05 (TMEM softmax), ragged tails on mma.sync; both must agree
+    with each other and with the oracle, with padded and un-padded rows and key tiles that end mid-tile."""
+    from oracle import esm2 as O
+    from procyon_b200 import _lib
+
+    L, d, H = 2, 256, 4
+    sd = O.random_esm_state_dict(L, d, seed=21)
+    toks = O.random_protein_tokens(3, 0, seed=9, lengths=[298, 131, 260])  # T = 300: 2 full tiles + 44 tail rows
+    m = _build("custom", sd, custom=(L, d, H))
+    lib = _lib.load()
+    try:
+        lib.pcy_set_esm_tc_attention(1)
+        a = m.encode_tokens(toks.cuda()).float().cpu()
+        lib.pcy_set_esm_tc_attention(0)
+        b = m.encode_tokens(toks.cuda()).float().cpu()
+    finally:
+        lib.pcy_set_esm_tc_attention(1)
+    nonpad = toks != O.PAD_IDX
+    torch.testing.assert_close(a[nonpad], b[nonpad], rtol=2e-2, atol=2e-2)
+    ref = O.esm2_forward(sd, toks, L, H, act_round="bf16")
+    torch.testing.assert_close(a[nonpad], ref[nonpad], rtol=3e-2, atol=3e-2)
