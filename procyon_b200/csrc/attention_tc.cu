@@ -133,49 +133,64 @@ esm_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcAttnPa
     for (int i = 0; i < THD; ++i) o[i] = 0.f;
     float m_run = -INFINITY, l_run = 0.f;
     const uint8_t* valid_g = p.key_valid ? p.key_valid + (int64_t)b * p.T : nullptr;
+    uint32_t* vwords = reinterpret_cast<uint32_t*>(valid_smem);  // [2 parities][4 words]: validity bit per key
     for (int j = 0; j < n_kv; ++j) {
       const int kbase = j * TBN;
-      // key validity bytes of this tile (double-buffered by tile parity)
-      uint8_t* vs = valid_smem + (j & 1) * TBN;
       {
         const int kidx = kbase + r;
-        uint8_t ok = kidx < p.T;
-        if (ok && valid_g) ok = valid_g[kidx];
-        vs[r] = ok;
+        bool ok = kidx < p.T;
+        if (ok && valid_g) ok = valid_g[kidx] != 0;
+        const uint32_t word = __ballot_sync(0xffffffffu, ok);
+        if (lane == 0) vwords[(j & 1) * 4 + warp] = word;
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");  // the 4 softmax warps only
+      const uint32_t mw0 = vwords[(j & 1) * 4 + 0], mw1 = vwords[(j & 1) * 4 + 1], mw2 = vwords[(j & 1) * 4 + 2],
+                     mw3 = vwords[(j & 1) * 4 + 3];
+      const bool all_valid = (mw0 & mw1 & mw2 & mw3) == 0xffffffffu;
       mbar_wait(s_full, j & 1);
       tc_fence_after();
       const int keys = min(TBN, p.T - kbase);
       const int n_mma = (keys + 15) & ~15;
-      float mx = -INFINITY;
-      // pass 1: row max over the valid keys
+      // pass 1: row max over the valid keys (4 independent chains)
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll 1
       for (int c = 0; c < n_mma; c += 32) {
         uint32_t v[32];
         tmem_ld_32x32b_x32(t_lane + c, v);
         tc_wait_ld();
+        if (all_valid) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (c + i < n_mma && vs[c + i]) mx = fmaxf(mx, __uint_as_float(v[i]));
+          for (int i = 0; i < 32; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(v[i]));
+        } else {
+          const uint32_t mw = (c == 0) ? mw0 : (c == 32) ? mw1 : (c == 64) ? mw2 : mw3;
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            mx4[i & 3] = fmaxf(mx4[i & 3], ((mw >> i) & 1u) ? __uint_as_float(v[i]) : -INFINITY);
+        }
       }
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
       const float m_new = fmaxf(m_run, mx);
       const float corr = (m_new == -INFINITY) ? 1.f : exp2f((m_run - m_new) * p.scale_log2);
       const float moff = (m_new == -INFINITY) ? 0.f : m_new * p.scale_log2;
       // pass 2: p = exp2(s*scale - moff) -> bf16 -> swizzled smem (A operand of the second MMA)
-      float lsum = 0.f;
+      float ls4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
       for (int c = 0; c < n_mma; c += 32) {
         uint32_t v[32];
         tmem_ld_32x32b_x32(t_lane + c, v);
         tc_wait_ld();
         uint32_t packed[16];
+        const uint32_t mw = all_valid ? 0xffffffffu : ((c == 0) ? mw0 : (c == 32) ? mw1 : (c == 64) ? mw2 : mw3);
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          float p0 = 0.f, p1 = 0.f;
-          if (c + i < n_mma && vs[c + i]) p0 = exp2f(__uint_as_float(v[i]) * p.scale_log2 - moff);
-          if (c + i + 1 < n_mma && vs[c + i + 1]) p1 = exp2f(__uint_as_float(v[i + 1]) * p.scale_log2 - moff);
-          lsum += p0 + p1;
+          float p0, p1;
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(fmaf(__uint_as_float(v[i]), p.scale_log2, -moff)));
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(fmaf(__uint_as_float(v[i + 1]), p.scale_log2, -moff)));
+          if (!all_valid) {
+            p0 = ((mw >> i) & 1u) ? p0 : 0.f;
+            p1 = ((mw >> (i + 1)) & 1u) ? p1 : 0.f;
+          }
+          ls4[(i >> 1) & 3] += p0 + p1;
           packed[i >> 1] = pack_bf16x2(p0, p1);
         }
         // 32 keys = 4 chunks of 16 bytes; key c..c+31 lives in block c/64, chunks ((c%64)/8 .. +3)
@@ -189,13 +204,13 @@ esm_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcAttnPa
                        : "memory");
         }
       }
-      l_run = l_run * corr + lsum;
+      l_run = l_run * corr + ((ls4[0] + ls4[1]) + (ls4[2] + ls4[3]));
       m_run = m_new;
-      // the previous O_tile has been consumed (below, previous iteration); publish P
+      // publish P (the previous O_tile was consumed at the end of the previous iteration)
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(p_ready);
-      // O += corr-scaled accumulate of this tile's P V
+      // O = O * corr + P V of this tile
       mbar_wait(o_full, j & 1);
       tc_fence_after();
 #pragma unroll
@@ -204,7 +219,7 @@ esm_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcAttnPa
         tmem_ld_32x32b_x32(t_lane + TBN + c, v);
         tc_wait_ld();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) o[c + i] = o[c + i] * corr + __uint_as_float(v[i]);
+        for (int i = 0; i < 32; ++i) o[c + i] = fmaf(o[c + i], corr, __uint_as_float(v[i]));
       }
       tc_fence_before();
     }

@@ -43,7 +43,51 @@ struct EpiParams {
   int act;
   float scale;
   int scale_ncols;
+  const float* rope;  // fp32 [P][rope_hd/2][2] or null: rotate-half RoPE on columns < rope_ncols, position = row % rope_T
+  int rope_hd, rope_T, rope_ncols;
 };
+
+// v += bias; v *= scale on the leading columns
+__device__ __forceinline__ void epi_bias_scale(float (&v)[32], int col0, const EpiParams& p) {
+  const bool full_cols = (col0 + 32 <= p.N);
+  if (p.bias != nullptr) {
+    if (full_cols) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+        v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);
+    }
+  }
+  if (col0 < p.scale_ncols) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (col0 + j < p.scale_ncols) v[j] *= p.scale;
+  }
+}
+
+__device__ __forceinline__ void epi_store_bf16(const float (&v)[32], int row, int col0, const EpiParams& p) {
+  bf16* cp = reinterpret_cast<bf16*>(p.C) + (int64_t)row * p.ldc + col0;
+  if ((col0 + 32 <= p.N) && ((reinterpret_cast<uintptr_t>(cp) & 15) == 0)) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      uint4 u;
+      u.x = pack_bf16x2(v[j], v[j + 1]);
+      u.y = pack_bf16x2(v[j + 2], v[j + 3]);
+      u.z = pack_bf16x2(v[j + 4], v[j + 5]);
+      u.w = pack_bf16x2(v[j + 6], v[j + 7]);
+      *reinterpret_cast<uint4*>(cp + j) = u;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (col0 + j < p.N) cp[j] = __float2bfloat16_rn(v[j]);
+  }
+}
 
 template <int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -161,6 +205,36 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       for (int c = 0; c < BN / 32; ++c) {
         const int col0 = n_blk * BN + c * 32;
         if (col0 >= p.N) break;  // warp-uniform
+        if (p.rope != nullptr && col0 < p.rope_ncols) {
+          // fused rotate-half RoPE: columns (i, i + hd/2) of a head are in chunks c and c + hd/64
+          const int half = p.rope_hd >> 1;
+          const int in_head = col0 % p.rope_hd;
+          if (in_head >= half) continue;  // second-half chunk: written together with its partner
+          uint32_t ra[32], rb[32];
+          tmem_ld_32x32b_x32(t_addr + (uint32_t)(c * 32), ra);
+          tmem_ld_32x32b_x32(t_addr + (uint32_t)(c * 32 + half), rb);
+          tc_wait_ld();
+          float lo[32], hi[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { lo[j] = __uint_as_float(ra[j]); hi[j] = __uint_as_float(rb[j]); }
+          epi_bias_scale(lo, col0, p);
+          epi_bias_scale(hi, col0 + half, p);
+          if (row_ok) {
+            const int pos = row % p.rope_T;
+            const float2* cs = reinterpret_cast<const float2*>(p.rope) + (int64_t)pos * half + in_head;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float2 t = __ldg(cs + j);
+              // the un-fused path stores q/k in bf16 before rotating them: keep that rounding point
+              const float a = bf16_round(lo[j]), b = bf16_round(hi[j]);
+              lo[j] = a * t.x - b * t.y;
+              hi[j] = b * t.x + a * t.y;
+            }
+            epi_store_bf16(lo, row, col0, p);
+            epi_store_bf16(hi, row, col0 + half, p);
+          }
+          continue;
+        }
         uint32_t r[32];
         tmem_ld_32x32b_x32(t_addr + (uint32_t)(c * 32), r);
         tc_wait_ld();
@@ -374,6 +448,7 @@ int launch(const GemmArgs& a, cudaStream_t stream) {
   p.C = a.C; p.ldc = a.ldc; p.bias = a.bias; p.residual = a.residual; p.ldr = a.ldr;
   p.M = a.M; p.N = a.N; p.K = a.K; p.c_fp32 = a.c_fp32; p.act = a.act; p.scale = a.scale;
   p.scale_ncols = a.scale_ncols;
+  p.rope = a.rope; p.rope_hd = a.rope_hd; p.rope_T = a.rope_T; p.rope_ncols = a.rope ? a.rope_ncols : 0;
   const int tiles = ceil_div(a.M, BM) * ceil_div(a.N, BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
   gemm_bf16_tcgen05_kernel<BN><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
@@ -390,6 +465,11 @@ int gemm_bf16_tc(const GemmArgs& a, cudaStream_t stream) {
               "gemm: A and W must be 16-byte aligned");
   if (a.act == ACT_SWIGLU) {
     PCY_REQUIRE(a.N % 32 == 0 && !a.c_fp32, "gemm: SwiGLU needs N %% 32 == 0 and bf16 output");
+  }
+  if (a.rope != nullptr) {
+    PCY_REQUIRE((a.rope_hd == 64 || a.rope_hd == 128) && a.rope_ncols % a.rope_hd == 0 && a.rope_ncols <= a.N &&
+                    a.rope_T > 0 && a.act == ACT_NONE && !a.c_fp32 && a.residual == nullptr,
+                "gemm: fused RoPE needs head_dim 64/128, bf16 output, no activation/residual");
   }
   // Tile choice: 128x256 unless that leaves most SMs idle / wastes a wide tail.
   const int sms = num_sms();

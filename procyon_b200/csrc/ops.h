@@ -30,6 +30,10 @@ struct GemmArgs {
   int act = ACT_NONE;
   float scale = 1.0f;
   int scale_ncols = 0;
+  // tensor-core path only: fused rotate-half RoPE on columns [0, rope_ncols) (heads of rope_hd = 64 | 128 columns),
+  // position = row % rope_T, table fp32 [P][rope_hd/2][2]; applied after bias/scale
+  const float* rope = nullptr;
+  int rope_hd = 0, rope_T = 0, rope_ncols = 0;
 };
 
 // tcgen05 + TMA GEMM (any M; pads with TMA zero fill). Requires K % 8 == 0 and 16-byte aligned rows.
