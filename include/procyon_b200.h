@@ -98,8 +98,8 @@ enum {
 
 /* head_dim-64 encoders run attention on tcgen05 by default; 0 selects the mma.sync kernel for every row (tests) */
 int pcy_set_esm_tc_attention(int enabled);
-/* head_dim 64/128 encoders apply RoPE in the QKV GEMM epilogue by default; 0 selects the separate RoPE kernel (tests) */
-int pcy_set_esm_fused_rope(int enabled);
+/* 1: apply RoPE in the QKV GEMM epilogue (head_dim 64/128, tensor-core path); 0 (default): separate vectorised pass */
+int pcy_set_fused_rope(int enabled);
 int pcy_esm_create(const pcy_esm_config* cfg, void** handle);
 int pcy_esm_destroy(void* handle);
 /* src may be a host or a device pointer; the library keeps its own packed copy */

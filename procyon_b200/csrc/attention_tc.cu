@@ -54,7 +54,9 @@ esm_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcAttnPa
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q_tile = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-  const int q0 = q_tile * TBM;
+  // the last tile is shifted back to end exactly at T (it recomputes some rows of the previous tile; identical
+  // values are written twice) so that no ragged tail is left for another kernel
+  const int q0 = min(q_tile * TBM, p.T - TBM);
   const int row_base = b * p.T;  // first row of this sequence in the [B*T, 3d] matrix
   const int n_kv = (p.T + TBN - 1) / TBN;
 
@@ -274,13 +276,13 @@ int make_qkv_map(const bf16* qkv, int64_t rows, int64_t cols, int64_t ld, CUtens
 
 }  // namespace
 
-// qkv bf16 [B*T, 3d] (q pre-scaled, RoPE applied), out bf16 [B*T, d]; handles query rows [0, floor(T/128)*128) of
-// every sequence and returns the number of rows covered in *rows_done.
+// qkv bf16 [B*T, 3d] (q pre-scaled, RoPE applied), out bf16 [B*T, d]; covers all T query rows of every sequence when
+// T >= 128 and head_dim == 64 (*rows_done = T), otherwise does nothing (*rows_done = 0).
 int esm_attention_tc(const bf16* qkv, const uint8_t* key_valid, bf16* out, int B, int T, int n_heads, int d,
                      float scale, int* rows_done, cudaStream_t stream) {
   *rows_done = 0;
-  const int n_q_tiles = T / TBM;
-  if (n_q_tiles == 0 || d / n_heads != THD) return 0;
+  if (T < TBM || d / n_heads != THD) return 0;
+  const int n_q_tiles = (T + TBM - 1) / TBM;
   static bool attr_set = false;
   if (!attr_set) {
     PCY_CUDA(cudaFuncSetAttribute(esm_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
@@ -294,7 +296,7 @@ int esm_attention_tc(const bf16* qkv, const uint8_t* key_valid, bf16* out, int B
   dim3 grid(n_q_tiles, n_heads, B);
   esm_attention_tc_kernel<<<grid, TC_THREADS, TC_SMEM, stream>>>(tmap, p);
   PCY_LAUNCH_CHECK();
-  *rows_done = n_q_tiles * TBM;
+  *rows_done = T;
   return 0;
 }
 

@@ -23,6 +23,7 @@ int cuda_error(cudaError_t e, const char* what, const char* file, int line);
 int num_sms();
 // Counts kernels launched by this library (bench.py reports it as gpu_launches).
 void count_launch(int n = 1);
+extern bool g_fused_rope;
 
 #define PCY_CUDA(expr)                                                     \
   do {                                                                     \

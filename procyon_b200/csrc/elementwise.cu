@@ -197,6 +197,39 @@ llama_embed_splice_kernel(const int32_t* __restrict__ ids, const bf16* __restric
 __global__ void __launch_bounds__(ROW_THREADS)
 rope_kernel(bf16* __restrict__ x, int64_t rows, int T, int n_heads, int head_dim, int64_t ld, int col0,
             const float* __restrict__ cos_sin, const int32_t* __restrict__ pos_ptr, int pos0) {
+  // one thread = 8 consecutive columns of the low half of a head and their partners in the high half
+  const int half = head_dim >> 1;
+  const int per_head = half >> 3;  // threads per head (head_dim % 16 == 0 on this path)
+  const int64_t per_row = (int64_t)n_heads * per_head;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < rows * per_row;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = idx / per_row;
+    const int rem = (int)(idx - row * per_row);
+    const int h = rem / per_head, i = (rem - h * per_head) * 8;
+    const int pos = (pos_ptr ? pos_ptr[0] : pos0) + (int)(row % T);
+    bf16* p = x + row * ld + col0 + h * head_dim + i;
+    const float4* cs = reinterpret_cast<const float4*>(cos_sin + ((int64_t)pos * half + i) * 2);
+    float lo[8], hi[8];
+    unpack8(*reinterpret_cast<const uint4*>(p), lo);
+    unpack8(*reinterpret_cast<const uint4*>(p + half), hi);
+    float ol[8], oh[8];
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+      const float4 t = __ldg(cs + (j >> 1));  // (cos_j, sin_j, cos_j+1, sin_j+1)
+      ol[j] = lo[j] * t.x - hi[j] * t.y;
+      oh[j] = hi[j] * t.x + lo[j] * t.y;
+      ol[j + 1] = lo[j + 1] * t.z - hi[j + 1] * t.w;
+      oh[j + 1] = hi[j + 1] * t.z + lo[j + 1] * t.w;
+    }
+    *reinterpret_cast<uint4*>(p) = pack8(ol);
+    *reinterpret_cast<uint4*>(p + half) = pack8(oh);
+  }
+}
+
+// scalar variant for head dims that are not multiples of 16 (ESM2-35M: 24): one warp per (row, head)
+__global__ void __launch_bounds__(ROW_THREADS)
+rope_kernel_generic(bf16* __restrict__ x, int64_t rows, int T, int n_heads, int head_dim, int64_t ld, int col0,
+                    const float* __restrict__ cos_sin, const int32_t* __restrict__ pos_ptr, int pos0) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t idx = (int64_t)blockIdx.x * ROW_WARPS + warp;
   if (idx >= rows * n_heads) return;
@@ -351,8 +384,15 @@ int rope_inplace(bf16* x, int64_t rows, int T, int n_heads, int head_dim, int64_
   PCY_REQUIRE(head_dim % 4 == 0 && col0 % 2 == 0 && ld % 2 == 0, "rope: head_dim %% 4, col0 %% 2, ld %% 2 must be 0");
   if (rows == 0) return 0;
   const int64_t units = rows * n_heads;
-  rope_kernel<<<ceil_div(units, ROW_WARPS), ROW_THREADS, 0, stream>>>(x, rows, T, n_heads, head_dim, ld, col0,
-                                                                      cos_sin, pos_ptr, pos0);
+  if (head_dim % 16 == 0 && ld % 8 == 0 && col0 % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    const int64_t threads = units * (head_dim / 16);
+    int64_t grid = (threads + ROW_THREADS - 1) / ROW_THREADS;
+    if (grid > (int64_t)num_sms() * 32) grid = (int64_t)num_sms() * 32;
+    rope_kernel<<<(int)grid, ROW_THREADS, 0, stream>>>(x, rows, T, n_heads, head_dim, ld, col0, cos_sin, pos_ptr, pos0);
+  } else {
+    rope_kernel_generic<<<ceil_div(units, ROW_WARPS), ROW_THREADS, 0, stream>>>(x, rows, T, n_heads, head_dim, ld,
+                                                                                col0, cos_sin, pos_ptr, pos0);
+  }
   PCY_LAUNCH_CHECK();
   return 0;
 }

@@ -40,7 +40,6 @@ T* carve(uint8_t*& p, int64_t n) {
 using namespace pcy;
 
 static bool g_esm_tc_attention = true;
-static bool g_esm_fused_rope = true;
 
 extern "C" {
 
@@ -49,8 +48,8 @@ int pcy_set_esm_tc_attention(int enabled) {
   return 0;
 }
 
-int pcy_set_esm_fused_rope(int enabled) {
-  g_esm_fused_rope = enabled != 0;
+int pcy_set_fused_rope(int enabled) {
+  g_fused_rope = enabled != 0;
   return 0;
 }
 
@@ -194,7 +193,7 @@ int pcy_esm_encode(void* handle, const int32_t* tokens, int B, int T, void* out_
     GemmArgs g;
     g.A = h; g.lda = d; g.W = y.wqkv; g.ldw = d; g.C = big; g.ldc = 3 * d; g.M = (int)n; g.N = 3 * d; g.K = d;
     g.bias = y.bqkv; g.scale = q_scale; g.scale_ncols = d;  // q = (x Wq + bq) * head_dim^-0.5
-    const bool fuse_rope = g_esm_fused_rope && (hd == 64 || hd == 128) && n > 16;
+    const bool fuse_rope = g_fused_rope && (hd == 64 || hd == 128) && n > 16;
     if (fuse_rope) { g.rope = m->rope; g.rope_hd = hd; g.rope_T = T; g.rope_ncols = 2 * d; }  // q and k heads
     PCY_TRY(gemm_bf16(g, stream));
     if (!fuse_rope) PCY_TRY(rope_inplace(big, n, T, 2 * H, hd, 3 * d, 0, m->rope, nullptr, 0, stream));

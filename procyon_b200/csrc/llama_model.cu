@@ -232,7 +232,7 @@ int pcy_llama_prefill(void* handle, const void* input_embeds, const uint8_t* key
     PCY_TRY(rmsnorm_bf16(x, y.ln1, h, n, d, c.rms_eps, stream));
     GemmArgs g;
     g.A = h; g.lda = d; g.W = y.wqkv; g.ldw = d; g.C = qkv; g.ldc = qkv_dim; g.M = (int)n; g.N = qkv_dim; g.K = d;
-    const bool fuse_rope = n > 16;  // tensor-core path: RoPE of the q and k heads in the GEMM epilogue
+    const bool fuse_rope = g_fused_rope && n > 16;  // optional: RoPE of the q and k heads in the GEMM epilogue
     if (fuse_rope) { g.rope = m->rope; g.rope_hd = hd; g.rope_T = S; g.rope_ncols = (H + KVH) * hd; }
     PCY_TRY(gemm_bf16(g, stream));
     if (!fuse_rope) PCY_TRY(rope_inplace(qkv, n, S, H + KVH, hd, qkv_dim, 0, m->rope, nullptr, 0, stream));

@@ -35,6 +35,10 @@ int num_sms() {
   return sms;
 }
 
+// RoPE in the QKV GEMM epilogue (1) or as a separate vectorised pass (0, default: measured faster on B200 because
+// the table look-ups lengthen the epilogue past the MMA time of the tile)
+bool g_fused_rope = false;
+
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
 void reset_launch_count() { g_launches.store(0, std::memory_order_relaxed); }

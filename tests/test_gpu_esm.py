@@ -100,14 +100,14 @@ def test_esm_tcgen05_attention_matches_mma_sync_and_oracle(cuda_device):
     lib = _lib.load()
     try:
         lib.pcy_set_esm_tc_attention(1)
-        lib.pcy_set_esm_fused_rope(1)
+        lib.pcy_set_fused_rope(1)
         a = m.encode_tokens(toks.cuda()).float().cpu()
         lib.pcy_set_esm_tc_attention(0)
-        lib.pcy_set_esm_fused_rope(0)
+        lib.pcy_set_fused_rope(0)
         b = m.encode_tokens(toks.cuda()).float().cpu()
     finally:
         lib.pcy_set_esm_tc_attention(1)
-        lib.pcy_set_esm_fused_rope(1)
+        lib.pcy_set_fused_rope(0)
     nonpad = toks != O.PAD_IDX
     torch.testing.assert_close(a[nonpad], b[nonpad], rtol=2e-2, atol=2e-2)
     ref = O.esm2_forward(sd, toks, L, H, act_round="bf16")
