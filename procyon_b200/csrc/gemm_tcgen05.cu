@@ -29,7 +29,8 @@ struct TileCfg {
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int TMEM_COLS = 2 * BN;  // two accumulator buffers (256 or 512 columns: powers of two)
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int STAGING_BYTES = NUM_EPI_WARPS * 32 * 128;  // per warp: 32 rows x 64 bf16 columns
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 struct EpiParams {
@@ -89,6 +90,20 @@ __device__ __forceinline__ void epi_store_bf16(const float (&v)[32], int row, in
   }
 }
 
+// Tile order: bands of GROUP_M row-blocks, row-block fastest inside a band. The ~148 tiles in flight then cover a
+// compact (GROUP_M x ~18) patch of the output, so every A and B tile fetched from HBM is reused out of L2 by the
+// other tiles of the patch (a plain row-major order re-reads A once per column block when A does not fit in L2).
+constexpr int GROUP_M = 8;
+__device__ __forceinline__ void tile_coords(int tile, int m_blocks, int n_blocks, int& m_blk, int& n_blk) {
+  const int per_group = GROUP_M * n_blocks;
+  const int g = tile / per_group;
+  const int first_m = g * GROUP_M;
+  const int rows = min(GROUP_M, m_blocks - first_m);
+  const int local = tile - g * per_group;
+  m_blk = first_m + local % rows;
+  n_blk = local / rows;
+}
+
 template <int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -97,7 +112,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
+  const uint32_t staging_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
+  const uint32_t bar_base = staging_base + Cfg::STAGING_BYTES;
   // barrier layout (8 bytes each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], then tmem ptr
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
@@ -142,8 +158,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile % m_blocks;
-        const int n_blk = tile / m_blocks;
+        int m_blk, n_blk;
+        tile_coords(tile, m_blocks, n_blocks, m_blk, n_blk);
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
@@ -193,9 +209,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     int acc = 0;
     uint32_t acc_phase = 0;
     const bool swiglu = (p.act == ACT_SWIGLU);
+    // bf16 output with 16-byte aligned rows (and residual rows): eligible for the coalesced smem-staged path
+    const bool fast_store = !swiglu && !p.c_fp32 && (p.ldc % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
+                            (p.residual == nullptr ||
+                             ((p.ldr % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0)));
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_blk = tile % m_blocks;
-      const int n_blk = tile / m_blocks;
+      int m_blk, n_blk;
+      tile_coords(tile, m_blocks, n_blocks, m_blk, n_blk);
       const int row = m_blk * BM + quad * 32 + lane;
       const bool row_ok = row < p.M;
       mbar_wait(tfull_bar(acc), acc_phase);
@@ -233,6 +253,68 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             epi_store_bf16(lo, row, col0, p);
             epi_store_bf16(hi, row, col0 + half, p);
           }
+          continue;
+        }
+        if (fast_store && (c & 1) == 0 && col0 + 64 <= p.N) {
+          // ---- coalesced path: 64 columns (two chunks) of this warp's 32 rows go through a swizzled smem block so
+          // that every global load / store instruction moves four full 128-byte row segments ----
+          const uint32_t stg = staging_base + (uint32_t)(warp - 2) * (32 * 128);
+          const int row0 = m_blk * BM + quad * 32;
+          if (p.residual != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int rr = (lane >> 3) + 4 * i, ch = lane & 7;
+              uint4 u = make_uint4(0, 0, 0, 0);
+              if (row0 + rr < p.M)
+                u = *reinterpret_cast<const uint4*>(p.residual + (int64_t)(row0 + rr) * p.ldr + col0 + ch * 8);
+              asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(stg + rr * 128 + ((ch ^ (rr & 7)) << 4)),
+                           "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w) : "memory");
+            }
+            __syncwarp();
+          }
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            uint32_t r2[32];
+            tmem_ld_32x32b_x32(t_addr + (uint32_t)((c + hf) * 32), r2);
+            tc_wait_ld();
+            float v2[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v2[j] = __uint_as_float(r2[j]);
+            epi_bias_scale(v2, col0 + hf * 32, p);
+            if (p.act == ACT_GELU) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v2[j] = gelu_erf(v2[j]);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint32_t addr = stg + lane * 128 + (((hf * 4 + q) ^ (lane & 7)) << 4);
+              if (p.residual != nullptr) {
+                uint4 u;
+                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w)
+                             : "r"(addr));
+                const float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z),
+                             f3 = unpack_bf16x2(u.w);
+                v2[8 * q] += f0.x; v2[8 * q + 1] += f0.y; v2[8 * q + 2] += f1.x; v2[8 * q + 3] += f1.y;
+                v2[8 * q + 4] += f2.x; v2[8 * q + 5] += f2.y; v2[8 * q + 6] += f3.x; v2[8 * q + 7] += f3.y;
+              }
+              asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(pack_bf16x2(v2[8 * q], v2[8 * q + 1])),
+                           "r"(pack_bf16x2(v2[8 * q + 2], v2[8 * q + 3])), "r"(pack_bf16x2(v2[8 * q + 4], v2[8 * q + 5])),
+                           "r"(pack_bf16x2(v2[8 * q + 6], v2[8 * q + 7])) : "memory");
+            }
+          }
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr = (lane >> 3) + 4 * i, ch = lane & 7;
+            if (row0 + rr < p.M) {
+              uint4 u;
+              asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w)
+                           : "r"(stg + rr * 128 + ((ch ^ (rr & 7)) << 4)));
+              *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.C) + (int64_t)(row0 + rr) * p.ldc + col0 + ch * 8) = u;
+            }
+          }
+          __syncwarp();
+          ++c;  // the partner chunk is done
           continue;
         }
         uint32_t r[32];
