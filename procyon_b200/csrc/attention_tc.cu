@@ -19,11 +19,13 @@ namespace {
 constexpr int TBM = 128;  // queries per CTA
 constexpr int TBN = 128;  // keys per step
 constexpr int THD = 64;   // head dim
-constexpr int TC_THREADS = 160;  // warps 0-3: softmax rows; warp 4: TMA + MMA issue
+constexpr int SM_WARPS = 8;       // softmax warps: two threads per query row (64 of the 128 key columns each)
+constexpr int TC_THREADS = (SM_WARPS + 1) * 32;  // + warp 8: TMA + MMA issue
 constexpr int Q_BYTES = TBM * THD * 2;
 constexpr int KV_BYTES = TBN * THD * 2;
 constexpr int P_BYTES = TBM * TBN * 2;
-constexpr int TC_SMEM = Q_BYTES + 2 * 2 * KV_BYTES + P_BYTES + TBN * 2 /*valid*/ + 256 /*barriers*/;
+constexpr int TC_SMEM = Q_BYTES + 2 * 2 * KV_BYTES + P_BYTES + 2 * TBM * 2 /*row max exchange (bf16)*/ + 32 /*valid*/ + 80 /*barriers*/;
+static_assert(2 * (TC_SMEM + 1024) <= 228 * 1024, "two CTAs per SM must fit");
 constexpr int TMEM_COLS_ATT = 256;  // S: [0,128), O_tile: [128,192)
 
 struct TcAttnParams {
@@ -46,11 +48,14 @@ esm_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcAttnPa
   const uint32_t sK = sQ + Q_BYTES;            // 2 stages
   const uint32_t sV = sK + 2 * KV_BYTES;       // 2 stages
   const uint32_t sP = sV + 2 * KV_BYTES;       // [2 blocks of 64 keys][128 rows][128 B]
-  const uint32_t sValid = sP + P_BYTES;        // 2 x 128 bytes
-  const uint32_t bars = sValid + 2 * TBN;
+  const uint32_t sXchg = sP + P_BYTES;         // bf16 [2 halves][128 rows]
+  const uint32_t sValid = sXchg + 2 * TBM * 2; // 2 parities x 4 words
+  const uint32_t bars = sValid + 32;
   const uint32_t q_full = bars, kv_full0 = bars + 8, kv_empty0 = bars + 24, s_full = bars + 40, p_ready = bars + 48,
-                 o_full = bars + 56, tmem_slot = bars + 64;
+                 o_full = bars + 56, tmem_slot = bars + 64;  // 68 bytes used of 80
   uint8_t* valid_smem = smem_raw + (sValid - smem_u32(smem_raw));
+  __nv_bfloat16* xchg = reinterpret_cast<__nv_bfloat16*>(smem_raw + (sXchg - smem_u32(smem_raw)));
+  float* xchg_f = reinterpret_cast<float*>(smem_raw + (sP - smem_u32(smem_raw)));  // P region, free after the last tile
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q_tile = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -68,11 +73,11 @@ esm_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcAttnPa
     mbar_init(kv_empty0, 1);
     mbar_init(kv_empty0 + 8, 1);
     mbar_init(s_full, 1);
-    mbar_init(p_ready, TBM);
+    mbar_init(p_ready, SM_WARPS * 32);
     mbar_init(o_full, 1);
     fence_barrier_init();
   }
-  if (warp == 4) {
+  if (warp == SM_WARPS) {
     tmem_alloc(tmem_slot, TMEM_COLS_ATT);
     tmem_relinquish();
   }
@@ -82,7 +87,7 @@ esm_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcAttnPa
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-  if (warp == 4) {
+  if (warp == SM_WARPS) {
     if (lane == 0) {
       // ---------------- TMA producer + MMA issuer (one thread) ----------------
       mbar_arrive_expect_tx(q_full, Q_BYTES);
@@ -127,36 +132,40 @@ esm_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcAttnPa
       }
     }
   } else {
-    // ---------------- softmax / accumulate: thread = query row ----------------
-    const int r = threadIdx.x;  // 0..127, TMEM lane
-    const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
-    float o[THD];
+    // ---------------- softmax / accumulate: two threads per query row ----------------
+    // warp w may touch TMEM lanes 32*(w%4)..+31: warps w and w+4 share a row quadrant and split the key columns
+    const int quad = warp & 3, half = warp >> 2;
+    const int r = quad * 32 + lane;  // query row within the tile = TMEM lane
+    const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
+    constexpr int OH = THD / 2;  // output columns per thread
+    float o[OH];
 #pragma unroll
-    for (int i = 0; i < THD; ++i) o[i] = 0.f;
+    for (int i = 0; i < OH; ++i) o[i] = 0.f;
     float m_run = -INFINITY, l_run = 0.f;
     const uint8_t* valid_g = p.key_valid ? p.key_valid + (int64_t)b * p.T : nullptr;
     uint32_t* vwords = reinterpret_cast<uint32_t*>(valid_smem);  // [2 parities][4 words]: validity bit per key
     for (int j = 0; j < n_kv; ++j) {
       const int kbase = j * TBN;
-      {
+      if (half == 0) {
         const int kidx = kbase + r;
         bool ok = kidx < p.T;
         if (ok && valid_g) ok = valid_g[kidx] != 0;
         const uint32_t word = __ballot_sync(0xffffffffu, ok);
-        if (lane == 0) vwords[(j & 1) * 4 + warp] = word;
+        if (lane == 0) vwords[(j & 1) * 4 + quad] = word;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");  // the 4 softmax warps only
-      const uint32_t mw0 = vwords[(j & 1) * 4 + 0], mw1 = vwords[(j & 1) * 4 + 1], mw2 = vwords[(j & 1) * 4 + 2],
-                     mw3 = vwords[(j & 1) * 4 + 3];
-      const bool all_valid = (mw0 & mw1 & mw2 & mw3) == 0xffffffffu;
       mbar_wait(s_full, j & 1);
       tc_fence_after();
       const int keys = min(TBN, p.T - kbase);
       const int n_mma = (keys + 15) & ~15;
-      // pass 1: row max over the valid keys (4 independent chains)
+      const int c_lo = half * 64, c_hi = min(n_mma, c_lo + 64);  // this thread's key columns
+      // pass 1: row max over this thread's columns (validity is applied in pass 2: masked keys only raise the max,
+      // which is harmless for the softmax value... but not for -inf rows, so mask here too)
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // validity words visible
+      const uint32_t mwa = vwords[(j & 1) * 4 + half * 2], mwb = vwords[(j & 1) * 4 + half * 2 + 1];
+      const bool all_valid = (mwa & mwb) == 0xffffffffu;
       float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll 1
-      for (int c = 0; c < n_mma; c += 32) {
+      for (int c = c_lo; c < c_hi; c += 32) {
         uint32_t v[32];
         tmem_ld_32x32b_x32(t_lane + c, v);
         tc_wait_ld();
@@ -164,25 +173,30 @@ esm_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcAttnPa
 #pragma unroll
           for (int i = 0; i < 32; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(v[i]));
         } else {
-          const uint32_t mw = (c == 0) ? mw0 : (c == 32) ? mw1 : (c == 64) ? mw2 : mw3;
+          const uint32_t mw = (c == c_lo) ? mwa : mwb;
 #pragma unroll
           for (int i = 0; i < 32; ++i)
             mx4[i & 3] = fmaxf(mx4[i & 3], ((mw >> i) & 1u) ? __uint_as_float(v[i]) : -INFINITY);
         }
       }
-      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+      // the two threads of a row must agree on the offset exactly; any value >= the true max works, so exchange the
+      // max rounded UP to bf16 (halves the exchange buffer: the kernel sits 100 bytes under the 2-CTA/SM smem limit)
+      const __nv_bfloat16 mx_own_b = __float2bfloat16_ru(fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])));
+      xchg[half * TBM + r] = mx_own_b;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const float mx = fmaxf(__bfloat162float(mx_own_b), __bfloat162float(xchg[(half ^ 1) * TBM + r]));
       const float m_new = fmaxf(m_run, mx);
       const float corr = (m_new == -INFINITY) ? 1.f : exp2f((m_run - m_new) * p.scale_log2);
       const float moff = (m_new == -INFINITY) ? 0.f : m_new * p.scale_log2;
-      // pass 2: p = exp2(s*scale - moff) -> bf16 -> swizzled smem (A operand of the second MMA)
+      // pass 2: p = exp2(s*scale - moff) -> bf16 -> swizzled smem block `half` (A operand of the second MMA)
       float ls4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
-      for (int c = 0; c < n_mma; c += 32) {
+      for (int c = c_lo; c < c_hi; c += 32) {
         uint32_t v[32];
         tmem_ld_32x32b_x32(t_lane + c, v);
         tc_wait_ld();
         uint32_t packed[16];
-        const uint32_t mw = all_valid ? 0xffffffffu : ((c == 0) ? mw0 : (c == 32) ? mw1 : (c == 64) ? mw2 : mw3);
+        const uint32_t mw = all_valid ? 0xffffffffu : ((c == c_lo) ? mwa : mwb);
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
           float p0, p1;
@@ -195,8 +209,7 @@ esm_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcAttnPa
           ls4[(i >> 1) & 3] += p0 + p1;
           packed[i >> 1] = pack_bf16x2(p0, p1);
         }
-        // 32 keys = 4 chunks of 16 bytes; key c..c+31 lives in block c/64, chunks ((c%64)/8 .. +3)
-        const uint32_t blk = sP + (uint32_t)(c >> 6) * (TBM * 128) + (uint32_t)r * 128;
+        const uint32_t blk = sP + (uint32_t)half * (TBM * 128) + (uint32_t)r * 128;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int chunk = ((c & 63) >> 3) + q;
@@ -206,32 +219,35 @@ esm_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcAttnPa
                        : "memory");
         }
       }
-      l_run = l_run * corr + ((ls4[0] + ls4[1]) + (ls4[2] + ls4[3]));
+      l_run = l_run * corr + ((ls4[0] + ls4[1]) + (ls4[2] + ls4[3]));  // partial sum over this thread's columns
       m_run = m_new;
       // publish P (the previous O_tile was consumed at the end of the previous iteration)
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(p_ready);
-      // O = O * corr + P V of this tile
+      // O = O * corr + P V of this tile (this thread's 32 output columns)
       mbar_wait(o_full, j & 1);
       tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < THD; c += 32) {
+      {
         uint32_t v[32];
-        tmem_ld_32x32b_x32(t_lane + TBN + c, v);
+        tmem_ld_32x32b_x32(t_lane + TBN + half * OH, v);
         tc_wait_ld();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) o[c + i] = fmaf(o[c + i], corr, __uint_as_float(v[i]));
+        for (int i = 0; i < OH; ++i) o[i] = fmaf(o[i], corr, __uint_as_float(v[i]));
       }
       tc_fence_before();
     }
-    // ---- finalize ----
+    // ---- finalize: row sum = both halves ----
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    xchg_f[half * TBM + r] = l_run;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    const float l_tot = l_run + xchg_f[(half ^ 1) * TBM + r];
     const int qrow = q0 + r;
     if (qrow < p.T) {
-      const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
-      bf16* op = p.o + (int64_t)(row_base + qrow) * p.o_rs + h * THD;
+      const float inv = l_tot > 0.f ? 1.f / l_tot : 0.f;
+      bf16* op = p.o + (int64_t)(row_base + qrow) * p.o_rs + h * THD + half * OH;
 #pragma unroll
-      for (int c = 0; c < THD; c += 8) {
+      for (int c = 0; c < OH; c += 8) {
         uint4 u;
         u.x = pack_bf16x2(o[c] * inv, o[c + 1] * inv);
         u.y = pack_bf16x2(o[c + 2] * inv, o[c + 3] * inv);
@@ -243,7 +259,7 @@ esm_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcAttnPa
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == SM_WARPS) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS_ATT);
   }

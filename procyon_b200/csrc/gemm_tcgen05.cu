@@ -19,7 +19,7 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle span
 constexpr int UMMA_K = 16;
-constexpr int NUM_EPI_WARPS = 4;
+constexpr int NUM_EPI_WARPS = 8;  // two per TMEM lane quadrant: each takes half of the tile's columns
 constexpr int NUM_THREADS = 64 + NUM_EPI_WARPS * 32;
 
 template <int BN>
@@ -104,7 +104,7 @@ __device__ __forceinline__ void tile_coords(int tile, int m_blocks, int n_blocks
   n_blk = local / rows;
 }
 
-template <int BN>
+template <int BN, bool ROPE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          const EpiParams p) {
@@ -206,6 +206,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   } else {
     // ===================== epilogue warps =====================
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    const int chalf = (warp - 2) >> 2;  // which half of the tile's columns this warp drains
+    constexpr int C_PER = BN / 32 / 2;
     int acc = 0;
     uint32_t acc_phase = 0;
     const bool swiglu = (p.act == ACT_SWIGLU);
@@ -222,10 +224,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = chalf * C_PER; c < (chalf + 1) * C_PER; ++c) {
         const int col0 = n_blk * BN + c * 32;
         if (col0 >= p.N) break;  // warp-uniform
-        if (p.rope != nullptr && col0 < p.rope_ncols) {
+        if (ROPE && p.rope != nullptr && col0 < p.rope_ncols) {
           // fused rotate-half RoPE: columns (i, i + hd/2) of a head are in chunks c and c + hd/64
           const int half = p.rope_hd >> 1;
           const int in_head = col0 % p.rope_hd;
@@ -514,12 +516,12 @@ int get_tensor_map(const bf16* ptr, int64_t rows, int64_t cols, int64_t ld, int 
   return 0;
 }
 
-template <int BN>
+template <int BN, bool ROPE>
 int launch(const GemmArgs& a, cudaStream_t stream) {
   using Cfg = TileCfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
-    PCY_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    PCY_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, ROPE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   Cfg::SMEM_BYTES));
     attr_set = true;
   }
@@ -533,7 +535,7 @@ int launch(const GemmArgs& a, cudaStream_t stream) {
   p.rope = a.rope; p.rope_hd = a.rope_hd; p.rope_T = a.rope_T; p.rope_ncols = a.rope ? a.rope_ncols : 0;
   const int tiles = ceil_div(a.M, BM) * ceil_div(a.N, BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_bf16_tcgen05_kernel<BN><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
+  gemm_bf16_tcgen05_kernel<BN, ROPE><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
   PCY_LAUNCH_CHECK();
   return 0;
 }
@@ -564,7 +566,8 @@ int gemm_bf16_tc(const GemmArgs& a, cudaStream_t stream) {
     const double w128 = (double)tiles128 / (double)(ceil_div(tiles128, sms) * sms);
     if (w128 > w256 * 1.15) use128 = true;
   }
-  return use128 ? launch<128>(a, stream) : launch<256>(a, stream);
+  if (a.rope != nullptr) return use128 ? launch<128, true>(a, stream) : launch<256, true>(a, stream);
+  return use128 ? launch<128, false>(a, stream) : launch<256, false>(a, stream);
 }
 
 }  // namespace pcy
