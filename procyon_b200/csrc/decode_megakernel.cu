@@ -1,13 +1,23 @@
 // One persistent kernel per Llama decode step (rows = n_inputs * beams <= 4): one CTA per SM streams its balanced
 // slice of every weight matrix exactly once, phases are separated by a grid-wide barrier, activations (a few KB)
-// bounce through L2.  Per layer:  P1 qkv = Wqkv . rms(x)  |  P2 RoPE + KV append + split-KV attention partials
-// |  P2c combine  |  P3 x += Wo . attn  |  P4 act = silu(Wg . rms(x)) * (Wu . rms(x))  |  P5 x += Wdown . act,
-// then logits = Wlm . rms(x).  Batch-1 decode is pure weight streaming (15 GB per token for Llama-3-8B): what this
-// design buys over one launch per op is no launch / ramp-up / tail per op (160 of them per token) and L2 prefetch
-// of the next phase's first weight rows while CTAs wait at the barrier.
+// bounce through L2.  Per layer:  P1 qkv = Wqkv . rms(x)  |  P2 RoPE + KV append + split-KV attention (the last CTA
+// of a kv head merges the splits)  |  P3 x += Wo . attn  |  P4 act = silu(Wg . rms(x)) * (Wu . rms(x))
+// |  P5 x += Wdown . act, then logits = Wlm . rms(x).
+//
+// Batch-1 decode is pure weight streaming (15 GB per token for Llama-3-8B), so the kernel is built around keeping
+// HBM busy: a dedicated producer warp walks the CTA's weight slices of ALL phases in order and copies them with
+// cp.async.bulk (TMA, 8 KB per copy) into a 192 KB shared-memory ring guarded by full/empty mbarriers.  The weights
+// do not depend on activations, so the producer runs ahead across grid barriers, activation staging, epilogues and
+// the attention phase: up to a ring's worth of the next phase is already on chip when its consumers start.  The
+// number of slots is a multiple of 12 and slot s always belongs to consumer warp s % 12, which takes its chunks in
+// order (one consumer per mbarrier: parity waits cannot alias), FMAs them against the activations staged in shared
+// memory and reduces.  12 consumer warps + 1 producer warp = 13 warps keeps 128 registers per thread.
 //
 // Replaces the per-token HF LlamaForCausalLM forward of the reference's generate loops
 // (procyon/model/model_unified.py:769, :887 -> procyon/model/pmc_llama.py:581).
+#include <algorithm>
+#include <cstdlib>
+
 #include "common.cuh"
 #include "ops.h"
 
@@ -15,35 +25,62 @@ namespace pcy {
 
 namespace {
 
-constexpr int MK_THREADS = 512;
-constexpr int MK_WARPS = MK_THREADS / 32;
-constexpr int UL = 8;          // 512-byte weight segments in flight per warp (one 16-byte load per lane each)
+constexpr int MK_WARPS = 12;                 // consumer warps
+constexpr int MK_THREADS = MK_WARPS * 32;    // 384 consumer threads
+constexpr int MK_BLOCK = MK_THREADS + 32;    // + one producer warp (warp 12)
+constexpr int CH = 4096;                     // weight elements per ring slot (one bulk copy)
+constexpr int SLOT_BYTES = CH * 2;
 constexpr int HD = 128;
-constexpr int ATT_CHUNK = 128;  // keys per attention work item (8 per warp)
+constexpr int KPW = 8;                       // keys per warp and attention work item
+constexpr int ATT_CHUNK = KPW * MK_WARPS;    // 96 keys per attention work item
 constexpr int PSTR = HD + 4;    // floats per (split, head) attention partial: 128 outputs, max, sum (16-byte rows)
-constexpr int MAX_OUT_PER_CTA = 1024;
+constexpr int MERGE_B = 12;     // splits merged per batch of independent loads
 
 __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
   unsigned int v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void red_release_add(unsigned int* p, unsigned int v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// barrier over the consumer threads only (the producer warp never joins a CTA-wide barrier)
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(MK_THREADS) : "memory"); }
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+// global -> shared bulk copy (TMA, no tensor map), completion counted in bytes on an mbarrier
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+      ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(pol)
+      : "memory");
+}
+__device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
+  uint4 u;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(addr));
+  return u;
+}
 // activations written by other CTAs earlier in this kernel must be read through L2 (L1 is not coherent)
 __device__ __forceinline__ float ldcg_bf16(const bf16* p) {
   return __bfloat162float(__ushort_as_bfloat16(__ldcg(reinterpret_cast<const unsigned short*>(p))));
 }
 
+// Grid-wide barrier over the consumer threads of all CTAs (cooperative launch: all CTAs are resident).
+// Thread 0 publishes the CTA's writes with a release reduction (cumulative over the CTA barrier before it) and
+// acquires everybody else's; the second CTA barrier hands that view to the other threads, which read remote data
+// through L2 (ld.cg) only.
 struct GridBarrier {
   unsigned int* counter;
   unsigned int target;
   unsigned int nblocks;
   __device__ __forceinline__ void sync() {
-    __syncthreads();
+    consumer_sync();
     if (threadIdx.x == 0) {
       target += nblocks;
-      __threadfence();
-      atomicAdd(counter, 1u);
+      red_release_add(counter, 1u);
       uint64_t t0 = 0;
       for (uint32_t it = 0; ld_acquire_u32(counter) < target; ++it) {
         if ((it & 0x3fffu) == 0x3fffu) {  // bounded: a scheduling bug must trap, not hang the GPU
@@ -52,9 +89,8 @@ struct GridBarrier {
           else if (now - t0 > 4000000000ull) __trap();
         }
       }
-      __threadfence();
     }
-    __syncthreads();
+    consumer_sync();
   }
 };
 
@@ -69,17 +105,34 @@ __device__ __forceinline__ float dot8f(const uint4& a, const uint4& w, float s) 
 }
 
 enum : int { EPI_BF16 = 0, EPI_RESIDUAL = 1, EPI_SWIGLU = 2, EPI_FP32 = 3 };
-enum : int { STAGE_PLAIN = 0, STAGE_RMS = 1, STAGE_ATTN = 2 };
+enum : int { STAGE_PLAIN = 0, STAGE_RMS = 1 };
+
+// slot / parity of ring chunk g (g mod ns and g / ns by multiply-high: exact for g < 2^32 / ns)
+struct RingGeom {
+  int ns;
+  uint32_t magic;  // ceil(2^32 / ns)
+  __device__ __forceinline__ void locate(uint32_t g, uint32_t& slot, uint32_t& par) const {
+    const uint32_t q = __umulhi(g, magic);
+    slot = g - q * (uint32_t)ns;
+    par = q & 1u;
+  }
+};
 
 struct Smem {
   bf16* a;       // [MT][K] staged activations
-  float* out;    // [MAX_OUT_PER_CTA * 2][MT] partial sums
+  float* out;    // [out_rows][MT] partial sums
   float* red;    // [MK_WARPS * 4] scratch
+  // weight ring: slot i at ring + i * SLOT_BYTES, full barrier at bars + 8 i, empty barrier at bars + 8 (ns + i)
+  uint32_t ring, bars;
+  RingGeom rg;
+  uint32_t chunk0;  // ring chunks consumed by the phases before the current one (same count in the producer)
   unsigned long long* tbuf;  // profiling stamps (CTA 0, thread 0) or null
-  int* tix;
-  __device__ __forceinline__ void stamp() const {
-    if (tbuf != nullptr && blockIdx.x == 0 && threadIdx.x == 0) tbuf[*tix] = globaltimer_ns();
-    if (tbuf != nullptr) ++*tix;
+  int tix;
+  __device__ __forceinline__ void stamp() {
+    if (tbuf != nullptr) {
+      if (blockIdx.x == 0 && threadIdx.x == 0) tbuf[tix] = globaltimer_ns();
+      ++tix;
+    }
   }
 };
 
@@ -96,128 +149,136 @@ __device__ __forceinline__ int weight_row(int epi, int o_lo, int r) {
   return (j >> 4) * 32 + (j & 15) + ((r & 1) ? 16 : 0);
 }
 
-// L2 prefetch of this CTA's slice of a coming phase: lines [line0, line0 + n_lines) of the slice, issued before the
-// grid barrier so that HBM keeps streaming while CTAs wait and stage activations.
-__device__ void prefetch_phase(const bf16* W, int64_t ldw, int n_out, int K, int epi, int line0, int n_lines) {
+constexpr int PL = 8;  // producer lanes: chunks g .. g+7 are issued side by side (needs ns >= 12 > PL)
+
+// Producer side of one phase: this CTA's rows of W, cut into chunks of <= CH elements of one row, each one bulk copy
+// into the next ring slot.  `g` is the running chunk counter shared by convention with the consumers, which walk the
+// identical chunk list in gemv_phase.  One thread cannot issue the copies fast enough for 44 GB/s per SM (wait +
+// address arithmetic ~0.25 us per chunk), so PL lanes of the producer warp each take every PL-th chunk.  The lanes
+// stay converged: nobody issues before every lane's slot is free.  (Chunk g reuses the slot of chunk g - ns, issued in
+// an earlier iteration because ns > PL, so no lane ever waits on a lane of its own iteration.)
+__device__ __noinline__ void produce_phase(uint32_t ring, uint32_t bars, RingGeom rg, uint32_t& g, const bf16* W,
+                                           int64_t ldw, int n_out, int K, int epi, uint64_t pol) {
   int lo, hi;
   cta_range(n_out, lo, hi);
   const int rpo = (epi == EPI_SWIGLU) ? 2 : 1;
   const int n_rows = (hi - lo) * rpo;
-  const int lines_per_row = (K * 2) / 128;
-  const int total = n_rows * lines_per_row;
-  const int end = min(total, line0 + n_lines);
-  for (int i = line0 + threadIdx.x; i < end; i += MK_THREADS) {
-    const int r = i / lines_per_row, l = i % lines_per_row;
-    prefetch_l2(W + (int64_t)weight_row(epi, lo, r) * ldw + l * 64);
+  const int cpr = (K + CH - 1) / CH;
+  const int n_chunks = n_rows * cpr;
+  const int lane = threadIdx.x & 31;
+  constexpr uint32_t LANES = (1u << PL) - 1u;
+  for (int c0 = 0; c0 < n_chunks; c0 += PL) {
+    const int c = c0 + lane;
+    const bool active = c < n_chunks;
+    uint32_t slot = 0, par = 0, bytes = 0;
+    const bf16* src = W;
+    if (active) {
+      const int r = c / cpr, kc = c - r * cpr;
+      rg.locate(g + (uint32_t)c, slot, par);
+      src = W + (int64_t)weight_row(epi, lo, r) * ldw + kc * CH;
+      bytes = (uint32_t)min(CH, K - kc * CH) * 2u;
+    }
+    bool ok = !active;
+    uint64_t t0 = 0;
+    for (uint32_t it = 0;; ++it) {
+      if (!ok) ok = mbar_try_wait(bars + 8u * (rg.ns + slot), par ^ 1u);  // slot drained by its consumer warp
+      if (__all_sync(LANES, ok)) break;
+      if ((it & 0xfffu) == 0xfffu) {  // bounded: a pipeline bug must trap, not hang the GPU
+        const uint64_t now = globaltimer_ns();
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > 4000000000ull) __trap();
+      }
+    }
+    if (active) {
+      mbar_arrive_expect_tx(bars + 8u * slot, bytes);
+      bulk_g2s(ring + slot * SLOT_BYTES, src, bytes, bars + 8u * slot, pol);
+    }
   }
+  g += (uint32_t)n_chunks;
 }
 
-struct AttnSrc {  // STAGE_ATTN: A[m][head*128 + dim] = merge over splits of the attention partials
-  const float* part;
-  int n_splits, max_splits, KVH, GQ;
-};
-
-// out = epi(W[n_out(x2), K] . A[MT, K]).  The CTA's slice of W is treated as a flat list of 512-byte segments that is
-// divided evenly among the 16 warps (a warp's range may start and end inside a row); the first batch of weight loads
-// is issued before the activations are staged, so its latency overlaps the staging.
+// out = epi(W[n_out(x2), K] . A[MT, K]).  The CTA's slice of W arrives through the ring in chunks of <= CH elements
+// of one row.
 template <int MT>
-__device__ void gemv_phase(const Smem& sm, const bf16* __restrict__ W, int64_t ldw, int n_out, int K, int stage,
-                           const bf16* A, int64_t lda, const AttnSrc& asrc, int rows, const bf16* __restrict__ rms_w,
-                           float eps, int epi, void* out, int64_t ldo) {
+__device__ __noinline__ void gemv_phase(Smem& sm, int n_out, int K, int stage, const bf16* A, int64_t lda, int rows,
+                                        const bf16* __restrict__ rms_w, float eps, int epi, void* out, int64_t ldo) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   int o_lo, o_hi;
   cta_range(n_out, o_lo, o_hi);
   const int rpo = (epi == EPI_SWIGLU) ? 2 : 1;
   const int n_rows = (o_hi - o_lo) * rpo;
-  // work unit = (local row, K chunk of 2048 elements): 8 x 16-byte loads per lane; units go round-robin to warps
-  constexpr int KCH = UL * 256;
-  const int kc_per_row = (K + KCH - 1) / KCH;
-  const int n_units = n_rows * kc_per_row;
-  uint4 wb[UL];
-#define PCY_LOAD_UNIT(U)                                                                     \
-  {                                                                                          \
-    const int r_ = (U) / kc_per_row, kc_ = (U) - r_ * kc_per_row;                            \
-    const bf16* wrow_ = W + (int64_t)weight_row(epi, o_lo, r_) * ldw + kc_ * KCH;            \
-    const int k_rem_ = K - kc_ * KCH;                                                        \
-    _Pragma("unroll") for (int j = 0; j < UL; ++j) {                                         \
-      const int k_ = j * 256 + lane * 8;                                                     \
-      wb[j] = (k_ < k_rem_) ? ldg_nc_v4(wrow_ + k_) : make_uint4(0, 0, 0, 0);                \
-    }                                                                                        \
-  }
+  const int cpr = (K + CH - 1) / CH;
+  const int n_chunks = n_rows * cpr;
 
-  // ---- stage A (plain | RMS-normalised with HF rounding | merged attention partials) ----
+  // ---- stage A (plain | RMS-normalised with HF rounding) ----
+  constexpr int HOLD = 2;  // 16-byte pieces of a row a thread keeps in registers between the two RMS passes
+  const bool rms_in_regs = K <= MK_THREADS * 8 * HOLD;
   for (int m = 0; m < MT; ++m) {
     bf16* dst = sm.a + (int64_t)m * K;
     if (m >= rows) {
       for (int k = tid * 8; k < K; k += MK_THREADS * 8) *reinterpret_cast<uint4*>(dst + k) = make_uint4(0, 0, 0, 0);
       continue;
     }
-    if (stage == STAGE_ATTN) {
-      for (int k = tid * 8; k < K; k += MK_THREADS * 8) {
-        const int head = k / HD, dim = k % HD;
-        const int kvh = head / asrc.GQ, hq = head % asrc.GQ;
-        const float* ps = asrc.part + (((int64_t)m * asrc.KVH + kvh) * asrc.max_splits) * asrc.GQ * PSTR + hq * PSTR;
-        const int64_t stride = (int64_t)asrc.GQ * PSTR;
-        float mx = -INFINITY;
-        for (int sp = 0; sp < asrc.n_splits; ++sp) mx = fmaxf(mx, __ldcg(ps + sp * stride + HD));
-        float l = 0.f, acc[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-        for (int sp = 0; sp < asrc.n_splits; ++sp) {
-          const float ms = __ldcg(ps + sp * stride + HD);
-          if (ms == -INFINITY) continue;
-          const float w = exp2f(ms - mx);
-          l += w * __ldcg(ps + sp * stride + HD + 1);
-          const float4 v0 = __ldcg(reinterpret_cast<const float4*>(ps + sp * stride + dim));
-          const float4 v1 = __ldcg(reinterpret_cast<const float4*>(ps + sp * stride + dim + 4));
-          acc[0] += w * v0.x; acc[1] += w * v0.y; acc[2] += w * v0.z; acc[3] += w * v0.w;
-          acc[4] += w * v1.x; acc[5] += w * v1.y; acc[6] += w * v1.z; acc[7] += w * v1.w;
-        }
-        const float inv = l > 0.f ? 1.f / l : 0.f;
-        *reinterpret_cast<uint4*>(dst + k) =
-            make_uint4(pack_bf16x2(acc[0] * inv, acc[1] * inv), pack_bf16x2(acc[2] * inv, acc[3] * inv),
-                       pack_bf16x2(acc[4] * inv, acc[5] * inv), pack_bf16x2(acc[6] * inv, acc[7] * inv));
-      }
+    const bf16* src = A + (int64_t)m * lda;
+    if (stage == STAGE_PLAIN) {
+      for (int k = tid * 8; k < K; k += MK_THREADS * 8)
+        *reinterpret_cast<uint4*>(dst + k) = __ldcg(reinterpret_cast<const uint4*>(src + k));
       continue;
     }
-    const bf16* src = A + (int64_t)m * lda;
-    float rstd = 1.f;
-    if (stage == STAGE_RMS) {
-      float ss = 0.f;
+    uint4 held[HOLD];
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < HOLD; ++i) {
+      const int k = (tid + i * MK_THREADS) * 8;
+      held[i] = (rms_in_regs && k < K) ? __ldcg(reinterpret_cast<const uint4*>(src + k)) : make_uint4(0, 0, 0, 0);
+    }
+    if (rms_in_regs) {
+#pragma unroll
+      for (int i = 0; i < HOLD; ++i) {
+        const float2 a = unpack_bf16x2(held[i].x), b = unpack_bf16x2(held[i].y), c = unpack_bf16x2(held[i].z),
+                     d = unpack_bf16x2(held[i].w);
+        ss += a.x * a.x + a.y * a.y + b.x * b.x + b.y * b.y + c.x * c.x + c.y * c.y + d.x * d.x + d.y * d.y;
+      }
+    } else {
       for (int k = tid * 8; k < K; k += MK_THREADS * 8) {
         const uint4 u = __ldcg(reinterpret_cast<const uint4*>(src + k));
         const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
         ss += a.x * a.x + a.y * a.y + b.x * b.x + b.y * b.y + c.x * c.x + c.y * c.y + d.x * d.x + d.y * d.y;
       }
-      ss = warp_sum(ss);
-      if (lane == 0) sm.red[warp] = ss;
-      __syncthreads();
-      float tot = 0.f;
-#pragma unroll
-      for (int w = 0; w < MK_WARPS; ++w) tot += sm.red[w];
-      rstd = rsqrtf(tot / (float)K + eps);
-      __syncthreads();
     }
-    for (int k = tid * 8; k < K; k += MK_THREADS * 8) {
-      const uint4 u = __ldcg(reinterpret_cast<const uint4*>(src + k));
-      if (stage == STAGE_RMS) {
-        const uint4 g = *reinterpret_cast<const uint4*>(rms_w + k);
-        const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
-        const uint32_t gg[4] = {g.x, g.y, g.z, g.w};
-        uint32_t oo[4];
+    ss = warp_sum(ss);
+    if (lane == 0) sm.red[warp] = ss;
+    consumer_sync();
+    float tot = 0.f;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float2 x = unpack_bf16x2(uu[i]);
-          const float2 w = unpack_bf16x2(gg[i]);
-          oo[i] = pack_bf16x2(w.x * bf16_round(x.x * rstd), w.y * bf16_round(x.y * rstd));  // HF LlamaRMSNorm
-        }
-        *reinterpret_cast<uint4*>(dst + k) = make_uint4(oo[0], oo[1], oo[2], oo[3]);
-      } else {
-        *reinterpret_cast<uint4*>(dst + k) = u;
+    for (int w = 0; w < MK_WARPS; ++w) tot += sm.red[w];
+    const float rstd = rsqrtf(tot / (float)K + eps);
+    consumer_sync();
+    auto normalise = [&](const uint4& u, int k) {
+      const uint4 g = *reinterpret_cast<const uint4*>(rms_w + k);
+      const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+      const uint32_t gg[4] = {g.x, g.y, g.z, g.w};
+      uint32_t oo[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 x = unpack_bf16x2(uu[i]);
+        const float2 w = unpack_bf16x2(gg[i]);
+        oo[i] = pack_bf16x2(w.x * bf16_round(x.x * rstd), w.y * bf16_round(x.y * rstd));  // HF LlamaRMSNorm
       }
+      *reinterpret_cast<uint4*>(dst + k) = make_uint4(oo[0], oo[1], oo[2], oo[3]);
+    };
+    if (rms_in_regs) {
+#pragma unroll
+      for (int i = 0; i < HOLD; ++i) {
+        const int k = (tid + i * MK_THREADS) * 8;
+        if (k < K) normalise(held[i], k);
+      }
+    } else {
+      for (int k = tid * 8; k < K; k += MK_THREADS * 8) normalise(__ldcg(reinterpret_cast<const uint4*>(src + k)), k);
     }
   }
-  for (int i = tid; i < n_rows * MT; i += MK_THREADS) sm.out[i] = 0.f;
+  if (cpr > 1)
+    for (int i = tid; i < n_rows * MT; i += MK_THREADS) sm.out[i] = 0.f;
   // residual values are final since two phases ago: fetch them now, off the critical path
   const int n_o = o_hi - o_lo;
   float res_pre = 0.f;
@@ -225,36 +286,53 @@ __device__ void gemv_phase(const Smem& sm, const bf16* __restrict__ W, int64_t l
     const int o = tid / MT, m = tid % MT;
     if (m < rows) res_pre = ldcg_bf16(reinterpret_cast<const bf16*>(out) + (int64_t)m * ldo + o_lo + o);
   }
-  __syncthreads();
+  consumer_sync();
   sm.stamp();
 
-  // ---- stream the weights ----
-  for (int u = warp; u < n_units; u += MK_WARPS) {
-    PCY_LOAD_UNIT(u)
-    const int r = u / kc_per_row, kc = u - r * kc_per_row;
-    const int k_rem = K - kc * KCH;
-    float acc[MT];
+  // ---- consume the ring: chunk g of the step lives in slot g % ns and belongs to warp g % 12 ----
+  const uint32_t a_base = smem_u32(sm.a);
+  for (int c = (int)((warp + MK_WARPS - sm.chunk0 % MK_WARPS) % MK_WARPS); c < n_chunks; c += MK_WARPS) {
+    uint32_t slot, par;
+    sm.rg.locate(sm.chunk0 + (uint32_t)c, slot, par);
+    const int r = c / cpr, kc = c - r * cpr;
+    const int len = min(CH, K - kc * CH);
+    const uint32_t wsm = sm.ring + slot * SLOT_BYTES + lane * 16;
+    const uint32_t asm0 = a_base + (uint32_t)(kc * CH) * 2u + lane * 16;
+    mbar_wait(sm.bars + 8u * slot, par);
+    float acc[MT], acc2[MT];
 #pragma unroll
-    for (int m = 0; m < MT; ++m) acc[m] = 0.f;
+    for (int m = 0; m < MT; ++m) acc[m] = acc2[m] = 0.f;
+    int j = 0;
+#pragma unroll 2
+    for (; j + 2 <= len / 256; j += 2) {  // two independent FMA chains per row
+      const uint4 w0 = lds_v4(wsm + j * 512), w1 = lds_v4(wsm + j * 512 + 512);
 #pragma unroll
-    for (int j = 0; j < UL; ++j) {
-      const int k = j * 256 + lane * 8;
-      if (k < k_rem) {
-#pragma unroll
-        for (int m = 0; m < MT; ++m) {
-          const uint4 a = *reinterpret_cast<const uint4*>(sm.a + (int64_t)m * K + kc * KCH + k);
-          acc[m] = dot8f(a, wb[j], acc[m]);
-        }
+      for (int m = 0; m < MT; ++m) {
+        const uint4 a0 = lds_v4(asm0 + (uint32_t)m * (uint32_t)K * 2u + j * 512);
+        const uint4 a1 = lds_v4(asm0 + (uint32_t)m * (uint32_t)K * 2u + j * 512 + 512);
+        acc[m] = dot8f(a0, w0, acc[m]);
+        acc2[m] = dot8f(a1, w1, acc2[m]);
       }
     }
+    if (j < len / 256) {
+      const uint4 w0 = lds_v4(wsm + j * 512);
+#pragma unroll
+      for (int m = 0; m < MT; ++m)
+        acc[m] = dot8f(lds_v4(asm0 + (uint32_t)m * (uint32_t)K * 2u + j * 512), w0, acc[m]);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(sm.bars + 8u * (sm.rg.ns + slot));  // slot free: the producer may refill it
 #pragma unroll
     for (int m = 0; m < MT; ++m) {
-      const float v = warp_sum(acc[m]);
-      if (lane == 0) atomicAdd(&sm.out[r * MT + m], v);
+      const float v = warp_sum(acc[m] + acc2[m]);
+      if (lane == 0) {
+        if (cpr > 1) atomicAdd(&sm.out[r * MT + m], v);
+        else sm.out[r * MT + m] = v;
+      }
     }
   }
-#undef PCY_LOAD_UNIT
-  __syncthreads();
+  sm.chunk0 += (uint32_t)n_chunks;
+  consumer_sync();
   sm.stamp();
 
   // ---- epilogue ----
@@ -297,23 +375,36 @@ struct MegaParams {
   // scratch (global)
   bf16* x;      // [rows][d]
   bf16* qkv;    // [rows][qkv_dim]
+  bf16* attn;   // [rows][H * HD] merged attention output
   bf16* act;    // [rows][ffn]
   float* part;  // [rows][KVH][max_splits][GQ][PSTR]
   int max_splits;
-  unsigned int* barrier;
+  int ring_slots;
+  int out_rows;         // capacity (rows) of the per-CTA partial-sum buffer
+  uint32_t ring_magic;  // ceil(2^32 / ring_slots)
+  unsigned int* barrier;  // [0] grid barrier counter, [32 + row * KVH + kvh] attention tickets
   unsigned long long* timing;  // optional: globaltimer at every phase boundary (CTA 0), for profiling
 };
 
-// P2: one work item = (row, kv head, split of 256 keys): RoPE(q, k_new), KV append, scores, softmax, P.V -> partial.
-// The partials are merged by the next phase while it stages its activations (no combine pass, no extra barrier).
+// P2: one work item = (row, kv head, split of ATT_CHUNK keys); warp w owns keys 8w .. 8w+7 of the split.
+//   scores : lane (sub, l8) dots 16 dims of key 8w + 4 it + sub with the 4 query heads, 3 shuffles finish the dot
+//   P.V    : lane owns dims 4 lane .. 4 lane + 3 of the 4 heads and loops over the warp's 8 keys (no shuffles);
+//            the 12 per-warp partial outputs meet in shared memory
+// The K / V rows of an item (everything but the current token, which is still being produced by P1) are requested
+// BEFORE the grid barrier that ends P1, so their HBM latency overlaps the barrier.  The CTA that finishes the last
+// split of a (row, kv head) merges the partials (ticket counter) and writes the bf16 attention output, so that the
+// o_proj phase stages 8 KB per row instead of every CTA re-reading every partial.
 template <int GQ>
-__device__ void attention_items(const MegaParams& p, uint8_t* smem_raw, int layer) {
-  float* s_q = reinterpret_cast<float*>(smem_raw);  // [GQ][HD]
+__device__ __noinline__ void attention_phase(const MegaParams& p, uint8_t* smem_raw, int layer, GridBarrier& bar,
+                                             Smem& sm) {
+  static_assert(GQ == 4, "the P.V loop reads the 4 head probabilities of a key as one float4");
+  float* s_q = reinterpret_cast<float*>(smem_raw);  // [GQ][HD], pre-scaled by log2(e) / sqrt(HD)
   float* s_knew = s_q + GQ * HD;                    // [HD]
   float* s_vnew = s_knew + HD;                      // [HD]
-  float* s_sc = s_vnew + HD;                        // [GQ][ATT_CHUNK]
+  float* s_sc = s_vnew + HD;                        // [ATT_CHUNK][GQ]
   float* s_ml = s_sc + GQ * ATT_CHUNK;              // [GQ][2]
-  float* s_po = s_ml + GQ * 2;                      // [MK_WARPS][GQ][HD]
+  int* s_flag = reinterpret_cast<int*>(s_ml + GQ * 2);  // [4]
+  float* s_po = s_ml + GQ * 2 + 4;                  // [MK_WARPS][GQ][HD]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int H = p.cfg.n_heads, KVH = p.cfg.n_kv_heads;
   const int kvd = KVH * HD, qkv_dim = (H + 2 * KVH) * HD;
@@ -327,46 +418,66 @@ __device__ void attention_items(const MegaParams& p, uint8_t* smem_raw, int laye
   const bf16* vp = p.kv_prompt + ((int64_t)layer * 2 + 1) * n_prompt * kvd;
   bf16* kg = p.kv_gen + ((int64_t)layer * 2 + 0) * n_gen * kvd;
   bf16* vg = p.kv_gen + ((int64_t)layer * 2 + 1) * n_gen * kvd;
-  const int sub = lane >> 3, l8 = lane & 7;  // 8 lanes per key, 16 dims per lane
-  constexpr int KPW = ATT_CHUNK / MK_WARPS / 4;  // key iterations per warp (4 keys each)
+  const int sub = lane >> 3, l8 = lane & 7;  // scores: 8 lanes per key, 16 dims per lane
 
-  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+  uint4 kreg[KPW / 4][2];
+  uint2 vreg[KPW];
+  uint32_t vmask = 0;  // bit j: V row of key j was requested from global memory
+  bool khave[KPW / 4], kvalid[KPW / 4];
+  // element offset of the K / V row of key position `pos`
+  auto row_off = [&](int row, int input, int kvh, int pos, bool& in_prompt) -> int64_t {
+    in_prompt = pos < p.S;
+    if (in_prompt) return ((int64_t)input * p.S + pos) * kvd + kvh * HD;
+    const int g = pos - p.S;
+    const int prow = p.slots[(int64_t)row * p.max_gen + g];
+    return ((int64_t)prow * p.max_gen + g) * kvd + kvh * HD;
+  };
+  auto request = [&](int item) {  // issue the K and V loads of `item`
     const int split = item % n_splits, kvh = (item / n_splits) % KVH, row = item / (n_splits * KVH);
     const int input = row / p.beams;
-    const bf16* qkv_row = p.qkv + (int64_t)row * qkv_dim;
     const int k0 = split * ATT_CHUNK;
     const int n_keys = min(ctx, k0 + ATT_CHUNK) - k0;
-    // K/V row pointers of this lane's keys (nullptr = the current token, held in smem; or out of range)
-    const bf16* kptr[KPW];
-    const bf16* vptr[KPW];
-    bool valid[KPW];
-    uint4 kreg[KPW][2];
 #pragma unroll
-    for (int it = 0; it < KPW; ++it) {
-      const int kk = (it * MK_WARPS + warp) * 4 + sub;
+    for (int it = 0; it < KPW / 4; ++it) {
+      const int kk = warp * KPW + it * 4 + sub;
       const int pos = k0 + kk;
-      kptr[it] = vptr[it] = nullptr;
-      valid[it] = kk < n_keys;
-      if (valid[it] && pos != pos_cur) {
-        if (pos < p.S) {
-          const int64_t base = ((int64_t)input * p.S + pos) * kvd + kvh * HD + l8 * 16;
-          kptr[it] = kp + base;
-          vptr[it] = vp + base;
-          if (p.prompt_valid) valid[it] = p.prompt_valid[(int64_t)input * p.S + pos] != 0;
-        } else {
-          const int g = pos - p.S;
-          const int prow = p.slots[(int64_t)row * p.max_gen + g];
-          const int64_t base = ((int64_t)prow * p.max_gen + g) * kvd + kvh * HD + l8 * 16;
-          kptr[it] = kg + base;
-          vptr[it] = vg + base;
-        }
-      }
-      if (kptr[it] != nullptr) {  // issue all K loads before touching shared memory
-        kreg[it][0] = __ldcg(reinterpret_cast<const uint4*>(kptr[it]));
-        kreg[it][1] = __ldcg(reinterpret_cast<const uint4*>(kptr[it] + 8));
+      kvalid[it] = kk < n_keys;
+      khave[it] = kvalid[it] && pos != pos_cur;
+      if (khave[it]) {
+        bool in_prompt;
+        const int64_t off = row_off(row, input, kvh, pos, in_prompt) + l8 * 16;
+        const bf16* kptr = (in_prompt ? kp : kg) + off;
+        if (in_prompt && p.prompt_valid) kvalid[it] = p.prompt_valid[(int64_t)input * p.S + pos] != 0;
+        kreg[it][0] = __ldcg(reinterpret_cast<const uint4*>(kptr));
+        kreg[it][1] = __ldcg(reinterpret_cast<const uint4*>(kptr + 8));
       }
     }
-    __syncthreads();  // previous item done with the shared buffers
+    vmask = 0;
+#pragma unroll
+    for (int j = 0; j < KPW; ++j) {
+      const int kk = warp * KPW + j;
+      const int pos = k0 + kk;
+      vreg[j] = make_uint2(0, 0);
+      if (kk < n_keys && pos != pos_cur) {
+        bool in_prompt;
+        const int64_t off = row_off(row, input, kvh, pos, in_prompt) + lane * 4;
+        vreg[j] = __ldcg(reinterpret_cast<const uint2*>((in_prompt ? vp : vg) + off));
+        vmask |= 1u << j;
+      }
+    }
+  };
+
+  int item = blockIdx.x;
+  if (item < n_items) request(item);
+  sm.stamp();
+  bar.sync();  // qkv of this step is complete
+  sm.stamp();
+
+  for (; item < n_items; item += gridDim.x) {
+    const int split = item % n_splits, kvh = (item / n_splits) % KVH, row = item / (n_splits * KVH);
+    const bf16* qkv_row = p.qkv + (int64_t)row * qkv_dim;
+    const int k0 = split * ATT_CHUNK;
+    const bool first_item = item == (int)blockIdx.x;  // profiling stamps cover the first item only
     {
       const float2* cs = reinterpret_cast<const float2*>(p.rope) + (int64_t)pos_cur * (HD / 2);
       for (int i = tid; i < (GQ + 1) * (HD / 2); i += MK_THREADS) {
@@ -385,7 +496,8 @@ __device__ void attention_items(const MegaParams& p, uint8_t* smem_raw, int laye
       }
       if (tid < HD) s_vnew[tid] = ldcg_bf16(qkv_row + (H + KVH + kvh) * HD + tid);
     }
-    __syncthreads();
+    consumer_sync();
+    if (first_item) sm.stamp();
     if (pos_cur >= k0 && pos_cur < k0 + ATT_CHUNK && tid < HD) {
       const int64_t off = ((int64_t)row * p.max_gen + g_cur) * kvd + kvh * HD + tid;
       kg[off] = __float2bfloat16_rn(s_knew[tid]);
@@ -393,10 +505,10 @@ __device__ void attention_items(const MegaParams& p, uint8_t* smem_raw, int laye
     }
     // ---- scores ----
 #pragma unroll
-    for (int it = 0; it < KPW; ++it) {
-      const int kk = (it * MK_WARPS + warp) * 4 + sub;
+    for (int it = 0; it < KPW / 4; ++it) {
+      const int kk = warp * KPW + it * 4 + sub;
       float kf[16];
-      if (kptr[it] != nullptr) {
+      if (khave[it]) {
         const uint32_t w[8] = {kreg[it][0].x, kreg[it][0].y, kreg[it][0].z, kreg[it][0].w,
                                kreg[it][1].x, kreg[it][1].y, kreg[it][1].z, kreg[it][1].w};
 #pragma unroll
@@ -409,128 +521,196 @@ __device__ void attention_items(const MegaParams& p, uint8_t* smem_raw, int laye
 #pragma unroll
         for (int j = 0; j < 16; ++j) kf[j] = s_knew[l8 * 16 + j];  // current token (or unused)
       }
+      float a[GQ];
 #pragma unroll
       for (int h = 0; h < GQ; ++h) {
-        float a = 0.f;
+        float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) a = fmaf(kf[j], s_q[h * HD + l8 * 16 + j], a);
-        a += __shfl_xor_sync(0xffffffffu, a, 1);
-        a += __shfl_xor_sync(0xffffffffu, a, 2);
-        a += __shfl_xor_sync(0xffffffffu, a, 4);
-        if (l8 == 0) s_sc[h * ATT_CHUNK + kk] = valid[it] ? a : -INFINITY;
+        for (int j = 0; j < 16; j += 2) {
+          s0 = fmaf(kf[j], s_q[h * HD + l8 * 16 + j], s0);
+          s1 = fmaf(kf[j + 1], s_q[h * HD + l8 * 16 + j + 1], s1);
+        }
+        a[h] = s0 + s1;
+      }
+#pragma unroll
+      for (int o = 1; o < 8; o <<= 1) {
+#pragma unroll
+        for (int h = 0; h < GQ; ++h) a[h] += __shfl_xor_sync(0xffffffffu, a[h], o);
+      }
+      if (l8 == 0) {
+        const bool v = kvalid[it];
+        *reinterpret_cast<float4*>(s_sc + kk * GQ) =
+            make_float4(v ? a[0] : -INFINITY, v ? a[1] : -INFINITY, v ? a[2] : -INFINITY, v ? a[3] : -INFINITY);
       }
     }
-    // V loads in flight while the softmax statistics are computed
-    uint4 vreg[KPW][2];
-#pragma unroll
-    for (int it = 0; it < KPW; ++it) {
-      if (vptr[it] != nullptr) {
-        vreg[it][0] = __ldcg(reinterpret_cast<const uint4*>(vptr[it]));
-        vreg[it][1] = __ldcg(reinterpret_cast<const uint4*>(vptr[it] + 8));
-      }
-    }
-    __syncthreads();
+    consumer_sync();
+    if (first_item) sm.stamp();
     if (warp < GQ) {
       const int h = warp;
       float m = -INFINITY;
-      for (int k = lane; k < ATT_CHUNK; k += 32) m = fmaxf(m, s_sc[h * ATT_CHUNK + k]);
+      for (int k = lane; k < ATT_CHUNK; k += 32) m = fmaxf(m, s_sc[k * GQ + h]);
       m = warp_max(m);
       float l = 0.f;
       for (int k = lane; k < ATT_CHUNK; k += 32) {
-        const float pr = (m == -INFINITY) ? 0.f : exp2f(s_sc[h * ATT_CHUNK + k] - m);
-        s_sc[h * ATT_CHUNK + k] = pr;
+        const float pr = (m == -INFINITY) ? 0.f : exp2f(s_sc[k * GQ + h] - m);
+        s_sc[k * GQ + h] = pr;
         l += pr;
       }
       l = warp_sum(l);
       if (lane == 0) { s_ml[h * 2] = m; s_ml[h * 2 + 1] = l; }
     }
-    __syncthreads();
-    // ---- P.V: two heads at a time to bound the accumulator registers ----
+    consumer_sync();
+    if (first_item) sm.stamp();
+    // ---- P.V ----
+    {
+      float acc[GQ][4];
 #pragma unroll
-    for (int hp = 0; hp < GQ; hp += 2) {
-      float acc[2][16];
+      for (int h = 0; h < GQ; ++h) acc[h][0] = acc[h][1] = acc[h][2] = acc[h][3] = 0.f;
 #pragma unroll
-      for (int j = 0; j < 16; ++j) acc[0][j] = acc[1][j] = 0.f;
-#pragma unroll
-      for (int it = 0; it < KPW; ++it) {
-        const int kk = (it * MK_WARPS + warp) * 4 + sub;
-        float vf[16];
-        if (vptr[it] != nullptr) {
-          const uint32_t w[8] = {vreg[it][0].x, vreg[it][0].y, vreg[it][0].z, vreg[it][0].w,
-                                 vreg[it][1].x, vreg[it][1].y, vreg[it][1].z, vreg[it][1].w};
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float2 f = unpack_bf16x2(w[j]);
-            vf[2 * j] = f.x;
-            vf[2 * j + 1] = f.y;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) vf[j] = bf16_round(s_vnew[l8 * 16 + j]);
+      for (int j = 0; j < KPW; ++j) {
+        const int kk = warp * KPW + j;
+        float v0, v1, v2, v3;
+        if (vmask & (1u << j)) {
+          const float2 f0 = unpack_bf16x2(vreg[j].x), f1 = unpack_bf16x2(vreg[j].y);
+          v0 = f0.x; v1 = f0.y; v2 = f1.x; v3 = f1.y;
+        } else {  // the current token (its probability is 0 for keys past the context)
+          const float4 f = *reinterpret_cast<const float4*>(s_vnew + lane * 4);
+          v0 = bf16_round(f.x); v1 = bf16_round(f.y); v2 = bf16_round(f.z); v3 = bf16_round(f.w);
         }
-        const float p0 = s_sc[hp * ATT_CHUNK + kk];
-        const float p1 = (hp + 1 < GQ) ? s_sc[(hp + 1) * ATT_CHUNK + kk] : 0.f;
+        const float4 pr = *reinterpret_cast<const float4*>(s_sc + kk * GQ);
+        const float ph[GQ] = {pr.x, pr.y, pr.z, pr.w};
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          acc[0][j] = fmaf(p0, vf[j], acc[0][j]);
-          acc[1][j] = fmaf(p1, vf[j], acc[1][j]);
+        for (int h = 0; h < GQ; ++h) {
+          acc[h][0] = fmaf(ph[h], v0, acc[h][0]);
+          acc[h][1] = fmaf(ph[h], v1, acc[h][1]);
+          acc[h][2] = fmaf(ph[h], v2, acc[h][2]);
+          acc[h][3] = fmaf(ph[h], v3, acc[h][3]);
         }
       }
 #pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        if (hp + q < GQ) {
+      for (int h = 0; h < GQ; ++h)
+        *reinterpret_cast<float4*>(s_po + (warp * GQ + h) * HD + lane * 4) =
+            make_float4(acc[h][0], acc[h][1], acc[h][2], acc[h][3]);
+    }
+    consumer_sync();
+    if (first_item) sm.stamp();
+    float* part = p.part + (((int64_t)row * KVH + kvh) * p.max_splits + split) * GQ * PSTR;
+    for (int o = tid; o < GQ * HD; o += MK_THREADS) {
+      const int hh = o / HD, dim = o % HD;
+      float s = 0.f;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float v = acc[q][j];
-            v += __shfl_xor_sync(0xffffffffu, v, 8);
-            v += __shfl_xor_sync(0xffffffffu, v, 16);
-            if (sub == 0) s_po[(warp * GQ + hp + q) * HD + l8 * 16 + j] = v;
+      for (int w = 0; w < MK_WARPS; ++w) s += s_po[(w * GQ + hh) * HD + dim];
+      part[hh * PSTR + dim] = s;
+    }
+    if (tid < GQ) {
+      part[tid * PSTR + HD] = s_ml[tid * 2];
+      part[tid * PSTR + HD + 1] = s_ml[tid * 2 + 1];
+    }
+    // ---- ticket: the CTA that completes the last split of (row, kv head) merges them ----
+    consumer_sync();
+    if (tid == 0) {
+      __threadfence();
+      const unsigned int tk = atomicAdd(p.barrier + 32 + row * KVH + kvh, 1u);
+      const int last = tk == (unsigned int)(n_splits * (layer + 1) - 1);
+      if (last) __threadfence();
+      s_flag[0] = last;
+    }
+    consumer_sync();
+    if (s_flag[0]) {
+      const float* base = p.part + (((int64_t)row * KVH + kvh) * p.max_splits) * GQ * PSTR;
+      const int64_t stride = (int64_t)GQ * PSTR;
+      for (int o = tid; o < GQ * HD; o += MK_THREADS) {
+        const int hh = o / HD, dim = o % HD;
+        const float* ph = base + hh * PSTR;
+        float mx = -INFINITY;
+        for (int s0 = 0; s0 < n_splits; s0 += MERGE_B) {
+          float mv[MERGE_B];
+#pragma unroll
+          for (int i = 0; i < MERGE_B; ++i) mv[i] = (s0 + i < n_splits) ? __ldcg(ph + (s0 + i) * stride + HD) : -INFINITY;
+#pragma unroll
+          for (int i = 0; i < MERGE_B; ++i) mx = fmaxf(mx, mv[i]);
+        }
+        float l = 0.f, acc = 0.f;
+        for (int s0 = 0; s0 < n_splits; s0 += MERGE_B) {
+          float mv[MERGE_B], lv[MERGE_B], vv[MERGE_B];
+#pragma unroll
+          for (int i = 0; i < MERGE_B; ++i) {
+            const bool in = s0 + i < n_splits;
+            mv[i] = in ? __ldcg(ph + (s0 + i) * stride + HD) : -INFINITY;
+            lv[i] = in ? __ldcg(ph + (s0 + i) * stride + HD + 1) : 0.f;
+            vv[i] = in ? __ldcg(ph + (s0 + i) * stride + dim) : 0.f;
+          }
+#pragma unroll
+          for (int i = 0; i < MERGE_B; ++i) {
+            const float w = (mv[i] == -INFINITY) ? 0.f : exp2f(mv[i] - mx);
+            l = fmaf(w, lv[i], l);
+            acc = fmaf(w, vv[i], acc);
           }
         }
+        p.attn[(int64_t)row * (H * HD) + (kvh * GQ + hh) * HD + dim] = __float2bfloat16_rn(l > 0.f ? acc / l : 0.f);
       }
     }
-    __syncthreads();
-    float* part = p.part + (((int64_t)row * KVH + kvh) * p.max_splits + split) * GQ * PSTR;
-    {
-      const int h = tid / HD, dim = tid % HD;  // 512 threads = 4 heads x 128 dims
-      for (int hh = h; hh < GQ; hh += MK_THREADS / HD) {
-        float s = 0.f;
-#pragma unroll
-        for (int w = 0; w < MK_WARPS; ++w) s += s_po[(w * GQ + hh) * HD + dim];
-        part[hh * PSTR + dim] = s;
-      }
-      if (tid < GQ) {
-        part[tid * PSTR + HD] = s_ml[tid * 2];
-        part[tid * PSTR + HD + 1] = s_ml[tid * 2 + 1];
-      }
+    if (first_item) sm.stamp();
+    if (item + (int)gridDim.x < n_items) {
+      request(item + gridDim.x);
+      consumer_sync();  // this item is done with the shared buffers
     }
   }
 }
 
 template <int MT, int GQ>
-__global__ void __launch_bounds__(MK_THREADS, 1)
+__global__ void __launch_bounds__(MK_BLOCK, 1)
 llama_decode_megakernel(const MegaParams p) {
-  extern __shared__ __align__(16) uint8_t mk_smem[];
+  extern __shared__ __align__(128) uint8_t mk_smem[];
   const pcy_llama_config& c = p.cfg;
   const int d = c.d_model, f = c.ffn_dim, H = c.n_heads, KVH = c.n_kv_heads;
   const int qkv_dim = (H + 2 * KVH) * HD;
   const int kmax = f > d ? f : d;
+  const int ns = p.ring_slots;
+  // layout: [ring: ns slots][barriers: 2 ns x 8 B, padded to 1 KB][activations | attention scratch][out][red]
+  const uint32_t ring = smem_u32(mk_smem);
+  const uint32_t bars = ring + (uint32_t)ns * SLOT_BYTES;
+  uint8_t* work = mk_smem + (size_t)ns * SLOT_BYTES + 1024;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < ns; ++i) {
+      mbar_init(bars + 8u * i, 1);         // full: the producer's arrive.expect_tx (+ the copy's bytes)
+      mbar_init(bars + 8u * (ns + i), 1);  // empty: lane 0 of the consuming warp
+    }
+    fence_barrier_init();
+  }
+  __syncthreads();  // the only CTA-wide barrier: after it the producer warp goes its own way
+
+  if (threadIdx.x >= MK_THREADS) {
+    // ===================== producer warp: every weight byte of this CTA, in phase order =====================
+    if (threadIdx.x < MK_THREADS + PL) {
+      const RingGeom rg{ns, p.ring_magic};
+      const uint64_t pol = l2_evict_first_policy();  // weights are read once per step: keep L2 for KV / activations
+      uint32_t g = 0;
+      for (int l = 0; l < c.n_layers; ++l) {
+        const LlamaLayerPtrs& y = p.layers[l];
+        produce_phase(ring, bars, rg, g, y.wqkv, d, qkv_dim, d, EPI_BF16, pol);
+        produce_phase(ring, bars, rg, g, y.wo, H * HD, d, H * HD, EPI_RESIDUAL, pol);
+        produce_phase(ring, bars, rg, g, y.wgu, d, f, d, EPI_SWIGLU, pol);
+        produce_phase(ring, bars, rg, g, y.wdown, f, d, f, EPI_RESIDUAL, pol);
+      }
+      produce_phase(ring, bars, rg, g, p.lm_head, d, c.vocab, d, EPI_FP32, pol);
+    }
+    return;
+  }
+
   Smem sm;
-  sm.a = reinterpret_cast<bf16*>(mk_smem);
-  sm.out = reinterpret_cast<float*>(mk_smem + (size_t)MT * kmax * 2);
-  sm.red = sm.out + MAX_OUT_PER_CTA * 2 * MT;
-  uint8_t* att_smem = mk_smem;  // the attention phase reuses the activation staging area
+  sm.a = reinterpret_cast<bf16*>(work);
+  sm.out = reinterpret_cast<float*>(work + (size_t)MT * kmax * 2);
+  sm.red = sm.out + (size_t)p.out_rows * MT;
+  sm.ring = ring; sm.bars = bars; sm.rg = RingGeom{ns, p.ring_magic}; sm.chunk0 = 0;
+  sm.tbuf = p.timing;
+  sm.tix = 0;
+  uint8_t* att_smem = work;  // the attention phase reuses the activation staging area
 
   GridBarrier bar{p.barrier, 0u, gridDim.x};
   const int t = p.state[0];
-  const int n_splits = (p.S + t + ATT_CHUNK - 1) / ATT_CHUNK;
-  const AttnSrc no_attn{nullptr, 0, 0, 0, 0};
-  const AttnSrc attn_src{p.part, n_splits, p.max_splits, KVH, GQ};
-  int tix = 0;
-  sm.tbuf = p.timing;
-  sm.tix = &tix;
-  auto stamp = [&]() { sm.stamp(); };
-  stamp();
+  sm.stamp();
 
   for (int l = 0; l < c.n_layers; ++l) {
     const LlamaLayerPtrs& y = p.layers[l];
@@ -548,51 +728,70 @@ llama_decode_megakernel(const MegaParams p) {
       }
       if (p.rows == 1) {  // read the row straight from the table (x is not globally visible yet)
         const int tok = p.tokens[t - 1];
-        gemv_phase<MT>(sm, y.wqkv, d, qkv_dim, d, STAGE_RMS, p.embed + (int64_t)tok * d, d, no_attn, 1, y.ln1,
-                       c.rms_eps, EPI_BF16, p.qkv, qkv_dim);
+        gemv_phase<MT>(sm, qkv_dim, d, STAGE_RMS, p.embed + (int64_t)tok * d, d, 1, y.ln1, c.rms_eps, EPI_BF16, p.qkv,
+                       qkv_dim);
       } else {
         bar.sync();
-        gemv_phase<MT>(sm, y.wqkv, d, qkv_dim, d, STAGE_RMS, p.x, d, no_attn, p.rows, y.ln1, c.rms_eps, EPI_BF16,
-                       p.qkv, qkv_dim);
+        gemv_phase<MT>(sm, qkv_dim, d, STAGE_RMS, p.x, d, p.rows, y.ln1, c.rms_eps, EPI_BF16, p.qkv, qkv_dim);
       }
     } else {
-      gemv_phase<MT>(sm, y.wqkv, d, qkv_dim, d, STAGE_RMS, p.x, d, no_attn, p.rows, y.ln1, c.rms_eps, EPI_BF16, p.qkv,
-                     qkv_dim);
+      gemv_phase<MT>(sm, qkv_dim, d, STAGE_RMS, p.x, d, p.rows, y.ln1, c.rms_eps, EPI_BF16, p.qkv, qkv_dim);
     }
-    prefetch_phase(y.wo, H * HD, d, H * HD, EPI_RESIDUAL, 0, 512);
-    stamp();
+    // ---- P2: attention (K/V requested before the barrier inside; last split of a kv head merges) ----
+    attention_phase<GQ>(p, att_smem, l, bar, sm);
+    sm.stamp();
     bar.sync();
-    stamp();
-    // ---- P2: attention partials ----
-    attention_items<GQ>(p, att_smem, l);
-    stamp();
+    sm.stamp();
+    // ---- P3: x += Wo . attn ----
+    gemv_phase<MT>(sm, d, H * HD, STAGE_PLAIN, p.attn, H * HD, p.rows, nullptr, 0.f, EPI_RESIDUAL, p.x, d);
+    sm.stamp();
     bar.sync();
-    stamp();
-    // ---- P3: x += Wo . attn (the attention partials are merged while staging) ----
-    gemv_phase<MT>(sm, y.wo, H * HD, d, H * HD, STAGE_ATTN, nullptr, 0, attn_src, p.rows, nullptr, 0.f, EPI_RESIDUAL,
-                   p.x, d);
-    stamp();
-    bar.sync();
-    stamp();
+    sm.stamp();
     // ---- P4: act = silu(Wg . rms(x)) * (Wu . rms(x)) ----
-    gemv_phase<MT>(sm, y.wgu, d, f, d, STAGE_RMS, p.x, d, no_attn, p.rows, y.ln2, c.rms_eps, EPI_SWIGLU, p.act, f);
-    stamp();
+    gemv_phase<MT>(sm, f, d, STAGE_RMS, p.x, d, p.rows, y.ln2, c.rms_eps, EPI_SWIGLU, p.act, f);
+    sm.stamp();
     bar.sync();
-    stamp();
+    sm.stamp();
     // ---- P5: x += Wdown . act ----
-    gemv_phase<MT>(sm, y.wdown, f, d, f, STAGE_PLAIN, p.act, f, no_attn, p.rows, nullptr, 0.f, EPI_RESIDUAL, p.x, d);
-    stamp();
+    gemv_phase<MT>(sm, d, f, STAGE_PLAIN, p.act, f, p.rows, nullptr, 0.f, EPI_RESIDUAL, p.x, d);
+    sm.stamp();
     bar.sync();
-    stamp();
+    sm.stamp();
   }
   // ---- logits = Wlm . rms(x) ----
-  gemv_phase<MT>(sm, p.lm_head, d, c.vocab, d, STAGE_RMS, p.x, d, no_attn, p.rows, p.norm, c.rms_eps, EPI_FP32,
-                 p.logits, c.vocab);
-  __syncthreads();
-  stamp();
+  gemv_phase<MT>(sm, c.vocab, d, STAGE_RMS, p.x, d, p.rows, p.norm, c.rms_eps, EPI_FP32, p.logits, c.vocab);
+  consumer_sync();
+  sm.stamp();
 }
 
 unsigned long long* g_timing = nullptr;
+
+constexpr size_t SMEM_LIMIT = 227 * 1024;
+
+// rows of the widest per-CTA slice (SwiGLU phases hold a gate and an up row per output)
+int out_rows_for(const pcy_llama_config& c) {
+  const int sms = num_sms();
+  const int qkv = (c.n_heads + 2 * c.n_kv_heads) * HD;
+  int r = ceil_div(c.vocab, sms) + 1;
+  r = std::max(r, 2 * (ceil_div(c.ffn_dim, sms) + 1));
+  r = std::max(r, ceil_div(qkv, sms) + 1);
+  r = std::max(r, ceil_div(c.d_model, sms) + 1);
+  return (int)round_up(r, 64);
+}
+// bytes of the non-ring part of shared memory: barriers + max(gemv staging, attention scratch)
+size_t work_smem_bytes(const pcy_llama_config& c, int mt) {
+  const int kmax = std::max(std::max(c.ffn_dim, c.d_model), c.n_heads * HD);
+  const size_t smem_gemv = (size_t)mt * kmax * 2 + (size_t)out_rows_for(c) * mt * 4 + MK_WARPS * 4 * 4;
+  const size_t smem_att = (size_t)(4 * HD + 2 * HD + 4 * ATT_CHUNK + 8 + 4 + MK_WARPS * 4 * HD) * 4 + 64;
+  return 1024 + (smem_gemv > smem_att ? smem_gemv : smem_att);
+}
+// slots: a multiple of 12 (slot s is owned by consumer warp s % 12), at most 60 (2 x 60 barriers fit the 1 KB block)
+int ring_slots_for(const pcy_llama_config& c, int mt) {
+  const size_t w = work_smem_bytes(c, mt);
+  if (w + MK_WARPS * SLOT_BYTES > SMEM_LIMIT) return 0;
+  const int ns = (int)((SMEM_LIMIT - w) / SLOT_BYTES) / MK_WARPS * MK_WARPS;
+  return ns > 60 ? 60 : ns;
+}
 
 }  // namespace
 
@@ -601,7 +800,8 @@ void decode_megakernel_set_timing(unsigned long long* dev_buf) { g_timing = dev_
 int64_t decode_megakernel_scratch_bytes(const pcy_llama_config& c, int rows, int S, int max_gen) {
   const int64_t d = c.d_model, qkv = (int64_t)(c.n_heads + 2 * c.n_kv_heads) * HD;
   const int max_splits = ceil_div(S + max_gen, ATT_CHUNK);
-  int64_t b = round_up(rows * d * 2, 256) * 2 + round_up(rows * qkv * 2, 256) + round_up((int64_t)rows * c.ffn_dim * 2, 256);
+  int64_t b = 512 + round_up(rows * d * 2, 256) * 2 + round_up(rows * qkv * 2, 256) +
+              round_up((int64_t)rows * c.n_heads * HD * 2, 256) + round_up((int64_t)rows * c.ffn_dim * 2, 256);
   b += round_up((int64_t)rows * c.n_kv_heads * max_splits * (c.n_heads / c.n_kv_heads) * PSTR * 4, 256);
   b += 1024;
   return b;
@@ -611,10 +811,9 @@ bool decode_megakernel_supported(const pcy_llama_config& c, int rows) {
   const int gq = c.n_heads / c.n_kv_heads;
   if (rows < 1 || rows > 4 || c.head_dim != HD || gq != 4) return false;
   if (c.d_model % 256 != 0 || c.ffn_dim % 256 != 0) return false;
-  const int sms = num_sms();
-  // every CTA's slice of the widest phase must fit the shared-memory partial-sum buffer
-  if (ceil_div(c.vocab, sms) + 1 > MAX_OUT_PER_CTA || ceil_div(c.ffn_dim, sms) + 1 > MAX_OUT_PER_CTA) return false;
-  return true;
+  if (rows * c.n_kv_heads > 96) return false;  // attention ticket counters live in the 512-byte barrier block
+  const int mt = rows <= 1 ? 1 : rows <= 2 ? 2 : 4;
+  return ring_slots_for(c, mt) >= MK_WARPS;
 }
 
 int decode_megakernel(const pcy_llama_config& c, const LlamaLayerPtrs* layers_dev, const bf16* embed,
@@ -631,11 +830,11 @@ int decode_megakernel(const pcy_llama_config& c, const LlamaLayerPtrs* layers_de
   const int64_t d = c.d_model, qkv = (int64_t)(c.n_heads + 2 * c.n_kv_heads) * HD;
   uint8_t* s = reinterpret_cast<uint8_t*>(round_up(reinterpret_cast<int64_t>(scratch), 256));
   auto carve = [&](int64_t bytes) { uint8_t* r = s; s += round_up(bytes, 256); return r; };
-  p.barrier = reinterpret_cast<unsigned int*>(carve(256));
-  carve(256);
+  p.barrier = reinterpret_cast<unsigned int*>(carve(512));
   p.x = reinterpret_cast<bf16*>(carve(rows * d * 2));
   carve(rows * d * 2);
   p.qkv = reinterpret_cast<bf16*>(carve(rows * qkv * 2));
+  p.attn = reinterpret_cast<bf16*>(carve((int64_t)rows * c.n_heads * HD * 2));
   p.act = reinterpret_cast<bf16*>(carve((int64_t)rows * c.ffn_dim * 2));
   p.max_splits = ceil_div(b->S + b->max_gen, ATT_CHUNK);
   p.part = reinterpret_cast<float*>(s);
@@ -643,11 +842,11 @@ int decode_megakernel(const pcy_llama_config& c, const LlamaLayerPtrs* layers_de
   PCY_CUDA(cudaMemsetAsync(p.barrier, 0, 512, stream));  // barrier counter + tickets
 
   const int mt = rows <= 1 ? 1 : rows <= 2 ? 2 : 4;
-  const int kmax = c.ffn_dim > c.d_model ? c.ffn_dim : c.d_model;
-  const size_t smem_gemv = (size_t)mt * kmax * 2 + (size_t)MAX_OUT_PER_CTA * 2 * mt * 4 + MK_WARPS * 4 * 4;
-  const size_t smem_att = (size_t)(4 * HD + 2 * HD + 4 * ATT_CHUNK + 8 + MK_WARPS * 4 * HD) * 4 + 64;
-  const size_t smem = smem_gemv > smem_att ? smem_gemv : smem_att;
-  PCY_REQUIRE(smem <= 220 * 1024, "decode megakernel: needs %zu bytes of shared memory", smem);
+  p.ring_slots = ring_slots_for(c, mt);
+  p.out_rows = out_rows_for(c);
+  p.ring_magic = (uint32_t)(((1ull << 32) + p.ring_slots - 1) / p.ring_slots);
+  const size_t smem = (size_t)p.ring_slots * SLOT_BYTES + work_smem_bytes(c, mt);
+  PCY_REQUIRE(smem <= SMEM_LIMIT, "decode megakernel: needs %zu bytes of shared memory", smem);
   void* fn = nullptr;
   if (mt == 1) fn = (void*)llama_decode_megakernel<1, 4>;
   else if (mt == 2) fn = (void*)llama_decode_megakernel<2, 4>;
@@ -660,7 +859,7 @@ int decode_megakernel(const pcy_llama_config& c, const LlamaLayerPtrs* layers_de
   }
   void* args[] = {(void*)&p};
   // cooperative launch: guarantees that all CTAs are co-resident (the grid barrier needs it)
-  PCY_CUDA(cudaLaunchCooperativeKernel(fn, dim3(num_sms()), dim3(MK_THREADS), args, smem, stream));
+  PCY_CUDA(cudaLaunchCooperativeKernel(fn, dim3(num_sms()), dim3(MK_BLOCK), args, smem, stream));
   count_launch();
   return 0;
 }

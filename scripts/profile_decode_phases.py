@@ -22,8 +22,9 @@ def main():
     sess.reset(logits)
     sess.select(SELECT_GREEDY, 1, 0.0, -1, False)
     L = te.model.config.num_hidden_layers
-    # stamps per layer: P1 [stage, stream, epi, bar], P2 [work, bar], P3 [4], P4 [4], P5 [4] = 18; + lm head [stage, stream, end]
-    per_layer = 18
+    # stamps per layer: P1 [stage, stream, epi+kv request, bar], P2 [q/rope, scores, softmax, pv, partials+merge, tail,
+    # bar], P3 [4], P4 [4], P5 [4] = 23; + lm head [stage, stream, end]
+    per_layer = 23
     n_stamps = 1 + per_layer * L + 3
     buf = torch.zeros(n_stamps + 8, device=dev, dtype=torch.int64)
     lib = _lib.load()
@@ -42,9 +43,10 @@ def main():
     lib.pcy_set_decode_timing_buffer(ctypes.c_void_p(0))
     acc /= n * 1e3  # us
     per = acc[: per_layer * L].view(L, per_layer)[1:].mean(0)  # skip layer 0 (different P1)
-    names = ["P1 stage", "P1 stream", "P1 epilogue", "P1 barrier", "P2 attention work", "P2 barrier", "P3 stage(+merge)",
-             "P3 stream", "P3 epilogue", "P3 barrier", "P4 stage", "P4 stream", "P4 epilogue", "P4 barrier", "P5 stage",
-             "P5 stream", "P5 epilogue", "P5 barrier"]
+    names = ["P1 stage", "P1 stream", "P1 epilogue+kv request", "P1 barrier", "P2 q load + rope", "P2 scores", "P2 softmax",
+             "P2 p.v", "P2 partials + ticket merge", "P2 tail", "P2 barrier", "P3 stage", "P3 stream", "P3 epilogue",
+             "P3 barrier", "P4 stage", "P4 stream", "P4 epilogue", "P4 barrier", "P5 stage", "P5 stream", "P5 epilogue",
+             "P5 barrier"]
     for nm, v in zip(names, per.tolist()):
         print(f"{nm:22s} {v:8.2f} us")
     print(f"layer total            {per.sum():8.2f} us   (ideal streaming 66.7 us)")

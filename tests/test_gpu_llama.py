@@ -11,9 +11,11 @@ def _cfgs(kind="gq2"):
 
     # gq2: 4 query / 2 kv heads -> one-launch-per-op decode path; gq4: 8 / 2 heads (Llama-3's ratio) -> rows <= 4 take
     # the persistent decode kernel
-    H, d = (4, 512) if kind == "gq2" else (8, 1024)
-    oc = LlamaCfg(d_model=d, n_layers=2, n_heads=H, n_kv_heads=2, ffn_dim=1024, vocab=1003, max_pos=512)
-    pc = LlamaConfig(hidden_size=d, intermediate_size=1024, num_hidden_layers=2, num_attention_heads=H,
+    # gq4wide: ffn 8448 = 2 full 4096-element weight chunks + a 256-element tail per w_down row (multi-chunk rows of
+    # the persistent kernel's weight ring)
+    H, d, f = {"gq2": (4, 512, 1024), "gq4": (8, 1024, 1024), "gq4wide": (8, 1024, 8448)}[kind]
+    oc = LlamaCfg(d_model=d, n_layers=2, n_heads=H, n_kv_heads=2, ffn_dim=f, vocab=1003, max_pos=512)
+    pc = LlamaConfig(hidden_size=d, intermediate_size=f, num_hidden_layers=2, num_attention_heads=H,
                      num_key_value_heads=2, vocab_size=1003, max_position_embeddings=512)
     return oc, pc
 
@@ -156,16 +158,17 @@ def test_beam_search_stops_on_eos(llama):
         torch.testing.assert_close(lp2, rlp, rtol=1e-2, atol=6e-2)
 
 
-def test_persistent_and_per_op_decode_agree(cuda_device):
+@pytest.mark.parametrize("kind,rows", [("gq4", 3), ("gq4wide", 1), ("gq4wide", 2), ("gq4wide", 4)])
+def test_persistent_and_per_op_decode_agree(cuda_device, kind, rows):
     """The single-launch decode step and the one-launch-per-op path implement the same math."""
     from oracle.llama import random_llama_state_dict
     from procyon_b200 import _lib
     from procyon_b200.model.generation import generate_greedy
 
-    oc, pc = _cfgs("gq4")
+    oc, pc = _cfgs(kind)
     sd = random_llama_state_dict(oc, seed=3)
     m = _build(sd, pc)
-    ids, emb, mask = _inputs(oc, sd, 3, 50, seed=7, pad_left=4)
+    ids, emb, mask = _inputs(oc, sd, rows, 50, seed=7, pad_left=4)
     lib = _lib.load()
     try:
         lib.pcy_set_decode_megakernel(1)
