@@ -36,9 +36,13 @@ constexpr int ATT_CHUNK = KPW * MK_WARPS;    // 96 keys per attention work item
 constexpr int PSTR = HD + 4;    // floats per (split, head) attention partial: 128 outputs, max, sum (16-byte rows)
 constexpr int MERGE_B = 12;     // splits merged per batch of independent loads
 
-__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
+// The poll is a relaxed load and no fence follows it: an acquire load / __threadfence() compiles to ... + CCTL.IVALL,
+// which flushes the SM's whole L1 including the local-memory lines (parameters, spills) every warp keeps there, and
+// every phase would then start with a chain of L2 round trips.  Nothing needs the invalidation: data written by
+// other CTAs is only ever read with ld.cg (L2), after the CTA barrier that follows the poll.
+__device__ __forceinline__ unsigned int ld_relaxed_u32(const unsigned int* p) {
   unsigned int v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
 __device__ __forceinline__ void red_release_add(unsigned int* p, unsigned int v) {
@@ -69,8 +73,8 @@ __device__ __forceinline__ float ldcg_bf16(const bf16* p) {
 }
 
 // Grid-wide barrier over the consumer threads of all CTAs (cooperative launch: all CTAs are resident).
-// Thread 0 publishes the CTA's writes with a release reduction (cumulative over the CTA barrier before it) and
-// acquires everybody else's; the second CTA barrier hands that view to the other threads, which read remote data
+// Thread 0 publishes the CTA's writes with a release reduction (cumulative over the CTA barrier before it) and polls
+// until everybody has arrived; the second CTA barrier hands that view to the other threads, which read remote data
 // through L2 (ld.cg) only.
 struct GridBarrier {
   unsigned int* counter;
@@ -82,7 +86,7 @@ struct GridBarrier {
       target += nblocks;
       red_release_add(counter, 1u);
       uint64_t t0 = 0;
-      for (uint32_t it = 0; ld_acquire_u32(counter) < target; ++it) {
+      for (uint32_t it = 0; ld_relaxed_u32(counter) < target; ++it) {
         if ((it & 0x3fffu) == 0x3fffu) {  // bounded: a scheduling bug must trap, not hang the GPU
           const uint64_t now = globaltimer_ns();
           if (t0 == 0) t0 = now;
@@ -157,8 +161,13 @@ constexpr int PL = 8;  // producer lanes: chunks g .. g+7 are issued side by sid
 // address arithmetic ~0.25 us per chunk), so PL lanes of the producer warp each take every PL-th chunk.  The lanes
 // stay converged: nobody issues before every lane's slot is free.  (Chunk g reuses the slot of chunk g - ns, issued in
 // an earlier iteration because ns > PL, so no lane ever waits on a lane of its own iteration.)
-__device__ __noinline__ void produce_phase(uint32_t ring, uint32_t bars, RingGeom rg, uint32_t& g, const bf16* W,
-                                           int64_t ldw, int n_out, int K, int epi, uint64_t pol) {
+//
+// `window` bounds the copies IN FLIGHT: chunk g is not issued before chunk g - window has landed.  Consumers drain
+// slots faster than HBM fills them, so without the bound every slot of every SM would sit in the DRAM queues (28 MB,
+// ~4 us) and the latency-critical DRAM reads of the attention phase (K / V rows) would wait behind them.  The rest
+// of the ring fills up only while the consumers are stalled, which is what it is for.
+__device__ __noinline__ void produce_phase(uint32_t ring, uint32_t bars, RingGeom rg, uint32_t& g, int window,
+                                           const bf16* W, int64_t ldw, int n_out, int K, int epi, uint64_t pol) {
   int lo, hi;
   cta_range(n_out, lo, hi);
   const int rpo = (epi == EPI_SWIGLU) ? 2 : 1;
@@ -170,19 +179,25 @@ __device__ __noinline__ void produce_phase(uint32_t ring, uint32_t bars, RingGeo
   for (int c0 = 0; c0 < n_chunks; c0 += PL) {
     const int c = c0 + lane;
     const bool active = c < n_chunks;
-    uint32_t slot = 0, par = 0, bytes = 0;
+    uint32_t slot = 0, par = 0, bytes = 0, wslot = 0, wpar = 0;
     const bf16* src = W;
+    bool ok = !active, landed = true;
     if (active) {
       const int r = c / cpr, kc = c - r * cpr;
-      rg.locate(g + (uint32_t)c, slot, par);
+      const uint32_t gc = g + (uint32_t)c;
+      rg.locate(gc, slot, par);
       src = W + (int64_t)weight_row(epi, lo, r) * ldw + kc * CH;
       bytes = (uint32_t)min(CH, K - kc * CH) * 2u;
+      if (gc >= (uint32_t)window) {
+        rg.locate(gc - (uint32_t)window, wslot, wpar);
+        landed = false;
+      }
     }
-    bool ok = !active;
     uint64_t t0 = 0;
     for (uint32_t it = 0;; ++it) {
-      if (!ok) ok = mbar_try_wait(bars + 8u * (rg.ns + slot), par ^ 1u);  // slot drained by its consumer warp
-      if (__all_sync(LANES, ok)) break;
+      if (!landed) landed = mbar_try_wait(bars + 8u * wslot, wpar);               // chunk g - window has arrived
+      if (!ok) ok = mbar_try_wait(bars + 8u * (rg.ns + slot), par ^ 1u);          // slot drained by its consumer warp
+      if (__all_sync(LANES, ok && landed)) break;
       if ((it & 0xfffu) == 0xfffu) {  // bounded: a pipeline bug must trap, not hang the GPU
         const uint64_t now = globaltimer_ns();
         if (t0 == 0) t0 = now;
@@ -221,16 +236,31 @@ __device__ __noinline__ void gemv_phase(Smem& sm, int n_out, int K, int stage, c
     }
     const bf16* src = A + (int64_t)m * lda;
     if (stage == STAGE_PLAIN) {
-      for (int k = tid * 8; k < K; k += MK_THREADS * 8)
-        *reinterpret_cast<uint4*>(dst + k) = __ldcg(reinterpret_cast<const uint4*>(src + k));
+      // all loads of a batch are issued before the first store (one L2 round trip per batch, not per piece)
+      constexpr int PB = 5;
+      for (int k0 = tid * 8; k0 < K; k0 += MK_THREADS * 8 * PB) {
+        uint4 u[PB];
+#pragma unroll
+        for (int i = 0; i < PB; ++i) {
+          const int k = k0 + i * MK_THREADS * 8;
+          if (k < K) u[i] = __ldcg(reinterpret_cast<const uint4*>(src + k));
+        }
+#pragma unroll
+        for (int i = 0; i < PB; ++i) {
+          const int k = k0 + i * MK_THREADS * 8;
+          if (k < K) *reinterpret_cast<uint4*>(dst + k) = u[i];
+        }
+      }
       continue;
     }
-    uint4 held[HOLD];
+    uint4 held[HOLD], held_w[HOLD];
     float ss = 0.f;
 #pragma unroll
     for (int i = 0; i < HOLD; ++i) {
       const int k = (tid + i * MK_THREADS) * 8;
-      held[i] = (rms_in_regs && k < K) ? __ldcg(reinterpret_cast<const uint4*>(src + k)) : make_uint4(0, 0, 0, 0);
+      const bool in = rms_in_regs && k < K;
+      held[i] = in ? __ldcg(reinterpret_cast<const uint4*>(src + k)) : make_uint4(0, 0, 0, 0);
+      held_w[i] = in ? *reinterpret_cast<const uint4*>(rms_w + k) : make_uint4(0, 0, 0, 0);  // off the critical path
     }
     if (rms_in_regs) {
 #pragma unroll
@@ -254,8 +284,7 @@ __device__ __noinline__ void gemv_phase(Smem& sm, int n_out, int K, int stage, c
     for (int w = 0; w < MK_WARPS; ++w) tot += sm.red[w];
     const float rstd = rsqrtf(tot / (float)K + eps);
     consumer_sync();
-    auto normalise = [&](const uint4& u, int k) {
-      const uint4 g = *reinterpret_cast<const uint4*>(rms_w + k);
+    auto normalise = [&](const uint4& u, const uint4& g, int k) {
       const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
       const uint32_t gg[4] = {g.x, g.y, g.z, g.w};
       uint32_t oo[4];
@@ -271,10 +300,11 @@ __device__ __noinline__ void gemv_phase(Smem& sm, int n_out, int K, int stage, c
 #pragma unroll
       for (int i = 0; i < HOLD; ++i) {
         const int k = (tid + i * MK_THREADS) * 8;
-        if (k < K) normalise(held[i], k);
+        if (k < K) normalise(held[i], held_w[i], k);
       }
     } else {
-      for (int k = tid * 8; k < K; k += MK_THREADS * 8) normalise(__ldcg(reinterpret_cast<const uint4*>(src + k)), k);
+      for (int k = tid * 8; k < K; k += MK_THREADS * 8)
+        normalise(__ldcg(reinterpret_cast<const uint4*>(src + k)), *reinterpret_cast<const uint4*>(rms_w + k), k);
     }
   }
   if (cpr > 1)
@@ -381,10 +411,55 @@ struct MegaParams {
   int max_splits;
   int ring_slots;
   int out_rows;         // capacity (rows) of the per-CTA partial-sum buffer
+  int layers_off;       // byte offset of the shared-memory copy of the layer pointer table
+  int window;           // bulk copies in flight per SM (chunks)
   uint32_t ring_magic;  // ceil(2^32 / ring_slots)
   unsigned int* barrier;  // [0] grid barrier counter, [32 + row * KVH + kvh] attention tickets
   unsigned long long* timing;  // optional: globaltimer at every phase boundary (CTA 0), for profiling
 };
+
+// Merge of the split-KV partials of one (row, kv head): out[h][dim] = sum_s w_s acc_s / sum_s w_s l_s, w_s = 2^(m_s - max).
+// All loads of a batch of MERGE_B splits are independent (one L2 round trip per batch).
+template <int GQ>
+__device__ __noinline__ void merge_splits(const float* base, int n_splits, bf16* out) {
+  const int64_t stride = (int64_t)GQ * PSTR;
+  for (int o = threadIdx.x; o < GQ * HD; o += MK_THREADS) {
+    const int hh = o / HD, dim = o % HD;
+    const float* ph = base + hh * PSTR;
+    float mx = -INFINITY;
+    if (n_splits > MERGE_B) {  // otherwise the one batch below carries its own maxima
+      for (int s0 = 0; s0 < n_splits; s0 += MERGE_B) {
+        float mv[MERGE_B];
+#pragma unroll
+        for (int i = 0; i < MERGE_B; ++i) mv[i] = (s0 + i < n_splits) ? __ldcg(ph + (s0 + i) * stride + HD) : -INFINITY;
+#pragma unroll
+        for (int i = 0; i < MERGE_B; ++i) mx = fmaxf(mx, mv[i]);
+      }
+    }
+    float l = 0.f, acc = 0.f;
+    for (int s0 = 0; s0 < n_splits; s0 += MERGE_B) {
+      float mv[MERGE_B], lv[MERGE_B], vv[MERGE_B];
+#pragma unroll
+      for (int i = 0; i < MERGE_B; ++i) {
+        const bool in = s0 + i < n_splits;
+        mv[i] = in ? __ldcg(ph + (s0 + i) * stride + HD) : -INFINITY;
+        lv[i] = in ? __ldcg(ph + (s0 + i) * stride + HD + 1) : 0.f;
+        vv[i] = in ? __ldcg(ph + (s0 + i) * stride + dim) : 0.f;
+      }
+      if (n_splits <= MERGE_B) {
+#pragma unroll
+        for (int i = 0; i < MERGE_B; ++i) mx = fmaxf(mx, mv[i]);
+      }
+#pragma unroll
+      for (int i = 0; i < MERGE_B; ++i) {
+        const float w = (mv[i] == -INFINITY) ? 0.f : exp2f(mv[i] - mx);
+        l = fmaf(w, lv[i], l);
+        acc = fmaf(w, vv[i], acc);
+      }
+    }
+    out[hh * HD + dim] = __float2bfloat16_rn(l > 0.f ? acc / l : 0.f);
+  }
+}
 
 // P2: one work item = (row, kv head, split of ATT_CHUNK keys); warp w owns keys 8w .. 8w+7 of the split.
 //   scores : lane (sub, l8) dots 16 dims of key 8w + 4 it + sub with the 4 query heads, 3 shuffles finish the dot
@@ -395,9 +470,10 @@ struct MegaParams {
 // split of a (row, kv head) merges the partials (ticket counter) and writes the bf16 attention output, so that the
 // o_proj phase stages 8 KB per row instead of every CTA re-reading every partial.
 template <int GQ>
-__device__ __noinline__ void attention_phase(const MegaParams& p, uint8_t* smem_raw, int layer, GridBarrier& bar,
-                                             Smem& sm) {
+__device__ __noinline__ void attention_phase(const MegaParams& p, uint8_t* smem_raw, int layer, int t,
+                                             GridBarrier& bar, Smem& sm) {
   static_assert(GQ == 4, "the P.V loop reads the 4 head probabilities of a key as one float4");
+  sm.stamp();
   float* s_q = reinterpret_cast<float*>(smem_raw);  // [GQ][HD], pre-scaled by log2(e) / sqrt(HD)
   float* s_knew = s_q + GQ * HD;                    // [HD]
   float* s_vnew = s_knew + HD;                      // [HD]
@@ -408,7 +484,6 @@ __device__ __noinline__ void attention_phase(const MegaParams& p, uint8_t* smem_
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int H = p.cfg.n_heads, KVH = p.cfg.n_kv_heads;
   const int kvd = KVH * HD, qkv_dim = (H + 2 * KVH) * HD;
-  const int t = p.state[0];
   const int g_cur = t - 1, pos_cur = p.S + g_cur, ctx = pos_cur + 1;
   const int n_splits = (ctx + ATT_CHUNK - 1) / ATT_CHUNK;
   const int n_items = p.rows * KVH * n_splits;
@@ -453,31 +528,46 @@ __device__ __noinline__ void attention_phase(const MegaParams& p, uint8_t* smem_
       }
     }
     vmask = 0;
+    const int pos0 = k0 + warp * KPW;
+    if (pos0 + KPW <= p.S) {
+      // the warp's 8 keys are all prompt positions (the common case): one base pointer, constant stride
+      const bf16* vb = vp + ((int64_t)input * p.S + pos0) * kvd + kvh * HD + lane * 4;
 #pragma unroll
-    for (int j = 0; j < KPW; ++j) {
-      const int kk = warp * KPW + j;
-      const int pos = k0 + kk;
-      vreg[j] = make_uint2(0, 0);
-      if (kk < n_keys && pos != pos_cur) {
-        bool in_prompt;
-        const int64_t off = row_off(row, input, kvh, pos, in_prompt) + lane * 4;
-        vreg[j] = __ldcg(reinterpret_cast<const uint2*>((in_prompt ? vp : vg) + off));
-        vmask |= 1u << j;
+      for (int j = 0; j < KPW; ++j) vreg[j] = __ldcg(reinterpret_cast<const uint2*>(vb + (int64_t)j * kvd));
+      vmask = (1u << KPW) - 1u;
+    } else {
+#pragma unroll
+      for (int j = 0; j < KPW; ++j) {
+        const int kk = warp * KPW + j;
+        const int pos = k0 + kk;
+        vreg[j] = make_uint2(0, 0);
+        if (kk < n_keys && pos != pos_cur) {
+          bool in_prompt;
+          const int64_t off = row_off(row, input, kvh, pos, in_prompt) + lane * 4;
+          vreg[j] = __ldcg(reinterpret_cast<const uint2*>((in_prompt ? vp : vg) + off));
+          vmask |= 1u << j;
+        }
       }
     }
   };
 
-  int item = blockIdx.x;
-  if (item < n_items) request(item);
-  sm.stamp();
-  bar.sync();  // qkv of this step is complete
-  sm.stamp();
-
-  for (; item < n_items; item += gridDim.x) {
+  // (one call site for request(): inlined, so that the loaded rows stay in registers)
+  for (int item = blockIdx.x;; item += gridDim.x) {
+    const bool first_item = item == (int)blockIdx.x;  // profiling stamps cover the first item only
+    if (!first_item) {  // (only with rows > 1 or very long contexts: more items than CTAs)
+      if (item >= n_items) break;
+      consumer_sync();  // the previous item is done with the shared buffers
+    }
+    if (item < n_items) request(item);
+    if (first_item) {
+      sm.stamp();
+      bar.sync();  // qkv of this step is complete
+      sm.stamp();
+      if (item >= n_items) break;
+    }
     const int split = item % n_splits, kvh = (item / n_splits) % KVH, row = item / (n_splits * KVH);
     const bf16* qkv_row = p.qkv + (int64_t)row * qkv_dim;
     const int k0 = split * ATT_CHUNK;
-    const bool first_item = item == (int)blockIdx.x;  // profiling stamps cover the first item only
     {
       const float2* cs = reinterpret_cast<const float2*>(p.rope) + (int64_t)pos_cur * (HD / 2);
       for (int i = tid; i < (GQ + 1) * (HD / 2); i += MK_THREADS) {
@@ -521,26 +611,24 @@ __device__ __noinline__ void attention_phase(const MegaParams& p, uint8_t* smem_
 #pragma unroll
         for (int j = 0; j < 16; ++j) kf[j] = s_knew[l8 * 16 + j];  // current token (or unused)
       }
-      float a[GQ];
-#pragma unroll
+      // one head at a time (not unrolled: 64 query values in flight would push the K / V rows out of registers)
+#pragma unroll 1
       for (int h = 0; h < GQ; ++h) {
+        const float4* q4 = reinterpret_cast<const float4*>(s_q + h * HD + l8 * 16);
         float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-        for (int j = 0; j < 16; j += 2) {
-          s0 = fmaf(kf[j], s_q[h * HD + l8 * 16 + j], s0);
-          s1 = fmaf(kf[j + 1], s_q[h * HD + l8 * 16 + j + 1], s1);
+        for (int j = 0; j < 4; ++j) {
+          const float4 q = q4[j];
+          s0 = fmaf(kf[4 * j], q.x, s0);
+          s1 = fmaf(kf[4 * j + 1], q.y, s1);
+          s0 = fmaf(kf[4 * j + 2], q.z, s0);
+          s1 = fmaf(kf[4 * j + 3], q.w, s1);
         }
-        a[h] = s0 + s1;
-      }
-#pragma unroll
-      for (int o = 1; o < 8; o <<= 1) {
-#pragma unroll
-        for (int h = 0; h < GQ; ++h) a[h] += __shfl_xor_sync(0xffffffffu, a[h], o);
-      }
-      if (l8 == 0) {
-        const bool v = kvalid[it];
-        *reinterpret_cast<float4*>(s_sc + kk * GQ) =
-            make_float4(v ? a[0] : -INFINITY, v ? a[1] : -INFINITY, v ? a[2] : -INFINITY, v ? a[3] : -INFINITY);
+        float a = s0 + s1;
+        a += __shfl_xor_sync(0xffffffffu, a, 1);
+        a += __shfl_xor_sync(0xffffffffu, a, 2);
+        a += __shfl_xor_sync(0xffffffffu, a, 4);
+        if (l8 == 0) s_sc[kk * GQ + h] = kvalid[it] ? a : -INFINITY;
       }
     }
     consumer_sync();
@@ -609,52 +697,16 @@ __device__ __noinline__ void attention_phase(const MegaParams& p, uint8_t* smem_
     // ---- ticket: the CTA that completes the last split of (row, kv head) merges them ----
     consumer_sync();
     if (tid == 0) {
-      __threadfence();
-      const unsigned int tk = atomicAdd(p.barrier + 32 + row * KVH + kvh, 1u);
-      const int last = tk == (unsigned int)(n_splits * (layer + 1) - 1);
-      if (last) __threadfence();
-      s_flag[0] = last;
+      unsigned int tk;  // release: the CTA's partials are visible before the ticket is; partials are read with ld.cg
+      asm volatile("atom.release.gpu.global.add.u32 %0, [%1], 1;"
+                   : "=r"(tk) : "l"(p.barrier + 32 + row * KVH + kvh) : "memory");
+      s_flag[0] = tk == (unsigned int)(n_splits * (layer + 1) - 1);
     }
     consumer_sync();
-    if (s_flag[0]) {
-      const float* base = p.part + (((int64_t)row * KVH + kvh) * p.max_splits) * GQ * PSTR;
-      const int64_t stride = (int64_t)GQ * PSTR;
-      for (int o = tid; o < GQ * HD; o += MK_THREADS) {
-        const int hh = o / HD, dim = o % HD;
-        const float* ph = base + hh * PSTR;
-        float mx = -INFINITY;
-        for (int s0 = 0; s0 < n_splits; s0 += MERGE_B) {
-          float mv[MERGE_B];
-#pragma unroll
-          for (int i = 0; i < MERGE_B; ++i) mv[i] = (s0 + i < n_splits) ? __ldcg(ph + (s0 + i) * stride + HD) : -INFINITY;
-#pragma unroll
-          for (int i = 0; i < MERGE_B; ++i) mx = fmaxf(mx, mv[i]);
-        }
-        float l = 0.f, acc = 0.f;
-        for (int s0 = 0; s0 < n_splits; s0 += MERGE_B) {
-          float mv[MERGE_B], lv[MERGE_B], vv[MERGE_B];
-#pragma unroll
-          for (int i = 0; i < MERGE_B; ++i) {
-            const bool in = s0 + i < n_splits;
-            mv[i] = in ? __ldcg(ph + (s0 + i) * stride + HD) : -INFINITY;
-            lv[i] = in ? __ldcg(ph + (s0 + i) * stride + HD + 1) : 0.f;
-            vv[i] = in ? __ldcg(ph + (s0 + i) * stride + dim) : 0.f;
-          }
-#pragma unroll
-          for (int i = 0; i < MERGE_B; ++i) {
-            const float w = (mv[i] == -INFINITY) ? 0.f : exp2f(mv[i] - mx);
-            l = fmaf(w, lv[i], l);
-            acc = fmaf(w, vv[i], acc);
-          }
-        }
-        p.attn[(int64_t)row * (H * HD) + (kvh * GQ + hh) * HD + dim] = __float2bfloat16_rn(l > 0.f ? acc / l : 0.f);
-      }
-    }
+    if (s_flag[0])
+      merge_splits<GQ>(p.part + (((int64_t)row * KVH + kvh) * p.max_splits) * GQ * PSTR, n_splits,
+                       p.attn + (int64_t)row * (H * HD) + kvh * GQ * HD);
     if (first_item) sm.stamp();
-    if (item + (int)gridDim.x < n_items) {
-      request(item + gridDim.x);
-      consumer_sync();  // this item is done with the shared buffers
-    }
   }
 }
 
@@ -671,6 +723,10 @@ llama_decode_megakernel(const MegaParams p) {
   const uint32_t ring = smem_u32(mk_smem);
   const uint32_t bars = ring + (uint32_t)ns * SLOT_BYTES;
   uint8_t* work = mk_smem + (size_t)ns * SLOT_BYTES + 1024;
+  // the per-layer weight pointers, copied once so that no phase starts with a dependent global load
+  LlamaLayerPtrs* s_layers = reinterpret_cast<LlamaLayerPtrs*>(mk_smem + p.layers_off);
+  for (int i = threadIdx.x; i < c.n_layers * (int)(sizeof(LlamaLayerPtrs) / 8); i += MK_BLOCK)
+    reinterpret_cast<uint64_t*>(s_layers)[i] = reinterpret_cast<const uint64_t*>(p.layers)[i];
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < ns; ++i) {
@@ -688,13 +744,13 @@ llama_decode_megakernel(const MegaParams p) {
       const uint64_t pol = l2_evict_first_policy();  // weights are read once per step: keep L2 for KV / activations
       uint32_t g = 0;
       for (int l = 0; l < c.n_layers; ++l) {
-        const LlamaLayerPtrs& y = p.layers[l];
-        produce_phase(ring, bars, rg, g, y.wqkv, d, qkv_dim, d, EPI_BF16, pol);
-        produce_phase(ring, bars, rg, g, y.wo, H * HD, d, H * HD, EPI_RESIDUAL, pol);
-        produce_phase(ring, bars, rg, g, y.wgu, d, f, d, EPI_SWIGLU, pol);
-        produce_phase(ring, bars, rg, g, y.wdown, f, d, f, EPI_RESIDUAL, pol);
+        const LlamaLayerPtrs& y = s_layers[l];
+        produce_phase(ring, bars, rg, g, p.window, y.wqkv, d, qkv_dim, d, EPI_BF16, pol);
+        produce_phase(ring, bars, rg, g, p.window, y.wo, H * HD, d, H * HD, EPI_RESIDUAL, pol);
+        produce_phase(ring, bars, rg, g, p.window, y.wgu, d, f, d, EPI_SWIGLU, pol);
+        produce_phase(ring, bars, rg, g, p.window, y.wdown, f, d, f, EPI_RESIDUAL, pol);
       }
-      produce_phase(ring, bars, rg, g, p.lm_head, d, c.vocab, d, EPI_FP32, pol);
+      produce_phase(ring, bars, rg, g, p.window, p.lm_head, d, c.vocab, d, EPI_FP32, pol);
     }
     return;
   }
@@ -713,7 +769,7 @@ llama_decode_megakernel(const MegaParams p) {
   sm.stamp();
 
   for (int l = 0; l < c.n_layers; ++l) {
-    const LlamaLayerPtrs& y = p.layers[l];
+    const LlamaLayerPtrs& y = s_layers[l];
     // ---- P1: qkv = Wqkv . rms(x) ----
     if (l == 0) {
       // the residual stream starts as the embedding of the last token of every row: each CTA mirrors its column
@@ -738,7 +794,7 @@ llama_decode_megakernel(const MegaParams p) {
       gemv_phase<MT>(sm, qkv_dim, d, STAGE_RMS, p.x, d, p.rows, y.ln1, c.rms_eps, EPI_BF16, p.qkv, qkv_dim);
     }
     // ---- P2: attention (K/V requested before the barrier inside; last split of a kv head merges) ----
-    attention_phase<GQ>(p, att_smem, l, bar, sm);
+    attention_phase<GQ>(p, att_smem, l, t, bar, sm);
     sm.stamp();
     bar.sync();
     sm.stamp();
@@ -785,9 +841,10 @@ size_t work_smem_bytes(const pcy_llama_config& c, int mt) {
   const size_t smem_att = (size_t)(4 * HD + 2 * HD + 4 * ATT_CHUNK + 8 + 4 + MK_WARPS * 4 * HD) * 4 + 64;
   return 1024 + (smem_gemv > smem_att ? smem_gemv : smem_att);
 }
+size_t layer_table_bytes(const pcy_llama_config& c) { return round_up((size_t)c.n_layers * sizeof(LlamaLayerPtrs), 16); }
 // slots: a multiple of 12 (slot s is owned by consumer warp s % 12), at most 60 (2 x 60 barriers fit the 1 KB block)
 int ring_slots_for(const pcy_llama_config& c, int mt) {
-  const size_t w = work_smem_bytes(c, mt);
+  const size_t w = work_smem_bytes(c, mt) + layer_table_bytes(c);
   if (w + MK_WARPS * SLOT_BYTES > SMEM_LIMIT) return 0;
   const int ns = (int)((SMEM_LIMIT - w) / SLOT_BYTES) / MK_WARPS * MK_WARPS;
   return ns > 60 ? 60 : ns;
@@ -845,7 +902,13 @@ int decode_megakernel(const pcy_llama_config& c, const LlamaLayerPtrs* layers_de
   p.ring_slots = ring_slots_for(c, mt);
   p.out_rows = out_rows_for(c);
   p.ring_magic = (uint32_t)(((1ull << 32) + p.ring_slots - 1) / p.ring_slots);
-  const size_t smem = (size_t)p.ring_slots * SLOT_BYTES + work_smem_bytes(c, mt);
+  static const int window_env = [] {
+    const char* e = getenv("PCY_DECODE_WINDOW");  // tuning knob: weight chunks (8 KB) in flight per SM
+    return e ? atoi(e) : 24;
+  }();
+  p.window = std::min(std::max(window_env, PL), p.ring_slots);
+  p.layers_off = (int)((size_t)p.ring_slots * SLOT_BYTES + work_smem_bytes(c, mt));
+  const size_t smem = (size_t)p.layers_off + layer_table_bytes(c);
   PCY_REQUIRE(smem <= SMEM_LIMIT, "decode megakernel: needs %zu bytes of shared memory", smem);
   void* fn = nullptr;
   if (mt == 1) fn = (void*)llama_decode_megakernel<1, 4>;

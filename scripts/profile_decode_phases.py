@@ -24,7 +24,7 @@ def main():
     L = te.model.config.num_hidden_layers
     # stamps per layer: P1 [stage, stream, epi+kv request, bar], P2 [q/rope, scores, softmax, pv, partials+merge, tail,
     # bar], P3 [4], P4 [4], P5 [4] = 23; + lm head [stage, stream, end]
-    per_layer = 23
+    per_layer = 24
     n_stamps = 1 + per_layer * L + 3
     buf = torch.zeros(n_stamps + 8, device=dev, dtype=torch.int64)
     lib = _lib.load()
@@ -43,7 +43,7 @@ def main():
     lib.pcy_set_decode_timing_buffer(ctypes.c_void_p(0))
     acc /= n * 1e3  # us
     per = acc[: per_layer * L].view(L, per_layer)[1:].mean(0)  # skip layer 0 (different P1)
-    names = ["P1 stage", "P1 stream", "P1 epilogue+kv request", "P1 barrier", "P2 q load + rope", "P2 scores", "P2 softmax",
+    names = ["P1 stage", "P1 stream", "P1 epilogue", "P2 kv request", "P1 barrier", "P2 q load + rope", "P2 scores", "P2 softmax",
              "P2 p.v", "P2 partials + ticket merge", "P2 tail", "P2 barrier", "P3 stage", "P3 stream", "P3 epilogue",
              "P3 barrier", "P4 stage", "P4 stream", "P4 epilogue", "P4 barrier", "P5 stage", "P5 stream", "P5 epilogue",
              "P5 barrier"]
