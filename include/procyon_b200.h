@@ -100,6 +100,9 @@ enum {
 int pcy_set_esm_tc_attention(int enabled);
 /* 1: apply RoPE in the QKV GEMM epilogue (head_dim 64/128, tensor-core path); 0 (default): separate vectorised pass */
 int pcy_set_fused_rope(int enabled);
+/* 1: tcgen05 GEMMs with >= 2 row-blocks run as 2-CTA clusters sharing the weight tile by TMA multicast;
+   0 (default): independent CTAs. Both paths are bit-identical (tests); measured equal speed on B200 */
+int pcy_set_gemm_cluster(int enabled);
 int pcy_esm_create(const pcy_esm_config* cfg, void** handle);
 int pcy_esm_destroy(void* handle);
 /* src may be a host or a device pointer; the library keeps its own packed copy */
@@ -176,8 +179,10 @@ typedef struct {
 
 /* rows <= 4 use one persistent kernel per decode step by default; 0 selects the one-launch-per-op path (tests) */
 int pcy_set_decode_megakernel(int enabled);
-/* profiling aid: device uint64 buffer [18*L + 12] that receives %globaltimer at every phase boundary of the persistent
- * decode kernel (NULL disables) */
+/* profiling aid: device uint64 buffer of >= 4096 words (zeroed) that receives %globaltimer at every phase boundary of
+ * the persistent decode kernel: 24 stamps per layer + 4, written by CTA 0 (NULL disables).  If word 4095 holds the tag
+ * 0x534B4557 the buffer must have 4096 + (4 L + 1) * n_sms * 2 words, and every CTA also records (time, SM id) when it
+ * finishes streaming each weight phase (skew analysis, scripts/profile_decode_skew.py). */
 int pcy_set_decode_timing_buffer(void* dev_u64);
 int64_t pcy_llama_decode_workspace_bytes(void* handle, int rows, int S, int max_gen);
 /* clears state/tokens/slots/log-probs/workspace; copies prefill_logits fp32 [n_inputs,V] to every beam row */

@@ -24,6 +24,7 @@ int num_sms();
 // Counts kernels launched by this library (bench.py reports it as gpu_launches).
 void count_launch(int n = 1);
 extern bool g_fused_rope;
+extern bool g_gemm_cluster;
 
 #define PCY_CUDA(expr)                                                     \
   do {                                                                     \
@@ -177,6 +178,30 @@ __device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const void* desc,
       : "memory");
 }
 
+// multicast variant: the box lands at the same CTA-relative offset in every CTA of `cta_mask`, and completes
+// `bytes` on the mbarrier at the same CTA-relative offset in each of them
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t smem_dst, const void* desc, uint32_t bar, int32_t c0, int32_t c1,
+                                               uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_dst), "l"(desc), "r"(bar), "r"(c0), "r"(c1), "h"(cta_mask)
+      : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// thread-block clusters
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // ---------------------------------------------------------------------------------------------
 // tcgen05 / TMEM
 // ---------------------------------------------------------------------------------------------
@@ -197,6 +222,14 @@ __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sy
 // tcgen05.commit: arrive on an mbarrier once all previously issued MMAs of this thread retire.
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// same, arriving on the mbarrier at this CTA-relative offset in every CTA of `cta_mask`
+__device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(bar), "h"(cta_mask)
+      : "memory");
 }
 
 // D[tmem] (+)= A[smem desc] * B[smem desc], bf16 inputs, fp32 accumulate.

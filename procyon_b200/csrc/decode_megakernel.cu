@@ -17,6 +17,7 @@
 // (procyon/model/model_unified.py:769, :887 -> procyon/model/pmc_llama.py:581).
 #include <algorithm>
 #include <cstdlib>
+#include <vector>
 
 #include "common.cuh"
 #include "ops.h"
@@ -98,14 +99,22 @@ struct GridBarrier {
   }
 };
 
-__device__ __forceinline__ float dot8f(const uint4& a, const uint4& w, float s) {
-  const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), a2 = unpack_bf16x2(a.z), a3 = unpack_bf16x2(a.w);
-  const float2 w0 = unpack_bf16x2(w.x), w1 = unpack_bf16x2(w.y), w2 = unpack_bf16x2(w.z), w3 = unpack_bf16x2(w.w);
-  s = fmaf(a0.x, w0.x, s); s = fmaf(a0.y, w0.y, s);
-  s = fmaf(a1.x, w1.x, s); s = fmaf(a1.y, w1.y, s);
-  s = fmaf(a2.x, w2.x, s); s = fmaf(a2.y, w2.y, s);
-  s = fmaf(a3.x, w3.x, s); s = fmaf(a3.y, w3.y, s);
-  return s;
+// ---- legacy tensor-core path for the ring consumers -------------------------------------------------------------
+// A weight chunk is one row: 256 consecutive weights (32 segments of 16 B) are read as a 16x16 A fragment by one
+// ldmatrix.x4 (lane l supplies segment l: conflict-free), the matching 256 activations as two 16x8 B fragments, and
+// two mma.sync m16n8k16 put the 16 partial dot products of the segments pairs on the diagonals D1[n][n] and
+// D2[n+8][n].  Everything off the diagonals is discarded - the point is not the FLOPs but the issue slots: 4
+// instructions per 512 B of weights instead of ~27 with scalar FMAs (unpacking bf16 costs more than the math), which
+// lets the consumers drain a prefetched ring ~6x faster than HBM refills it.
+__device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
 enum : int { EPI_BF16 = 0, EPI_RESIDUAL = 1, EPI_SWIGLU = 2, EPI_FP32 = 3 };
@@ -122,6 +131,13 @@ struct RingGeom {
   }
 };
 
+// balanced contiguous range of `n` items for this CTA.  (Equal slices: with all SMs pulling from HBM at once some
+// get up to ~20 % less bandwidth than others - scripts/profile_decode_skew.py - but the pattern differs from GPU to
+// GPU, and slices sized from a calibration run did not pay off; see DESIGN.md.)
+__device__ __forceinline__ void cta_range(int n, int& lo, int& hi) {
+  lo = (int)(((int64_t)n * blockIdx.x) / gridDim.x);
+  hi = (int)(((int64_t)n * (blockIdx.x + 1)) / gridDim.x);
+}
 struct Smem {
   bf16* a;       // [MT][K] staged activations
   float* out;    // [out_rows][MT] partial sums
@@ -132,6 +148,8 @@ struct Smem {
   uint32_t chunk0;  // ring chunks consumed by the phases before the current one (same count in the producer)
   unsigned long long* tbuf;  // profiling stamps (CTA 0, thread 0) or null
   int tix;
+  int phase_ix;  // weight phases finished so far (profiling: per-CTA stream-end times at tbuf[4096 + ...])
+  bool skew;     // the timing buffer is large enough for them (the caller wrote the "SKEW" tag at tbuf[4095])
   __device__ __forceinline__ void stamp() {
     if (tbuf != nullptr) {
       if (blockIdx.x == 0 && threadIdx.x == 0) tbuf[tix] = globaltimer_ns();
@@ -139,12 +157,6 @@ struct Smem {
     }
   }
 };
-
-// balanced contiguous range of `n` items for this CTA
-__device__ __forceinline__ void cta_range(int n, int& lo, int& hi) {
-  lo = (int)(((int64_t)n * blockIdx.x) / gridDim.x);
-  hi = (int)(((int64_t)n * (blockIdx.x + 1)) / gridDim.x);
-}
 
 // weight row of local row r (within the CTA's range starting at logical output o_lo)
 __device__ __forceinline__ int weight_row(int epi, int o_lo, int r) {
@@ -320,6 +332,8 @@ __device__ __noinline__ void gemv_phase(Smem& sm, int n_out, int K, int stage, c
   sm.stamp();
 
   // ---- consume the ring: chunk g of the step lives in slot g % ns and belongs to warp g % 12 ----
+  // (Taking a warp's two slots together to share the activation unpack was measured slower: with 24 slots a warp
+  // owns exactly two, and holding both leaves the producer nothing to refill while the warp computes.)
   const uint32_t a_base = smem_u32(sm.a);
   for (int c = (int)((warp + MK_WARPS - sm.chunk0 % MK_WARPS) % MK_WARPS); c < n_chunks; c += MK_WARPS) {
     uint32_t slot, par;
@@ -329,32 +343,35 @@ __device__ __noinline__ void gemv_phase(Smem& sm, int n_out, int K, int stage, c
     const uint32_t wsm = sm.ring + slot * SLOT_BYTES + lane * 16;
     const uint32_t asm0 = a_base + (uint32_t)(kc * CH) * 2u + lane * 16;
     mbar_wait(sm.bars + 8u * slot, par);
-    float acc[MT], acc2[MT];
+    float d1[MT][4], d2[MT][4];
 #pragma unroll
-    for (int m = 0; m < MT; ++m) acc[m] = acc2[m] = 0.f;
-    int j = 0;
-#pragma unroll 2
-    for (; j + 2 <= len / 256; j += 2) {  // two independent FMA chains per row
-      const uint4 w0 = lds_v4(wsm + j * 512), w1 = lds_v4(wsm + j * 512 + 512);
+    for (int m = 0; m < MT; ++m) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) d1[m][i] = d2[m][i] = 0.f;
+    }
+    // activation segment of this lane for the B fragments: [0-7 | 16-23 | 8-15 | 24-31] -> (B1 k-lo, B1 k-hi, B2 k-lo,
+    // B2 k-hi), pairing segment n with A rows n and segment 8 + n with A rows 8 + n
+    const uint32_t bseg = (lane < 8 || lane >= 24) ? lane : (lane < 16 ? lane + 8 : lane - 8);
+    const uint32_t asmB = asm0 - lane * 16 + bseg * 16;
+#pragma unroll 4
+    for (int j = 0; j < len / 256; ++j) {
+      uint32_t af[4];
+      ldmatrix_x4(wsm + j * 512, af);
 #pragma unroll
       for (int m = 0; m < MT; ++m) {
-        const uint4 a0 = lds_v4(asm0 + (uint32_t)m * (uint32_t)K * 2u + j * 512);
-        const uint4 a1 = lds_v4(asm0 + (uint32_t)m * (uint32_t)K * 2u + j * 512 + 512);
-        acc[m] = dot8f(a0, w0, acc[m]);
-        acc2[m] = dot8f(a1, w1, acc2[m]);
+        uint32_t bf[4];
+        ldmatrix_x4(asmB + (uint32_t)m * (uint32_t)K * 2u + j * 512, bf);
+        mma_bf16_16816(d1[m], af, bf[0], bf[1]);
+        mma_bf16_16816(d2[m], af, bf[2], bf[3]);
       }
-    }
-    if (j < len / 256) {
-      const uint4 w0 = lds_v4(wsm + j * 512);
-#pragma unroll
-      for (int m = 0; m < MT; ++m)
-        acc[m] = dot8f(lds_v4(asm0 + (uint32_t)m * (uint32_t)K * 2u + j * 512), w0, acc[m]);
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(sm.bars + 8u * (sm.rg.ns + slot));  // slot free: the producer may refill it
 #pragma unroll
     for (int m = 0; m < MT; ++m) {
-      const float v = warp_sum(acc[m] + acc2[m]);
+      // diagonals: D1[n][n] sits in c0 / c1 and D2[n+8][n] in c2 / c3 of the lanes with lane/4 == 2 (lane%4) (+1)
+      const int gq = lane >> 2, q2 = (lane & 3) * 2;
+      const float v = warp_sum(gq == q2 ? d1[m][0] + d2[m][2] : (gq == q2 + 1 ? d1[m][1] + d2[m][3] : 0.f));
       if (lane == 0) {
         if (cpr > 1) atomicAdd(&sm.out[r * MT + m], v);
         else sm.out[r * MT + m] = v;
@@ -363,6 +380,14 @@ __device__ __noinline__ void gemv_phase(Smem& sm, int n_out, int K, int stage, c
   }
   sm.chunk0 += (uint32_t)n_chunks;
   consumer_sync();
+  if (sm.skew && threadIdx.x == 0) {  // profiling: when did each CTA finish streaming this phase?
+    unsigned int smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    unsigned long long* sk = sm.tbuf + 4096 + ((size_t)sm.phase_ix * gridDim.x + blockIdx.x) * 2;
+    sk[0] = globaltimer_ns();
+    sk[1] = smid;
+  }
+  ++sm.phase_ix;
   sm.stamp();
 
   // ---- epilogue ----
@@ -762,6 +787,8 @@ llama_decode_megakernel(const MegaParams p) {
   sm.ring = ring; sm.bars = bars; sm.rg = RingGeom{ns, p.ring_magic}; sm.chunk0 = 0;
   sm.tbuf = p.timing;
   sm.tix = 0;
+  sm.phase_ix = 0;
+  sm.skew = p.timing != nullptr && p.timing[4095] == 0x534B4557ull;
   uint8_t* att_smem = work;  // the attention phase reuses the activation staging area
 
   GridBarrier bar{p.barrier, 0u, gridDim.x};

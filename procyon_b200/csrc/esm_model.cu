@@ -53,6 +53,11 @@ int pcy_set_fused_rope(int enabled) {
   return 0;
 }
 
+int pcy_set_gemm_cluster(int enabled) {
+  pcy::g_gemm_cluster = enabled != 0;
+  return 0;
+}
+
 int pcy_esm_create(const pcy_esm_config* cfg, void** handle) {
   PCY_REQUIRE(cfg && handle, "esm_create: null argument");
   PCY_REQUIRE(cfg->d_model % cfg->n_heads == 0, "esm_create: d_model %% n_heads != 0");

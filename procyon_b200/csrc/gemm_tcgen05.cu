@@ -1,11 +1,17 @@
 // bf16 GEMM on the sm_100a 5th-gen tensor cores: TMA-staged 128B-swizzled tiles -> tcgen05.mma
 // (accumulator in TMEM, double buffered) -> tcgen05.ld epilogue with fused bias / scale / GELU /
 // SwiGLU / residual.  Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer
-// (+ TMEM allocator), warps 2..5 = epilogue (one TMEM lane quadrant each).
+// (+ TMEM allocator), warps 2..9 = epilogue (two per TMEM lane quadrant).
+//
+// CL = 2: CTAs run as clusters of two that work on vertically adjacent output tiles (same columns).  The W tile they
+// share is fetched once from L2: each CTA loads half of it with TMA multicast into both CTAs' shared memory.  A
+// 128x256 tile per SM needs (128 + 256) x 64 x 2 B per 64-deep k-block, i.e. ~16 TB/s of L2 -> SM traffic at full
+// tensor rate, which is what bounds the one-CTA kernel on the ESM2 / Llama shapes; sharing W cuts it by a third.
 //
 // Replaces, on the hot path, every nn.Linear of fair-esm ESM2 (q/k/v/out_proj, fc1, fc2 — reached via
 // procyon/model/esm.py:536), of HF LlamaDecoderLayer (q/k/v/o_proj, gate/up/down_proj — reached via
 // procyon/model/pmc_llama.py:571) and of create_mlp (procyon/model/model_utils.py:13-41).
+#include <algorithm>
 #include <mutex>
 #include <unordered_map>
 
@@ -13,6 +19,8 @@
 #include "ops.h"
 
 namespace pcy {
+
+bool g_gemm_cluster = false;  // pcy_set_gemm_cluster(1): 2-CTA clusters sharing the W tile by TMA multicast (measured: no gain)
 
 namespace {
 
@@ -104,7 +112,19 @@ __device__ __forceinline__ void tile_coords(int tile, int m_blocks, int n_blocks
   n_blk = local / rows;
 }
 
-template <int BN, bool ROPE>
+// pair order for CL = 2: the same banding over PAIRS of row-blocks
+__device__ __forceinline__ void pair_coords(int pair, int m_pairs, int n_blocks, int& m_pair, int& n_blk) {
+  constexpr int GROUP_P = GROUP_M / 2;
+  const int per_group = GROUP_P * n_blocks;
+  const int g = pair / per_group;
+  const int first = g * GROUP_P;
+  const int rows = min(GROUP_P, m_pairs - first);
+  const int local = pair - g * per_group;
+  m_pair = first + local % rows;
+  n_blk = local / rows;
+}
+
+template <int BN, bool ROPE, int CL>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          const EpiParams p) {
@@ -126,15 +146,29 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 
   const int m_blocks = (p.M + BM - 1) / BM;
   const int n_blocks = (p.N + BN - 1) / BN;
-  const int num_tiles = m_blocks * n_blocks;
   const int k_blocks = (p.K + BK - 1) / BK;
+  // work items: tiles (CL = 1) or vertical tile pairs shared by the two CTAs of a cluster (CL = 2; an odd last
+  // row-block is paired with an all-padding one, whose rows the epilogue masks like any M tail)
+  const int m_units = (m_blocks + CL - 1) / CL;
+  const int num_tiles = m_units * n_blocks;
+  const int unit0 = blockIdx.x / CL, unit_step = gridDim.x / CL;
+  const uint32_t cta_rank = (CL == 2) ? cluster_ctarank() : 0u;
+  auto coords = [&](int unit, int& m_blk, int& n_blk) {
+    if (CL == 1) {
+      tile_coords(unit, m_blocks, n_blocks, m_blk, n_blk);
+    } else {
+      int m_pair;
+      pair_coords(unit, m_units, n_blocks, m_pair, n_blk);
+      m_blk = 2 * m_pair + (int)cta_rank;
+    }
+  };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
     for (int s = 0; s < Cfg::STAGES; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(empty_bar(s), CL);  // a slot is refilled (in both CTAs) once both CTAs' MMAs have read it
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
@@ -148,6 +182,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   }
   tc_fence_before();
   __syncthreads();
+  if (CL == 2) cluster_sync_all();  // the peer's barriers exist before anything can arrive on them
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
@@ -157,16 +192,22 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = unit0; tile < num_tiles; tile += unit_step) {
         int m_blk, n_blk;
-        tile_coords(tile, m_blocks, n_blocks, m_blk, n_blk);
+        coords(tile, m_blk, n_blk);
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
           const uint32_t sb = sa + Cfg::A_BYTES;
           mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
           tma_load_2d(sa, &tmap_a, full_bar(stage), kb * BK, m_blk * BM);
-          tma_load_2d(sb, &tmap_b, full_bar(stage), kb * BK, n_blk * BN);
+          if (CL == 1) {
+            tma_load_2d(sb, &tmap_b, full_bar(stage), kb * BK, n_blk * BN);
+          } else {
+            // my half of the shared W tile, delivered to both CTAs (the other half arrives from the peer)
+            tma_load_2d_mc(sb + cta_rank * (Cfg::B_BYTES / 2), &tmap_b, full_bar(stage), kb * BK,
+                           n_blk * BN + (int)cta_rank * (BN / 2), (uint16_t)0x3);
+          }
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -179,7 +220,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = unit0; tile < num_tiles; tile += unit_step) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1);  // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
@@ -196,7 +237,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             tc_mma_bf16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
                         (kb > 0 || k > 0) ? 1u : 0u);
           }
-          tc_commit(empty_bar(stage));  // frees the smem slot once these MMAs retire
+          // frees the smem slot once these MMAs retire (in both CTAs: either one's next load writes into both)
+          if (CL == 1) tc_commit(empty_bar(stage));
+          else tc_commit_mc(empty_bar(stage), (uint16_t)0x3);
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
         tc_commit(tfull_bar(acc));  // accumulator complete -> epilogue
@@ -215,9 +258,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     const bool fast_store = !swiglu && !p.c_fp32 && (p.ldc % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
                             (p.residual == nullptr ||
                              ((p.ldr % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0)));
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = unit0; tile < num_tiles; tile += unit_step) {
       int m_blk, n_blk;
-      tile_coords(tile, m_blocks, n_blocks, m_blk, n_blk);
+      coords(tile, m_blk, n_blk);
       const int row = m_blk * BM + quad * 32 + lane;
       const bool row_ok = row < p.M;
       mbar_wait(tfull_bar(acc), acc_phase);
@@ -438,6 +481,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 
   tc_fence_before();
   __syncthreads();
+  if (CL == 2) cluster_sync_all();  // nobody leaves while the peer can still multicast into it / arrive on its barriers
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
@@ -516,26 +560,44 @@ int get_tensor_map(const bf16* ptr, int64_t rows, int64_t cols, int64_t ld, int 
   return 0;
 }
 
-template <int BN, bool ROPE>
+template <int BN, bool ROPE, int CL>
 int launch(const GemmArgs& a, cudaStream_t stream) {
   using Cfg = TileCfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
-    PCY_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, ROPE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    PCY_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, ROPE, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   Cfg::SMEM_BYTES));
     attr_set = true;
   }
   CUtensorMap ta, tb;
   PCY_TRY(get_tensor_map(a.A, a.M, a.K, a.lda, BM, &ta));
-  PCY_TRY(get_tensor_map(a.W, a.N, a.K, a.ldw, BN, &tb));
+  PCY_TRY(get_tensor_map(a.W, a.N, a.K, a.ldw, BN / CL, &tb));  // CL = 2: each CTA loads half of the W tile
   EpiParams p;
   p.C = a.C; p.ldc = a.ldc; p.bias = a.bias; p.residual = a.residual; p.ldr = a.ldr;
   p.M = a.M; p.N = a.N; p.K = a.K; p.c_fp32 = a.c_fp32; p.act = a.act; p.scale = a.scale;
   p.scale_ncols = a.scale_ncols;
   p.rope = a.rope; p.rope_hd = a.rope_hd; p.rope_T = a.rope_T; p.rope_ncols = a.rope ? a.rope_ncols : 0;
-  const int tiles = ceil_div(a.M, BM) * ceil_div(a.N, BN);
-  const int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_bf16_tcgen05_kernel<BN, ROPE><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
+  if (CL == 1) {
+    const int tiles = ceil_div(a.M, BM) * ceil_div(a.N, BN);
+    const int grid = tiles < num_sms() ? tiles : num_sms();
+    gemm_bf16_tcgen05_kernel<BN, ROPE, CL><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
+  } else {
+    const int pairs = ceil_div(ceil_div(a.M, BM), 2) * ceil_div(a.N, BN);
+    const int clusters = std::min(pairs, num_sms() / 2);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * clusters);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    PCY_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<BN, ROPE, CL>, ta, tb, p));
+  }
   PCY_LAUNCH_CHECK();
   return 0;
 }
@@ -566,8 +628,14 @@ int gemm_bf16_tc(const GemmArgs& a, cudaStream_t stream) {
     const double w128 = (double)tiles128 / (double)(ceil_div(tiles128, sms) * sms);
     if (w128 > w256 * 1.15) use128 = true;
   }
-  if (a.rope != nullptr) return use128 ? launch<128, true>(a, stream) : launch<256, true>(a, stream);
-  return use128 ? launch<128, false>(a, stream) : launch<256, false>(a, stream);
+  // two or more row-blocks: cluster pairs share the W tile through TMA multicast
+  const bool pair = g_gemm_cluster && ceil_div(a.M, BM) >= 2;
+  if (a.rope != nullptr) {
+    if (pair) return use128 ? launch<128, true, 2>(a, stream) : launch<256, true, 2>(a, stream);
+    return use128 ? launch<128, true, 1>(a, stream) : launch<256, true, 1>(a, stream);
+  }
+  if (pair) return use128 ? launch<128, false, 2>(a, stream) : launch<256, false, 2>(a, stream);
+  return use128 ? launch<128, false, 1>(a, stream) : launch<256, false, 1>(a, stream);
 }
 
 }  // namespace pcy

@@ -1,6 +1,7 @@
 #!/bin/bash
-# decode megakernel iteration: parity tests for the Llama paths, phase stamps, bench line
 mkdir -p gpurun_out
+echo "== uncalibrated"; PCY_DECODE_CALIBRATE=0 timeout 600 python scripts/profile_decode_skew.py 2>&1 | grep -E "phase|spread|mean lag SM" | head -20
+echo "== calibrated"; timeout 600 python scripts/profile_decode_skew.py 2>&1 | grep -E "phase|spread|mean lag SM|Error|error" | head -20
 timeout 600 python -m pytest tests/test_gpu_llama.py tests/test_gpu_unified.py -m gpu -q -x > gpurun_out/pytest_llama.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_llama.log
 tail -3 gpurun_out/pytest_llama.log
 timeout 600 python scripts/profile_decode_phases.py > gpurun_out/decode_phases.log 2>&1

@@ -26,7 +26,7 @@ def main():
     # bar], P3 [4], P4 [4], P5 [4] = 23; + lm head [stage, stream, end]
     per_layer = 24
     n_stamps = 1 + per_layer * L + 3
-    buf = torch.zeros(n_stamps + 8, device=dev, dtype=torch.int64)
+    buf = torch.zeros(max(n_stamps + 8, 4200), device=dev, dtype=torch.int64)  # (word 4095 = optional "SKEW" tag)
     lib = _lib.load()
     for _ in range(3):
         sess.forward()

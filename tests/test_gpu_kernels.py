@@ -53,6 +53,34 @@ def test_linear_parity(cuda_device, M, N, K, force, epi):
     torch.testing.assert_close(out32.cpu(), ref, rtol=2e-4, atol=2e-4 * ref.abs().max().item())
 
 
+@pytest.mark.parametrize("M,N,K", [(129, 256, 64), (300, 1000, 200), (514, 3840, 1280), (257, 520, 1288),
+                                   (4096, 1280, 5120), (1280, 2560, 320)])
+def test_cluster_multicast_gemm_is_bit_identical(cuda_device, M, N, K):
+    """2-CTA clusters sharing the weight tile by TMA multicast run the same MMAs in the same order as independent
+    CTAs: results must be bit-identical (odd numbers of row-blocks pair the last one with padding)."""
+    from procyon_b200 import _lib, ops
+
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(M + N + K)
+    a = (torch.randn(M, K, generator=g) * 0.5).bfloat16().cuda()
+    w = (torch.randn(N, K, generator=g) / math.sqrt(K)).bfloat16().cuda()
+    bias = torch.randn(N, generator=g).cuda()
+    res = torch.randn(M, N, generator=g).bfloat16().cuda()
+    try:
+        lib.pcy_set_gemm_cluster(0)
+        o0 = ops.linear(a, w, bias, residual=res, act=1, force="tc")
+        f0 = ops.linear(a, w, bias, force="tc", out_fp32=True)
+        lib.pcy_set_gemm_cluster(1)
+        o1 = ops.linear(a, w, bias, residual=res, act=1, force="tc")
+        f1 = ops.linear(a, w, bias, force="tc", out_fp32=True)
+    finally:
+        lib.pcy_set_gemm_cluster(0)
+    assert torch.equal(o0, o1)
+    assert torch.equal(f0, f1)
+    ref = _cpu_linear(a.cpu(), w.cpu(), bias.cpu())
+    torch.testing.assert_close(f1.cpu(), ref, rtol=2e-4, atol=2e-4 * ref.abs().max().item())
+
+
 @pytest.mark.parametrize("M,force", [(1, "skinny"), (4, "skinny"), (9, "skinny"), (200, "tc")])
 def test_swiglu_parity(cuda_device, M, force):
     from procyon_b200 import ops
