@@ -227,7 +227,7 @@ __device__ __noinline__ void produce_phase(uint32_t ring, uint32_t bars, RingGeo
 // out = epi(W[n_out(x2), K] . A[MT, K]).  The CTA's slice of W arrives through the ring in chunks of <= CH elements
 // of one row.
 template <int MT>
-__device__ __noinline__ void gemv_phase(Smem& sm, int n_out, int K, int stage, const bf16* A, int64_t lda, int rows,
+__device__ __forceinline__ void gemv_phase(Smem& sm, int n_out, int K, int stage, const bf16* A, int64_t lda, int rows,
                                         const bf16* __restrict__ rms_w, float eps, int epi, void* out, int64_t ldo) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   int o_lo, o_hi;
@@ -495,7 +495,7 @@ __device__ __noinline__ void merge_splits(const float* base, int n_splits, bf16*
 // split of a (row, kv head) merges the partials (ticket counter) and writes the bf16 attention output, so that the
 // o_proj phase stages 8 KB per row instead of every CTA re-reading every partial.
 template <int GQ>
-__device__ __noinline__ void attention_phase(const MegaParams& p, uint8_t* smem_raw, int layer, int t,
+__device__ __forceinline__ void attention_phase(const MegaParams& p, uint8_t* smem_raw, int layer, int t,
                                              GridBarrier& bar, Smem& sm) {
   static_assert(GQ == 4, "the P.V loop reads the 4 head probabilities of a key as one float4");
   sm.stamp();
@@ -735,6 +735,35 @@ __device__ __noinline__ void attention_phase(const MegaParams& p, uint8_t* smem_
   }
 }
 
+// Touches the K / V pages this CTA's first attention item of `layer` will read (one word each, result unused), long
+// before the attention phase: each layer's K and V live on 2 MB pages last used a whole step (15 GB of weight
+// traffic) ago, so the first access pays a full page-table walk under load (~4 us, measured as a stall of the load
+// ISSUE in the attention phase).  Issued from one thread while the CTA streams the MLP weights, the walk is free.
+__device__ __forceinline__ void touch_kv_pages(const MegaParams& p, int layer, int t) {
+  const int KVH = p.cfg.n_kv_heads, kvd = KVH * HD;
+  const int ctx = p.S + t;
+  const int n_splits = (ctx + ATT_CHUNK - 1) / ATT_CHUNK;
+  const int item = blockIdx.x;
+  if (layer >= p.cfg.n_layers || item >= p.rows * KVH * n_splits) return;
+  const int split = item % n_splits, kvh = (item / n_splits) % KVH, row = item / (n_splits * KVH);
+  const int input = row / p.beams;
+  const int64_t n_prompt = (int64_t)(p.rows / p.beams) * p.S, n_gen = (int64_t)p.rows * p.max_gen;
+  const int pos0 = split * ATT_CHUNK, pos1 = min(ctx - 1, pos0 + ATT_CHUNK - 1);
+#pragma unroll
+  for (int kv = 0; kv < 2; ++kv) {
+    const bf16* pp = p.kv_prompt + ((int64_t)layer * 2 + kv) * n_prompt * kvd;
+    const bf16* pg = p.kv_gen + ((int64_t)layer * 2 + kv) * n_gen * kvd;
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int pos = e ? pos1 : pos0;
+      const bf16* a = pos < p.S ? pp + ((int64_t)input * p.S + pos) * kvd + kvh * HD
+                                : pg + ((int64_t)row * p.max_gen + (pos - p.S)) * kvd + kvh * HD;
+      unsigned int dummy;
+      asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(dummy) : "l"(a) : "memory");
+    }
+  }
+}
+
 template <int MT, int GQ>
 __global__ void __launch_bounds__(MK_BLOCK, 1)
 llama_decode_megakernel(const MegaParams p) {
@@ -793,58 +822,63 @@ llama_decode_megakernel(const MegaParams p) {
 
   GridBarrier bar{p.barrier, 0u, gridDim.x};
   const int t = p.state[0];
+  if (threadIdx.x == 32) touch_kv_pages(p, 0, t);
   sm.stamp();
 
-  for (int l = 0; l < c.n_layers; ++l) {
-    const LlamaLayerPtrs& y = s_layers[l];
-    // ---- P1: qkv = Wqkv . rms(x) ----
-    if (l == 0) {
-      // the residual stream starts as the embedding of the last token of every row: each CTA mirrors its column
-      // slice of the rows into x
-      for (int m = 0; m < p.rows; ++m) {
-        const int tok = p.tokens[(int64_t)m * p.max_gen + (t - 1)];
-        const bf16* src = p.embed + (int64_t)tok * d;
-        int clo, chi;
-        cta_range(d / 8, clo, chi);
-        for (int k8 = clo + threadIdx.x; k8 < chi; k8 += MK_THREADS)
-          *reinterpret_cast<uint4*>(p.x + (int64_t)m * d + k8 * 8) = *reinterpret_cast<const uint4*>(src + k8 * 8);
+  // One flat loop over the 4 L + 1 weight phases, so that gemv_phase and attention_phase each have a single call site
+  // and can be inlined: as out-of-line functions they took the kernel parameters and `sm` by reference, i.e. through
+  // per-thread copies in local memory (~500 B x 416 threads against the ~28 KB of L1 left beside the ring), and every
+  // phase began with chains of local loads served by L2.
+  const int n_phases = 4 * c.n_layers + 1;
+  for (int ph = 0; ph < n_phases; ++ph) {
+    const int l = ph >> 2;
+    const int kind = ph == n_phases - 1 ? 4 : (ph & 3);  // 0 qkv | 1 o_proj | 2 gate/up | 3 down | 4 lm head
+    const LlamaLayerPtrs& y = s_layers[kind == 4 ? 0 : l];
+    int n_out, K, stage, epi, rows = p.rows;
+    const bf16 *A, *rms_w = nullptr;
+    int64_t lda, ldo;
+    void* out;
+    if (kind == 0) {         // qkv = Wqkv . rms(x)
+      n_out = qkv_dim; K = d; stage = STAGE_RMS; A = p.x; lda = d; rms_w = y.ln1; epi = EPI_BF16; out = p.qkv; ldo = qkv_dim;
+      if (l == 0) {
+        // the residual stream starts as the embedding of the last token of every row: each CTA mirrors its column
+        // slice of the rows into x
+        for (int m = 0; m < p.rows; ++m) {
+          const int tok = p.tokens[(int64_t)m * p.max_gen + (t - 1)];
+          const bf16* src = p.embed + (int64_t)tok * d;
+          int clo, chi;
+          cta_range(d / 8, clo, chi);
+          for (int k8 = clo + threadIdx.x; k8 < chi; k8 += MK_THREADS)
+            *reinterpret_cast<uint4*>(p.x + (int64_t)m * d + k8 * 8) = *reinterpret_cast<const uint4*>(src + k8 * 8);
+        }
+        if (p.rows == 1) A = p.embed + (int64_t)p.tokens[t - 1] * d;  // straight from the table (x is not visible yet)
+        else bar.sync();
       }
-      if (p.rows == 1) {  // read the row straight from the table (x is not globally visible yet)
-        const int tok = p.tokens[t - 1];
-        gemv_phase<MT>(sm, qkv_dim, d, STAGE_RMS, p.embed + (int64_t)tok * d, d, 1, y.ln1, c.rms_eps, EPI_BF16, p.qkv,
-                       qkv_dim);
-      } else {
-        bar.sync();
-        gemv_phase<MT>(sm, qkv_dim, d, STAGE_RMS, p.x, d, p.rows, y.ln1, c.rms_eps, EPI_BF16, p.qkv, qkv_dim);
-      }
-    } else {
-      gemv_phase<MT>(sm, qkv_dim, d, STAGE_RMS, p.x, d, p.rows, y.ln1, c.rms_eps, EPI_BF16, p.qkv, qkv_dim);
+    } else if (kind == 1) {  // attention, then x += Wo . attn
+      attention_phase<GQ>(p, att_smem, l, t, bar, sm);  // (K/V requested before the barrier inside)
+      sm.stamp();
+      bar.sync();
+      sm.stamp();
+      n_out = d; K = H * HD; stage = STAGE_PLAIN; A = p.attn; lda = H * HD; epi = EPI_RESIDUAL; out = p.x; ldo = d;
+    } else if (kind == 2) {  // act = silu(Wg . rms(x)) * (Wu . rms(x))
+      if (threadIdx.x == 32) touch_kv_pages(p, l + 1, t);
+      n_out = f; K = d; stage = STAGE_RMS; A = p.x; lda = d; rms_w = y.ln2; epi = EPI_SWIGLU; out = p.act; ldo = f;
+    } else if (kind == 3) {  // x += Wdown . act
+      n_out = d; K = f; stage = STAGE_PLAIN; A = p.act; lda = f; epi = EPI_RESIDUAL; out = p.x; ldo = d;
+    } else {                 // logits = Wlm . rms(x)
+      n_out = c.vocab; K = d; stage = STAGE_RMS; A = p.x; lda = d; rms_w = p.norm; epi = EPI_FP32; out = p.logits;
+      ldo = c.vocab;
     }
-    // ---- P2: attention (K/V requested before the barrier inside; last split of a kv head merges) ----
-    attention_phase<GQ>(p, att_smem, l, t, bar, sm);
-    sm.stamp();
-    bar.sync();
-    sm.stamp();
-    // ---- P3: x += Wo . attn ----
-    gemv_phase<MT>(sm, d, H * HD, STAGE_PLAIN, p.attn, H * HD, p.rows, nullptr, 0.f, EPI_RESIDUAL, p.x, d);
-    sm.stamp();
-    bar.sync();
-    sm.stamp();
-    // ---- P4: act = silu(Wg . rms(x)) * (Wu . rms(x)) ----
-    gemv_phase<MT>(sm, f, d, STAGE_RMS, p.x, d, p.rows, y.ln2, c.rms_eps, EPI_SWIGLU, p.act, f);
-    sm.stamp();
-    bar.sync();
-    sm.stamp();
-    // ---- P5: x += Wdown . act ----
-    gemv_phase<MT>(sm, d, f, STAGE_PLAIN, p.act, f, p.rows, nullptr, 0.f, EPI_RESIDUAL, p.x, d);
-    sm.stamp();
-    bar.sync();
-    sm.stamp();
+    gemv_phase<MT>(sm, n_out, K, stage, A, lda, rows, rms_w, c.rms_eps, epi, out, ldo);
+    if (kind == 4) {
+      consumer_sync();
+      sm.stamp();
+    } else if (kind != 0) {  // (the barrier after the qkv phase is inside attention_phase)
+      sm.stamp();
+      bar.sync();
+      sm.stamp();
+    }
   }
-  // ---- logits = Wlm . rms(x) ----
-  gemv_phase<MT>(sm, c.vocab, d, STAGE_RMS, p.x, d, p.rows, p.norm, c.rms_eps, EPI_FP32, p.logits, c.vocab);
-  consumer_sync();
-  sm.stamp();
 }
 
 unsigned long long* g_timing = nullptr;
