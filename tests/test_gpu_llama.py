@@ -5,7 +5,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def _cfgs(kind="gq2"):
+def _cfgs(kind="gq2", max_pos=512):
     from oracle.llama import LlamaCfg
     from procyon_b200.model.pmc_llama import LlamaConfig
 
@@ -14,9 +14,9 @@ def _cfgs(kind="gq2"):
     # gq4wide: ffn 8448 = 2 full 4096-element weight chunks + a 256-element tail per w_down row (multi-chunk rows of
     # the persistent kernel's weight ring)
     H, d, f = {"gq2": (4, 512, 1024), "gq4": (8, 1024, 1024), "gq4wide": (8, 1024, 8448)}[kind]
-    oc = LlamaCfg(d_model=d, n_layers=2, n_heads=H, n_kv_heads=2, ffn_dim=f, vocab=1003, max_pos=512)
+    oc = LlamaCfg(d_model=d, n_layers=2, n_heads=H, n_kv_heads=2, ffn_dim=f, vocab=1003, max_pos=max_pos)
     pc = LlamaConfig(hidden_size=d, intermediate_size=f, num_hidden_layers=2, num_attention_heads=H,
-                     num_key_value_heads=2, vocab_size=1003, max_position_embeddings=512)
+                     num_key_value_heads=2, vocab_size=1003, max_position_embeddings=max_pos)
     return oc, pc
 
 
@@ -180,3 +180,27 @@ def test_persistent_and_per_op_decode_agree(cuda_device, kind, rows):
     torch.testing.assert_close(lg1[:, 1], lg2[:, 1], rtol=2e-2, atol=3e-2)  # first decode step: same inputs
     agree = (o1 == o2).float().mean().item()
     assert agree > 0.7, agree
+
+
+@pytest.mark.parametrize("rows,S", [(1, 1300), (4, 1800)])
+def test_persistent_decode_long_context(cuda_device, rows, S):
+    """Long prompts in the single-launch decode step: more than 12 KV splits per head (two-pass merge of the split
+    partials) and, with 4 rows x 2 kv heads x 19 splits, more attention work items than CTAs (several per CTA)."""
+    from oracle.llama import random_llama_state_dict
+    from procyon_b200 import _lib
+    from procyon_b200.model.generation import generate_greedy
+
+    oc, pc = _cfgs("gq4", max_pos=2048)
+    sd = random_llama_state_dict(oc, seed=5)
+    m = _build(sd, pc)
+    ids, emb, mask = _inputs(oc, sd, rows, S, seed=11, pad_left=7)
+    lib = _lib.load()
+    try:
+        lib.pcy_set_decode_megakernel(1)
+        o1, lp1, lg1 = generate_greedy(m, emb.cuda(), mask.cuda(), max_len=6)
+        lib.pcy_set_decode_megakernel(0)
+        o2, lp2, lg2 = generate_greedy(m, emb.cuda(), mask.cuda(), max_len=6, use_graph=False)
+    finally:
+        lib.pcy_set_decode_megakernel(1)
+    torch.testing.assert_close(lg1[:, 1], lg2[:, 1], rtol=2e-2, atol=3e-2)  # first decode step: same inputs
+    assert (o1 == o2).float().mean().item() > 0.7
