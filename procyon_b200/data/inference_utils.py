@@ -103,3 +103,29 @@ class ShardedProteinIndex:
     def topk(self, query_embeddings: torch.Tensor, k: int = 20):
         s = self.scores(query_embeddings)
         return torch.topk(s, min(k, self.N), dim=-1)
+
+
+# ---- QA inference (procyon/data/inference_utils.py:581-655) --------------------------------------------------------
+from ..training.train_utils import get_qa_logits_inference  # noqa: E402,F401  (same home as in the reference)
+
+
+class ProCyonQAInference:
+    """Yes/no question answering on top of UnifiedProCyon.forward: `qa(model_inputs)["pred"]` holds the probabilities
+    over the vocabulary at the answer position (reference: `ProCyonQAInference.fwd_pass`).  Only the B answer rows
+    go through the LM head."""
+
+    def __init__(self, model, device=None):
+        model.eval()
+        self.device = device
+        self.model = model.to(device) if device is not None else model
+        self.yes_token, self.no_token = model.yes_token, model.no_token
+
+    @torch.no_grad()
+    def __call__(self, *args, **kwargs):
+        return self.fwd_pass(*args, **kwargs)
+
+    def fwd_pass(self, model_inputs, aaseq_type: str = "protein", output_attentions=None):
+        out = self.model(model_inputs, return_mlm=False, retrieval=False, get_full_labels=True, aaseq_type=aaseq_type,
+                         crop_off=True, output_attentions=output_attentions)
+        pred, _ = get_qa_logits_inference(out, answer_token=self.model.answer_idx)
+        return {"pred": pred, "y": None, "out": out}

@@ -189,6 +189,16 @@ class CausalLMOutput:
         self.loss = loss
         self.past_key_values = past
 
+    def logits_at(self, positions: torch.Tensor) -> torch.Tensor:
+        """fp32 logits [B, V] of one position per sequence: the LM head runs on B gathered rows only (QA scoring
+        needs the yes/no decision at a single position; the reference softmaxes the whole (B, S, V) tensor on the
+        CPU for it, procyon/training/train_utils.py:1048-1070)."""
+        if self._logits is not None:
+            return self._logits[torch.arange(self._logits.shape[0], device=self._logits.device), positions]
+        h = self.hidden_states[-1]
+        rows = h[torch.arange(h.shape[0], device=h.device), positions.to(h.device)]
+        return self._owner.lm_head_logits(rows.contiguous())
+
     @property
     def logits(self):
         if self._logits is None:  # full-sequence logits are only computed when somebody asks for them

@@ -121,3 +121,100 @@ def unwrap_model(model):
 def barrier():
     if torch.distributed.is_available() and torch.distributed.is_initialized():
         torch.distributed.barrier()
+
+
+# ---- QA / retrieval scoring of a forward pass ------------------------------------------
+def decompose_dataset_name(name: str):
+    """'{aaseq_type}_{text_type}_{relation...}' -> its three parts (procyon/training/train_utils.py:1741-1748)."""
+    parts = name.split("_")
+    return parts[0], parts[1], "_".join(parts[2:])
+
+
+def get_final_tokens(text_toks: torch.Tensor, padding_token: int) -> torch.Tensor:
+    """Index of the last token before EOS in right-padded rows (train_utils.py:1095-1101): S - n_pad - 2."""
+    n_pad = (text_toks == padding_token).sum(dim=-1)
+    return text_toks.shape[1] - n_pad - 2
+
+
+def get_after_answer_tokens(text_toks: torch.Tensor, answer_token: int, get_final: bool = True) -> torch.Tensor:
+    """Position right after the (last) [ANSWER] token of every row (train_utils.py:1104-1117), without the
+    per-row Python loop of the reference."""
+    is_ans = text_toks == answer_token
+    if not get_final:
+        return is_ans.nonzero()[:, 1] + 1
+    if not bool(is_ans.any(dim=1).all()):
+        raise ValueError("a row without an [ANSWER] token")  # the reference fails on .max() of an empty tensor
+    cols = torch.arange(text_toks.shape[1], device=text_toks.device)
+    return (is_ans * cols).max(dim=1).values + 1
+
+
+def _answer_positions(model_out, padding_token=None, answer_token=None):
+    y_all = model_out["text_toks"].detach()
+    if padding_token is not None:
+        idx = get_final_tokens(y_all, padding_token)
+    elif answer_token is not None:
+        idx = get_after_answer_tokens(y_all, answer_token)
+    else:
+        raise ValueError("One of padding_token or answer_token for get_qa_metrics must not be None")
+    return y_all, idx
+
+
+def get_qa_scores(model_out, padding_token=None, answer_token=None):
+    """(pred_toks, y_toks): the model's argmax token at the answer position and the label there
+    (train_utils.py:1048-1070).  The prediction for position i is read at i - 1 (causal shift).  Only the B rows
+    that matter go through the LM head (argmax of softmax == argmax of logits)."""
+    y_all, idx = _answer_positions(model_out, padding_token, answer_token)
+    rows = torch.arange(y_all.shape[0], device=y_all.device)
+    y_toks = y_all[rows, idx]
+    logits = model_out["outputs"].logits_at(idx - 1)
+    return logits.argmax(dim=-1).cpu(), y_toks.cpu()
+
+
+def get_qa_logits_inference(model_out, padding_token=None, answer_token=None):
+    """(probabilities [B, V] at the answer position, labels) as procyon/data/inference_utils.py:581-604."""
+    y_all, idx = _answer_positions(model_out, padding_token, answer_token)
+    rows = torch.arange(y_all.shape[0], device=y_all.device)
+    probs = model_out["outputs"].logits_at(idx - 1).softmax(dim=-1)
+    return probs.cpu(), y_all[rows, idx].cpu()
+
+
+def get_qa_metrics_from_preds(pred_toks, y_toks, yes_token: int, no_token: int, padding_token=None):
+    """accuracy and macro-F1 of yes/no predictions (train_utils.py:1167-1190)."""
+    from sklearn.metrics import f1_score
+
+    n_yes_no = int((y_toks == yes_token).sum() + (y_toks == no_token).sum())
+    assert n_yes_no == y_toks.numel(), \
+        f"Tokens in y other than yes/no ({y_toks.numel() - n_yes_no} of {y_toks.numel()})"
+    acc = (pred_toks == y_toks).float().mean()
+    f1 = f1_score(y_toks.numpy(), pred_toks.numpy(), average="macro")
+    return acc, f1
+
+
+def get_qa_metrics(model_out, yes_token: int, no_token: int, padding_token=None, answer_token=None):
+    """train_utils.py:1120-1164."""
+    pred, y = get_qa_scores(model_out, padding_token=padding_token, answer_token=answer_token)
+    return get_qa_metrics_from_preds(pred, y, yes_token, no_token)
+
+
+def get_retrieval_scores_inbatch(cdict):
+    """Cosine scores of the in-batch pairs: diagonal = positives, off-diagonal = negatives
+    (train_utils.py:996-1019)."""
+    import torch.nn.functional as F
+
+    s = F.normalize(cdict["positive"]["sequence"].detach().float().cpu(), dim=-1)
+    t = F.normalize(cdict["positive"]["text"].detach().float().cpu(), dim=-1)
+    scores = s @ t.t()
+    n = scores.shape[0]
+    off = ~torch.eye(n, dtype=torch.bool)
+    return torch.diagonal(scores).clone(), scores[off]
+
+
+def get_cl_metrics(pos_scores, neg_scores):
+    """(n_pos, n_neg, AUROC, AUPRC) of positive vs negative scores (train_utils.py:966-978)."""
+    import numpy as np
+    from sklearn.metrics import average_precision_score, roc_auc_score
+
+    pos, neg = np.asarray(pos_scores), np.asarray(neg_scores)
+    labels = np.concatenate([np.ones(len(pos)), np.zeros(len(neg))])
+    both = np.concatenate([pos, neg])
+    return len(pos), len(neg), roc_auc_score(labels, both), average_precision_score(labels, both)

@@ -115,6 +115,42 @@ def golden_host_utils():
     save("host_utils.pt", out)
 
 
+def golden_qa_retrieval_metrics():
+    """QA / retrieval scoring helpers of the reference trainer (train_utils.py:966-1190, 1741), executed unmodified."""
+    import types
+
+    g = torch.Generator().manual_seed(21)
+    B, S, V, yes, no, ans, pad = 6, 12, 40, 7, 9, 33, 0
+    toks = torch.randint(10, 30, (B, S), generator=g)
+    y = torch.tensor([yes, no, no, yes, yes, no])
+    ans_pos = torch.tensor([4, 7, 3, 9, 5, 6])
+    for i in range(B):
+        toks[i, ans_pos[i]] = ans
+        toks[i, ans_pos[i] + 1] = y[i]
+        toks[i, ans_pos[i] + 2] = 2  # eos
+        toks[i, ans_pos[i] + 3:] = pad
+    toks[1, 2] = ans  # an earlier [ANSWER] (in-context example): the LAST one counts
+    logits = torch.randn(B, S, V, generator=g)
+    for i in range(B):  # make 4 of 6 predictions right
+        logits[i, ans_pos[i], yes if (y[i] == yes) == (i != 2 and i != 4) else no] += 9.0
+    out = {"outputs": types.SimpleNamespace(logits=logits), "text_toks": toks}
+    res = dict(toks=toks, logits=logits, yes=yes, no=no, ans=ans, pad=pad)
+    res["after_answer"] = ref_tu.get_after_answer_tokens(toks, answer_token=ans)
+    res["final_tokens"] = ref_tu.get_final_tokens(toks, padding_token=pad)
+    res["qa_scores_answer"] = ref_tu.get_qa_scores(out, answer_token=ans)
+    res["qa_scores_pad"] = ref_tu.get_qa_scores(out, padding_token=pad)
+    acc, f1 = ref_tu.get_qa_metrics(out, yes_token=yes, no_token=no, answer_token=ans)
+    res["qa_metrics"] = (float(acc), float(f1))
+    zs, zt = torch.randn(5, 16, generator=g), torch.randn(5, 16, generator=g)
+    cd = {"positive": {"sequence": zs.bfloat16(), "text": zt.bfloat16()}}
+    pos, neg = ref_tu.get_retrieval_scores_inbatch(cd)
+    res["retrieval_inbatch"] = dict(zs=zs.bfloat16(), zt=zt.bfloat16(), pos=pos, neg=neg,
+                                    metrics=tuple(float(v) for v in ref_tu.get_cl_metrics(pos.numpy(), neg.numpy())))
+    res["decompose"] = {n: ref_tu.decompose_dataset_name(n) for n in ("protein_go_process", "domain_pfam_all",
+                                                                      "protein_drugbank_drug_target")}
+    save("qa_retrieval_metrics.pt", res)
+
+
 class _FakeSelf:
     """Just enough of UnifiedProCyon for its unbound methods to run."""
 
@@ -290,6 +326,7 @@ if __name__ == "__main__":
     golden_mlp()
     golden_infonce()
     golden_host_utils()
+    golden_qa_retrieval_metrics()
     golden_prompt_and_labels()
     golden_beam_search()
     golden_hf_esm()

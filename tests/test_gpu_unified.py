@@ -215,3 +215,52 @@ def test_pooler_and_mlp_match_reference_goldens(cuda_device):
         mlp.load_state_dict(c["state_dict"])
         y = mlp.cuda()(c["x"].cuda())
         torch.testing.assert_close(y.float().cpu(), c["y"], rtol=3e-2, atol=3e-2)
+
+
+def test_trainer_loss_forward_and_qa_scoring(cuda_device):
+    """Forward half of ProCyonTrainer.compute_lm_loss / compute_retrieval_loss and the QA scoring
+    path: the LM head on the B answer rows must agree with the full (B, S, V) logits the reference softmaxes."""
+    import types
+
+    from procyon_b200.training import train_utils as tu
+    from procyon_b200.training.trainIT import compute_lm_loss, compute_retrieval_loss
+
+    m = _tiny_model()
+    inputs = _inputs()
+    yes_word, no_word = "yes", "no"
+    inputs["instructions"] = ["Protein : <|protein|> Context : [EXT] Is it a kinase ? [ANSWER] " + yes_word,
+                              "Protein : <|protein|> Context : [EXT] Is it secreted ? [ANSWER] " + no_word]
+    m.yes_token = m.tokenizer.encode(yes_word, add_special_tokens=False)[0]
+    m.no_token = m.tokenizer.encode(no_word, add_special_tokens=False)[0]
+    args = types.SimpleNamespace(qa_loss_weight=0.5, caption_loss_weight=2.0, retrieval_loss_weight=3.0)
+    logged = {}
+    loss = compute_lm_loss(m, inputs, "qa", args, dataset_key="protein_go_process", log=logged.__setitem__)
+    out = m(inputs, retrieval=False, get_full_labels=True, aaseq_type="protein")
+    assert abs(loss.item() - 0.5 * out["outputs"].loss.item()) < 1e-6
+    assert {"protein_go_process_batch_train_qa_acc", "protein_go_process_batch_train_qa_f1",
+            "protein_go_process_batch_train_qa_ppl", "protein_go_process_batch_train_qa_loss"} <= set(logged)
+    # answer-row LM head == gather of the full logits (same kernel family; bf16 inputs, fp32 accumulate)
+    idx = tu.get_after_answer_tokens(out["text_toks"], m.answer_idx) - 1
+    rows = out["outputs"].logits_at(idx)
+    full = out["outputs"].logits
+    torch.testing.assert_close(rows, full[torch.arange(full.shape[0], device=full.device), idx], rtol=1e-3, atol=1e-3)
+    pred, y = tu.get_qa_scores(out, answer_token=m.answer_idx)
+    assert y.tolist() == [m.yes_token, m.no_token]
+    assert torch.equal(pred, full.argmax(-1)[torch.arange(2, device=full.device), idx].cpu())
+    # caption weighting with the per-dataset rescale table
+    cap = compute_lm_loss(m, _inputs(), "caption", args, dataset_key="protein_go_process",
+                          caption_loss_rescale={"protein_go": 0.25})
+    base = m(_inputs(), retrieval=False, get_full_labels=True, crop_off=True)["outputs"].loss.item()
+    assert abs(cap.item() - 2.0 * 0.25 * base) < 1e-5
+    # retrieval: loss x weight, metrics from the in-batch score matrix
+    r_in = _inputs()
+    r_in["target"]["seq"] = {"positive": [0, 2], "negative": None}
+    logged.clear()
+    m.train()  # (in eval mode the model returns the reference's -999.0 placeholder, model_unified.py:691)
+    try:
+        rl = compute_retrieval_loss(m, r_in, args, dataset_key="protein_go_process", log=logged.__setitem__)
+        ro = m(r_in, retrieval=True, aaseq_type="protein")
+    finally:
+        m.eval()
+    assert abs(float(rl) - 3.0 * float(ro["contrastive_loss"])) < 1e-4
+    assert "protein_go_process_batch_train_retrieval_auroc" in logged
