@@ -128,6 +128,21 @@ def esm2_forward(
     return x
 
 
+def esm2_lm_head(sd: Dict[str, torch.Tensor], z: torch.Tensor, *, act_round: str = "none",
+                 ln_eps: float = 1e-5) -> torch.Tensor:
+    """fair-esm 2.0.0 `RobertaLMHead` (esm/modules.py; absent from /root/reference, pinned through HF EsmLMHead):
+    logits = layer_norm(gelu(dense(z))) @ weight^T + bias with `weight` tied to embed_tokens.weight.  The reference
+    returns them from ESM_PLM.forward (procyon/model/esm.py:549-555) for the `return_mlm` path
+    (procyon/model/model_unified.py:505-509)."""
+    rnd = _rounder(act_round)
+    g = lambda k: sd[k].float()
+    d = z.shape[-1]
+    w = g("lm_head.weight") if "lm_head.weight" in sd else g("embed_tokens.weight")
+    h = rnd(F.gelu(z @ g("lm_head.dense.weight").t() + g("lm_head.dense.bias")))
+    h = rnd(F.layer_norm(h, (d,), g("lm_head.layer_norm.weight"), g("lm_head.layer_norm.bias"), ln_eps))
+    return h @ w.t() + g("lm_head.bias")
+
+
 def batched_split_long_seq(toks: torch.Tensor, padding_idx: int = PAD_IDX, eos_idx: int = EOS_IDX,
                            max_protein_len: int = 1024):
     """'split' strategy of procyon/training/train_utils.py:1497-1596 (does NOT mutate its input).
@@ -254,6 +269,13 @@ def random_esm_state_dict(n_layers: int, d: int, ffn: Optional[int] = None, seed
         sd[p + "fc2.bias"] = w(d, s=0.02)
     sd["emb_layer_norm_after.weight"] = (1 + 0.1 * torch.randn(d, generator=g)).to(dtype)
     sd["emb_layer_norm_after.bias"] = w(d, s=0.05)
+    # masked-LM head (drawn after everything else, so the encoder weights of a given seed are unchanged)
+    sd["lm_head.dense.weight"] = w(d, d, s=1.0 / math.sqrt(d))
+    sd["lm_head.dense.bias"] = w(d, s=0.02)
+    sd["lm_head.layer_norm.weight"] = (1 + 0.1 * torch.randn(d, generator=g)).to(dtype)
+    sd["lm_head.layer_norm.bias"] = w(d, s=0.05)
+    sd["lm_head.weight"] = sd["embed_tokens.weight"]  # tied
+    sd["lm_head.bias"] = w(VOCAB, s=0.1)
     return sd
 
 

@@ -88,6 +88,17 @@ class _EsmLayerP(nn.Module):
         self.final_layer_norm = _LayerNormP(d)
 
 
+class _EsmLMHeadP(nn.Module):
+    """fair-esm RobertaLMHead parameters: dense -> gelu -> layer_norm -> tied decoder (+ bias)."""
+
+    def __init__(self, d: int, embed_weight: nn.Parameter):
+        super().__init__()
+        self.dense = _Linear(d, d)
+        self.layer_norm = _LayerNormP(d)
+        self.weight = embed_weight  # shared with embed_tokens.weight, as in fair-esm
+        self.bias = nn.Parameter(torch.zeros(embed_weight.shape[0]), requires_grad=False)
+
+
 class ESM2Params(nn.Module):
     """fair-esm `ESM2` parameter tree (names only): embed_tokens, layers.N.*, emb_layer_norm_after."""
 
@@ -99,11 +110,12 @@ class ESM2Params(nn.Module):
         self.embed_tokens.weight.requires_grad_(False)
         self.layers = nn.ModuleList([_EsmLayerP(d, self.ffn_dim) for _ in range(n_layers)])
         self.emb_layer_norm_after = _LayerNormP(d)
+        self.lm_head = _EsmLMHeadP(d, self.embed_tokens.weight)
         self.token_dropout = True
         for p in self.parameters():
             if p.dim() > 1:
                 nn.init.normal_(p, std=0.02)
-            elif p is not self.emb_layer_norm_after.weight and not any(
+            elif p is not self.emb_layer_norm_after.weight and p is not self.lm_head.layer_norm.weight and not any(
                     p is l.self_attn_layer_norm.weight or p is l.final_layer_norm.weight for l in self.layers):
                 nn.init.zeros_(p)
 
@@ -317,9 +329,25 @@ class ESM_PLM(nn.Module):
                                  c_i64(self._workspace.numel()), stream_ptr(dev)), "pcy_esm_encode")
         return out
 
+    def lm_head_logits(self, z: torch.Tensor) -> torch.Tensor:
+        """fair-esm RobertaLMHead on residue states [B, T, d] -> logits [B, T, 33] in z's dtype:
+        layer_norm(gelu(dense(z))) @ embed_tokens.weight^T + bias (procyon/model/esm.py:549-555 passes them on)."""
+        from .. import ops
+
+        B, T, d = z.shape
+        hp = self.model.lm_head
+        dev = z.device
+        x = z.reshape(B * T, d).contiguous()
+        h = ops.linear(x, hp.dense.weight.detach().to(dev, torch.bfloat16), hp.dense.bias.detach().to(dev, torch.float32),
+                       act=ops.ACT_GELU)
+        h = ops.layernorm(h, hp.layer_norm.weight.detach(), hp.layer_norm.bias.detach(), eps=1e-5)
+        logits = ops.linear(h, hp.weight.detach().to(dev, torch.bfloat16), hp.bias.detach().to(dev, torch.float32),
+                            out_fp32=True)
+        return logits.view(B, T, -1).to(z.dtype)
+
     def forward(self, tokens: torch.Tensor, aggregate: bool = True):
-        """Same contract as the reference: returns (z, logits). `logits` is None — the LM head output is
-        discarded by every caller on the pooled path (procyon/model/model_unified.py:391), so it is not computed."""
+        """Same contract as the reference: returns (z, logits). On the pooled path `logits` is None — every caller
+        discards them there (procyon/model/model_unified.py:391), so they are not computed."""
         _lib.require_cuda(tokens)
         if self.long_protein_strategy == "split":
             batch_tokens, batch_keys, eos_loc = batched_split_long_seq(
@@ -334,11 +362,13 @@ class ESM_PLM(nn.Module):
         Bp, T = batch_tokens.shape
         d = self.embedding_size
         dev = tokens.device
-        if not aggregate:
+        if not aggregate:  # residue states + masked-LM logits (the `return_mlm` path, model_unified.py:505-509)
             z = self.encode_tokens(batch_tokens)
+            logits = self.lm_head_logits(z)
             if eos_loc is not None and Bp != tokens.shape[0]:
                 z = reverse_batched_split(z, batch_keys, eos_locs=eos_loc)
-            return z, None
+                logits = reverse_batched_split(logits, batch_keys, eos_locs=eos_loc)
+            return z, logits
 
         rows_per_pass = max(1, self.max_tokens_per_pass // T)
         if self.max_batch_forward_pass is not None:

@@ -371,8 +371,10 @@ class UnifiedProCyon(nn.Module):
     def forward(self, inputs, return_mlm=False, retrieval=False, get_full_labels=False, aaseq_type="protein",
                 exclude_protein_structure=False, crop_off=False, output_attentions=False):
         """model_unified.py:483-699."""
-        if return_mlm:
-            raise NotImplementedError("return_mlm (ESM LM head) is the next-tier item of SURVEY §8(f)")
+        if return_mlm:  # masked-LM logits of the protein encoder only; the text encoder is not touched (:505-509)
+            _, logits = self.protein_seq_encoder(inputs["data"]["seq"].to(self.input_embeddings.weight.device),
+                                                 aggregate=False)
+            return {"mlm": logits}
         ignore_struct = (inputs["target"]["seq"] is not None) and self.training and not exclude_protein_structure
         (input_embeds, input_ids, attn_masks, ret_output_indices, protein_token_embeddings,
          protein_ret_embeddings) = self._preprocessing(inputs, aaseq_type=aaseq_type, crop_off=crop_off,

@@ -68,3 +68,16 @@ def pack_gate_up(gate: torch.Tensor, up: torch.Tensor) -> torch.Tensor:
     check(lib.pcy_pack_gate_up(ptr(gate.contiguous()), ptr(up.contiguous()), ptr(packed), c_int(F), c_int(K),
                                stream_ptr(gate.device)), "pcy_pack_gate_up")
     return packed
+
+
+def layernorm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
+    """torch.nn.LayerNorm over the last dim of bf16 rows [n, d] (pcy_layernorm_bf16); weight / bias bf16."""
+    lib = _lib.load()
+    _lib.require_cuda(x)
+    x = _bf16_2d(x, "x").contiguous()
+    w = weight.to(device=x.device, dtype=torch.bfloat16).contiguous()
+    b = bias.to(device=x.device, dtype=torch.bfloat16).contiguous()
+    y = torch.empty_like(x)
+    check(lib.pcy_layernorm_bf16(ptr(x), ptr(w), ptr(b), ptr(y), c_i64(x.shape[0]), c_int(x.shape[1]), c_float(eps),
+                                 stream_ptr(x.device)), "pcy_layernorm_bf16")
+    return y

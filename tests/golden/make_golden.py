@@ -293,6 +293,49 @@ def golden_hf_esm():
     save("hf_esm.pt", cases)
 
 
+def golden_hf_esm_lm_head():
+    """Masked-LM logits of HF EsmForMaskedLM (same head as fair-esm's RobertaLMHead) with the head's weights under
+    their fair-esm names: pins oracle.esm2.esm2_lm_head and the product's `return_mlm` path."""
+    from transformers import EsmConfig, EsmForMaskedLM
+
+    torch.manual_seed(7)
+    L, d, H, lens = 2, 64, 4, [20, 9, 31]
+    cfg = EsmConfig(vocab_size=33, mask_token_id=32, pad_token_id=1, hidden_size=d, num_hidden_layers=L,
+                    num_attention_heads=H, intermediate_size=4 * d, position_embedding_type="rotary",
+                    token_dropout=True, emb_layer_norm_before=False, layer_norm_eps=1e-5,
+                    attn_implementation="eager", hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    m = EsmForMaskedLM(cfg).eval()
+    for p in m.parameters():
+        torch.nn.init.normal_(p, std=0.1)
+    m.lm_head.decoder.weight = m.esm.embeddings.word_embeddings.weight  # tied, as in fair-esm
+    hsd = m.state_dict()
+    sd = {"embed_tokens.weight": hsd["esm.embeddings.word_embeddings.weight"]}
+    for l in range(L):
+        h, p = f"esm.encoder.layer.{l}.", f"layers.{l}."
+        for a, b in (("query", "q_proj"), ("key", "k_proj"), ("value", "v_proj")):
+            sd[p + f"self_attn.{b}.weight"] = hsd[h + f"attention.self.{a}.weight"]
+            sd[p + f"self_attn.{b}.bias"] = hsd[h + f"attention.self.{a}.bias"]
+        sd[p + "self_attn.out_proj.weight"] = hsd[h + "attention.output.dense.weight"]
+        sd[p + "self_attn.out_proj.bias"] = hsd[h + "attention.output.dense.bias"]
+        sd[p + "self_attn_layer_norm.weight"] = hsd[h + "attention.LayerNorm.weight"]
+        sd[p + "self_attn_layer_norm.bias"] = hsd[h + "attention.LayerNorm.bias"]
+        sd[p + "fc1.weight"], sd[p + "fc1.bias"] = hsd[h + "intermediate.dense.weight"], hsd[h + "intermediate.dense.bias"]
+        sd[p + "fc2.weight"], sd[p + "fc2.bias"] = hsd[h + "output.dense.weight"], hsd[h + "output.dense.bias"]
+        sd[p + "final_layer_norm.weight"], sd[p + "final_layer_norm.bias"] = hsd[h + "LayerNorm.weight"], hsd[h + "LayerNorm.bias"]
+    sd["emb_layer_norm_after.weight"] = hsd["esm.encoder.emb_layer_norm_after.weight"]
+    sd["emb_layer_norm_after.bias"] = hsd["esm.encoder.emb_layer_norm_after.bias"]
+    sd["lm_head.dense.weight"], sd["lm_head.dense.bias"] = hsd["lm_head.dense.weight"], hsd["lm_head.dense.bias"]
+    sd["lm_head.layer_norm.weight"] = hsd["lm_head.layer_norm.weight"]
+    sd["lm_head.layer_norm.bias"] = hsd["lm_head.layer_norm.bias"]
+    sd["lm_head.weight"], sd["lm_head.bias"] = hsd["esm.embeddings.word_embeddings.weight"], hsd["lm_head.bias"]
+    toks = OE.random_protein_tokens(len(lens), 0, seed=5, lengths=lens)
+    toks[1, 4] = 32
+    with torch.no_grad():
+        out = m(input_ids=toks, attention_mask=(toks != 1).long(), output_hidden_states=True)
+    save("hf_esm_lm_head.pt", dict(n_layers=L, d=d, n_heads=H, state_dict={k: v.clone() for k, v in sd.items()},
+                                   tokens=toks, states=out.hidden_states[-1], logits=out.logits))
+
+
 def golden_hf_llama():
     from transformers import LlamaConfig, LlamaForCausalLM
 
@@ -330,4 +373,5 @@ if __name__ == "__main__":
     golden_prompt_and_labels()
     golden_beam_search()
     golden_hf_esm()
+    golden_hf_esm_lm_head()
     golden_hf_llama()

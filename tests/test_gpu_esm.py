@@ -112,3 +112,38 @@ def test_esm_tcgen05_attention_matches_mma_sync_and_oracle(cuda_device):
     torch.testing.assert_close(a[nonpad], b[nonpad], rtol=2e-2, atol=2e-2)
     ref = O.esm2_forward(sd, toks, L, H, act_round="bf16")
     torch.testing.assert_close(a[nonpad], ref[nonpad], rtol=3e-2, atol=3e-2)
+
+
+def test_return_mlm_logits(cuda_device):
+    """`return_mlm` path: residue states + masked-LM head, incl. proteins longer than
+    max_protein_len (chunk -> encode -> stitch back for states AND logits).  Golden: HF EsmForMaskedLM."""
+    import os
+
+    from oracle import esm2 as O
+
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "hf_esm_lm_head.pt"), weights_only=False)
+    L, d, H = g["n_layers"], g["d"], g["n_heads"]
+    m = _build("custom", {k: v.bfloat16() for k, v in g["state_dict"].items()}, custom=(L, d, H))
+    z, logits = m(g["tokens"].cuda(), aggregate=False)
+    keep = g["tokens"] != O.PAD_IDX
+    assert logits.shape == g["logits"].shape and logits.dtype == z.dtype
+    # bf16 weights + activations vs the fp32 HF run: a few bf16 ulps of O(1) values
+    torch.testing.assert_close(logits.float().cpu()[keep], g["logits"][keep], rtol=5e-2, atol=5e-2)
+    # oracle with the same roundings, longer-than-max proteins
+    sd = O.random_esm_state_dict(2, 64, seed=11)
+    toks = O.random_protein_tokens(3, 0, seed=4, lengths=[70, 30, 45])
+    m2 = _build("custom", sd, custom=(2, 64, 4), max_len=32)
+    z2, lg2 = m2(toks.cuda(), aggregate=False)
+    bt, keys, eos = O.batched_split_long_seq(toks, max_protein_len=32)
+    zr = O.esm2_forward(sd, bt, 2, 4, act_round="bf16")
+    lr = O.esm2_lm_head(sd, zr, act_round="bf16")
+    zr, lr = O.reverse_batched_split(zr, keys, eos), O.reverse_batched_split(lr, keys, eos)
+    keep2 = toks != O.PAD_IDX
+    assert lg2.shape == lr.shape
+    torch.testing.assert_close(z2.float().cpu()[keep2], zr[keep2], rtol=3e-2, atol=3e-2)
+    # logits are O(5) here (embedding rows of std 0.5 against LayerNorm outputs): the 3e-2 state tolerance, carried
+    # through dense -> gelu -> LayerNorm -> 64-term dot products, is a few % of the logit scale at worst and far
+    # less on average
+    scale = lr[keep2].abs().max().item()
+    err = (lg2.float().cpu()[keep2] - lr[keep2]).abs()
+    assert err.max().item() < 5e-2 * scale and err.mean().item() < 5e-3 * scale, (err.max().item(), err.mean().item(), scale)
