@@ -103,6 +103,9 @@ int pcy_set_fused_rope(int enabled);
 /* 1: tcgen05 GEMMs with >= 2 row-blocks run as 2-CTA clusters sharing the weight tile by TMA multicast;
    0 (default): independent CTAs. Both paths are bit-identical (tests); measured equal speed on B200 */
 int pcy_set_gemm_cluster(int enabled);
+/* 1 (default): linears with 5..16 activation rows and no fused norm stream the weights through mma.sync (tensor
+   cores); 0: the scalar-FMA weight-streaming kernel for every M <= 16 */
+int pcy_set_skinny_mma(int enabled);
 int pcy_esm_create(const pcy_esm_config* cfg, void** handle);
 int pcy_esm_destroy(void* handle);
 /* src may be a host or a device pointer; the library keeps its own packed copy */

@@ -25,6 +25,7 @@ int num_sms();
 void count_launch(int n = 1);
 extern bool g_fused_rope;
 extern bool g_gemm_cluster;
+extern bool g_skinny_mma;
 
 #define PCY_CUDA(expr)                                                     \
   do {                                                                     \

@@ -53,6 +53,11 @@ int pcy_set_fused_rope(int enabled) {
   return 0;
 }
 
+int pcy_set_skinny_mma(int enabled) {
+  pcy::g_skinny_mma = enabled != 0;
+  return 0;
+}
+
 int pcy_set_gemm_cluster(int enabled) {
   pcy::g_gemm_cluster = enabled != 0;
   return 0;

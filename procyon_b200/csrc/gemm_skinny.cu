@@ -6,10 +6,14 @@
 //
 // Replaces cuBLAS GEMV calls under HF LlamaDecoderLayer at decode time (procyon/model/model_unified.py:769)
 // and create_mlp at M = #proteins (procyon/model/model_unified.py:402-405).
+#include <algorithm>
+
 #include "common.cuh"
 #include "ops.h"
 
 namespace pcy {
+
+bool g_skinny_mma = true;  // pcy_set_skinny_mma(0): scalar-FMA kernel for every M <= 16 (A/B measurements, tests)
 
 namespace {
 
@@ -212,6 +216,162 @@ int launch_skinny(SkinnyParams p, cudaStream_t stream) {
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// 5..16 activation rows (beam search: the reference's evaluation default is beam_size = 10): the scalar kernel above
+// needs ~2 FMA-pipe instructions per weight element and row and is ALU-bound there (18.8 ms per Llama-3-8B decode step
+// at 10 rows against 3.2 ms at 1 row).  Here the legacy tensor cores do the math: a CTA of 4 warps owns 16 weight rows
+// (32 for SwiGLU: the 16 gate rows and their 16 up rows), warp w streams k-blocks w, w+4, ... of 64 elements through
+// its own cp.async ring (weights 16 x 128 B and the matching slice of the <= 16 activation rows, XOR-swizzled),
+// ldmatrix + mma.sync.m16n8k16 with the weights as A and the activations as B, then the four partial accumulators
+// meet in shared memory for the fused epilogue.  Every weight byte is still read exactly once.
+constexpr int TK = 64;          // k elements per stage
+constexpr int T_WARPS = 4;
+constexpr int T_THREADS = T_WARPS * 32;
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
+  const int sz = valid ? 16 : 0;  // src-size 0: zero fill
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <bool SWIGLU, int STG>
+__global__ void __launch_bounds__(T_THREADS)
+gemm_skinny_mma_kernel(const SkinnyParams p) {
+  constexpr int WT = SWIGLU ? 2 : 1;                 // 16-row weight tiles per CTA tile
+  constexpr int STAGE_BYTES = (WT + 1) * 16 * 128;   // weights + activations
+  extern __shared__ __align__(128) uint8_t tk_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t ring = smem_u32(tk_smem) + warp * (STG * STAGE_BYTES);
+  float* red = reinterpret_cast<float*>(tk_smem + T_WARPS * STG * STAGE_BYTES);  // [T_WARPS][32][8 WT]
+  const int n_tiles = (p.N + 16 * WT - 1) / (16 * WT);
+  const int k_blocks = p.K / TK;
+  const int my_blocks = (k_blocks - warp + T_WARPS - 1) / T_WARPS;  // k-blocks warp, warp + 4, ...
+
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int row0 = tile * 16 * WT;
+    auto issue = [&](int i) {  // k-block warp + 4 i of this tile -> ring slot i % STG
+      const int k0 = (warp + i * T_WARPS) * TK;
+      const uint32_t st = ring + (i % STG) * STAGE_BYTES;
+#pragma unroll
+      for (int j = 0; j < 4 * WT; ++j) {  // weights: 16 WT rows x 8 chunks of 16 B
+        const int c = lane + 32 * j, r = c >> 3, ch = c & 7;
+        const int row = min(row0 + r, p.N - 1);  // (rows past N are computed and dropped)
+        cp_async16(st + r * 128 + ((ch ^ (r & 7)) << 4), p.W + (int64_t)row * p.ldw + k0 + ch * 8, true);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {       // activations: 16 rows (zero past M) x 8 chunks
+        const int c = lane + 32 * j, r = c >> 3, ch = c & 7;
+        const bool ok = r < p.M;
+        cp_async16(st + WT * 2048 + r * 128 + ((ch ^ (r & 7)) << 4), p.A + (int64_t)(ok ? r : 0) * p.lda + k0 + ch * 8,
+                   ok);
+      }
+    };
+    float acc[WT][2][4];
+#pragma unroll
+    for (int t = 0; t < WT; ++t)
+#pragma unroll
+      for (int n = 0; n < 2; ++n) acc[t][n][0] = acc[t][n][1] = acc[t][n][2] = acc[t][n][3] = 0.f;
+#pragma unroll
+    for (int i = 0; i < STG - 1; ++i) {
+      if (i < my_blocks) issue(i);
+      cp_async_commit();
+    }
+    for (int i = 0; i < my_blocks; ++i) {
+      cp_async_wait<STG - 2>();
+      __syncwarp();
+      if (i + STG - 1 < my_blocks) issue(i + STG - 1);  // slot (i - 1) % STG: read by every lane before the sync above
+      cp_async_commit();
+      const uint32_t st = ring + (i % STG) * STAGE_BYTES;
+#pragma unroll
+      for (int ks = 0; ks < TK / 16; ++ks) {
+        uint32_t bf[4];
+        {  // activations as B: matrices (m 0-7, k lo) (m 0-7, k hi) (m 8-15, k lo) (m 8-15, k hi)
+          const int r = (lane & 7) + (lane >> 4) * 8, ch = ks * 2 + ((lane >> 3) & 1);
+          ldsm_x4(st + WT * 2048 + r * 128 + ((ch ^ (r & 7)) << 4), bf);
+        }
+#pragma unroll
+        for (int t = 0; t < WT; ++t) {
+          uint32_t af[4];  // weights as A: (rows 0-7, k lo) (rows 8-15, k lo) (rows 0-7, k hi) (rows 8-15, k hi)
+          const int r = (lane & 7) + ((lane >> 3) & 1) * 8, ch = ks * 2 + (lane >> 4);
+          ldsm_x4(st + t * 2048 + r * 128 + ((ch ^ (r & 7)) << 4), af);
+          mma16816(acc[t][0], af, bf[0], bf[1]);
+          mma16816(acc[t][1], af, bf[2], bf[3]);
+        }
+      }
+    }
+    cp_async_wait<0>();
+    // ---- the four warps' partial sums meet in shared memory ----
+#pragma unroll
+    for (int t = 0; t < WT; ++t)
+#pragma unroll
+      for (int n = 0; n < 2; ++n)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) red[(warp * 32 + lane) * (8 * WT) + t * 8 + n * 4 + j] = acc[t][n][j];
+    __syncthreads();
+    // fragment entry (lane', e): row = lane'/4 + 8 (e>>1 & 1), m = 2 (lane'%4) + (e & 1) + 8 (e >> 2)
+    for (int idx = threadIdx.x; idx < 32 * 8; idx += T_THREADS) {
+      const int ln = idx >> 3, e = idx & 7;
+      const int r = (ln >> 2) + ((e >> 1) & 1) * 8, m = (ln & 3) * 2 + (e & 1) + (e >> 2) * 8;
+      float v[WT];
+#pragma unroll
+      for (int t = 0; t < WT; ++t) {
+        v[t] = 0.f;
+#pragma unroll
+        for (int w = 0; w < T_WARPS; ++w) v[t] += red[(w * 32 + ln) * (8 * WT) + t * 8 + e];
+      }
+      if (m >= p.M) continue;
+      if (!SWIGLU) {
+        const int n = row0 + r;
+        if (n >= p.N) continue;
+        float x = v[0];
+        if (p.bias) x += p.bias[n];
+        if (n < p.scale_ncols) x *= p.scale;
+        if (p.act == ACT_GELU) x = gelu_erf(x);
+        if (p.residual) x += __bfloat162float(p.residual[(int64_t)m * p.ldr + n]);
+        if (p.c_fp32) reinterpret_cast<float*>(p.C)[(int64_t)m * p.ldc + n] = x;
+        else reinterpret_cast<bf16*>(p.C)[(int64_t)m * p.ldc + n] = __float2bfloat16_rn(x);
+      } else {
+        float g = v[0], u = v[WT - 1];
+        if (p.bias) { g += p.bias[row0 + r]; u += p.bias[row0 + 16 + r]; }
+        float x = silu(g) * u;
+        const int ocol = tile * 16 + r;
+        if (p.residual) x += __bfloat162float(p.residual[(int64_t)m * p.ldr + ocol]);
+        reinterpret_cast<bf16*>(p.C)[(int64_t)m * p.ldc + ocol] = __float2bfloat16_rn(x);
+      }
+    }
+    __syncthreads();  // red is reused by the next tile
+  }
+}
+
+template <bool SWIGLU, int STG>
+int launch_skinny_mma(const SkinnyParams& p, cudaStream_t stream) {
+  constexpr int WT = SWIGLU ? 2 : 1;
+  constexpr size_t smem = (size_t)T_WARPS * STG * (WT + 1) * 2048 + (size_t)T_WARPS * 32 * 8 * WT * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    PCY_CUDA(cudaFuncSetAttribute(gemm_skinny_mma_kernel<SWIGLU, STG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem));
+    attr_set = true;
+  }
+  const int n_tiles = ceil_div(p.N, 16 * WT);
+  const int grid = std::min(n_tiles, num_sms() * 8);
+  gemm_skinny_mma_kernel<SWIGLU, STG><<<grid, T_THREADS, smem, stream>>>(p);
+  PCY_LAUNCH_CHECK();
+  return 0;
+}
+
 template <int MT>
 int dispatch_mt(const SkinnyParams& p, bool asmem, cudaStream_t stream) {
   // enough units to give every SM several warps; wide rows-per-warp only when N is large
@@ -238,6 +398,11 @@ int gemm_bf16_skinny(const GemmArgs& a, const bf16* rms_weight, float rms_eps, c
   p.residual = a.residual; p.ldr = a.ldr; p.rms_weight = rms_weight; p.rms_eps = rms_eps;
   p.M = a.M; p.N = a.N; p.K = a.K; p.c_fp32 = a.c_fp32; p.act = a.act; p.scale = a.scale;
   p.scale_ncols = a.scale_ncols; p.num_units = 0;
+  // 5..16 rows without a fused norm: tensor-core kernel (needs whole 64-element k-blocks)
+  if (a.M > 4 && rms_weight == nullptr && a.K % TK == 0 && g_skinny_mma) {
+    if (a.act == ACT_SWIGLU) return launch_skinny_mma<true, 4>(p, stream);
+    return launch_skinny_mma<false, 6>(p, stream);
+  }
   const int mt = a.M <= 1 ? 1 : a.M <= 2 ? 2 : a.M <= 4 ? 4 : a.M <= 8 ? 8 : 16;
   const bool fits = (size_t)mt * a.K * 2 <= 160 * 1024;
   if (rms_weight != nullptr)

@@ -288,7 +288,7 @@ int64_t pcy_llama_decode_workspace_bytes(void* handle, int rows, int S, int max_
   if (!handle) return -1;
   LlamaModel* m = reinterpret_cast<LlamaModel*>(handle);
   const int64_t d = m->cfg.d_model;
-  int64_t b = 2 * round_up(rows * d * 2, 256) + round_up((int64_t)rows * m->qkv_dim() * 2, 256) +
+  int64_t b = 3 * round_up(rows * d * 2, 256) + round_up((int64_t)rows * m->qkv_dim() * 2, 256) +
               round_up((int64_t)rows * m->cfg.ffn_dim * 2, 256);
   b += round_up(decode_attention_partial_floats(rows, m->cfg.n_heads, m->cfg.n_kv_heads, S, max_gen) * 4, 256);
   b += round_up((int64_t)rows * m->cfg.n_kv_heads * 4, 256);
@@ -318,6 +318,7 @@ int pcy_llama_decode_forward(void* handle, const pcy_decode_buffers* b, void* st
   bf16* act = carve<bf16>(p, (int64_t)rows * f);
   float* partials = carve<float>(p, decode_attention_partial_floats(rows, H, KVH, b->S, b->max_gen));
   int32_t* tickets = carve<int32_t>(p, (int64_t)rows * KVH);  // zeroed by pcy_decode_reset
+  bf16* xn = carve<bf16>(p, (int64_t)rows * d);                // normalised rows (rows > 4 only)
   static const bool force_multi = getenv("PCY_DECODE_MULTIKERNEL") != nullptr;
   if (!force_multi && g_use_megakernel && decode_megakernel_supported(c, rows)) {
     // persistent single-launch step (rows <= 4): see decode_megakernel.cu
@@ -328,11 +329,20 @@ int pcy_llama_decode_forward(void* handle, const pcy_decode_buffers* b, void* st
   PCY_LAUNCH_CHECK();
   const int64_t n_prompt = (int64_t)b->n_inputs * b->S;
   const int64_t n_gen = (int64_t)rows * b->max_gen;
+  // 5..16 rows (beam search): the tensor-core weight-streaming kernel has no fused norm, so RMSNorm runs as its own
+  // (tiny) kernel; up to 4 rows keep the fused prologue of the scalar kernel
+  const bool split_norm = rows > 4 && g_skinny_mma;
+  auto normed_linear = [&](GemmArgs& g, const bf16* ln) -> int {
+    if (!split_norm) return gemm_bf16_skinny(g, ln, c.rms_eps, stream);
+    PCY_TRY(rmsnorm_bf16(x, ln, xn, rows, d, c.rms_eps, stream));
+    g.A = xn;
+    return gemm_bf16_skinny(g, nullptr, 0.f, stream);
+  };
   for (int l = 0; l < c.n_layers; ++l) {
     const LlamaLayer& y = m->layers[l];
     GemmArgs g;
     g.A = x; g.lda = d; g.W = y.wqkv; g.ldw = d; g.C = qkv; g.ldc = qkv_dim; g.M = rows; g.N = qkv_dim; g.K = d;
-    PCY_TRY(gemm_bf16_skinny(g, y.ln1, c.rms_eps, stream));
+    PCY_TRY(normed_linear(g, y.ln1));
     DecodeAttnArgs a;
     a.qkv = qkv; a.qkv_ld = qkv_dim; a.cos_sin = m->rope;
     a.k_prompt = reinterpret_cast<const bf16*>(b->kv_prompt) + ((int64_t)l * 2 + 0) * n_prompt * kvd;
@@ -350,7 +360,7 @@ int pcy_llama_decode_forward(void* handle, const pcy_decode_buffers* b, void* st
     GemmArgs gu;
     gu.A = x; gu.lda = d; gu.W = y.wgu; gu.ldw = d; gu.C = act; gu.ldc = f; gu.M = rows; gu.N = 2 * f; gu.K = d;
     gu.act = ACT_SWIGLU;
-    PCY_TRY(gemm_bf16_skinny(gu, y.ln2, c.rms_eps, stream));
+    PCY_TRY(normed_linear(gu, y.ln2));
     GemmArgs dn;
     dn.A = act; dn.lda = f; dn.W = y.wdown; dn.ldw = f; dn.C = x; dn.ldc = d; dn.M = rows; dn.N = d; dn.K = f;
     dn.residual = x; dn.ldr = d;
@@ -359,7 +369,7 @@ int pcy_llama_decode_forward(void* handle, const pcy_decode_buffers* b, void* st
   GemmArgs lm;
   lm.A = x; lm.lda = d; lm.W = m->lm_head; lm.ldw = d; lm.C = b->logits_cur; lm.ldc = c.vocab; lm.M = rows;
   lm.N = c.vocab; lm.K = d; lm.c_fp32 = 1;
-  PCY_TRY(gemm_bf16_skinny(lm, m->norm, c.rms_eps, stream));
+  PCY_TRY(normed_linear(lm, m->norm));
   return 0;
 }
 

@@ -81,6 +81,40 @@ def test_cluster_multicast_gemm_is_bit_identical(cuda_device, M, N, K):
     torch.testing.assert_close(f1.cpu(), ref, rtol=2e-4, atol=2e-4 * ref.abs().max().item())
 
 
+@pytest.mark.parametrize("M,N,K", [(5, 4096, 4096), (10, 6144, 4096), (16, 520, 1280), (7, 1003, 192), (10, 4096, 14336),
+                                   (12, 33, 64)])
+def test_skinny_tensor_core_kernel(cuda_device, M, N, K):
+    """5..16 activation rows: weights streamed through mma.sync vs the scalar-FMA kernel and vs fp32 torch, with
+    bias / GELU / residual / fp32-output epilogues, N not a multiple of the 16-row tile, and the SwiGLU layout."""
+    from procyon_b200 import _lib, ops
+
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(M * 131 + N + K)
+    a = (torch.randn(M, K, generator=g) * 0.5).bfloat16().cuda()
+    w = (torch.randn(N, K, generator=g) / math.sqrt(K)).bfloat16().cuda()
+    bias = torch.randn(N, generator=g).cuda()
+    res = torch.randn(M, N, generator=g).bfloat16().cuda()
+    try:
+        lib.pcy_set_skinny_mma(0)
+        o0 = ops.linear(a, w, bias, residual=res, act=1, force="skinny")
+        f0 = ops.linear(a, w, bias, force="skinny", out_fp32=True, scale=0.125, scale_ncols=min(N, 32))
+        lib.pcy_set_skinny_mma(1)
+        o1 = ops.linear(a, w, bias, residual=res, act=1, force="skinny")
+        f1 = ops.linear(a, w, bias, force="skinny", out_fp32=True, scale=0.125, scale_ncols=min(N, 32))
+    finally:
+        lib.pcy_set_skinny_mma(1)
+    ref = _cpu_linear(a.cpu(), w.cpu(), bias.cpu(), None, 0, 0.125, min(N, 32))
+    torch.testing.assert_close(f1.cpu(), ref, rtol=2e-4, atol=2e-4 * ref.abs().max().item())
+    torch.testing.assert_close(f1, f0, rtol=2e-4, atol=2e-4 * ref.abs().max().item())
+    torch.testing.assert_close(o1.float(), o0.float(), rtol=1e-2, atol=1e-2 * ref.abs().max().item())
+    if N % 32 == 0:
+        gate, up = w[: N // 2].contiguous(), w[N // 2:].contiguous()
+        packed = ops.pack_gate_up(gate, up)
+        s1 = ops.linear(a, packed, act=ops.ACT_SWIGLU, force="skinny")
+        sref = F.silu(a.float().cpu() @ gate.float().cpu().t()) * (a.float().cpu() @ up.float().cpu().t())
+        torch.testing.assert_close(s1.float().cpu(), sref, rtol=1e-2, atol=1e-2 * sref.abs().max().item())
+
+
 @pytest.mark.parametrize("M,force", [(1, "skinny"), (4, "skinny"), (9, "skinny"), (200, "tc")])
 def test_swiglu_parity(cuda_device, M, force):
     from procyon_b200 import ops
