@@ -190,6 +190,33 @@ def time_decode_kernel(model, sess, device, iters=20):
             "gbs": total / ms / 1e6}
 
 
+def time_beam_decode(model, x, device, beams=10, iters=30):
+    """ms per decode step (forward + diverse-beam selection, CUDA-graph replay) at the reference's evaluation default
+    beam_size = 10 (procyon/evaluate/framework/procyon.py:72-76): the one-launch-per-op path with the tensor-core
+    weight-streaming GEMM."""
+    from procyon_b200.model.pmc_llama import SELECT_BEAM
+
+    te = model.text_encoder
+    sess = te.get_session(1, beams, x.shape[1], GEN_LEN, device, False, False)
+    sel = torch.tensor([x.shape[1] - 1], device=device, dtype=torch.int32)
+    _, _, logits, _ = te.prefill(x, None, want_cache=True, want_hidden=False, sel_rows=sel, kv_out=sess.kv_prompt)
+    sess.reset(logits)
+    sess.select(SELECT_BEAM, beams // 2, 0.8, -1, False)
+    g = sess.step_graph(SELECT_BEAM, beams // 2, 0.8, -1, False)
+    for _ in range(5):
+        g.replay()
+    torch.cuda.synchronize(device)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        g.replay()
+    e1.record()
+    torch.cuda.synchronize(device)
+    ms = e0.elapsed_time(e1) / iters
+    return {"beams": beams, "ms_per_step": ms, "tokens_per_s_aggregate": beams / ms * 1e3,
+            "weight_stream_gbs": 15.009374208 / ms * 1e3}
+
+
 def time_esm_encode(model, device, world, rank, steps, warmup):
     """BASELINE configs[2] shape on a bounded batch: ESM_BATCH proteins of ESM_LEN residues per rank, pooled and
     all-gathered. Returns proteins/s (aggregate) and achieved TFLOP/s per GPU."""
@@ -326,8 +353,12 @@ def run_ours(args):
     dk = time_decode_kernel(model, sess, device)
     roofline = {"kernel": "llama_decode_megakernel<1,4> (one launch per generated token)", "bound": "hbm",
                 "achieved": dk["gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": dk["gbs"] / hbm_peak,
-                "peak_source": peak_src, "traffic": None, "bytes_per_launch": dk["bytes_per_launch"],
+                "peak_source": peak_src,
+                # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full
+                # (profiles/r01_ncu_decode_megakernel_final.txt): 15.146 GB read + 0.010 GB written
+                "traffic": 15.156e9, "bytes_per_launch": dk["bytes_per_launch"],
                 "ms_per_launch": dk["ms_per_launch"], "weight_bytes": dk["weight_bytes"], "kv_bytes": dk["kv_bytes"]}
+    beam = time_beam_decode(model, x, device) if rank == 0 else None
     esm = time_esm_encode(model, device, world, rank, steps=max(2, K // 2), warmup=2)
     esm["frac_of_bf16_peak"] = esm["tflops_per_gpu"] / tf_peak
     esm["frac_of_bf16_sustained"] = esm["tflops_per_gpu"] / tf_sus
@@ -351,7 +382,7 @@ def run_ours(args):
             "e2e": {"value": e2e_tok_s, "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "UnifiedProCyon.generate(inputs, max_len=128, method='greedy', return_logits=False)"},
             "gpu_launches": launches, "clocks": clocks.summary(), "roofline": roofline, "phases": phases,
-            "esm2_encode": esm, "cpu_baseline": cpu_base,
+            "esm2_encode": esm, "decode_beam10": beam, "cpu_baseline": cpu_base,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

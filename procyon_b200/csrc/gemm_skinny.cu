@@ -7,6 +7,7 @@
 // Replaces cuBLAS GEMV calls under HF LlamaDecoderLayer at decode time (procyon/model/model_unified.py:769)
 // and create_mlp at M = #proteins (procyon/model/model_unified.py:402-405).
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "ops.h"
@@ -14,6 +15,10 @@
 namespace pcy {
 
 bool g_skinny_mma = true;  // pcy_set_skinny_mma(0): scalar-FMA kernel for every M <= 16 (A/B measurements, tests)
+int skinny_mma_min_rows() {  // rows from which the tensor-core kernel is used (tuning knob)
+  static const int v = [] { const char* e = getenv("PCY_SKINNY_MMA_MIN_M"); return e ? atoi(e) : 5; }();
+  return v;
+}
 
 namespace {
 
@@ -399,7 +404,7 @@ int gemm_bf16_skinny(const GemmArgs& a, const bf16* rms_weight, float rms_eps, c
   p.M = a.M; p.N = a.N; p.K = a.K; p.c_fp32 = a.c_fp32; p.act = a.act; p.scale = a.scale;
   p.scale_ncols = a.scale_ncols; p.num_units = 0;
   // 5..16 rows without a fused norm: tensor-core kernel (needs whole 64-element k-blocks)
-  if (a.M > 4 && rms_weight == nullptr && a.K % TK == 0 && g_skinny_mma) {
+  if (a.M >= skinny_mma_min_rows() && rms_weight == nullptr && a.K % TK == 0 && g_skinny_mma) {
     if (a.act == ACT_SWIGLU) return launch_skinny_mma<true, 4>(p, stream);
     return launch_skinny_mma<false, 6>(p, stream);
   }

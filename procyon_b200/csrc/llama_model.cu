@@ -331,7 +331,7 @@ int pcy_llama_decode_forward(void* handle, const pcy_decode_buffers* b, void* st
   const int64_t n_gen = (int64_t)rows * b->max_gen;
   // 5..16 rows (beam search): the tensor-core weight-streaming kernel has no fused norm, so RMSNorm runs as its own
   // (tiny) kernel; up to 4 rows keep the fused prologue of the scalar kernel
-  const bool split_norm = rows > 4 && g_skinny_mma;
+  const bool split_norm = rows >= skinny_mma_min_rows() && g_skinny_mma;
   auto normed_linear = [&](GemmArgs& g, const bf16* ln) -> int {
     if (!split_norm) return gemm_bf16_skinny(g, ln, c.rms_eps, stream);
     PCY_TRY(rmsnorm_bf16(x, ln, xn, rows, d, c.rms_eps, stream));

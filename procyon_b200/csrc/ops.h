@@ -43,6 +43,7 @@ int gemm_bf16_tc(const GemmArgs& a, cudaStream_t stream);
 int gemm_bf16_skinny(const GemmArgs& a, const bf16* rms_weight, float rms_eps, cudaStream_t stream);
 // Dispatch: skinny for M <= 16, tensor-core otherwise.
 int gemm_bf16(const GemmArgs& a, cudaStream_t stream);
+int skinny_mma_min_rows();
 
 // ---- normalisation ------------------------------------------------------------------------------
 int layernorm_bf16(const bf16* x, const bf16* gamma, const bf16* beta, bf16* y, int64_t rows, int d, float eps,

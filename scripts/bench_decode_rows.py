@@ -16,7 +16,7 @@ def main():
     inputs = bench.synth_inputs(model)
     (x, ids, am, _, _, _) = model._preprocessing(inputs, crop_off=True, no_pad=True, left_pad=True)
     te = model.text_encoder
-    for beams in (1, 4, 10):
+    for beams in [int(b) for b in (sys.argv[1].split(",") if len(sys.argv) > 1 else ["1", "4", "10"])]:
         sess = te.get_session(1, beams, x.shape[1], bench.GEN_LEN, dev, False, False)
         sel = torch.tensor([x.shape[1] - 1], device=dev, dtype=torch.int32)
         _, _, logits, _ = te.prefill(x, None, want_cache=True, want_hidden=False, sel_rows=sel, kv_out=sess.kv_prompt)
