@@ -21,7 +21,7 @@ def main():
         sel = torch.tensor([x.shape[1] - 1], device=dev, dtype=torch.int32)
         _, _, logits, _ = te.prefill(x, None, want_cache=True, want_hidden=False, sel_rows=sel, kv_out=sess.kv_prompt)
         mode = SELECT_GREEDY if beams == 1 else SELECT_BEAM
-        group = 1 if beams == 1 else beams // 2
+        group = 1 if beams == 1 else (beams // 2 if beams % 2 == 0 else beams)
         sess.reset(logits)
         sess.select(mode, group, 0.8, -1, False)
         g = sess.step_graph(mode, group, 0.8, -1, False)
