@@ -443,6 +443,79 @@ struct MegaParams {
   unsigned long long* timing;  // optional: globaltimer at every phase boundary (CTA 0), for profiling
 };
 
+// The K and V rows one thread needs for an attention work item (see attention_phase for the thread mapping), held in
+// registers.  For a CTA's first item they are requested at the START of the qkv phase of the layer: requested just
+// before the attention phase (even before the grid barrier in front of it) they arrived ~5 us late - the SM can only
+// keep so many missing lines in flight - while seven microseconds of weight streaming hide them completely.
+struct AttnLoads {
+  uint4 k[KPW / 4][2];
+  uint2 v[KPW];
+  uint32_t vmask;  // bit j: V row of key j was requested from global memory
+  bool khave[KPW / 4], kvalid[KPW / 4];
+
+  __device__ __forceinline__ void request(const MegaParams& p, int layer, int t, int item) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int sub = lane >> 3, l8 = lane & 7;
+    const int KVH = p.cfg.n_kv_heads, kvd = KVH * HD;
+    const int pos_cur = p.S + t - 1, ctx = pos_cur + 1;
+    const int n_splits = (ctx + ATT_CHUNK - 1) / ATT_CHUNK;
+    const int64_t n_prompt = (int64_t)(p.rows / p.beams) * p.S, n_gen = (int64_t)p.rows * p.max_gen;
+    const bf16* kp = p.kv_prompt + ((int64_t)layer * 2 + 0) * n_prompt * kvd;
+    const bf16* vp = p.kv_prompt + ((int64_t)layer * 2 + 1) * n_prompt * kvd;
+    const bf16* kg = p.kv_gen + ((int64_t)layer * 2 + 0) * n_gen * kvd;
+    const bf16* vg = p.kv_gen + ((int64_t)layer * 2 + 1) * n_gen * kvd;
+    const int split = item % n_splits, kvh = (item / n_splits) % KVH, row = item / (n_splits * KVH);
+    const int input = row / p.beams;
+    const int k0 = split * ATT_CHUNK;
+    const int n_keys = min(ctx, k0 + ATT_CHUNK) - k0;
+    // element offset of the K / V row of key position `pos`
+    auto row_off = [&](int pos, bool& in_prompt) -> int64_t {
+      in_prompt = pos < p.S;
+      if (in_prompt) return ((int64_t)input * p.S + pos) * kvd + kvh * HD;
+      const int g = pos - p.S;
+      const int prow = p.slots[(int64_t)row * p.max_gen + g];
+      return ((int64_t)prow * p.max_gen + g) * kvd + kvh * HD;
+    };
+#pragma unroll
+    for (int it = 0; it < KPW / 4; ++it) {
+      const int kk = warp * KPW + it * 4 + sub;
+      const int pos = k0 + kk;
+      kvalid[it] = kk < n_keys;
+      khave[it] = kvalid[it] && pos != pos_cur;
+      if (khave[it]) {
+        bool in_prompt;
+        const int64_t off = row_off(pos, in_prompt) + l8 * 16;
+        const bf16* kptr = (in_prompt ? kp : kg) + off;
+        if (in_prompt && p.prompt_valid) kvalid[it] = p.prompt_valid[(int64_t)input * p.S + pos] != 0;
+        k[it][0] = __ldcg(reinterpret_cast<const uint4*>(kptr));
+        k[it][1] = __ldcg(reinterpret_cast<const uint4*>(kptr + 8));
+      }
+    }
+    vmask = 0;
+    const int pos0 = k0 + warp * KPW;
+    if (pos0 + KPW <= p.S) {
+      // the warp's 8 keys are all prompt positions (the common case): one base pointer, constant stride
+      const bf16* vb = vp + ((int64_t)input * p.S + pos0) * kvd + kvh * HD + lane * 4;
+#pragma unroll
+      for (int j = 0; j < KPW; ++j) v[j] = __ldcg(reinterpret_cast<const uint2*>(vb + (int64_t)j * kvd));
+      vmask = (1u << KPW) - 1u;
+    } else {
+#pragma unroll
+      for (int j = 0; j < KPW; ++j) {
+        const int kk = warp * KPW + j;
+        const int pos = k0 + kk;
+        v[j] = make_uint2(0, 0);
+        if (kk < n_keys && pos != pos_cur) {
+          bool in_prompt;
+          const int64_t off = row_off(pos, in_prompt) + lane * 4;
+          v[j] = __ldcg(reinterpret_cast<const uint2*>((in_prompt ? vp : vg) + off));
+          vmask |= 1u << j;
+        }
+      }
+    }
+  }
+};
+
 // Merge of the split-KV partials of one (row, kv head): out[h][dim] = sum_s w_s acc_s / sum_s w_s l_s, w_s = 2^(m_s - max).
 // All loads of a batch of MERGE_B splits are independent (one L2 round trip per batch).
 template <int GQ>
@@ -496,7 +569,7 @@ __device__ __noinline__ void merge_splits(const float* base, int n_splits, bf16*
 // o_proj phase stages 8 KB per row instead of every CTA re-reading every partial.
 template <int GQ>
 __device__ __forceinline__ void attention_phase(const MegaParams& p, uint8_t* smem_raw, int layer, int t,
-                                             GridBarrier& bar, Smem& sm) {
+                                                GridBarrier& bar, Smem& sm, AttnLoads& L) {
   static_assert(GQ == 4, "the P.V loop reads the 4 head probabilities of a key as one float4");
   sm.stamp();
   // [GQ][HD], pre-scaled by log2(e) / sqrt(HD), dims permuted: dim d = 16 l8 + 4 j + e sits at 32 j + 4 l8 + e, so that
@@ -523,70 +596,14 @@ __device__ __forceinline__ void attention_phase(const MegaParams& p, uint8_t* sm
   bf16* vg = p.kv_gen + ((int64_t)layer * 2 + 1) * n_gen * kvd;
   const int sub = lane >> 3, l8 = lane & 7;  // scores: 8 lanes per key, 16 dims per lane
 
-  uint4 kreg[KPW / 4][2];
-  uint2 vreg[KPW];
-  uint32_t vmask = 0;  // bit j: V row of key j was requested from global memory
-  bool khave[KPW / 4], kvalid[KPW / 4];
-  // element offset of the K / V row of key position `pos`
-  auto row_off = [&](int row, int input, int kvh, int pos, bool& in_prompt) -> int64_t {
-    in_prompt = pos < p.S;
-    if (in_prompt) return ((int64_t)input * p.S + pos) * kvd + kvh * HD;
-    const int g = pos - p.S;
-    const int prow = p.slots[(int64_t)row * p.max_gen + g];
-    return ((int64_t)prow * p.max_gen + g) * kvd + kvh * HD;
-  };
-  auto request = [&](int item) {  // issue the K and V loads of `item`
-    const int split = item % n_splits, kvh = (item / n_splits) % KVH, row = item / (n_splits * KVH);
-    const int input = row / p.beams;
-    const int k0 = split * ATT_CHUNK;
-    const int n_keys = min(ctx, k0 + ATT_CHUNK) - k0;
-#pragma unroll
-    for (int it = 0; it < KPW / 4; ++it) {
-      const int kk = warp * KPW + it * 4 + sub;
-      const int pos = k0 + kk;
-      kvalid[it] = kk < n_keys;
-      khave[it] = kvalid[it] && pos != pos_cur;
-      if (khave[it]) {
-        bool in_prompt;
-        const int64_t off = row_off(row, input, kvh, pos, in_prompt) + l8 * 16;
-        const bf16* kptr = (in_prompt ? kp : kg) + off;
-        if (in_prompt && p.prompt_valid) kvalid[it] = p.prompt_valid[(int64_t)input * p.S + pos] != 0;
-        kreg[it][0] = __ldcg(reinterpret_cast<const uint4*>(kptr));
-        kreg[it][1] = __ldcg(reinterpret_cast<const uint4*>(kptr + 8));
-      }
-    }
-    vmask = 0;
-    const int pos0 = k0 + warp * KPW;
-    if (pos0 + KPW <= p.S) {
-      // the warp's 8 keys are all prompt positions (the common case): one base pointer, constant stride
-      const bf16* vb = vp + ((int64_t)input * p.S + pos0) * kvd + kvh * HD + lane * 4;
-#pragma unroll
-      for (int j = 0; j < KPW; ++j) vreg[j] = __ldcg(reinterpret_cast<const uint2*>(vb + (int64_t)j * kvd));
-      vmask = (1u << KPW) - 1u;
-    } else {
-#pragma unroll
-      for (int j = 0; j < KPW; ++j) {
-        const int kk = warp * KPW + j;
-        const int pos = k0 + kk;
-        vreg[j] = make_uint2(0, 0);
-        if (kk < n_keys && pos != pos_cur) {
-          bool in_prompt;
-          const int64_t off = row_off(row, input, kvh, pos, in_prompt) + lane * 4;
-          vreg[j] = __ldcg(reinterpret_cast<const uint2*>((in_prompt ? vp : vg) + off));
-          vmask |= 1u << j;
-        }
-      }
-    }
-  };
-
-  // (one call site for request(): inlined, so that the loaded rows stay in registers)
+  // (the first item's rows were requested at the start of the qkv phase, see the phase loop)
   for (int item = blockIdx.x;; item += gridDim.x) {
     const bool first_item = item == (int)blockIdx.x;  // profiling stamps cover the first item only
     if (!first_item) {  // (only with rows > 1 or very long contexts: more items than CTAs)
       if (item >= n_items) break;
       consumer_sync();  // the previous item is done with the shared buffers
     }
-    if (item < n_items) request(item);
+    if (!first_item) L.request(p, layer, t, item);
     if (first_item) {
       sm.stamp();
       bar.sync();  // qkv of this step is complete
@@ -627,9 +644,9 @@ __device__ __forceinline__ void attention_phase(const MegaParams& p, uint8_t* sm
     for (int it = 0; it < KPW / 4; ++it) {
       const int kk = warp * KPW + it * 4 + sub;
       float kf[16];
-      if (khave[it]) {
-        const uint32_t w[8] = {kreg[it][0].x, kreg[it][0].y, kreg[it][0].z, kreg[it][0].w,
-                               kreg[it][1].x, kreg[it][1].y, kreg[it][1].z, kreg[it][1].w};
+      if (L.khave[it]) {
+        const uint32_t w[8] = {L.k[it][0].x, L.k[it][0].y, L.k[it][0].z, L.k[it][0].w,
+                               L.k[it][1].x, L.k[it][1].y, L.k[it][1].z, L.k[it][1].w};
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float2 f = unpack_bf16x2(w[j]);
@@ -657,7 +674,7 @@ __device__ __forceinline__ void attention_phase(const MegaParams& p, uint8_t* sm
         a += __shfl_xor_sync(0xffffffffu, a, 1);
         a += __shfl_xor_sync(0xffffffffu, a, 2);
         a += __shfl_xor_sync(0xffffffffu, a, 4);
-        if (l8 == 0) s_sc[kk * GQ + h] = kvalid[it] ? a : -INFINITY;
+        if (l8 == 0) s_sc[kk * GQ + h] = L.kvalid[it] ? a : -INFINITY;
       }
     }
     consumer_sync();
@@ -687,8 +704,8 @@ __device__ __forceinline__ void attention_phase(const MegaParams& p, uint8_t* sm
       for (int j = 0; j < KPW; ++j) {
         const int kk = warp * KPW + j;
         float v0, v1, v2, v3;
-        if (vmask & (1u << j)) {
-          const float2 f0 = unpack_bf16x2(vreg[j].x), f1 = unpack_bf16x2(vreg[j].y);
+        if (L.vmask & (1u << j)) {
+          const float2 f0 = unpack_bf16x2(L.v[j].x), f1 = unpack_bf16x2(L.v[j].y);
           v0 = f0.x; v1 = f0.y; v2 = f1.x; v3 = f1.y;
         } else {  // the current token (its probability is 0 for keys past the context)
           const float4 f = *reinterpret_cast<const float4*>(s_vnew + lane * 4);
@@ -834,6 +851,9 @@ llama_decode_megakernel(const MegaParams p) {
   // per-thread copies in local memory (~500 B x 416 threads against the ~28 KB of L1 left beside the ring), and every
   // phase began with chains of local loads served by L2.
   const int n_phases = 4 * c.n_layers + 1;
+  const int n_att_items = p.rows * KVH * ((p.S + t + ATT_CHUNK - 1) / ATT_CHUNK);
+  AttnLoads att_loads;
+  att_loads.vmask = 0;
   for (int ph = 0; ph < n_phases; ++ph) {
     const int l = ph >> 2;
     const int kind = ph == n_phases - 1 ? 4 : (ph & 3);  // 0 qkv | 1 o_proj | 2 gate/up | 3 down | 4 lm head
@@ -843,6 +863,7 @@ llama_decode_megakernel(const MegaParams p) {
     int64_t lda, ldo;
     void* out;
     if (kind == 0) {         // qkv = Wqkv . rms(x)
+      if ((int)blockIdx.x < n_att_items) att_loads.request(p, l, t, blockIdx.x);  // K / V of this layer's attention
       n_out = qkv_dim; K = d; stage = STAGE_RMS; A = p.x; lda = d; rms_w = y.ln1; epi = EPI_BF16; out = p.qkv; ldo = qkv_dim;
       if (l == 0) {
         // the residual stream starts as the embedding of the last token of every row: each CTA mirrors its column
@@ -859,7 +880,7 @@ llama_decode_megakernel(const MegaParams p) {
         else bar.sync();
       }
     } else if (kind == 1) {  // attention, then x += Wo . attn
-      attention_phase<GQ>(p, att_smem, l, t, bar, sm);  // (K/V requested before the barrier inside)
+      attention_phase<GQ>(p, att_smem, l, t, bar, sm, att_loads);
       sm.stamp();
       bar.sync();
       sm.stamp();
