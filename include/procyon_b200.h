@@ -187,6 +187,11 @@ int pcy_set_decode_megakernel(int enabled);
  * 0x534B4557 the buffer must have 4096 + (4 L + 1) * n_sms * 2 words, and every CTA also records (time, SM id) when it
  * finishes streaming each weight phase (skew analysis, scripts/profile_decode_skew.py). */
 int pcy_set_decode_timing_buffer(void* dev_u64);
+/* Relative weight-streaming rates of the SMs (host array, one entry per SM id, SM ids must be 0..n-1), measured by the
+   caller with the timing buffer's per-CTA stamps: the persistent decode kernel then cuts every weight matrix into
+   slices proportional to them (clamped to 0.85..1.15 of the equal slice) instead of equal ones.  Results do not
+   change: a row's dot product is the same wherever it is computed.  NULL / 0 restores equal slices. */
+int pcy_set_decode_sm_shares(const float* shares, int n);
 int64_t pcy_llama_decode_workspace_bytes(void* handle, int rows, int S, int max_gen);
 /* clears state/tokens/slots/log-probs/workspace; copies prefill_logits fp32 [n_inputs,V] to every beam row */
 int pcy_decode_reset(void* handle, const pcy_decode_buffers* b, const float* prefill_logits, void* stream);

@@ -18,6 +18,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <vector>
+#include <vector>
 
 #include "common.cuh"
 #include "ops.h"
@@ -131,12 +132,25 @@ struct RingGeom {
   }
 };
 
-// balanced contiguous range of `n` items for this CTA.  (Equal slices: with all SMs pulling from HBM at once some
-// get up to ~20 % less bandwidth than others - scripts/profile_decode_skew.py - but the pattern differs from GPU to
-// GPU, and slices sized from a calibration run did not pay off; see DESIGN.md.)
-__device__ __forceinline__ void cta_range(int n, int& lo, int& hi) {
-  lo = (int)(((int64_t)n * blockIdx.x) / gridDim.x);
-  hi = (int)(((int64_t)n * (blockIdx.x + 1)) / gridDim.x);
+// This CTA's slice of every phase, as a pair of cumulative fractions scaled to 2^32.  Equal slices by default; after
+// pcy_set_decode_sm_shares() proportional to the streaming rate measured for the SM the CTA runs on: with all 148
+// SMs pulling flat out some get up to ~20 % less HBM bandwidth than others (systematic by SM id, different from GPU
+// to GPU - scripts/profile_decode_skew.py), and with equal slices every grid barrier waits for the slowest.
+struct Share {
+  uint64_t lo, hi;
+};
+__device__ __forceinline__ Share cta_share(const uint64_t* table) {
+  if (table != nullptr) {
+    unsigned int smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    return Share{table[smid], table[smid + 1]};
+  }
+  return Share{((uint64_t)blockIdx.x << 32) / gridDim.x, ((uint64_t)(blockIdx.x + 1) << 32) / gridDim.x};
+}
+// contiguous range of `n` items for this CTA
+__device__ __forceinline__ void cta_range(const Share& sh, int n, int& lo, int& hi) {
+  lo = (int)(((uint64_t)n * sh.lo) >> 32);
+  hi = (int)(((uint64_t)n * sh.hi) >> 32);
 }
 struct Smem {
   bf16* a;       // [MT][K] staged activations
@@ -146,6 +160,7 @@ struct Smem {
   uint32_t ring, bars;
   RingGeom rg;
   uint32_t chunk0;  // ring chunks consumed by the phases before the current one (same count in the producer)
+  Share share;      // this CTA's slice of every phase
   unsigned long long* tbuf;  // profiling stamps (CTA 0, thread 0) or null
   int tix;
   int phase_ix;  // weight phases finished so far (profiling: per-CTA stream-end times at tbuf[4096 + ...])
@@ -179,9 +194,10 @@ constexpr int PL = 8;  // producer lanes: chunks g .. g+7 are issued side by sid
 // ~4 us) and the latency-critical DRAM reads of the attention phase (K / V rows) would wait behind them.  The rest
 // of the ring fills up only while the consumers are stalled, which is what it is for.
 __device__ __noinline__ void produce_phase(uint32_t ring, uint32_t bars, RingGeom rg, uint32_t& g, int window,
-                                           const bf16* W, int64_t ldw, int n_out, int K, int epi, uint64_t pol) {
+                                           Share sh, const bf16* W, int64_t ldw, int n_out, int K, int epi,
+                                           uint64_t pol) {
   int lo, hi;
-  cta_range(n_out, lo, hi);
+  cta_range(sh, n_out, lo, hi);
   const int rpo = (epi == EPI_SWIGLU) ? 2 : 1;
   const int n_rows = (hi - lo) * rpo;
   const int cpr = (K + CH - 1) / CH;
@@ -231,7 +247,7 @@ __device__ __forceinline__ void gemv_phase(Smem& sm, int n_out, int K, int stage
                                         const bf16* __restrict__ rms_w, float eps, int epi, void* out, int64_t ldo) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   int o_lo, o_hi;
-  cta_range(n_out, o_lo, o_hi);
+  cta_range(sm.share, n_out, o_lo, o_hi);
   const int rpo = (epi == EPI_SWIGLU) ? 2 : 1;
   const int n_rows = (o_hi - o_lo) * rpo;
   const int cpr = (K + CH - 1) / CH;
@@ -439,6 +455,7 @@ struct MegaParams {
   int layers_off;       // byte offset of the shared-memory copy of the layer pointer table
   int window;           // bulk copies in flight per SM (chunks)
   uint32_t ring_magic;  // ceil(2^32 / ring_slots)
+  const uint64_t* shares;  // [n_sms + 1] cumulative slice boundaries by SM id (x 2^32), or null = equal slices
   unsigned int* barrier;  // [0] grid barrier counter, [32 + row * KVH + kvh] attention tickets
   unsigned long long* timing;  // optional: globaltimer at every phase boundary (CTA 0), for profiling
 };
@@ -817,15 +834,16 @@ llama_decode_megakernel(const MegaParams p) {
     if (threadIdx.x < MK_THREADS + PL) {
       const RingGeom rg{ns, p.ring_magic};
       const uint64_t pol = l2_evict_first_policy();  // weights are read once per step: keep L2 for KV / activations
+      const Share sh = cta_share(p.shares);
       uint32_t g = 0;
       for (int l = 0; l < c.n_layers; ++l) {
         const LlamaLayerPtrs& y = s_layers[l];
-        produce_phase(ring, bars, rg, g, p.window, y.wqkv, d, qkv_dim, d, EPI_BF16, pol);
-        produce_phase(ring, bars, rg, g, p.window, y.wo, H * HD, d, H * HD, EPI_RESIDUAL, pol);
-        produce_phase(ring, bars, rg, g, p.window, y.wgu, d, f, d, EPI_SWIGLU, pol);
-        produce_phase(ring, bars, rg, g, p.window, y.wdown, f, d, f, EPI_RESIDUAL, pol);
+        produce_phase(ring, bars, rg, g, p.window, sh, y.wqkv, d, qkv_dim, d, EPI_BF16, pol);
+        produce_phase(ring, bars, rg, g, p.window, sh, y.wo, H * HD, d, H * HD, EPI_RESIDUAL, pol);
+        produce_phase(ring, bars, rg, g, p.window, sh, y.wgu, d, f, d, EPI_SWIGLU, pol);
+        produce_phase(ring, bars, rg, g, p.window, sh, y.wdown, f, d, f, EPI_RESIDUAL, pol);
       }
-      produce_phase(ring, bars, rg, g, p.window, p.lm_head, d, c.vocab, d, EPI_FP32, pol);
+      produce_phase(ring, bars, rg, g, p.window, sh, p.lm_head, d, c.vocab, d, EPI_FP32, pol);
     }
     return;
   }
@@ -834,6 +852,7 @@ llama_decode_megakernel(const MegaParams p) {
   sm.a = reinterpret_cast<bf16*>(work);
   sm.out = reinterpret_cast<float*>(work + (size_t)MT * kmax * 2);
   sm.red = sm.out + (size_t)p.out_rows * MT;
+  sm.share = cta_share(p.shares);
   sm.ring = ring; sm.bars = bars; sm.rg = RingGeom{ns, p.ring_magic}; sm.chunk0 = 0;
   sm.tbuf = p.timing;
   sm.tix = 0;
@@ -872,7 +891,7 @@ llama_decode_megakernel(const MegaParams p) {
           const int tok = p.tokens[(int64_t)m * p.max_gen + (t - 1)];
           const bf16* src = p.embed + (int64_t)tok * d;
           int clo, chi;
-          cta_range(d / 8, clo, chi);
+          cta_range(sm.share, d / 8, clo, chi);
           for (int k8 = clo + threadIdx.x; k8 < chi; k8 += MK_THREADS)
             *reinterpret_cast<uint4*>(p.x + (int64_t)m * d + k8 * 8) = *reinterpret_cast<const uint4*>(src + k8 * 8);
         }
@@ -909,6 +928,8 @@ llama_decode_megakernel(const MegaParams p) {
 unsigned long long* g_timing = nullptr;
 
 constexpr size_t SMEM_LIMIT = 227 * 1024;
+constexpr double MAX_SHARE = 1.15;
+uint64_t* g_shares = nullptr;  // device table, see decode_megakernel_set_shares
 
 // rows of the widest per-CTA slice (SwiGLU phases hold a gate and an up row per output)
 int out_rows_for(const pcy_llama_config& c) {
@@ -918,7 +939,8 @@ int out_rows_for(const pcy_llama_config& c) {
   r = std::max(r, 2 * (ceil_div(c.ffn_dim, sms) + 1));
   r = std::max(r, ceil_div(qkv, sms) + 1);
   r = std::max(r, ceil_div(c.d_model, sms) + 1);
-  return (int)round_up(r, 64);
+  // head-room for measured (unequal) slices: shares are capped at MAX_SHARE x the equal slice
+  return (int)round_up((int)(r * MAX_SHARE) + 2, 64);
 }
 // bytes of the non-ring part of shared memory: barriers + max(gemv staging, attention scratch)
 size_t work_smem_bytes(const pcy_llama_config& c, int mt) {
@@ -939,6 +961,41 @@ int ring_slots_for(const pcy_llama_config& c, int mt) {
 }  // namespace
 
 void decode_megakernel_set_timing(unsigned long long* dev_buf) { g_timing = dev_buf; }
+
+int decode_megakernel_set_shares(const float* shares, int n) {
+  if (shares == nullptr || n == 0) {  // back to equal slices
+    g_shares = nullptr;               // (the table stays allocated: a launch in flight may still read it)
+    return 0;
+  }
+  PCY_REQUIRE(n == num_sms(), "decode shares: %d entries for %d SMs", n, num_sms());
+  std::vector<double> f(n);
+  double tot = 0.0;
+  for (int i = 0; i < n; ++i) {
+    PCY_REQUIRE(shares[i] > 0.f, "decode shares: entry %d is not positive", i);
+    tot += shares[i];
+  }
+  // clamp to [2 - MAX_SHARE, MAX_SHARE] x the equal slice (the per-CTA partial-sum buffer is sized for MAX_SHARE)
+  double used = 0.0;
+  for (int i = 0; i < n; ++i) {
+    f[i] = std::min(std::max(shares[i] / tot * n, 2.0 - MAX_SHARE), MAX_SHARE - 0.01);
+    used += f[i];
+  }
+  std::vector<uint64_t> cum(n + 1);
+  double run = 0.0;
+  for (int i = 0; i < n; ++i) {
+    cum[i] = (uint64_t)(run / used * 4294967296.0);
+    run += f[i];
+  }
+  cum[0] = 0;
+  cum[n] = 1ull << 32;
+  for (int i = 0; i < n; ++i)  // renormalisation must not push a slice over the cap
+    PCY_REQUIRE((double)(cum[i + 1] - cum[i]) / 4294967296.0 * n < MAX_SHARE, "decode shares: slice %d too large", i);
+  static uint64_t* dev = nullptr;
+  if (dev == nullptr) PCY_CUDA(cudaMalloc(&dev, (size_t)(n + 1) * sizeof(uint64_t)));
+  PCY_CUDA(cudaMemcpy(dev, cum.data(), (size_t)(n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice));
+  g_shares = dev;
+  return 0;
+}
 
 int64_t decode_megakernel_scratch_bytes(const pcy_llama_config& c, int rows, int S, int max_gen) {
   const int64_t d = c.d_model, qkv = (int64_t)(c.n_heads + 2 * c.n_kv_heads) * HD;
@@ -982,6 +1039,7 @@ int decode_megakernel(const pcy_llama_config& c, const LlamaLayerPtrs* layers_de
   p.max_splits = ceil_div(b->S + b->max_gen, ATT_CHUNK);
   p.part = reinterpret_cast<float*>(s);
   p.timing = g_timing;
+  p.shares = g_shares;
   PCY_CUDA(cudaMemsetAsync(p.barrier, 0, 512, stream));  // barrier counter + tickets
 
   const int mt = rows <= 1 ? 1 : rows <= 2 ? 2 : 4;

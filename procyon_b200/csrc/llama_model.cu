@@ -94,6 +94,8 @@ int pcy_set_decode_timing_buffer(void* dev_u64) {
   return 0;
 }
 
+int pcy_set_decode_sm_shares(const float* shares, int n) { return decode_megakernel_set_shares(shares, n); }
+
 int pcy_set_decode_megakernel(int enabled) {
   g_use_megakernel = enabled != 0;
   return 0;

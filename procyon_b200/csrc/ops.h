@@ -135,6 +135,7 @@ struct LlamaLayerPtrs {
 #include "../../include/procyon_b200.h"
 namespace pcy {
 void decode_megakernel_set_timing(unsigned long long* dev_buf);
+int decode_megakernel_set_shares(const float* shares, int n);
 bool decode_megakernel_supported(const pcy_llama_config& c, int rows);
 int64_t decode_megakernel_scratch_bytes(const pcy_llama_config& c, int rows, int S, int max_gen);
 int decode_megakernel(const pcy_llama_config& c, const LlamaLayerPtrs* layers_dev, const bf16* embed,

@@ -447,10 +447,79 @@ class LlamaPostTokenization(nn.Module):
             self._lm_cache_key = key
         return self._lm_cache
 
+    # ---- per-SM slice calibration of the persistent decode kernel ----------------------------------------------
+    _calibrated_devices = {}
+
+    def calibrate_decode_shares(self, device, rounds: int = 3, iters: int = 3):
+        """Measures, with the kernel's own per-CTA stamps, how fast each SM streams its slice of the long weight
+        phases (gate/up of every layer, LM head) and hands the rates to the library (pcy_set_decode_sm_shares),
+        which then sizes the slices accordingly.  With all SMs pulling from HBM at once some get up to ~20 % less
+        bandwidth than others (systematic by SM id, different from GPU to GPU), and with equal slices every grid
+        barrier waits for the slowest.  Results are unaffected.  Returns the shares (or None if SM ids are not
+        0..n-1, e.g. under MIG: equal slices stay)."""
+        lib = _lib.load()
+        dev = torch.device(device)
+        G = torch.cuda.get_device_properties(dev).multi_processor_count
+        L = self.model.config.num_hidden_layers
+        n_ph = 4 * L + 1
+        self._ensure_packed(dev)
+        self._ensure_rope(64, dev)
+        sess = DecodeSession(self, 1, 1, 16, 4, dev, False, False)
+        sess.kv_prompt.zero_()
+        sess.kv_gen.zero_()
+        sess.state[0] = 1
+        buf = torch.zeros(4096 + n_ph * G * 2 + 64, device=dev, dtype=torch.int64)
+        buf[4095] = 0x534B4557  # "SKEW": asks the kernel for the per-CTA phase-end stamps after the first 4096 words
+        shares = torch.ones(G, dtype=torch.float32)
+        set_shares = lib.pcy_set_decode_sm_shares
+        long_phases = [4 * l + 2 for l in range(1, L)] + [4 * L]  # gate/up of every layer + the LM head
+        ok = True
+        try:
+            for _ in range(rounds):
+                check(set_shares(shares.numpy().ctypes.data_as(ctypes.c_void_p), c_int(G)), "pcy_set_decode_sm_shares")
+                for _ in range(2):
+                    sess.forward()
+                lib.pcy_set_decode_timing_buffer(ctypes.c_void_p(buf.data_ptr()))
+                rate = torch.zeros(G, dtype=torch.float64)
+                for _ in range(iters):
+                    sess.forward()
+                    torch.cuda.synchronize(dev)
+                    t = buf[4096:4096 + n_ph * G * 2].cpu().view(n_ph, G, 2)
+                    smid = t[long_phases[0], :, 1]
+                    if sorted(smid.tolist()) != list(range(G)):
+                        ok = False
+                        break
+                    for ph in long_phases:
+                        start = t[ph - 1, :, 0].max()
+                        dur = (t[ph, :, 0] - start).double().clamp_min(1.0)
+                        sm = t[ph, :, 1]
+                        rate[sm] += float(dur.mean()) * shares[sm].double() / dur  # longer phases weigh more
+                lib.pcy_set_decode_timing_buffer(ctypes.c_void_p(0))
+                if not ok:
+                    break
+                new = (rate / rate.mean()).float()
+                shares = (0.5 * shares + 0.5 * new).clamp(0.86, 1.13)  # damped: rates shift when the slices do
+                shares = shares / shares.mean()
+        finally:
+            lib.pcy_set_decode_timing_buffer(ctypes.c_void_p(0))
+        if ok:
+            check(set_shares(shares.numpy().ctypes.data_as(ctypes.c_void_p), c_int(G)), "pcy_set_decode_sm_shares")
+        else:
+            check(set_shares(None, c_int(0)), "pcy_set_decode_sm_shares")
+        torch.cuda.synchronize(dev)
+        return shares if ok else None
+
     def get_session(self, n_inputs, beams, S, max_gen, device, masked, keep_logits) -> DecodeSession:
         """Decode sessions (KV caches, tables, captured step graph) are cached per shape and reused across calls."""
         self._ensure_packed(torch.device(device))
         self._ensure_rope(S + max_gen, device)
+        c = self.model.config
+        dkey = str(torch.device(device))
+        if (n_inputs * beams <= 4 and c.hidden_size >= 2048 and c.num_hidden_layers >= 8 and c.head_dim == 128
+                and dkey not in LlamaPostTokenization._calibrated_devices
+                and os.environ.get("PCY_DECODE_CALIBRATE", "0") == "1"):
+            LlamaPostTokenization._calibrated_devices[dkey] = True  # (set first: calibration builds a session itself)
+            LlamaPostTokenization._calibrated_devices[dkey] = self.calibrate_decode_shares(device)
         key = (n_inputs, beams, S, max_gen, str(device), bool(masked), bool(keep_logits), id(self._handle))
         cache = self.__dict__.setdefault("_sessions", {})
         if key not in cache:

@@ -1,11 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-echo "== uncalibrated"; PCY_DECODE_CALIBRATE=0 timeout 600 python scripts/profile_decode_skew.py 2>&1 | grep -E "phase|spread|mean lag SM" | head -20
-echo "== calibrated"; timeout 600 python scripts/profile_decode_skew.py 2>&1 | grep -E "phase|spread|mean lag SM|Error|error" | head -20
-timeout 600 python -m pytest tests/test_gpu_llama.py tests/test_gpu_unified.py -m gpu -q -x > gpurun_out/pytest_llama.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_llama.log
-tail -3 gpurun_out/pytest_llama.log
-timeout 600 python scripts/profile_decode_phases.py > gpurun_out/decode_phases.log 2>&1
-tail -30 gpurun_out/decode_phases.log
-timeout 900 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"
-python -c "
-import json;d=json.load(open('gpurun_out/bench.json'));print(d['value'],d['e2e']['value'],d['roofline']['achieved'],d['roofline']['ms_per_launch'],d['phases'])"; tail -5 gpurun_out/bench.err
+echo "== uncalibrated"; PCY_DECODE_CALIBRATE=0 timeout 600 python scripts/profile_decode_skew.py 2>&1 | grep -E "phase|spread|Error" | head -16
+PCY_DECODE_CALIBRATE=0 timeout 600 python scripts/bench_decode_rows.py 1 2>&1 | tail -1
+echo "== calibrated"; PCY_DECODE_CALIBRATE=1 timeout 600 python scripts/profile_decode_skew.py 2>&1 | grep -E "phase|spread|Error|error" | head -16
+PCY_DECODE_CALIBRATE=1 timeout 600 python scripts/bench_decode_rows.py 1 2>&1 | tail -1
