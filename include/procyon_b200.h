@@ -180,8 +180,9 @@ typedef struct {
 #define PCY_SELECT_GREEDY 0
 #define PCY_SELECT_BEAM 1
 
-/* rows <= 4 use one persistent kernel per decode step by default; 0 selects the one-launch-per-op path (tests) */
-int pcy_set_decode_megakernel(int enabled);
+/* Decode steps with up to `max_rows` rows (inputs x beams) run as ONE persistent kernel; default 2 (measured faster
+   than the one-launch-per-op path there), supported up to 4, 0 selects the per-op path for every row count. */
+int pcy_set_decode_megakernel(int max_rows);
 /* profiling aid: device uint64 buffer of >= 4096 words (zeroed) that receives %globaltimer at every phase boundary of
  * the persistent decode kernel: 24 stamps per layer + 4, written by CTA 0 (NULL disables).  If word 4095 holds the tag
  * 0x534B4557 the buffer must have 4096 + (4 L + 1) * n_sms * 2 words, and every CTA also records (time, SM id) when it

@@ -16,7 +16,7 @@ namespace pcy {
 
 bool g_skinny_mma = true;  // pcy_set_skinny_mma(0): scalar-FMA kernel for every M <= 16 (A/B measurements, tests)
 int skinny_mma_min_rows() {  // rows from which the tensor-core kernel is used (tuning knob)
-  static const int v = [] { const char* e = getenv("PCY_SKINNY_MMA_MIN_M"); return e ? atoi(e) : 5; }();
+  static const int v = [] { const char* e = getenv("PCY_SKINNY_MMA_MIN_M"); return e ? atoi(e) : 3; }();
   return v;
 }
 
@@ -222,7 +222,7 @@ int launch_skinny(SkinnyParams p, cudaStream_t stream) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// 5..16 activation rows (beam search: the reference's evaluation default is beam_size = 10): the scalar kernel above
+// 3..16 activation rows (beam search: the reference's evaluation default is beam_size = 10): the scalar kernel above
 // needs ~2 FMA-pipe instructions per weight element and row and is ALU-bound there (18.8 ms per Llama-3-8B decode step
 // at 10 rows against 3.2 ms at 1 row).  Here the legacy tensor cores do the math: a CTA of 4 warps owns 16 weight rows
 // (32 for SwiGLU: the 16 gate rows and their 16 up rows), warp w streams k-blocks w, w+4, ... of 64 elements through
@@ -403,7 +403,7 @@ int gemm_bf16_skinny(const GemmArgs& a, const bf16* rms_weight, float rms_eps, c
   p.residual = a.residual; p.ldr = a.ldr; p.rms_weight = rms_weight; p.rms_eps = rms_eps;
   p.M = a.M; p.N = a.N; p.K = a.K; p.c_fp32 = a.c_fp32; p.act = a.act; p.scale = a.scale;
   p.scale_ncols = a.scale_ncols; p.num_units = 0;
-  // 5..16 rows without a fused norm: tensor-core kernel (needs whole 64-element k-blocks)
+  // 3..16 rows without a fused norm: tensor-core kernel (needs whole 64-element k-blocks)
   if (a.M >= skinny_mma_min_rows() && rms_weight == nullptr && a.K % TK == 0 && g_skinny_mma) {
     if (a.act == ACT_SWIGLU) return launch_skinny_mma<true, 4>(p, stream);
     return launch_skinny_mma<false, 6>(p, stream);

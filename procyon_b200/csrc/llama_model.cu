@@ -85,7 +85,10 @@ __global__ void broadcast_rows_kernel(const float* __restrict__ in, float* __res
 
 using namespace pcy;
 
-static bool g_use_megakernel = true;
+// rows (inputs x beams) up to which a decode step runs as the one persistent kernel.  It supports 4, but measured on
+// B200 (scripts/bench_decode_rows.py) it wins only up to 2 rows: 3.1 / 4.6 ms against 6.1 / 6.5 ms at 3 / 4 rows, where
+// the one-launch-per-op path with the tensor-core GEMV and the shared-prompt attention takes 5.3 ms.
+static int g_megakernel_max_rows = 2;
 
 extern "C" {
 
@@ -96,8 +99,8 @@ int pcy_set_decode_timing_buffer(void* dev_u64) {
 
 int pcy_set_decode_sm_shares(const float* shares, int n) { return decode_megakernel_set_shares(shares, n); }
 
-int pcy_set_decode_megakernel(int enabled) {
-  g_use_megakernel = enabled != 0;
+int pcy_set_decode_megakernel(int max_rows) {
+  g_megakernel_max_rows = max_rows < 0 ? 0 : (max_rows > 4 ? 4 : max_rows);
   return 0;
 }
 
@@ -320,10 +323,10 @@ int pcy_llama_decode_forward(void* handle, const pcy_decode_buffers* b, void* st
   bf16* act = carve<bf16>(p, (int64_t)rows * f);
   float* partials = carve<float>(p, decode_attention_partial_floats(rows, H, KVH, b->S, b->max_gen));
   int32_t* tickets = carve<int32_t>(p, (int64_t)rows * KVH);  // zeroed by pcy_decode_reset
-  bf16* xn = carve<bf16>(p, (int64_t)rows * d);                // normalised rows (rows > 4 only)
+  bf16* xn = carve<bf16>(p, (int64_t)rows * d);                // normalised rows (3+ rows only)
   static const bool force_multi = getenv("PCY_DECODE_MULTIKERNEL") != nullptr;
-  if (!force_multi && g_use_megakernel && decode_megakernel_supported(c, rows)) {
-    // persistent single-launch step (rows <= 4): see decode_megakernel.cu
+  if (!force_multi && rows <= g_megakernel_max_rows && decode_megakernel_supported(c, rows)) {
+    // persistent single-launch step: see decode_megakernel.cu
     return decode_megakernel(c, m->layers_dev, m->embed, m->lm_head, m->norm, m->rope, b, p, stream);
   }
 
@@ -331,8 +334,8 @@ int pcy_llama_decode_forward(void* handle, const pcy_decode_buffers* b, void* st
   PCY_LAUNCH_CHECK();
   const int64_t n_prompt = (int64_t)b->n_inputs * b->S;
   const int64_t n_gen = (int64_t)rows * b->max_gen;
-  // 5..16 rows (beam search): the tensor-core weight-streaming kernel has no fused norm, so RMSNorm runs as its own
-  // (tiny) kernel; up to 4 rows keep the fused prologue of the scalar kernel
+  // 3..16 rows (beam search): the tensor-core weight-streaming kernel has no fused norm, so RMSNorm runs as its own
+  // (tiny) kernel; 1-2 rows keep the fused prologue of the scalar kernel
   const bool split_norm = rows >= skinny_mma_min_rows() && g_skinny_mma;
   auto normed_linear = [&](GemmArgs& g, const bf16* ln) -> int {
     if (!split_norm) return gemm_bf16_skinny(g, ln, c.rms_eps, stream);

@@ -21,7 +21,7 @@ m = _build(sd, pc)
 ids, emb, mask = _inputs(oc, sd, rows, 50, seed=7, pad_left=4)
 lib = _lib.load()
 if which in ("both", "mega"):
-    lib.pcy_set_decode_megakernel(1)
+    lib.pcy_set_decode_megakernel(4)
     o1, lp1, lg1 = generate_greedy(m, emb.cuda(), mask.cuda(), max_len=10)
     torch.cuda.synchronize()
     print("megakernel ok", o1[0].tolist())

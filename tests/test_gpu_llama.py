@@ -171,12 +171,12 @@ def test_persistent_and_per_op_decode_agree(cuda_device, kind, rows):
     ids, emb, mask = _inputs(oc, sd, rows, 50, seed=7, pad_left=4)
     lib = _lib.load()
     try:
-        lib.pcy_set_decode_megakernel(1)
+        lib.pcy_set_decode_megakernel(4)
         o1, lp1, lg1 = generate_greedy(m, emb.cuda(), mask.cuda(), max_len=10)
         lib.pcy_set_decode_megakernel(0)
         o2, lp2, lg2 = generate_greedy(m, emb.cuda(), mask.cuda(), max_len=10, use_graph=False)
     finally:
-        lib.pcy_set_decode_megakernel(1)
+        lib.pcy_set_decode_megakernel(2)
     torch.testing.assert_close(lg1[:, 1], lg2[:, 1], rtol=2e-2, atol=3e-2)  # first decode step: same inputs
     agree = (o1 == o2).float().mean().item()
     assert agree > 0.7, agree
@@ -196,12 +196,12 @@ def test_persistent_decode_long_context(cuda_device, rows, S):
     ids, emb, mask = _inputs(oc, sd, rows, S, seed=11, pad_left=7)
     lib = _lib.load()
     try:
-        lib.pcy_set_decode_megakernel(1)
+        lib.pcy_set_decode_megakernel(4)
         o1, lp1, lg1 = generate_greedy(m, emb.cuda(), mask.cuda(), max_len=6)
         lib.pcy_set_decode_megakernel(0)
         o2, lp2, lg2 = generate_greedy(m, emb.cuda(), mask.cuda(), max_len=6, use_graph=False)
     finally:
-        lib.pcy_set_decode_megakernel(1)
+        lib.pcy_set_decode_megakernel(2)
     torch.testing.assert_close(lg1[:, 1], lg2[:, 1], rtol=2e-2, atol=3e-2)  # first decode step: same inputs
     assert (o1 == o2).float().mean().item() > 0.7
 
