@@ -129,3 +129,28 @@ class ProCyonQAInference:
                          crop_off=True, output_attentions=output_attentions)
         pred, _ = get_qa_logits_inference(out, answer_token=self.model.answer_idx)
         return {"pred": pred, "y": None, "out": out}
+
+
+# ---- batching of single-query model inputs (procyon/data/inference_utils.py:848-884) ------------------------------
+def merge_model_input_dicts(dict_list):
+    """Concatenates single-query model-input dicts (as built by `create_input_retrieval`) into one batch: `data`
+    entries are concatenated, every `input` index list is shifted past the indices already in the batch and appended
+    as a new row, `instructions` are concatenated.  Like the reference, the first dict is extended in place."""
+    if len(dict_list) == 1:
+        return dict_list[0]
+    mega = dict_list[0]
+    for d in dict_list[1:]:
+        for k, v in d["data"].items():
+            if v is None:
+                continue
+            if isinstance(v, list):
+                mega["data"][k] = mega["data"][k] + v
+            else:
+                mega["data"][k] = torch.cat([mega["data"][k], v])
+        for k, v in d["input"].items():
+            if v is None:
+                continue
+            shift = max(max(r) for r in mega["input"][k]) + 1  # (the reference's np.max needs equally long rows)
+            mega["input"][k] += [[val + shift for val in v[0]]]
+        mega["instructions"] += d["instructions"]
+    return mega

@@ -64,6 +64,6 @@ class InfoNCEInBatch(nn.Module):
         scratch = torch.empty(2 * b * G, device=zs.device, dtype=torch.float32)
         loss = torch.empty(1, device=zs.device, dtype=torch.float32)
         check(lib.pcy_infonce_loss(ptr(zs), ptr(zt), ptr(all_s), ptr(all_t), ptr(mask), ptr(scratch), ptr(loss),
-                                   c_int(b), c_int(G), c_int(d), c_int(off), c_float(float(self.temperature)),
+                                   c_int(b), c_int(G), c_int(d), c_int(off), c_float(float(self.temperature.detach())),
                                    stream_ptr(zs.device)), "pcy_infonce_loss")
         return loss[0]

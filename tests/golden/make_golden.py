@@ -146,6 +146,30 @@ def golden_qa_retrieval_metrics():
     pos, neg = ref_tu.get_retrieval_scores_inbatch(cd)
     res["retrieval_inbatch"] = dict(zs=zs.bfloat16(), zt=zt.bfloat16(), pos=pos, neg=neg,
                                     metrics=tuple(float(v) for v in ref_tu.get_cl_metrics(pos.numpy(), neg.numpy())))
+    import ast
+    import copy
+    import types as _types
+
+    import numpy as _np
+
+    # procyon.data.inference_utils reads dataset files at import time; run just this one function of it, unmodified,
+    # from where it lies
+    _path = os.path.join(ref_import.REFERENCE_ROOT, "procyon", "data", "inference_utils.py")
+    _src = open(_path).read()
+    _fn = next(n for n in ast.parse(_src).body if isinstance(n, ast.FunctionDef) and n.name == "merge_model_input_dicts")
+    _ns = {"torch": torch, "np": _np, "List": list, "Dict": dict}
+    exec(compile(ast.Module(body=[_fn], type_ignores=[]), _path, "exec"), _ns)
+    ref_iu = _types.SimpleNamespace(merge_model_input_dicts=_ns["merge_model_input_dicts"])
+
+    def q(n_ex, text, instr):
+        return {"data": {"seq": torch.arange(n_ex) + 100, "seq_idx": torch.arange(n_ex) + 100,
+                         "text": [f"{text} ex{i}" for i in range(n_ex)] + [text], "drug": None},
+                "input": {"seq": torch.arange(n_ex).unsqueeze(0).tolist(),
+                          "text": torch.arange(n_ex + 1).unsqueeze(0).tolist(), "drug": None},
+                "target": {"seq": None, "text": None, "drug": None}, "instructions": [instr]}
+
+    singles = [q(1, "binds atp", "I1"), q(1, "kinase activity", "I2"), q(1, "membrane", "I3")]
+    res["merge_inputs"] = dict(singles=copy.deepcopy(singles), merged=ref_iu.merge_model_input_dicts(singles))
     res["decompose"] = {n: ref_tu.decompose_dataset_name(n) for n in ("protein_go_process", "domain_pfam_all",
                                                                       "protein_drugbank_drug_target")}
     save("qa_retrieval_metrics.pt", res)

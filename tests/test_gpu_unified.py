@@ -264,3 +264,38 @@ def test_trainer_loss_forward_and_qa_scoring(cuda_device):
         m.eval()
     assert abs(float(rl) - 3.0 * float(ro["contrastive_loss"])) < 1e-4
     assert "protein_go_process_batch_train_retrieval_auroc" in logged
+
+
+def test_batched_multi_query_retrieval(cuda_device):
+    """Multi-query retrieval: single-query inputs merged with merge_model_input_dicts give the same
+    query embeddings as one forward per query, and the scores against a protein DB rank identically."""
+    import copy
+
+    from oracle.esm2 import random_protein_tokens
+    from procyon_b200.data.inference_utils import get_proteins_from_batched_embeddings, merge_model_input_dicts
+
+    m = _tiny_model()
+
+    def single(seed, text, question):
+        toks = random_protein_tokens(1, 24, seed=seed)
+        return {"data": {"seq": toks, "seq_idx": torch.tensor([seed]), "text": [text], "text_idx": [seed], "drug": None},
+                "input": {"seq": [[0]], "text": [[0]], "drug": None},
+                "target": {"seq": None, "text": None, "drug": None},
+                "instructions": [f"Protein : <|protein|> Context : [EXT] {question} [ANSWER] [PROT]"],
+                "reference_indices": {"input": {"seq": [[seed]]}, "target": {"text": [0]}}}
+
+    singles = [single(3, "binds atp", "Which proteins bind it ?"), single(5, "kinase activity", "What phosphorylates ?"),
+               single(9, "membrane transport", "Which transporters ?")]
+    each = [m(copy.deepcopy(s), retrieval=True)["contrastive_out"]["positive"]["text"].float() for s in singles]
+    merged = merge_model_input_dicts(copy.deepcopy(singles))
+    assert merged["input"]["seq"] == [[0], [1], [2]] and merged["input"]["text"] == [[0], [1], [2]]
+    merged["reference_indices"] = {"input": {"seq": [[3], [5], [9]]}, "target": {"text": [0, 1, 2]}}
+    out = m(merged, retrieval=True)
+    q = out["contrastive_out"]["positive"]["text"].float()
+    assert q.shape == (3, each[0].shape[1])
+    torch.testing.assert_close(q, torch.cat(each), rtol=4e-2, atol=4e-2)  # left-padding differs: bf16 noise only
+    db = torch.randn(500, q.shape[1], generator=torch.Generator().manual_seed(1)).cuda()
+    db[17] = q[0] * 3.0
+    db[33] = q[1] * 0.5
+    sims = get_proteins_from_batched_embeddings(db, query_embeddings=q)
+    assert sims.shape == (3, 500) and int(sims[0].argmax()) == 17 and int(sims[1].argmax()) == 33
