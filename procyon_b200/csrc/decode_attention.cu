@@ -42,19 +42,42 @@ struct DecAttnParams {
 template <int GQ>
 __device__ __forceinline__ void combine_splits(const DecAttnParams& p, int row, int kvh, int tid) {
   const float* base = p.part + ((int64_t)row * p.KVH + kvh) * p.n_splits * GQ * (HD + 2);
+  constexpr int CB = 8;  // splits per batch of independent loads (one L2 round trip per batch, not per split)
   if (tid < HD) {
 #pragma unroll
     for (int h = 0; h < GQ; ++h) {
+      const float* ph = base + h * (HD + 2);
+      const int64_t stride = (int64_t)GQ * (HD + 2);
       float m = -INFINITY;
-      for (int s = 0; s < p.n_splits; ++s) m = fmaxf(m, __ldcg(base + (s * GQ + h) * (HD + 2) + HD));
+      if (p.n_splits > CB) {  // otherwise the single batch below carries its own maxima
+        for (int s0 = 0; s0 < p.n_splits; s0 += CB) {
+          float mv[CB];
+#pragma unroll
+          for (int i = 0; i < CB; ++i) mv[i] = (s0 + i < p.n_splits) ? __ldcg(ph + (s0 + i) * stride + HD) : -INFINITY;
+#pragma unroll
+          for (int i = 0; i < CB; ++i) m = fmaxf(m, mv[i]);
+        }
+      }
       float l = 0.f, acc = 0.f;
-      for (int s = 0; s < p.n_splits; ++s) {
-        const float* ps = base + (s * GQ + h) * (HD + 2);
-        const float ms = __ldcg(ps + HD);
-        if (ms == -INFINITY) continue;
-        const float w = exp2f(ms - m);
-        l += w * __ldcg(ps + HD + 1);
-        acc += w * __ldcg(ps + tid);
+      for (int s0 = 0; s0 < p.n_splits; s0 += CB) {
+        float mv[CB], lv[CB], vv[CB];
+#pragma unroll
+        for (int i = 0; i < CB; ++i) {
+          const bool in = s0 + i < p.n_splits;
+          mv[i] = in ? __ldcg(ph + (s0 + i) * stride + HD) : -INFINITY;
+          lv[i] = in ? __ldcg(ph + (s0 + i) * stride + HD + 1) : 0.f;
+          vv[i] = in ? __ldcg(ph + (s0 + i) * stride + tid) : 0.f;
+        }
+        if (p.n_splits <= CB) {
+#pragma unroll
+          for (int i = 0; i < CB; ++i) m = fmaxf(m, mv[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < CB; ++i) {
+          const float w = (mv[i] == -INFINITY) ? 0.f : exp2f(mv[i] - m);
+          l = fmaf(w, lv[i], l);
+          acc = fmaf(w, vv[i], acc);
+        }
       }
       const float r = (l > 0.f) ? acc / l : 0.f;
       p.out[(int64_t)row * (p.H * HD) + (kvh * GQ + h) * HD + tid] = __float2bfloat16_rn(r);
