@@ -158,6 +158,13 @@ int64_t pcy_llama_prefill_workspace_bytes(void* handle, int B, int S);
 int pcy_llama_prefill(void* handle, const void* input_embeds, const uint8_t* key_valid, int B, int S, void* kv_prompt,
                       void* hidden_out, const int32_t* sel_rows, int n_sel, float* sel_logits, void* workspace,
                       int64_t workspace_bytes, void* stream);
+/* same, plus: acc_out fp32 [n_acc, d] = sum over HF's L+1 `hidden_states` (embeddings, every layer's output, the last
+ * after the final norm) of the token rows acc_rows[n_acc] — `ret_token_access='all'`
+ * (procyon/model/model_unified.py:560-563); needs hidden_out */
+int pcy_llama_prefill_ex(void* handle, const void* input_embeds, const uint8_t* key_valid, int B, int S, void* kv_prompt,
+                         void* hidden_out, const int32_t* sel_rows, int n_sel, float* sel_logits,
+                         const int32_t* acc_rows, int n_acc, float* acc_out, void* workspace, int64_t workspace_bytes,
+                         void* stream);
 
 /* Device-resident state of one generate() call. rows = n_inputs * beams (<= 16). All pointers are device memory
  * owned by the caller. state[0] = t (tokens generated so far), state[2] = 1 once every beam of every input holds an

@@ -205,12 +205,40 @@ int64_t pcy_llama_prefill_workspace_bytes(void* handle, int B, int S) {
          4096;
 }
 
-// input_embeds bf16 [B*S, d]; key_valid uint8 [B,S] or NULL; kv_prompt bf16 [L][2][B][S][kv_dim] or NULL;
-// hidden_out bf16 [B*S, d] (post final norm) or NULL; sel_rows int32 [n_sel] flat token rows whose logits are
-// wanted -> sel_logits fp32 [n_sel, V] (NULL/0 to skip).
+// acc[i][:] (+)= x[rows[i]][:] in fp32: the sum over all L+1 hidden states of selected token rows
+// (ret_token_access = 'all', procyon/model/model_unified.py:560-563)
+__global__ void accumulate_rows_kernel(const bf16* __restrict__ x, const int32_t* __restrict__ rows, float* acc, int d,
+                                       int first) {
+  const int i = blockIdx.x;
+  const bf16* src = x + (int64_t)rows[i] * d;
+  float* dst = acc + (int64_t)i * d;
+  for (int k = threadIdx.x; k < d; k += blockDim.x) {
+    const float v = __bfloat162float(src[k]);
+    dst[k] = first ? v : dst[k] + v;
+  }
+}
+
+int pcy_llama_prefill_ex(void* handle, const void* input_embeds, const uint8_t* key_valid, int B, int S, void* kv_prompt,
+                         void* hidden_out, const int32_t* sel_rows, int n_sel, float* sel_logits,
+                         const int32_t* acc_rows, int n_acc, float* acc_out, void* workspace, int64_t workspace_bytes,
+                         void* stream_);
+
 int pcy_llama_prefill(void* handle, const void* input_embeds, const uint8_t* key_valid, int B, int S, void* kv_prompt,
                       void* hidden_out, const int32_t* sel_rows, int n_sel, float* sel_logits, void* workspace,
                       int64_t workspace_bytes, void* stream_) {
+  return pcy_llama_prefill_ex(handle, input_embeds, key_valid, B, S, kv_prompt, hidden_out, sel_rows, n_sel, sel_logits,
+                              nullptr, 0, nullptr, workspace, workspace_bytes, stream_);
+}
+
+// input_embeds bf16 [B*S, d]; key_valid uint8 [B,S] or NULL; kv_prompt bf16 [L][2][B][S][kv_dim] or NULL;
+// hidden_out bf16 [B*S, d] (post final norm) or NULL; sel_rows int32 [n_sel] flat token rows whose logits are
+// wanted -> sel_logits fp32 [n_sel, V] (NULL/0 to skip).  acc_rows int32 [n_acc] flat token rows whose L+1 hidden
+// states (embeddings, every layer's output, the last one after the final norm - HF's `hidden_states` tuple) are summed
+// in fp32 into acc_out [n_acc, d] (NULL/0 to skip).
+int pcy_llama_prefill_ex(void* handle, const void* input_embeds, const uint8_t* key_valid, int B, int S, void* kv_prompt,
+                         void* hidden_out, const int32_t* sel_rows, int n_sel, float* sel_logits,
+                         const int32_t* acc_rows, int n_acc, float* acc_out, void* workspace, int64_t workspace_bytes,
+                         void* stream_) {
   if (B == 0 || S == 0) return 0;
   PCY_REQUIRE(handle && input_embeds && workspace, "llama_prefill: null argument");
   LlamaModel* m = reinterpret_cast<LlamaModel*>(handle);
@@ -231,9 +259,14 @@ int pcy_llama_prefill(void* handle, const void* input_embeds, const uint8_t* key
   bf16* act = carve<bf16>(p, n * wide);
   bf16* qkv = carve<bf16>(p, n * qkv_dim);
 
+  PCY_REQUIRE(n_acc == 0 || (acc_rows && acc_out), "llama_prefill: acc_rows/acc_out missing");
   PCY_CUDA(cudaMemcpyAsync(x, input_embeds, n * d * 2, cudaMemcpyDeviceToDevice, stream));
   for (int l = 0; l < c.n_layers; ++l) {
     const LlamaLayer& y = m->layers[l];
+    if (n_acc > 0) {  // hidden_states[l]: the embeddings (l = 0) or the output of layer l - 1
+      accumulate_rows_kernel<<<n_acc, 256, 0, stream>>>(x, acc_rows, acc_out, d, l == 0);
+      PCY_LAUNCH_CHECK();
+    }
     PCY_TRY(rmsnorm_bf16(x, y.ln1, h, n, d, c.rms_eps, stream));
     GemmArgs g;
     g.A = h; g.lda = d; g.W = y.wqkv; g.ldw = d; g.C = qkv; g.ldc = qkv_dim; g.M = (int)n; g.N = qkv_dim; g.K = d;
@@ -272,6 +305,12 @@ int pcy_llama_prefill(void* handle, const void* input_embeds, const uint8_t* key
     PCY_TRY(gemm_bf16(dn, stream));
   }
   if (hidden_out) PCY_TRY(rmsnorm_bf16(x, m->norm, reinterpret_cast<bf16*>(hidden_out), n, d, c.rms_eps, stream));
+  if (n_acc > 0) {  // hidden_states[L]: the last layer's output AFTER the final norm
+    PCY_REQUIRE(hidden_out != nullptr, "llama_prefill: acc_rows needs hidden_out");
+    accumulate_rows_kernel<<<n_acc, 256, 0, stream>>>(reinterpret_cast<const bf16*>(hidden_out), acc_rows, acc_out, d,
+                                                      c.n_layers == 0);
+    PCY_LAUNCH_CHECK();
+  }
   if (n_sel > 0) {
     // gather the selected rows (pre-norm), then LM head with the final RMSNorm fused (or separate for many rows)
     bf16* sel = h;  // h is free here

@@ -391,21 +391,23 @@ class UnifiedProCyon(nn.Module):
                 all_masks |= mask_before(full_labels, self.answer_idx, before_last_answer=True)
             full_labels = torch.where(all_masks, -100, full_labels)
 
+        sum_all = retrieval and self.config.ret_token_access == "all"
         outputs = self.text_encoder(input_embeds=input_embeds, attn_masks=attn_masks, full_labels=full_labels,
-                                    output_attentions=output_attentions)
+                                    output_attentions=output_attentions,
+                                    sum_hidden_rows=ret_output_indices if sum_all else None)
         out_dict = {"outputs": outputs, "text_toks": input_ids,
                     "full_labels": full_labels if get_full_labels else None,
                     "contrastive_out": None, "contrastive_loss": None}
         if retrieval:
             contrastive_out = {"positive": {}, "negative": {}}
             if self.config.ret_token_access == "last":
-                pooled = outputs.hidden_states[-1]
+                extracted_ret = outputs.hidden_states[-1][ret_output_indices]
             elif self.config.ret_token_access == "all":
-                raise NotImplementedError("ret_token_access='all' (sum of all hidden states) is not built yet; "
-                                          "ProCyon-Full uses 'last' (llama3-full.yml:53)")
+                # sum over all L+1 hidden states (FROMAGe-style, model_unified.py:560-563), accumulated in fp32 at the
+                # [PROT] rows only while the layers run; rounded once like torch's bf16 sum
+                extracted_ret = outputs.hidden_sum.to(outputs.hidden_states[-1].dtype)
             else:
                 raise NotImplementedError("Invalid option {} for ret_token_access".format(self.config.ret_token_access))
-            extracted_ret = pooled[ret_output_indices]
             shared_lm_output = self.aaseq_lm_projector(extracted_ret)
             if inputs["target"]["text"] is None:
                 contrastive_out["positive"]["text"] = shared_lm_output

@@ -398,8 +398,11 @@ class LlamaPostTokenization(nn.Module):
 
     # ---- kernels-level entry points ---------------------------------------------------------------------------
     def prefill(self, input_embeds: torch.Tensor, attn_masks: Optional[torch.Tensor], *, want_cache: bool,
-                want_hidden: bool, sel_rows: Optional[torch.Tensor] = None, kv_out: Optional[torch.Tensor] = None):
-        """input_embeds bf16 [B,S,d] on CUDA. Returns (kv_prompt | None, hidden [B,S,d] | None, sel_logits | None)."""
+                want_hidden: bool, sel_rows: Optional[torch.Tensor] = None, kv_out: Optional[torch.Tensor] = None,
+                acc_rows: Optional[torch.Tensor] = None):
+        """input_embeds bf16 [B,S,d] on CUDA. Returns (kv_prompt | None, hidden [B,S,d] | None, sel_logits | None,
+        valid).  With `acc_rows` (flat token rows) the fp32 sum of all L+1 hidden states of those rows is left in
+        `self.last_hidden_sum` [n, d] (ret_token_access='all')."""
         lib = _lib.load()
         _lib.require_cuda(input_embeds)
         dev = input_embeds.device
@@ -425,9 +428,17 @@ class LlamaPostTokenization(nn.Module):
         f = lib.pcy_llama_prefill_workspace_bytes
         f.restype = ctypes.c_int64
         ws = self._workspace(f(self._handle, c_int(B), c_int(S)), dev)
-        check(lib.pcy_llama_prefill(self._handle, ptr(x), ptr(valid), c_int(B), c_int(S), ptr(kv), ptr(hidden),
-                                    ptr(sel_rows) if n_sel else None, c_int(n_sel), ptr(logits), ptr(ws),
-                                    c_i64(ws.numel()), stream_ptr(dev)), "pcy_llama_prefill")
+        n_acc, acc = 0, None
+        if acc_rows is not None and acc_rows.numel() > 0:
+            assert want_hidden, "acc_rows needs want_hidden=True"
+            acc_rows = acc_rows.to(device=dev, dtype=torch.int32).contiguous()
+            n_acc = acc_rows.numel()
+            acc = torch.empty((n_acc, d), device=dev, dtype=torch.float32)
+        check(lib.pcy_llama_prefill_ex(self._handle, ptr(x), ptr(valid), c_int(B), c_int(S), ptr(kv), ptr(hidden),
+                                       ptr(sel_rows) if n_sel else None, c_int(n_sel), ptr(logits),
+                                       ptr(acc_rows) if n_acc else None, c_int(n_acc), ptr(acc), ptr(ws),
+                                       c_i64(ws.numel()), stream_ptr(dev)), "pcy_llama_prefill_ex")
+        self.last_hidden_sum = acc
         return kv, hidden, logits, valid
 
     def lm_head_logits(self, hidden_rows: torch.Tensor) -> torch.Tensor:
@@ -530,7 +541,9 @@ class LlamaPostTokenization(nn.Module):
 
     # ---- reference-facing forward -------------------------------------------------------------------------------
     def forward(self, input_embeds=None, input_ids=None, attn_masks=None, full_labels=None, past_key_values=None,
-                use_cache=False, output_attentions=None):
+                use_cache=False, output_attentions=None, sum_hidden_rows=None):
+        """`sum_hidden_rows` (bool mask [B, S], extension): rows whose L+1 hidden states are summed on the fly
+        (-> `out.hidden_sum` [n, d] fp32); the reference stacks all 33 full tensors for that (ret_token_access='all')."""
         assert (input_embeds is not None) != (input_ids is not None), \
             "Only one of input_embeds or input_ids can be provided"
         if output_attentions:
@@ -554,8 +567,11 @@ class LlamaPostTokenization(nn.Module):
         sel = None
         if use_cache:
             sel = torch.arange(B, device=dev, dtype=torch.int32) * S + (S - 1)
+        acc_rows = None
+        if sum_hidden_rows is not None:
+            acc_rows = sum_hidden_rows.reshape(-1).nonzero().squeeze(-1)
         kv, hidden, sel_logits, valid = self.prefill(input_embeds, attn_masks, want_cache=use_cache, want_hidden=True,
-                                                     sel_rows=sel)
+                                                     sel_rows=sel, acc_rows=acc_rows)
         loss = None
         if full_labels is not None:
             from .model_utils import lm_loss
@@ -570,4 +586,5 @@ class LlamaPostTokenization(nn.Module):
                 past.prompt_valid.copy_(valid)
             past.reset(sel_logits)
         out = CausalLMOutput(self, hidden, n_layers, loss=loss, past=past)
+        out.hidden_sum = self.last_hidden_sum if sum_hidden_rows is not None else None
         return out

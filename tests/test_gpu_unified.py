@@ -299,3 +299,32 @@ def test_batched_multi_query_retrieval(cuda_device):
     db[33] = q[1] * 0.5
     sims = get_proteins_from_batched_embeddings(db, query_embeddings=q)
     assert sims.shape == (3, 500) and int(sims[0].argmax()) == 17 and int(sims[1].argmax()) == 33
+
+
+def test_ret_token_access_all(cuda_device):
+    """ret_token_access='all': the [PROT] representation is the sum of ALL L+1 hidden states (embeddings, each
+    layer's output, the last after the final norm; model_unified.py:560-563), here accumulated in fp32 at the [PROT]
+    rows while the layers run."""
+    from oracle.fusion import mlp_forward
+    from oracle.llama import llama_forward
+
+    m = _tiny_model()
+    m.config.ret_token_access = "all"
+    inputs = _inputs()
+    out_r = m(inputs, retrieval=True)
+    ids = out_r["text_toks"]
+    sd, pooled, z, ret = _oracle_embeds(m, inputs, ids)
+    oc, lsd = _llama_cfg_sd(m, sd)
+    mask = (ids.cpu() != m.tokenizer.pad_token_id).float()
+    ref = llama_forward(lsd, oc, inputs_embeds=z, attention_mask=mask, act_round="bf16")
+    hs = ref["hidden_states"]
+    assert len(hs) == oc.n_layers + 1
+    summed = torch.stack([h[ret] for h in hs], dim=-1).sum(-1)
+    got_sum = out_r["outputs"].hidden_sum.float().cpu()
+    assert got_sum.shape == summed.shape
+    # a sum of L+1 bf16-rounded states: tolerance of the single states times a few
+    torch.testing.assert_close(got_sum, summed, rtol=4e-2, atol=8e-2)
+    lm_sd = {k[len("aaseq_lm_projector."):]: v for k, v in sd.items() if k.startswith("aaseq_lm_projector.")}
+    ref_q = mlp_forward(lm_sd, summed.to(torch.bfloat16).float(), act_round="bf16")
+    got_q = out_r["contrastive_out"]["positive"]["text"].float().cpu()
+    torch.testing.assert_close(got_q, ref_q, rtol=6e-2, atol=8e-2)
