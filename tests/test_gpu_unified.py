@@ -328,3 +328,25 @@ def test_ret_token_access_all(cuda_device):
     ref_q = mlp_forward(lm_sd, summed.to(torch.bfloat16).float(), act_round="bf16")
     got_q = out_r["contrastive_out"]["positive"]["text"].float().cpu()
     torch.testing.assert_close(got_q, ref_q, rtol=6e-2, atol=8e-2)
+
+
+def test_protein_target_embeddings_roundtrip(cuda_device, tmp_path):
+    """Retrieval DB: build (forward_sequences 'shared' rows) -> save in the reference's pickle layout -> load ->
+    a query equal to a DB row retrieves that protein."""
+    from oracle.esm2 import random_protein_tokens
+    from procyon_b200.data.inference_utils import get_proteins_from_batched_embeddings
+    from procyon_b200.inference.retrieval_utils import (build_protein_target_embeddings, load_protein_target_embeddings,
+                                                        save_protein_target_embeddings)
+
+    m = _tiny_model()
+    toks = random_protein_tokens(37, 0, seed=2, lengths=[10 + (7 * i) % 40 for i in range(37)])
+    db = build_protein_target_embeddings(m, toks, batch_size=16)
+    assert db.shape[0] == 37 and db.dtype == torch.float32
+    one = m.forward_sequences(toks[5:6].cuda())["shared"].float()
+    torch.testing.assert_close(db[5:6], one, rtol=3e-2, atol=3e-2)  # batch composition only changes padding
+    ids = [f"P{i:05d}" for i in range(37)]
+    save_protein_target_embeddings(str(tmp_path), db, ids)
+    emb, ids2 = load_protein_target_embeddings(str(tmp_path))
+    assert ids2 == ids and torch.equal(emb, db.cpu())
+    sims = get_proteins_from_batched_embeddings(emb.cuda(), query_embeddings=db[[3, 30]])
+    assert sims.shape == (2, 37) and sims.argmax(dim=1).tolist() == [3, 30]
