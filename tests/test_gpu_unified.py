@@ -350,3 +350,60 @@ def test_protein_target_embeddings_roundtrip(cuda_device, tmp_path):
     assert ids2 == ids and torch.equal(emb, db.cpu())
     sims = get_proteins_from_batched_embeddings(emb.cuda(), query_embeddings=db[[3, 30]])
     assert sims.shape == (2, 37) and sims.argmax(dim=1).tolist() == [3, 30]
+
+
+def test_structure_and_drug_soft_tokens(cuda_device):
+    """ProCyon-Full's extra modalities (llama3-full.yml:66-67): a <|struct|> soft token (GearNet-table row of the
+    protein -> prot_structure projector) follows every <|protein|>, and <|drug|> placeholders inside the text take
+    the drug-table rows through the drug projector (model_unified.py:269-297, 409-460).  The spliced embeddings must
+    equal the oracle's splice of oracle-projected rows."""
+    from oracle.fusion import mlp_forward, splice
+    from procyon_b200.data.simple_tokenizer import SimpleTokenizer
+    from procyon_b200.model.model_unified import UnifiedProCyon
+    from procyon_b200.model.pmc_llama import LlamaConfig
+    from procyon_b200.training.training_args_IT import ModelArgs
+
+    torch.manual_seed(1)
+    cfg = ModelArgs(protein_encoder_num_params="custom", protein_pooling_opt="mean", max_text_len=64,
+                    num_layers_token_projector=3, num_layers_shared_projector=3, num_layers_lm_projector=3,
+                    hidden_size_token_projector=96, hidden_size_shared_projector=96, hidden_size_lm_projector=96,
+                    ret_token_access="last", roll_num=0, train_qa_full_lm=False, use_protein_struct=True,
+                    use_drug_embeddings=True, protein_struct_dropout=0.0)
+    lc = LlamaConfig(hidden_size=512, intermediate_size=1024, num_hidden_layers=2, num_attention_heads=4,
+                     num_key_value_heads=2, vocab_size=997, max_position_embeddings=512)
+    struct_table = torch.randn(40, 48)
+    drug_table = torch.randn(20, 24)
+    m = UnifiedProCyon(cfg, tokenizer=SimpleTokenizer(base_vocab=997), llama_config=lc, esm_custom_config=(2, 64, 4),
+                       protein_struct_embeddings=struct_table, drug_embeddings=drug_table)
+    for n, p in m.named_parameters():
+        if p.dim() > 1 and "projector" in n:
+            torch.nn.init.normal_(p, std=p.shape[1] ** -0.5)
+    m = m.bfloat16().eval().cuda()
+    inputs = _inputs()
+    inputs["data"]["text"] = ["binds atp \\nDrug: <|drug|>", "membrane transport complex subunit \\nDrug: <|drug|>"]
+    inputs["data"]["drug"] = torch.tensor([3, 11])
+    inputs["input"]["drug"] = [[0], [1]]
+    (emb, ids, am, ret, tok_emb, _) = m._preprocessing(inputs)
+    ids_c = ids.cpu()
+    assert int((ids_c == m.struct_idx).sum()) == 2 and int((ids_c == m.drug_idx).sum()) == 2
+    assert int((ids_c == m.prot_replacement_idx).sum()) == 2
+    sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+
+    def proj(name, x):
+        psd = {k[len(f"token_projectors.{name}."):]: v for k, v in sd.items() if k.startswith(f"token_projectors.{name}.")}
+        return mlp_forward(psd, x.to(torch.bfloat16).float(), act_round="bf16")
+
+    flat = [i for row in inputs["input"]["seq"] for i in row]
+    soft = proj("aaseq", tok_emb.float().cpu()[flat])
+    seq_idx = inputs["data"]["seq_idx"]
+    struct_rows = [proj("prot_structure", sd["protein_struct_embeddings.weight"].float()[seq_idx[row]])
+                   for row in inputs["input"]["seq"]]
+    drug_rows = proj("drug", sd["drug_structure_embeddings.weight"].float()[inputs["data"]["drug"]])
+    z, ret_ref = splice(ids_c, sd["input_embeddings.weight"].float(), m.prot_replacement_idx, soft, m.prot_retrieval_idx,
+                        struct_idx=m.struct_idx, struct_tokens=struct_rows, drug_idx=m.drug_idx, drug_tokens=drug_rows)
+    assert torch.equal(ret.cpu(), ret_ref)
+    torch.testing.assert_close(emb.float().cpu(), z, rtol=2e-2, atol=2e-2)
+    # and the full forward runs on them
+    out = m(inputs, retrieval=False, get_full_labels=True)
+    assert torch.isfinite(out["outputs"].loss)
+    assert int((out["full_labels"].cpu()[ids_c == m.drug_idx] != -100).sum()) == 0  # placeholders never count as labels
