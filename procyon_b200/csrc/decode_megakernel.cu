@@ -242,9 +242,12 @@ __device__ __noinline__ void produce_phase(uint32_t ring, uint32_t bars, RingGeo
 
 // out = epi(W[n_out(x2), K] . A[MT, K]).  The CTA's slice of W arrives through the ring in chunks of <= CH elements
 // of one row.
-template <int MT>
+// `hook` runs once per warp right after its first chunk (or after the loop if it has none): work that only has to be
+// ISSUED during the phase (the attention K / V requests) goes there, where the warp would otherwise wait for HBM.
+template <int MT, class Hook>
 __device__ __forceinline__ void gemv_phase(Smem& sm, int n_out, int K, int stage, const bf16* A, int64_t lda, int rows,
-                                        const bf16* __restrict__ rms_w, float eps, int epi, void* out, int64_t ldo) {
+                                        const bf16* __restrict__ rms_w, float eps, int epi, void* out, int64_t ldo,
+                                        Hook&& hook) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   int o_lo, o_hi;
   cta_range(sm.share, n_out, o_lo, o_hi);
@@ -351,6 +354,7 @@ __device__ __forceinline__ void gemv_phase(Smem& sm, int n_out, int K, int stage
   // (Taking a warp's two slots together to share the activation unpack was measured slower: with 24 slots a warp
   // owns exactly two, and holding both leaves the producer nothing to refill while the warp computes.)
   const uint32_t a_base = smem_u32(sm.a);
+  bool hooked = false;
   for (int c = (int)((warp + MK_WARPS - sm.chunk0 % MK_WARPS) % MK_WARPS); c < n_chunks; c += MK_WARPS) {
     uint32_t slot, par;
     sm.rg.locate(sm.chunk0 + (uint32_t)c, slot, par);
@@ -393,7 +397,12 @@ __device__ __forceinline__ void gemv_phase(Smem& sm, int n_out, int K, int stage
         else sm.out[r * MT + m] = v;
       }
     }
+    if (!hooked) {
+      hook();
+      hooked = true;
+    }
   }
+  if (!hooked) hook();
   sm.chunk0 += (uint32_t)n_chunks;
   consumer_sync();
   if (sm.skew && threadIdx.x == 0) {  // profiling: when did each CTA finish streaming this phase?
@@ -882,7 +891,6 @@ llama_decode_megakernel(const MegaParams p) {
     int64_t lda, ldo;
     void* out;
     if (kind == 0) {         // qkv = Wqkv . rms(x)
-      if ((int)blockIdx.x < n_att_items) att_loads.request(p, l, t, blockIdx.x);  // K / V of this layer's attention
       n_out = qkv_dim; K = d; stage = STAGE_RMS; A = p.x; lda = d; rms_w = y.ln1; epi = EPI_BF16; out = p.qkv; ldo = qkv_dim;
       if (l == 0) {
         // the residual stream starts as the embedding of the last token of every row: each CTA mirrors its column
@@ -913,7 +921,10 @@ llama_decode_megakernel(const MegaParams p) {
       n_out = c.vocab; K = d; stage = STAGE_RMS; A = p.x; lda = d; rms_w = p.norm; epi = EPI_FP32; out = p.logits;
       ldo = c.vocab;
     }
-    gemv_phase<MT>(sm, n_out, K, stage, A, lda, rows, rms_w, c.rms_eps, epi, out, ldo);
+    gemv_phase<MT>(sm, n_out, K, stage, A, lda, rows, rms_w, c.rms_eps, epi, out, ldo, [&]() {
+      // the K / V rows of this layer's attention item: requested while the qkv weights stream
+      if (kind == 0 && (int)blockIdx.x < n_att_items) att_loads.request(p, l, t, blockIdx.x);
+    });
     if (kind == 4) {
       consumer_sync();
       sm.stamp();
