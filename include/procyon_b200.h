@@ -103,9 +103,19 @@ int pcy_set_fused_rope(int enabled);
 /* 1: tcgen05 GEMMs with >= 2 row-blocks run as 2-CTA clusters sharing the weight tile by TMA multicast;
    0 (default): independent CTAs. Both paths are bit-identical (tests); measured equal speed on B200 */
 int pcy_set_gemm_cluster(int enabled);
+/* tcgen05 GEMMs as 2-CTA clusters issuing ONE tcgen05.mma.cta_group::2 of M = 256 per k-step (each CTA stages its 128
+   rows of A and half of the W tile; the leader CTA issues for both SMs). mode 0: never; 1 (default): for problems of
+   at least three waves of tiles, two or more row-blocks and N > 128; 2: whenever there are two row-blocks and N > 128
+   (tests). Same chain of k-steps per output element as the one-CTA kernel: results are bit-identical (tests) */
+int pcy_set_gemm_pair_mma(int mode);
 /* 1 (default): linears with 5..16 activation rows and no fused norm stream the weights through mma.sync (tensor
    cores); 0: the scalar-FMA weight-streaming kernel for every M <= 16 */
 int pcy_set_skinny_mma(int enabled);
+/* Profiling aid: pcy_esm_profile(1) makes every pcy_esm_encode record CUDA events between its kernels and sync at
+   the end; pcy_esm_profile_read returns the milliseconds accumulated since, per kernel class
+   [embed, layernorm, qkv, rope, attention, out_proj, fc1, fc2] (n >= 8). pcy_esm_profile(0) turns it off. */
+int pcy_esm_profile(int enabled);
+int pcy_esm_profile_read(double* ms, int n);
 int pcy_esm_create(const pcy_esm_config* cfg, void** handle);
 int pcy_esm_destroy(void* handle);
 /* src may be a host or a device pointer; the library keeps its own packed copy */

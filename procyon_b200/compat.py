@@ -21,6 +21,7 @@ _ALIASES = {
     "procyon.training.train_utils": "procyon_b200.training.train_utils",
     "procyon.inference.retrieval_utils": "procyon_b200.inference.retrieval_utils",
     "procyon.data.inference_utils": "procyon_b200.data.inference_utils",
+    "procyon.evaluate.framework.procyon": "procyon_b200.evaluate.framework.procyon",
 }
 
 
@@ -28,7 +29,8 @@ def install(force: bool = False) -> bool:
     real = sys.modules.get("procyon")
     if real is not None and getattr(real, "__file__", None) and not force:
         return False  # the real package is loaded; do not shadow it
-    for pkg in ("procyon", "procyon.model", "procyon.training", "procyon.inference", "procyon.data"):
+    for pkg in ("procyon", "procyon.model", "procyon.training", "procyon.inference", "procyon.data",
+                "procyon.evaluate", "procyon.evaluate.framework"):
         if pkg not in sys.modules:
             m = types.ModuleType(pkg)
             m.__path__ = []
@@ -54,3 +56,13 @@ def patch_reference():
     ref_mu.ESM_PLM = esm.ESM_PLM
     ref_mu.LlamaPostTokenization = pmc_llama.LlamaPostTokenization
     ref_mu.create_mlp = model_utils.create_mlp
+    try:  # the evaluation plugins core.py registers under "ProCyon" (evaluate/framework/core.py:68-110)
+        import procyon.evaluate.framework.core as ref_core
+
+        from .evaluate.framework import procyon as plugins
+
+        ref_core.caption_models["ProCyon"] = plugins.ProcyonCaptionEval
+        ref_core.qa_models["ProCyon"] = plugins.ProcyonQAEval
+        ref_core.retrieval_models["ProCyon"] = plugins.ProcyonRetrievalEval
+    except ImportError:  # the reference's evaluate package has heavy optional dependencies
+        pass

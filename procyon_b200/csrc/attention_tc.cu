@@ -144,15 +144,33 @@ esm_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcAttnPa
     float m_run = -INFINITY, l_run = 0.f;
     const uint8_t* valid_g = p.key_valid ? p.key_valid + (int64_t)b * p.T : nullptr;
     uint32_t* vwords = reinterpret_cast<uint32_t*>(valid_smem);  // [2 parities][4 words]: validity bit per key
+    // In the shifted last tile the rows below q_tile*TBM were already produced by the previous tile.  A warp whose 32
+    // rows are all such repeats keeps every barrier / mbarrier appointment (the MMAs are issued for the whole tile
+    // anyway, rows are independent in both products, and its rows of P / O are never read) but does none of the
+    // TMEM reads, exponentials or stores: at T = 514 that is 6 of the 8 softmax warps of every fifth tile.
+    const bool live = q0 + quad * 32 + 31 >= q_tile * TBM;
+    auto publish_valid = [&](int j) {  // validity bit of key j*TBN + r, one word per 32 keys (needed by every warp)
+      const int kidx = j * TBN + r;
+      bool ok = kidx < p.T;
+      if (ok && valid_g) ok = valid_g[kidx] != 0;
+      const uint32_t word = __ballot_sync(0xffffffffu, ok);
+      if (lane == 0) vwords[(j & 1) * 4 + quad] = word;
+    };
+    if (!live) {
+      for (int j = 0; j < n_kv; ++j) {
+        if (half == 0) publish_valid(j);
+        mbar_wait(s_full, j & 1);
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        mbar_arrive(p_ready);
+        mbar_wait(o_full, j & 1);
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    } else {
     for (int j = 0; j < n_kv; ++j) {
       const int kbase = j * TBN;
-      if (half == 0) {
-        const int kidx = kbase + r;
-        bool ok = kidx < p.T;
-        if (ok && valid_g) ok = valid_g[kidx] != 0;
-        const uint32_t word = __ballot_sync(0xffffffffu, ok);
-        if (lane == 0) vwords[(j & 1) * 4 + quad] = word;
-      }
+      if (half == 0) publish_valid(j);
       mbar_wait(s_full, j & 1);
       tc_fence_after();
       const int keys = min(TBN, p.T - kbase);
@@ -243,7 +261,7 @@ esm_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcAttnPa
     asm volatile("bar.sync 1, 256;" ::: "memory");
     const float l_tot = l_run + xchg_f[(half ^ 1) * TBM + r];
     const int qrow = q0 + r;
-    if (qrow < p.T) {
+    if (qrow < p.T && qrow >= q_tile * TBM) {  // rows below q_tile*TBM belong to the previous tile
       const float inv = l_tot > 0.f ? 1.f / l_tot : 0.f;
       bf16* op = p.o + (int64_t)(row_base + qrow) * p.o_rs + h * THD + half * OH;
 #pragma unroll
@@ -256,6 +274,7 @@ esm_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcAttnPa
         *reinterpret_cast<uint4*>(op + c) = u;
       }
     }
+    }  // live
   }
   tc_fence_before();
   __syncthreads();

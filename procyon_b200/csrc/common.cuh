@@ -25,6 +25,7 @@ int num_sms();
 void count_launch(int n = 1);
 extern bool g_fused_rope;
 extern bool g_gemm_cluster;
+extern int g_gemm_pair_mma;
 extern bool g_skinny_mma;
 
 #define PCY_CUDA(expr)                                                     \
@@ -99,9 +100,27 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
 }
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
-// exact (erf) GELU, as torch.nn.GELU() / fair-esm `gelu`. (An Abramowitz-Stegun erf with rcp + ex2 was measured
-// SLOWER than erff here: erff is a pure-FMA polynomial, the approximation needs two quarter-rate MUFU ops.)
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// erf GELU, as torch.nn.GELU() / fair-esm `gelu`:  gelu(x) = x * Phi(x),  Phi(x) = 1 - erfc(t)/2 for x >= 0 and
+// erfc(t)/2 for x < 0 with t = |x|/sqrt(2), and erfc(t) = 2^(t*Q(t)) where Q is the degree-6 near-minimax fit of
+// log2(erfc(t))/t on [0, 4] (t is clamped there: erfc(4) = 1.5e-8).  Measured against the fp64 erf form over
+// [-8, 8] in fp32 arithmetic: |error| <= 1.4e-6 absolute, <= 2.3e-5 relative for |x| < 5.5 — 170x below one bf16 ulp,
+// the precision every caller stores the result in.  14 instructions with one MUFU.EX2, where erff() costs 27 (two
+// coefficient sets picked by 9 FSELs): the fc1 epilogue of the ESM2 encoder was issue-bound on it (1028 TFLOP/s in
+// situ next to 1340-1470 for the other three GEMMs of the layer).  (An Abramowitz-Stegun erf with rcp + ex2 was
+// measured SLOWER than erff: two quarter-rate MUFU ops.)
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float t = fminf(fabsf(x) * 0.70710678118654752440f, 4.0f);
+  float q = -1.2784041246050037e-05f;
+  q = fmaf(q, t, 0.00038682681042701006f);
+  q = fmaf(q, t, -0.004717740695923567f);
+  q = fmaf(q, t, 0.03266161307692528f);
+  q = fmaf(q, t, -0.1509079933166504f);
+  q = fmaf(q, t, -0.9179017543792725f);
+  q = fmaf(q, t, -1.6279263496398926f);
+  float h;  // erfc(t) / 2
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(h) : "f"(fmaf(t, q, -1.0f)));
+  return x * (x >= 0.f ? 1.0f - h : h);
+}
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
 
 // 16-byte streaming loads / stores
@@ -231,6 +250,48 @@ __device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t cta_mask) {
       "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
       ::"r"(bar), "h"(cta_mask)
       : "memory");
+}
+
+// ---- cta_group::2: the two CTAs of a cluster pair run ONE MMA of M = 256; each holds its 128 rows of A, half of B's
+// rows and its 128 rows of the accumulator in its own shared memory / TMEM, and only the even-ranked CTA issues ----
+constexpr uint32_t PAIR_LEADER_MASK = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address (pair of 2)
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t smem_dst, uint32_t ncols) {  // one warp of EACH CTA, same offset
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_pair() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// TMA load into THIS CTA's shared memory whose bytes are counted on the LEADER CTA's mbarrier at the same offset
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t smem_dst, const void* desc, uint32_t bar, int32_t c0,
+                                                 int32_t c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_dst), "l"(desc), "r"(bar & PAIR_LEADER_MASK), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the mbarrier at this offset in every CTA of `cta_mask` once the pair's MMAs issued so far retire
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(bar), "h"(cta_mask)
+      : "memory");
+}
+// plain arrive on the LEADER CTA's mbarrier at this offset (from either CTA of the pair)
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & PAIR_LEADER_MASK) : "memory");
 }
 
 // D[tmem] (+)= A[smem desc] * B[smem desc], bf16 inputs, fp32 accumulate.

@@ -27,6 +27,39 @@ struct EsmModel {
 };
 
 namespace {
+// In-situ time per kernel class of the encoder (pcy_esm_profile): CUDA events between the ops of a real encode, so
+// the shares are taken at the clocks the step actually runs at (ncu serialises launches and measures them cold).
+enum { PC_EMBED = 0, PC_LN, PC_QKV, PC_ROPE, PC_ATTN, PC_OUT, PC_FC1, PC_FC2, PC_N };
+struct EsmProfile {
+  bool on = false;
+  std::vector<cudaEvent_t> pool;
+  std::vector<int> cls;  // class of the interval that ends at event i + 1
+  size_t used = 0;
+  double ms[PC_N] = {};
+  void mark(int c, cudaStream_t st) {
+    if (!on) return;
+    if (used == pool.size()) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      pool.push_back(e);
+    }
+    cudaEventRecord(pool[used++], st);
+    if (c >= 0) cls.push_back(c);
+  }
+  void collect() {
+    if (!on || used < 2) return;
+    cudaEventSynchronize(pool[used - 1]);
+    for (size_t i = 0; i + 1 < used; ++i) {
+      float t = 0.f;
+      cudaEventElapsedTime(&t, pool[i], pool[i + 1]);
+      ms[cls[i]] += t;
+    }
+    used = 0;
+    cls.clear();
+  }
+};
+EsmProfile g_prof;
+
 template <typename T>
 T* carve(uint8_t*& p, int64_t n) {
   T* r = reinterpret_cast<T*>(p);
@@ -60,6 +93,26 @@ int pcy_set_skinny_mma(int enabled) {
 
 int pcy_set_gemm_cluster(int enabled) {
   pcy::g_gemm_cluster = enabled != 0;
+  return 0;
+}
+
+int pcy_set_gemm_pair_mma(int mode) {
+  PCY_REQUIRE(mode >= 0 && mode <= 2, "set_gemm_pair_mma: mode %d not in {0, 1, 2}", mode);
+  pcy::g_gemm_pair_mma = mode;
+  return 0;
+}
+
+int pcy_esm_profile(int enabled) {
+  g_prof.collect();
+  g_prof.on = enabled != 0;
+  for (double& v : g_prof.ms) v = 0.0;
+  return 0;
+}
+
+// ms accumulated since pcy_esm_profile(1): [embed, layernorm, qkv, rope, attention, out_proj, fc1, fc2]
+int pcy_esm_profile_read(double* ms, int n) {
+  PCY_REQUIRE(ms && n >= PC_N, "esm_profile_read: need room for %d values", (int)PC_N);
+  for (int i = 0; i < PC_N; ++i) ms[i] = g_prof.ms[i];
   return 0;
 }
 
@@ -192,21 +245,26 @@ int pcy_esm_encode(void* handle, const int32_t* tokens, int B, int T, void* out_
   bf16* big = carve<bf16>(p, n * wide);
   uint8_t* valid = carve<uint8_t>(p, n);
 
+  g_prof.mark(-1, stream);
   PCY_TRY(esm_embed(tokens, m->embed, x, B, T, d, c.pad_idx, c.mask_idx, c.token_dropout, stream));
   PCY_TRY(make_key_valid(tokens, valid, n, c.pad_idx, stream));
+  g_prof.mark(PC_EMBED, stream);
   const float q_scale = 1.0f / sqrtf((float)hd);
 
   for (int l = 0; l < c.n_layers; ++l) {
     const EsmLayer& y = m->layers[l];
     // --- self attention block ---
     PCY_TRY(layernorm_bf16(x, y.ln1_g, y.ln1_b, h, n, d, c.ln_eps, stream));
+    g_prof.mark(PC_LN, stream);
     GemmArgs g;
     g.A = h; g.lda = d; g.W = y.wqkv; g.ldw = d; g.C = big; g.ldc = 3 * d; g.M = (int)n; g.N = 3 * d; g.K = d;
     g.bias = y.bqkv; g.scale = q_scale; g.scale_ncols = d;  // q = (x Wq + bq) * head_dim^-0.5
     const bool fuse_rope = g_fused_rope && (hd == 64 || hd == 128) && n > 16;
     if (fuse_rope) { g.rope = m->rope; g.rope_hd = hd; g.rope_T = T; g.rope_ncols = 2 * d; }  // q and k heads
     PCY_TRY(gemm_bf16(g, stream));
+    g_prof.mark(PC_QKV, stream);
     if (!fuse_rope) PCY_TRY(rope_inplace(big, n, T, 2 * H, hd, 3 * d, 0, m->rope, nullptr, 0, stream));
+    g_prof.mark(PC_ROPE, stream);
     int rows_done = 0;
     if (g_esm_tc_attention) PCY_TRY(esm_attention_tc(big, valid, h, B, T, H, d, 1.0f, &rows_done, stream));
     AttnArgs a;
@@ -217,22 +275,29 @@ int pcy_esm_encode(void* handle, const int32_t* tokens, int B, int T, void* out_
     a.B = B; a.H = H; a.KVH = H; a.Tq = T - rows_done; a.Tk = T; a.head_dim = hd;
     a.key_valid = valid; a.key_valid_bs = T; a.scale = 1.0f; a.causal = 0;
     if (rows_done < T) PCY_TRY(flash_attention(a, stream));  // ragged tail rows (or everything when hd != 64)
+    g_prof.mark(PC_ATTN, stream);
     GemmArgs o;
     o.A = h; o.lda = d; o.W = y.wo; o.ldw = d; o.C = x; o.ldc = d; o.M = (int)n; o.N = d; o.K = d;
     o.bias = y.bo; o.residual = x; o.ldr = d;
     PCY_TRY(gemm_bf16(o, stream));
+    g_prof.mark(PC_OUT, stream);
     // --- feed forward block ---
     PCY_TRY(layernorm_bf16(x, y.ln2_g, y.ln2_b, h, n, d, c.ln_eps, stream));
+    g_prof.mark(PC_LN, stream);
     GemmArgs f1;
     f1.A = h; f1.lda = d; f1.W = y.w1; f1.ldw = d; f1.C = big; f1.ldc = f; f1.M = (int)n; f1.N = f; f1.K = d;
     f1.bias = y.b1; f1.act = ACT_GELU;
     PCY_TRY(gemm_bf16(f1, stream));
+    g_prof.mark(PC_FC1, stream);
     GemmArgs f2;
     f2.A = big; f2.lda = f; f2.W = y.w2; f2.ldw = f; f2.C = x; f2.ldc = d; f2.M = (int)n; f2.N = d; f2.K = f;
     f2.bias = y.b2; f2.residual = x; f2.ldr = d;
     PCY_TRY(gemm_bf16(f2, stream));
+    g_prof.mark(PC_FC2, stream);
   }
   PCY_TRY(layernorm_bf16(x, m->lnf_g, m->lnf_b, reinterpret_cast<bf16*>(out_states), n, d, c.ln_eps, stream));
+  g_prof.mark(PC_LN, stream);
+  g_prof.collect();
   return 0;
 }
 

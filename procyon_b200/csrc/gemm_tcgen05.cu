@@ -8,6 +8,12 @@
 // 128x256 tile per SM needs (128 + 256) x 64 x 2 B per 64-deep k-block, i.e. ~16 TB/s of L2 -> SM traffic at full
 // tensor rate, which is what bounds the one-CTA kernel on the ESM2 / Llama shapes; sharing W cuts it by a third.
 //
+// U2 (with CL = 2): the pair runs ONE tcgen05.mma.cta_group::2 of M = 256 per k-step.  Each CTA stages only its 128
+// rows of A and HALF of the W tile (32 KB instead of 48 KB per k-block for BN = 256, so the ring holds 6 stages
+// instead of 4), both CTAs' TMA loads count on the leader's full barrier, the leader's single thread issues the MMAs
+// for both SMs and its commits arrive on both CTAs' empty / accumulator-full barriers; each CTA's epilogue warps drain
+// their own 128 accumulator rows and release the accumulator on the leader's barrier.
+//
 // Replaces, on the hot path, every nn.Linear of fair-esm ESM2 (q/k/v/out_proj, fc1, fc2 — reached via
 // procyon/model/esm.py:536), of HF LlamaDecoderLayer (q/k/v/o_proj, gate/up/down_proj — reached via
 // procyon/model/pmc_llama.py:571) and of create_mlp (procyon/model/model_utils.py:13-41).
@@ -21,6 +27,9 @@
 namespace pcy {
 
 bool g_gemm_cluster = false;  // pcy_set_gemm_cluster(1): 2-CTA clusters sharing the W tile by TMA multicast (measured: no gain)
+// pcy_set_gemm_pair_mma: 2-CTA clusters issuing cta_group::2 MMAs (M = 256 per pair).  0 = never, 1 = when the problem
+// has at least three waves of tiles (default), 2 = whenever there are two row-blocks (tests)
+int g_gemm_pair_mma = 1;
 
 namespace {
 
@@ -30,11 +39,11 @@ constexpr int UMMA_K = 16;
 constexpr int NUM_EPI_WARPS = 8;  // two per TMEM lane quadrant: each takes half of the tile's columns
 constexpr int NUM_THREADS = 64 + NUM_EPI_WARPS * 32;
 
-template <int BN>
+template <int BN, bool U2 = false>
 struct TileCfg {
-  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int STAGES = U2 ? ((BN == 256) ? 6 : 8) : ((BN == 256) ? 4 : 6);
   static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_BYTES = (U2 ? BN / 2 : BN) * BK * 2;  // U2: this CTA's half of the W tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int TMEM_COLS = 2 * BN;  // two accumulator buffers (256 or 512 columns: powers of two)
   static constexpr int STAGING_BYTES = NUM_EPI_WARPS * 32 * 128;  // per warp: 32 rows x 64 bf16 columns
@@ -124,11 +133,12 @@ __device__ __forceinline__ void pair_coords(int pair, int m_pairs, int n_blocks,
   n_blk = local / rows;
 }
 
-template <int BN, bool ROPE, int CL>
+template <int BN, bool ROPE, int CL, bool U2 = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          const EpiParams p) {
-  using Cfg = TileCfg<BN>;
+  static_assert(!U2 || CL == 2, "cta_group::2 needs the 2-CTA cluster");
+  using Cfg = TileCfg<BN, U2>;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -168,17 +178,28 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     tma_prefetch_desc(&tmap_b);
     for (int s = 0; s < Cfg::STAGES; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), CL);  // a slot is refilled (in both CTAs) once both CTAs' MMAs have read it
+      // a slot is refilled (in both CTAs) once both CTAs' MMAs have read it; U2: one pair-wide commit per use
+      mbar_init(empty_bar(s), U2 ? 1 : CL);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), NUM_EPI_WARPS);
+      // U2: the leader's MMAs write both CTAs' accumulators, so both CTAs' epilogue warps release on the leader's
+      mbar_init(tempty_bar(s), U2 ? 2 * NUM_EPI_WARPS : NUM_EPI_WARPS);
     }
     fence_barrier_init();
   }
+  if (U2) {
+    __syncthreads();
+    cluster_sync_all();  // both CTAs are resident (and their barriers exist) before the pair-wide allocation
+  }
   if (warp == 1) {
-    tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
-    tmem_relinquish();
+    if (U2) {
+      tmem_alloc_pair(tmem_ptr_smem, Cfg::TMEM_COLS);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -199,6 +220,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
           const uint32_t sb = sa + Cfg::A_BYTES;
+          if (U2) {
+            // both CTAs' boxes are counted on the leader's barrier (the only one the MMA thread waits on)
+            if (cta_rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::STAGE_BYTES);
+            tma_load_2d_pair(sa, &tmap_a, full_bar(stage), kb * BK, m_blk * BM);
+            tma_load_2d_pair(sb, &tmap_b, full_bar(stage), kb * BK, n_blk * BN + (int)cta_rank * (BN / 2));
+            if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+            continue;
+          }
           mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
           tma_load_2d(sa, &tmap_a, full_bar(stage), kb * BK, m_blk * BM);
           if (CL == 1) {
@@ -214,8 +243,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+    if (lane == 0 && !(U2 && cta_rank != 0)) {  // U2: the leader issues for the pair
+      constexpr uint32_t idesc = make_idesc_bf16(U2 ? 2 * BM : BM, BN);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -234,15 +263,22 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             // advance 32 bytes (16 bf16) along K inside the swizzle atom: +2 in the (addr >> 4) field
-            tc_mma_bf16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
-                        (kb > 0 || k > 0) ? 1u : 0u);
+            if (U2)
+              tc_mma_bf16_pair(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
+                               (kb > 0 || k > 0) ? 1u : 0u);
+            else
+              tc_mma_bf16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
+                          (kb > 0 || k > 0) ? 1u : 0u);
           }
           // frees the smem slot once these MMAs retire (in both CTAs: either one's next load writes into both)
           if (CL == 1) tc_commit(empty_bar(stage));
+          else if (U2) tc_commit_pair(empty_bar(stage), (uint16_t)0x3);
           else tc_commit_mc(empty_bar(stage), (uint16_t)0x3);
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
-        tc_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+        // accumulator complete -> epilogue (U2: of both CTAs)
+        if (U2) tc_commit_pair(tfull_bar(acc), (uint16_t)0x3);
+        else tc_commit(tfull_bar(acc));
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -474,7 +510,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       // all TMEM reads of this warp are complete (wait::ld above) -> release the accumulator
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (lane == 0) {
+        if (U2) mbar_arrive_leader(tempty_bar(acc));
+        else mbar_arrive(tempty_bar(acc));
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
@@ -484,7 +523,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   if (CL == 2) cluster_sync_all();  // nobody leaves while the peer can still multicast into it / arrive on its barriers
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if (U2) tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS);
+    else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
@@ -560,13 +600,13 @@ int get_tensor_map(const bf16* ptr, int64_t rows, int64_t cols, int64_t ld, int 
   return 0;
 }
 
-template <int BN, bool ROPE, int CL>
+template <int BN, bool ROPE, int CL, bool U2 = false>
 int launch(const GemmArgs& a, cudaStream_t stream) {
-  using Cfg = TileCfg<BN>;
+  using Cfg = TileCfg<BN, U2>;
   static bool attr_set = false;
   if (!attr_set) {
-    PCY_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, ROPE, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  Cfg::SMEM_BYTES));
+    PCY_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, ROPE, CL, U2>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
   CUtensorMap ta, tb;
@@ -580,7 +620,7 @@ int launch(const GemmArgs& a, cudaStream_t stream) {
   if (CL == 1) {
     const int tiles = ceil_div(a.M, BM) * ceil_div(a.N, BN);
     const int grid = tiles < num_sms() ? tiles : num_sms();
-    gemm_bf16_tcgen05_kernel<BN, ROPE, CL><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
+    gemm_bf16_tcgen05_kernel<BN, ROPE, CL, U2><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
   } else {
     const int pairs = ceil_div(ceil_div(a.M, BM), 2) * ceil_div(a.N, BN);
     const int clusters = std::min(pairs, num_sms() / 2);
@@ -596,7 +636,7 @@ int launch(const GemmArgs& a, cudaStream_t stream) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    PCY_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<BN, ROPE, CL>, ta, tb, p));
+    PCY_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<BN, ROPE, CL, U2>, ta, tb, p));
   }
   PCY_LAUNCH_CHECK();
   return 0;
@@ -628,7 +668,14 @@ int gemm_bf16_tc(const GemmArgs& a, cudaStream_t stream) {
     const double w128 = (double)tiles128 / (double)(ceil_div(tiles128, sms) * sms);
     if (w128 > w256 * 1.15) use128 = true;
   }
-  // two or more row-blocks: cluster pairs share the W tile through TMA multicast
+  // two or more row-blocks: cluster pairs share the W tile — as one cta_group::2 MMA, or through TMA multicast
+  // Measured on B200 (profiles/r01_gemm_shapes_pair.log): +5..12 % on the ESM2 shapes (M = 32 896) and on the Llama
+  // gate/up GEMM, i.e. at or above cuBLAS, but -5 % on problems of one or two waves (Llama q/k/v/o at M = 1024), where
+  // pairing halves the number of schedulable units.
+  const int tiles = use128 ? tiles128 : tiles256;
+  if (ceil_div(a.M, BM) >= 2 && a.N > 128 && a.rope == nullptr &&
+      (g_gemm_pair_mma == 2 || (g_gemm_pair_mma == 1 && tiles >= 3 * sms)))
+    return use128 ? launch<128, false, 2, true>(a, stream) : launch<256, false, 2, true>(a, stream);
   const bool pair = g_gemm_cluster && ceil_div(a.M, BM) >= 2;
   if (a.rope != nullptr) {
     if (pair) return use128 ? launch<128, true, 2>(a, stream) : launch<256, true, 2>(a, stream);

@@ -237,8 +237,10 @@ class ESM_PLM(nn.Module):
         self._packed_version = None
         self._rope_pos = 0
         self._workspace = None
-        # micro-batch budget for the layer stack (tokens per pass); 64 Ki tokens = 1.0 GB workspace at d=1280
-        self.max_tokens_per_pass = 64 * 1024
+        # micro-batch budget for the layer stack (tokens per pass); 128 Ki tokens = 2.0 GB workspace at d=1280.
+        # Passes are balanced (ceil(rows / n_passes) rows each): 256 proteins of 514 tokens run as 128 + 128
+        # rather than as two full passes and a sliver that cannot fill the GPU.
+        self.max_tokens_per_pass = 128 * 1024
 
     # ---- weight packing ------------------------------------------------------------------------------------
     def _param_version(self):
@@ -376,6 +378,7 @@ class ESM_PLM(nn.Module):
         if Bp <= rows_per_pass:
             z = self.encode_tokens(batch_tokens)
             return self.pooler(z, batch_keys=batch_keys, tokens=batch_tokens, padding_idx=self.padding_idx), None
+        rows_per_pass = -(-Bp // -(-Bp // rows_per_pass))  # same number of passes, equal sizes
 
         # micro-batched: keep all chunks of a protein in the same pass so pooling stays local to the pass
         keys_np = batch_keys.cpu().numpy()

@@ -34,6 +34,9 @@ from .model_utils import compute_conflict_matrix, create_mlp, left_pad_tensors
 from .pmc_llama import SELECT_GREEDY, LlamaConfig, LlamaPostTokenization
 
 DATASET_ID_PROTEIN = 0  # procyon/data/constants.py DATASET_ID["protein"]
+# procyon/model/model_unified.py:33 (`f'{DATA_DIR}/model_weights/'`); None when DATA_DIR is not configured
+DEFAULT_PRETRAINED_WEIGHTS_DIR = (os.path.join(os.environ["DATA_DIR"], "model_weights") + os.sep
+                                  if os.environ.get("DATA_DIR") else None)
 
 
 def mask_before(full_labels, answer_idx, before_last_answer=False):

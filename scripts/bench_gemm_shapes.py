@@ -1,4 +1,4 @@
-"""Isolated timing of the tcgen05 GEMM at the ESM2-650M / Llama-3-8B shapes, cluster multicast on and off, next to
+"""Isolated timing of the tcgen05 GEMM at the ESM2-650M / Llama-3-8B shapes, the cta_group::2 pair MMA on and off, next to
 torch.matmul (cuBLAS) on the same box.  CUDA events, 20 iterations after 5 warm-ups, operands rotated over buffers
 larger than L2.  Run on the B200 box."""
 import json
@@ -48,12 +48,17 @@ def main():
 
         fl = 2.0 * M * N * K
         lib.pcy_set_gemm_cluster(0)
+        lib.pcy_set_gemm_pair_mma(0)
         t0 = timeit(ours)
-        lib.pcy_set_gemm_cluster(1)
-        t1 = timeit(ours)
+        r0 = ops.linear(A[0], W[0], force="tc")
+        lib.pcy_set_gemm_pair_mma(2)
+        t2 = timeit(ours)
+        same = bool(torch.equal(r0, ops.linear(A[0], W[0], force="tc")))
+        lib.pcy_set_gemm_pair_mma(1)
         tc = timeit(cublas)
-        rows.append({"shape": name, "M": M, "N": N, "K": K, "single_cta_tflops": fl / t0 / 1e9,
-                     "cluster_mc_tflops": fl / t1 / 1e9, "cublas_tflops": fl / tc / 1e9})
+        rows.append({"shape": name, "M": M, "N": N, "K": K, "single_cta_tflops": round(fl / t0 / 1e9, 1),
+                     "pair_mma_tflops": round(fl / t2 / 1e9, 1), "pair_bit_identical": same,
+                     "cublas_tflops": round(fl / tc / 1e9, 1)})
         print(json.dumps(rows[-1]), flush=True)
 
 

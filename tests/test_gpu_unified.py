@@ -407,3 +407,107 @@ def test_structure_and_drug_soft_tokens(cuda_device):
     out = m(inputs, retrieval=False, get_full_labels=True)
     assert torch.isfinite(out["outputs"].loss)
     assert int((out["full_labels"].cpu()[ids_c == m.drug_idx] != -100).sum()) == 0  # placeholders never count as labels
+
+
+class _Loader(list):
+    """Stand-in for a torch DataLoader: iterable of collated batches with `.dataset` and `.collate_fn`."""
+
+    def __init__(self, batches, dataset=None, collate_fn=None):
+        super().__init__(batches)
+        self.dataset, self.collate_fn = dataset, collate_fn
+
+
+def test_eval_plugins_match_direct_calls(cuda_device, tmp_path):
+    """The evaluate-framework plugins (ProcyonCaptionEval / ProcyonQAEval / ProcyonRetrievalEval,
+    reference evaluate/framework/procyon.py:49-406) return what the reference's loops would build from the same
+    model calls: captions of the best beam per group, answer-row predictions, and the (queries x targets) cosine
+    matrix in the requested order (float64, CPU), with and without the cached target-embedding file."""
+    import copy
+    import types
+
+    from oracle.esm2 import random_protein_tokens
+    from oracle.fusion import cosine_scores as o_cos
+    from procyon_b200.evaluate.framework import (EvalArgs, ProcyonCaptionEval, ProcyonQAEval, ProcyonRetrievalEval,
+                                                 model_zoo)
+    from procyon_b200.training import train_utils as tu
+
+    m = _tiny_model()
+    dev = torch.device("cuda:0")
+    ds = types.SimpleNamespace(aaseq_type="protein", is_ppi=False)
+    assert model_zoo["retrieval"]["ProCyon"] is ProcyonRetrievalEval
+
+    # ---- captions ----
+    cap = ProcyonCaptionEval({"model": m, "num_captions": 2, "beam_group_size": 2}, EvalArgs(caption_max_len=5), None, dev)
+    assert cap.beam_size == 4
+    df = cap.get_predictions(_Loader([_inputs()], ds))
+    _, _, _, texts = m.generate(_inputs(), max_len=5, method="beam", beam_size=4, beam_group_size=2)
+    assert df["seq_id"].tolist() == [5, 5, 7, 7]
+    assert df["generated_caption"].tolist() == [texts[0][0], texts[0][2], texts[1][0], texts[1][2]]
+
+    # ---- yes / no QA ----
+    def qa_batch(q0, q1, answers):
+        b = _inputs()
+        b["instructions"] = [f"Protein : <|protein|> Context : [EXT] {q0} [ANSWER]",
+                             f"Protein : <|protein|> Context : [EXT] {q1} [ANSWER]"]
+        b["target"]["text"] = answers
+        b["reference_indices"]["input"]["text"] = [[4], [9]]
+        return b
+
+    m.yes_token = m.tokenizer.encode("yes", add_special_tokens=False)[0]
+    m.no_token = m.tokenizer.encode("no", add_special_tokens=False)[0]
+    batches = [qa_batch("Is it a kinase ?", "Is it secreted ?", ["yes", "no"]),
+               qa_batch("Does it bind atp ?", "Is it nuclear ?", ["no", "no"])]
+    qa = ProcyonQAEval({"model": m}, EvalArgs(), None, dev)
+    res = qa.get_predictions(_Loader(copy.deepcopy(batches), ds), aaseq_type="protein")
+    assert res["seq_ids"] == [5, 7, 5, 7] and res["text_ids"] == [4, 9, 4, 9]
+    assert res["y"].tolist() == [m.yes_token, m.no_token, m.no_token, m.no_token]
+    direct = [tu.get_qa_scores(m(copy.deepcopy(b), get_full_labels=True, crop_off=True), answer_token=m.answer_idx)[0]
+              for b in batches]
+    assert torch.equal(res["pred"], torch.cat(direct))
+    sub = ProcyonQAEval({"model": m}, EvalArgs(qa_num_samples=1, seed=3), None, dev)
+    assert sub.get_predictions(_Loader(copy.deepcopy(batches), ds))["pred"].shape[0] == 2  # one batch of two kept
+
+    # ---- retrieval ----
+    def query(qid, seed, text, question):
+        toks = random_protein_tokens(1, 24, seed=seed)
+        return {"data": {"seq": toks, "seq_idx": torch.tensor([seed]), "text": [text], "text_idx": [qid], "drug": None},
+                "input": {"seq": [[0]], "text": [[0]], "drug": None},
+                "target": {"seq": {"positive": [0], "negative": None}, "text": None, "drug": None},
+                "instructions": [f"Protein : <|protein|> Context : [EXT] {question} [ANSWER] [PROT]"],
+                "reference_indices": {"input": {"seq": [[seed]], "text": [[qid]]}, "target": {"text": [0]}}}
+
+    q_batches = [query(40, 3, "binds atp", "Which proteins bind it ?"),
+                 query(41, 5, "kinase activity", "What phosphorylates ?"),
+                 query(40, 9, "membrane transport", "Which transporters ?")]  # id 40 again: the LAST one counts
+    proteins = random_protein_tokens(6, 0, seed=21, lengths=[20, 33, 12, 27, 18, 30])
+    collate = types.SimpleNamespace(_convert_batch=lambda kind, ids: proteins[torch.as_tensor(ids)])
+    t_batches = [torch.tensor([0, 1, 2, 3]), torch.tensor([4, 5])]
+    query_order, target_order = [41, 40], [5, 0, 3, 1]
+
+    ret = ProcyonRetrievalEval({"model": m}, EvalArgs(), None, dev)
+    sims = ret.get_predictions(_Loader(copy.deepcopy(q_batches), ds, collate), _Loader(t_batches), query_order,
+                               target_order)
+    assert sims.dtype == torch.float64 and sims.device.type == "cpu" and sims.shape == (2, 4)
+    q_each = [m(copy.deepcopy(b), retrieval=True)["contrastive_out"]["positive"]["text"].float().cpu()
+              for b in q_batches]
+    t_all = torch.cat([m.forward_sequences(proteins[b].cuda())["shared"].float().cpu() for b in t_batches])
+    want = o_cos(torch.cat([q_each[1], q_each[2]]), t_all[target_order])
+    torch.testing.assert_close(sims.float(), want, rtol=1e-4, atol=1e-5)
+
+    # cached target embeddings: computed once through `all_targets_loader`, written in the reference's layout,
+    # then read back
+    calls = []
+
+    def all_targets(aaseq_type):
+        calls.append(aaseq_type)
+        return _Loader(t_batches)
+
+    cached = ProcyonRetrievalEval({"model": m, "checkpoint_dir": str(tmp_path), "all_targets_loader": all_targets},
+                                  EvalArgs(retrieval_use_cached_target_embeddings=True), None, dev)
+    for _ in range(2):
+        again = cached.get_predictions(_Loader(copy.deepcopy(q_batches), ds, collate), _Loader([]), query_order,
+                                       target_order)
+        torch.testing.assert_close(again, sims, rtol=1e-6, atol=1e-6)
+    assert calls == ["protein"]
+    emb, ids = torch.load(tmp_path / "protein_target_embeddings.pkl", weights_only=False)
+    assert emb.shape == (6, t_all.shape[1]) and ids == [0, 1, 2, 3, 4, 5] and emb.device.type == "cpu"
