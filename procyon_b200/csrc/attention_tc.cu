@@ -14,6 +14,10 @@
 
 namespace pcy {
 
+// pcy_set_esm_attention_steps64: 1 = 64-key steps with double-buffered S / P / P.V (esm_attention_tc64_kernel),
+// 0 = 128-key steps (esm_attention_tc_kernel)
+bool g_esm_attention_steps64 = true;
+
 namespace {
 
 constexpr int TBM = 128;  // queries per CTA
@@ -284,11 +288,272 @@ esm_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcAttnPa
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// 64-key steps, everything the tensor core touches double-buffered.
+//
+// In the 128-key kernel above a CTA's softmax warps and its MMAs take turns: S(j) -> softmax(j) -> P.V(j) -> O read ->
+// S(j+1) ... (ncu: 34 % of the warp samples sit in the waits for s_full and o_full; the second CTA on the SM hides only
+// part of it).  Here a step is 64 keys, so TMEM (256 columns) holds TWO S tiles and TWO P.V tiles and shared memory
+// two P tiles in the same 112 KB:
+//   * S(j+1) is issued at the START of the MMA thread's iteration j, before it waits for softmax(j);
+//   * softmax(j) keeps its 32 scores per thread in registers (one tcgen05.ld per step instead of two) and, once P(j) is
+//     published, folds in the P.V tile of step j-1, which has been complete for a whole step;
+// so in steady state neither side waits for the other.  Barriers come in pairs indexed by j & 1 (phase (j >> 1) & 1):
+// a barrier's next phase needs work that every waiter of the current phase has already passed.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int TBN2 = 64;                      // keys per step
+constexpr int KV2_STAGES = 4;
+constexpr int KV2_BYTES = TBN2 * THD * 2;     // 8 KB
+constexpr int P2_BYTES = TBM * TBN2 * 2;      // 16 KB: [128 rows][128 B], 128B swizzle
+constexpr int TC2_SMEM = Q_BYTES + 2 * KV2_STAGES * KV2_BYTES + 2 * P2_BYTES + 2 * TBM * 2 /*row max exchange*/ +
+                         16 /*valid words*/ + 144 /*barriers*/;
+static_assert(2 * (TC2_SMEM + 1024) <= 228 * 1024, "two CTAs per SM must fit");
+static_assert(2 * TBM * 4 <= 2 * P2_BYTES, "row-sum exchange reuses the P region");
+
+__global__ void __launch_bounds__(TC_THREADS, 2)
+esm_attention_tc64_kernel(const __grid_constant__ CUtensorMap tmap, const TcAttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = smem_u32(smem_raw);
+  if ((base & 1023u) != 0u) __trap();
+  const uint32_t sQ = base;
+  const uint32_t sK = sQ + Q_BYTES;                     // KV2_STAGES stages
+  const uint32_t sV = sK + KV2_STAGES * KV2_BYTES;      // KV2_STAGES stages
+  const uint32_t sP = sV + KV2_STAGES * KV2_BYTES;      // 2 buffers
+  const uint32_t sXchg = sP + 2 * P2_BYTES;             // bf16 [2 halves][128 rows]
+  const uint32_t sValid = sXchg + 2 * TBM * 2;          // [2 parities][2 words]
+  const uint32_t bars = sValid + 16;
+  const uint32_t q_full = bars, kv_full0 = bars + 8, kv_empty0 = kv_full0 + 8 * KV2_STAGES,
+                 s_full0 = kv_empty0 + 8 * KV2_STAGES, p_ready0 = s_full0 + 16, o_full0 = p_ready0 + 16,
+                 tmem_slot = o_full0 + 16;  // 124 bytes used of 144
+  uint8_t* valid_smem = smem_raw + (sValid - base);
+  __nv_bfloat16* xchg = reinterpret_cast<__nv_bfloat16*>(smem_raw + (sXchg - base));
+  float* xchg_f = reinterpret_cast<float*>(smem_raw + (sP - base));  // P region, free after the last P.V
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q_tile = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int q0 = min(q_tile * TBM, p.T - TBM);  // shifted last tile, see the kernel above
+  const int row_base = b * p.T;
+  const int n_kv = (p.T + TBN2 - 1) / TBN2;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmap);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < KV2_STAGES; ++s) {
+      mbar_init(kv_full0 + 8 * s, 1);
+      mbar_init(kv_empty0 + 8 * s, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(s_full0 + 8 * s, 1);
+      mbar_init(p_ready0 + 8 * s, SM_WARPS * 32);
+      mbar_init(o_full0 + 8 * s, 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == SM_WARPS) {
+    tmem_alloc(tmem_slot, TMEM_COLS_ATT);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  // TMEM columns: S buffers at 0 and 64, P.V tiles at 128 and 192
+
+  if (warp == SM_WARPS) {
+    if (lane == 0) {
+      // ---------------- TMA producer + MMA issuer (one thread) ----------------
+      mbar_arrive_expect_tx(q_full, Q_BYTES);
+      tma_load_2d(sQ, &tmap, q_full, h * THD, row_base + q0);
+      tma_load_2d(sQ + Q_BYTES / 2, &tmap, q_full, h * THD, row_base + q0 + TBN2);
+      auto load_kv = [&](int t) {
+        const int st = t & (KV2_STAGES - 1);
+        mbar_arrive_expect_tx(kv_full0 + 8 * st, 2 * KV2_BYTES);
+        tma_load_2d(sK + st * KV2_BYTES, &tmap, kv_full0 + 8 * st, p.d + h * THD, row_base + t * TBN2);
+        tma_load_2d(sV + st * KV2_BYTES, &tmap, kv_full0 + 8 * st, 2 * p.d + h * THD, row_base + t * TBN2);
+      };
+      auto issue_s = [&](int t) {  // S(t) = Q K(t)^T into S buffer t & 1
+        const int st = t & (KV2_STAGES - 1);
+        mbar_wait(kv_full0 + 8 * st, (t / KV2_STAGES) & 1);
+        tc_fence_after();
+        const int keys = min(TBN2, p.T - t * TBN2);
+        const uint32_t idesc_s = make_idesc_bf16(TBM, (keys + 15) & ~15);
+        const uint64_t qd = make_desc_kmajor_sw128(sQ);
+        const uint64_t kd = make_desc_kmajor_sw128(sK + st * KV2_BYTES);
+#pragma unroll
+        for (int k = 0; k < THD / 16; ++k)
+          tc_mma_bf16(tmem_base + (uint32_t)((t & 1) * TBN2), qd + 2 * k, kd + 2 * k, idesc_s, k > 0 ? 1u : 0u);
+        tc_commit(s_full0 + 8 * (t & 1));
+      };
+      for (int t = 0; t < min(KV2_STAGES - 1, n_kv); ++t) load_kv(t);
+      mbar_wait(q_full, 0);
+      issue_s(0);
+      const uint32_t idesc_o = make_idesc_bf16(TBM, THD, 0, 1);
+      for (int j = 0; j < n_kv; ++j) {
+        // S(j+1) goes into the buffer S(j-1) was read from; its readers arrived on p_ready(j-1), waited for below in
+        // the previous iteration
+        if (j + 1 < n_kv) issue_s(j + 1);
+        const int t = j + KV2_STAGES - 1;  // refill the stage tile j-1 used, once P.V(j-1) has retired
+        if (t < n_kv) {
+          if (t >= KV2_STAGES) mbar_wait(kv_empty0 + 8 * (t & (KV2_STAGES - 1)), ((t / KV2_STAGES) - 1) & 1);
+          load_kv(t);
+        }
+        // O_tile(j) = P(j) V(j) : M=128, N=64, K = keys of this step rounded up to 16; A = P (K-major), B = V (MN-major)
+        mbar_wait(p_ready0 + 8 * (j & 1), (j >> 1) & 1);
+        tc_fence_after();
+        const int st = j & (KV2_STAGES - 1);
+        const int n_mma = (min(TBN2, p.T - j * TBN2) + 15) & ~15;
+        for (int k = 0; k < n_mma / 16; ++k) {
+          const uint64_t pd = make_desc_kmajor_sw128(sP + (j & 1) * P2_BYTES + k * 32);
+          const uint64_t vd = make_desc_mnmajor_sw128(sV + st * KV2_BYTES + k * 2048, 1024);
+          tc_mma_bf16(tmem_base + (uint32_t)(2 * TBN2 + (j & 1) * THD), pd, vd, idesc_o, k > 0 ? 1u : 0u);
+        }
+        tc_commit(kv_empty0 + 8 * st);
+        tc_commit(o_full0 + 8 * (j & 1));
+      }
+    }
+  } else {
+    // ---------------- softmax / accumulate: two threads per query row, 32 of the step's 64 keys each ----------------
+    const int quad = warp & 3, half = warp >> 2;
+    const int r = quad * 32 + lane;  // query row within the tile = TMEM lane
+    const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
+    constexpr int OH = THD / 2;  // output columns per thread
+    const uint8_t* valid_g = p.key_valid ? p.key_valid + (int64_t)b * p.T : nullptr;
+    uint32_t* vwords = reinterpret_cast<uint32_t*>(valid_smem);  // [2 parities][2 words]: validity bit per key
+    const bool live = q0 + quad * 32 + 31 >= q_tile * TBM;  // see the kernel above
+    auto publish_valid = [&](int j) {  // threads r < 64 of half 0: validity bit of key j*64 + r
+      if (half == 0 && quad < 2) {
+        const int kidx = j * TBN2 + r;
+        bool ok = kidx < p.T;
+        if (ok && valid_g) ok = valid_g[kidx] != 0;
+        const uint32_t word = __ballot_sync(0xffffffffu, ok);
+        if (lane == 0) vwords[(j & 1) * 2 + quad] = word;
+      }
+    };
+    if (!live) {
+      for (int j = 0; j < n_kv; ++j) {
+        publish_valid(j);
+        mbar_wait(s_full0 + 8 * (j & 1), (j >> 1) & 1);
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        mbar_arrive(p_ready0 + 8 * (j & 1));
+        if (j > 0) mbar_wait(o_full0 + 8 * ((j - 1) & 1), ((j - 1) >> 1) & 1);
+      }
+      mbar_wait(o_full0 + 8 * ((n_kv - 1) & 1), ((n_kv - 1) >> 1) & 1);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    } else {
+      float o[OH];
+#pragma unroll
+      for (int i = 0; i < OH; ++i) o[i] = 0.f;
+      float m_run = -INFINITY, l_run = 0.f, corr_prev = 1.f;
+      auto fold_o = [&](int jj, float corr) {  // o = o * corr + P.V tile of step jj (this thread's 32 columns)
+        mbar_wait(o_full0 + 8 * (jj & 1), (jj >> 1) & 1);
+        tc_fence_after();
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(t_lane + (uint32_t)(2 * TBN2 + (jj & 1) * THD + half * OH), v);
+        tc_wait_ld();
+#pragma unroll
+        for (int i = 0; i < OH; ++i) o[i] = fmaf(o[i], corr, __uint_as_float(v[i]));
+      };
+      for (int j = 0; j < n_kv; ++j) {
+        publish_valid(j);
+        mbar_wait(s_full0 + 8 * (j & 1), (j >> 1) & 1);
+        tc_fence_after();
+        uint32_t v[32];  // this thread's 32 scores of the step stay in registers for both passes
+        tmem_ld_32x32b_x32(t_lane + (uint32_t)((j & 1) * TBN2 + half * 32), v);
+        tc_wait_ld();
+        asm volatile("bar.sync 1, 256;" ::: "memory");  // validity words visible
+        const uint32_t mw = vwords[(j & 1) * 2 + half];
+        // pass 1: row max over the valid columns (columns past the step's keys hold stale scores: their bits are 0)
+        float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        if (mw == 0xffffffffu) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(v[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            mx4[i & 3] = fmaxf(mx4[i & 3], ((mw >> i) & 1u) ? __uint_as_float(v[i]) : -INFINITY);
+        }
+        // the two threads of a row must agree on the offset exactly; any value >= the true max works: exchange the
+        // max rounded UP to bf16
+        const __nv_bfloat16 mx_own_b = __float2bfloat16_ru(fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])));
+        xchg[half * TBM + r] = mx_own_b;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const float mx = fmaxf(__bfloat162float(mx_own_b), __bfloat162float(xchg[(half ^ 1) * TBM + r]));
+        const float m_new = fmaxf(m_run, mx);
+        const float corr = (m_new == -INFINITY) ? 1.f : exp2f((m_run - m_new) * p.scale_log2);
+        const float moff = (m_new == -INFINITY) ? 0.f : m_new * p.scale_log2;
+        // pass 2: p = exp2(s*scale - moff) -> bf16 -> swizzled P buffer j & 1 (A operand of the second MMA)
+        float ls4[4] = {0.f, 0.f, 0.f, 0.f};
+        uint32_t packed[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float p0, p1;
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(fmaf(__uint_as_float(v[i]), p.scale_log2, -moff)));
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(fmaf(__uint_as_float(v[i + 1]), p.scale_log2, -moff)));
+          if (mw != 0xffffffffu) {
+            p0 = ((mw >> i) & 1u) ? p0 : 0.f;
+            p1 = ((mw >> (i + 1)) & 1u) ? p1 : 0.f;
+          }
+          ls4[(i >> 1) & 3] += p0 + p1;
+          packed[i >> 1] = pack_bf16x2(p0, p1);
+        }
+        const uint32_t blk = sP + (uint32_t)(j & 1) * P2_BYTES + (uint32_t)r * 128;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t addr = blk + (uint32_t)(((half * 4 + q) ^ (r & 7)) << 4);
+          asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(packed[4 * q]), "r"(packed[4 * q + 1]),
+                       "r"(packed[4 * q + 2]), "r"(packed[4 * q + 3])
+                       : "memory");
+        }
+        l_run = l_run * corr + ((ls4[0] + ls4[1]) + (ls4[2] + ls4[3]));
+        m_run = m_new;
+        // publish P(j); this arrive also tells the MMA thread that S buffer j & 1 and P.V tile (j-1) & 1's
+        // predecessor (folded at the end of the previous step) are free
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive(p_ready0 + 8 * (j & 1));
+        // fold in the P.V tile of the previous step (complete for about a step by now) with ITS correction factor
+        if (j > 0) fold_o(j - 1, corr_prev);
+        corr_prev = corr;
+      }
+      fold_o(n_kv - 1, corr_prev);
+      // ---- finalize: row sum = both halves ----
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      xchg_f[half * TBM + r] = l_run;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const float l_tot = l_run + xchg_f[(half ^ 1) * TBM + r];
+      const int qrow = q0 + r;
+      if (qrow < p.T && qrow >= q_tile * TBM) {  // rows below q_tile*TBM belong to the previous tile
+        const float inv = l_tot > 0.f ? 1.f / l_tot : 0.f;
+        bf16* op = p.o + (int64_t)(row_base + qrow) * p.o_rs + h * THD + half * OH;
+#pragma unroll
+        for (int c = 0; c < OH; c += 8) {
+          uint4 u;
+          u.x = pack_bf16x2(o[c] * inv, o[c + 1] * inv);
+          u.y = pack_bf16x2(o[c + 2] * inv, o[c + 3] * inv);
+          u.z = pack_bf16x2(o[c + 4] * inv, o[c + 5] * inv);
+          u.w = pack_bf16x2(o[c + 6] * inv, o[c + 7] * inv);
+          *reinterpret_cast<uint4*>(op + c) = u;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == SM_WARPS) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS_ATT);
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-int make_qkv_map(const bf16* qkv, int64_t rows, int64_t cols, int64_t ld, CUtensorMap* out) {
+int make_qkv_map(const bf16* qkv, int64_t rows, int64_t cols, int64_t ld, int box_rows, CUtensorMap* out) {
   static EncodeTiledFn enc = nullptr;
   if (!enc) {
     void* fp = nullptr;
@@ -300,7 +565,7 @@ int make_qkv_map(const bf16* qkv, int64_t rows, int64_t cols, int64_t ld, CUtens
   }
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {(cuuint32_t)THD, (cuuint32_t)TBN};
+  cuuint32_t box[2] = {(cuuint32_t)THD, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<bf16*>(qkv), gdim, gstr, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -321,15 +586,18 @@ int esm_attention_tc(const bf16* qkv, const uint8_t* key_valid, bf16* out, int B
   static bool attr_set = false;
   if (!attr_set) {
     PCY_CUDA(cudaFuncSetAttribute(esm_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+    PCY_CUDA(cudaFuncSetAttribute(esm_attention_tc64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC2_SMEM));
     attr_set = true;
   }
+  const bool steps64 = g_esm_attention_steps64;
   CUtensorMap tmap;
-  PCY_TRY(make_qkv_map(qkv, (int64_t)B * T, 3 * d, 3 * d, &tmap));
+  PCY_TRY(make_qkv_map(qkv, (int64_t)B * T, 3 * d, 3 * d, steps64 ? TBN2 : TBN, &tmap));
   TcAttnParams p;
   p.o = out; p.o_rs = d; p.key_valid = key_valid; p.B = B; p.H = n_heads; p.T = T; p.d = d; p.n_q_tiles = n_q_tiles;
   p.scale_log2 = scale * 1.4426950408889634f;
   dim3 grid(n_q_tiles, n_heads, B);
-  esm_attention_tc_kernel<<<grid, TC_THREADS, TC_SMEM, stream>>>(tmap, p);
+  if (steps64) esm_attention_tc64_kernel<<<grid, TC_THREADS, TC2_SMEM, stream>>>(tmap, p);
+  else esm_attention_tc_kernel<<<grid, TC_THREADS, TC_SMEM, stream>>>(tmap, p);
   PCY_LAUNCH_CHECK();
   *rows_done = T;
   return 0;

@@ -26,6 +26,7 @@ void count_launch(int n = 1);
 extern bool g_fused_rope;
 extern bool g_gemm_cluster;
 extern int g_gemm_pair_mma;
+extern bool g_esm_attention_steps64;
 extern bool g_skinny_mma;
 
 #define PCY_CUDA(expr)                                                     \

@@ -81,6 +81,11 @@ int pcy_set_esm_tc_attention(int enabled) {
   return 0;
 }
 
+int pcy_set_esm_attention_steps64(int enabled) {
+  pcy::g_esm_attention_steps64 = enabled != 0;
+  return 0;
+}
+
 int pcy_set_fused_rope(int enabled) {
   g_fused_rope = enabled != 0;
   return 0;

@@ -65,7 +65,7 @@ def main():
         torch.cuda.synchronize()
         return a.elapsed_time(b) / n
 
-    for budget in (32 * 1024, 64 * 1024, 128 * 1024, 256 * 1024):
+    for budget in (64 * 1024, 128 * 1024, 256 * 1024):
         m.max_tokens_per_pass = budget
         ms = run()
         print(json.dumps({"max_tokens_per_pass": budget, "ms": round(ms, 2), "proteins_per_s": round(N / ms * 1e3, 1),
@@ -88,20 +88,26 @@ def main():
                           "power_w_max": max(s[1] for s in samples), "reasons": sorted({s[2] for s in samples})}), flush=True)
 
     # per-class breakdown (events between kernels; adds a sync per encode, so the total is a little above `ms`)
-    lib.pcy_esm_profile(1)
-    reps = 3
-    for _ in range(reps):
-        m(toks)
-    buf = (ctypes.c_double * 8)()
-    lib.pcy_esm_profile_read(buf, 8)
-    lib.pcy_esm_profile(0)
-    per = {k: round(buf[i] / reps, 3) for i, k in enumerate(NAMES)}
-    tot = sum(per.values())
-    gemm_fl = {"qkv": 6, "out_proj": 2, "fc1": 8, "fc2": 8}
-    tf = {k: round(N * T * layers * v * d * d / per[k] / 1e9, 1) for k, v in gemm_fl.items() if per[k] > 0}
-    tf["attention"] = round(N * T * layers * 4 * T * d / per["attention"] / 1e9, 1) if per["attention"] > 0 else None
-    print(json.dumps({"ms_per_class": per, "sum_ms": round(tot, 2), "share": {k: round(v / tot, 3) for k, v in per.items()},
-                      "tflops_per_class": tf}), flush=True)
+    for steps64 in (1, 0):
+        lib.pcy_set_esm_attention_steps64(steps64)
+        ms = run(n=3, warm=1)
+        lib.pcy_esm_profile(1)
+        reps = 3
+        for _ in range(reps):
+            m(toks)
+        buf = (ctypes.c_double * 8)()
+        lib.pcy_esm_profile_read(buf, 8)
+        lib.pcy_esm_profile(0)
+        per = {k: round(buf[i] / reps, 3) for i, k in enumerate(NAMES)}
+        tot = sum(per.values())
+        gemm_fl = {"qkv": 6, "out_proj": 2, "fc1": 8, "fc2": 8}
+        tf = {k: round(N * T * layers * v * d * d / per[k] / 1e9, 1) for k, v in gemm_fl.items() if per[k] > 0}
+        tf["attention"] = round(N * T * layers * 4 * T * d / per["attention"] / 1e9, 1) if per["attention"] > 0 else None
+        print(json.dumps({"attention_kernel": "64-key steps, double-buffered" if steps64 else "128-key steps",
+                          "ms_untraced": round(ms, 2), "proteins_per_s": round(N / ms * 1e3, 1), "ms_per_class": per,
+                          "sum_ms": round(tot, 2), "share": {k: round(v / tot, 3) for k, v in per.items()},
+                          "tflops_per_class": tf}), flush=True)
+    lib.pcy_set_esm_attention_steps64(1)
 
 
 if __name__ == "__main__":

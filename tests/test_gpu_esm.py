@@ -87,31 +87,40 @@ def test_esm_empty_batch(cuda_device):
     assert out.shape == (0, 10, 64)
 
 
-def test_esm_tcgen05_attention_matches_mma_sync_and_oracle(cuda_device):
-    """head_dim 64: full 128-row query tiles run on tcgen05 (TMEM softmax), ragged tails on mma.sync; both must agree
-    with each other and with the oracle, with padded and un-padded rows and key tiles that end mid-tile."""
+@pytest.mark.parametrize("lengths", [[298, 131, 260], [512, 300, 130, 64]])
+def test_esm_tcgen05_attention_matches_mma_sync_and_oracle(cuda_device, lengths):
+    """head_dim 64: both tcgen05 kernels (64-key steps with double-buffered S / P / P.V, and 128-key steps) against
+    the mma.sync kernel and the oracle, with padded and un-padded rows, key tiles that end mid-tile (T = 300: 44 keys
+    in the last step; T = 514: 2 keys) and the shifted last query tile whose repeated rows are skipped."""
     from oracle import esm2 as O
     from procyon_b200 import _lib
 
     L, d, H = 2, 256, 4
     sd = O.random_esm_state_dict(L, d, seed=21)
-    toks = O.random_protein_tokens(3, 0, seed=9, lengths=[298, 131, 260])  # T = 300: 2 full tiles + 44 tail rows
+    toks = O.random_protein_tokens(len(lengths), 0, seed=9, lengths=lengths)
     m = _build("custom", sd, custom=(L, d, H))
     lib = _lib.load()
+    outs = {}
     try:
-        lib.pcy_set_esm_tc_attention(1)
-        lib.pcy_set_fused_rope(1)
-        a = m.encode_tokens(toks.cuda()).float().cpu()
+        for steps64 in (1, 0):
+            lib.pcy_set_esm_tc_attention(1)
+            lib.pcy_set_esm_attention_steps64(steps64)
+            lib.pcy_set_fused_rope(1 if steps64 == 0 else 0)
+            outs[steps64] = m.encode_tokens(toks.cuda()).float().cpu()
+            again = m.encode_tokens(toks.cuda()).float().cpu()
+            assert torch.equal(outs[steps64], again)  # deterministic
         lib.pcy_set_esm_tc_attention(0)
         lib.pcy_set_fused_rope(0)
         b = m.encode_tokens(toks.cuda()).float().cpu()
     finally:
         lib.pcy_set_esm_tc_attention(1)
+        lib.pcy_set_esm_attention_steps64(1)
         lib.pcy_set_fused_rope(0)
     nonpad = toks != O.PAD_IDX
-    torch.testing.assert_close(a[nonpad], b[nonpad], rtol=2e-2, atol=2e-2)
     ref = O.esm2_forward(sd, toks, L, H, act_round="bf16")
-    torch.testing.assert_close(a[nonpad], ref[nonpad], rtol=3e-2, atol=3e-2)
+    for steps64, a in outs.items():
+        torch.testing.assert_close(a[nonpad], b[nonpad], rtol=2e-2, atol=2e-2)
+        torch.testing.assert_close(a[nonpad], ref[nonpad], rtol=3e-2, atol=3e-2)
 
 
 def test_return_mlm_logits(cuda_device):
