@@ -14,9 +14,10 @@
 
 namespace pcy {
 
-// pcy_set_esm_attention_steps64: 1 = 64-key steps with double-buffered S / P / P.V (esm_attention_tc64_kernel),
-// 0 = 128-key steps (esm_attention_tc_kernel)
-bool g_esm_attention_steps64 = true;
+// pcy_set_esm_attention_kernel: 0 = 128-key steps (esm_attention_tc_kernel), 1 = 64-key steps with double-buffered
+// S / P / P.V (esm_attention_tc64_kernel), 2 = 64-key steps with Q and P in TMEM (esm_attention_ts_kernel), 3 = the
+// same with P packed on the ALU pipe
+int g_esm_attention_kernel = 2;
 
 namespace {
 
@@ -549,6 +550,265 @@ esm_attention_tc64_kernel(const __grid_constant__ CUtensorMap tmap, const TcAttn
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Same schedule as the 64-key kernel above, but both A operands live in TMEM.
+//
+// A tcgen05.mma whose A operand is a shared-memory descriptor reads 128 rows x 32 B of it per K = 16 step whatever N
+// is, so with N = 64 (this head dim, these 64-key steps) an instruction costs ~170 cycles instead of the N/2 = 32 the
+// tensor core needs (ncu of the 128-key kernel: 12 MMAs per 128 keys keep the tensor pipe busy for ~2050 cycles).
+// Here Q is written to TMEM once per CTA by the softmax threads (each its own row; it is the A operand of every
+// S = Q K^T), and P(j) is written over the first 32 columns of the S buffer it was computed from (bf16 pairs, one
+// tcgen05.st per thread) and consumed from there by P.V — no P tile in shared memory, no async-proxy fence.
+// TMEM columns: S/P buffers at 0 and 64, the P.V tile at 128, Q at 192 (32 columns).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int TS_SMEM = 2 * KV2_STAGES * KV2_BYTES + 2 * TBM * 2 /*row max exchange*/ + 2 * TBM * 4 /*row sums*/ +
+                        16 /*valid words*/ + 144 /*barriers*/;
+
+// ALU_PACK: the bf16 pairs of P are built with two integer adds (round half up) and one byte permute instead of
+// F2FP.BF16.PACK_AB, which shares the quarter-rate XU pipe with MUFU.EX2 (ncu: XU 43 % busy, 1.5 XU ops per score).
+template <bool ALU_PACK>
+__global__ void __launch_bounds__(TC_THREADS, 2)
+esm_attention_ts_kernel(const __grid_constant__ CUtensorMap tmap, const TcAttnParams p, const bf16* __restrict__ qkv) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = smem_u32(smem_raw);
+  if ((base & 1023u) != 0u) __trap();
+  const uint32_t sK = base;                             // KV2_STAGES stages
+  const uint32_t sV = sK + KV2_STAGES * KV2_BYTES;      // KV2_STAGES stages
+  const uint32_t sXchg = sV + KV2_STAGES * KV2_BYTES;   // bf16 [2 halves][128 rows]
+  const uint32_t sSum = sXchg + 2 * TBM * 2;            // float [2 halves][128 rows]
+  const uint32_t sValid = sSum + 2 * TBM * 4;           // [2 parities][2 words]
+  const uint32_t bars = sValid + 16;
+  const uint32_t q_full = bars, kv_full0 = bars + 8, kv_empty0 = kv_full0 + 8 * KV2_STAGES,
+                 s_full0 = kv_empty0 + 8 * KV2_STAGES, p_ready0 = s_full0 + 16, o_full = p_ready0 + 16,
+                 tmem_slot = o_full + 8;
+  uint8_t* valid_smem = smem_raw + (sValid - base);
+  __nv_bfloat16* xchg = reinterpret_cast<__nv_bfloat16*>(smem_raw + (sXchg - base));
+  float* xchg_f = reinterpret_cast<float*>(smem_raw + (sSum - base));
+  constexpr uint32_t COL_O = 2 * TBN2, COL_Q = 2 * TBN2 + THD;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q_tile = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int q0 = min(q_tile * TBM, p.T - TBM);  // shifted last tile, see the first kernel
+  const int row_base = b * p.T;
+  const int n_kv = (p.T + TBN2 - 1) / TBN2;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmap);
+    mbar_init(q_full, SM_WARPS * 32);
+    for (int s = 0; s < KV2_STAGES; ++s) {
+      mbar_init(kv_full0 + 8 * s, 1);
+      mbar_init(kv_empty0 + 8 * s, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(s_full0 + 8 * s, 1);
+      mbar_init(p_ready0 + 8 * s, SM_WARPS * 32);
+    }
+    mbar_init(o_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == SM_WARPS) {
+    tmem_alloc(tmem_slot, TMEM_COLS_ATT);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == SM_WARPS) {
+    if (lane == 0) {
+      // ---------------- TMA producer + MMA issuer (one thread) ----------------
+      auto load_kv = [&](int t) {
+        const int st = t & (KV2_STAGES - 1);
+        mbar_arrive_expect_tx(kv_full0 + 8 * st, 2 * KV2_BYTES);
+        tma_load_2d(sK + st * KV2_BYTES, &tmap, kv_full0 + 8 * st, p.d + h * THD, row_base + t * TBN2);
+        tma_load_2d(sV + st * KV2_BYTES, &tmap, kv_full0 + 8 * st, 2 * p.d + h * THD, row_base + t * TBN2);
+      };
+      auto issue_s = [&](int t) {  // S(t) = Q K(t)^T into S buffer t & 1; A = Q in TMEM
+        const int st = t & (KV2_STAGES - 1);
+        mbar_wait(kv_full0 + 8 * st, (t / KV2_STAGES) & 1);
+        tc_fence_after();
+        const int keys = min(TBN2, p.T - t * TBN2);
+        const uint32_t idesc_s = make_idesc_bf16(TBM, (keys + 15) & ~15);
+        const uint64_t kd = make_desc_kmajor_sw128(sK + st * KV2_BYTES);
+#pragma unroll
+        for (int k = 0; k < THD / 16; ++k)
+          tc_mma_bf16_ts(tmem_base + (uint32_t)((t & 1) * TBN2), tmem_base + COL_Q + 8 * k, kd + 2 * k, idesc_s,
+                         k > 0 ? 1u : 0u);
+        tc_commit(s_full0 + 8 * (t & 1));
+      };
+      for (int t = 0; t < min(KV2_STAGES - 1, n_kv); ++t) load_kv(t);
+      mbar_wait(q_full, 0);
+      tc_fence_after();
+      issue_s(0);
+      const uint32_t idesc_o = make_idesc_bf16(TBM, THD, 0, 1);
+      for (int j = 0; j < n_kv; ++j) {
+        // S(j+1) overwrites the buffer that held S(j-1) and P(j-1): the tensor core runs this thread's MMAs in issue
+        // order, so it follows P.V(j-1), and the readers of S(j-1) arrived on p_ready(j-1) before that was issued
+        if (j + 1 < n_kv) issue_s(j + 1);
+        const int t = j + KV2_STAGES - 1;  // refill the stage tile j-1 used, once P.V(j-1) has retired
+        if (t < n_kv) {
+          if (t >= KV2_STAGES) mbar_wait(kv_empty0 + 8 * (t & (KV2_STAGES - 1)), ((t / KV2_STAGES) - 1) & 1);
+          load_kv(t);
+        }
+        // O_tile(j) = P(j) V(j) : M=128, N=64, K = keys of this step rounded up to 16; A = P in TMEM, B = V (MN-major)
+        mbar_wait(p_ready0 + 8 * (j & 1), (j >> 1) & 1);
+        tc_fence_after();
+        const int st = j & (KV2_STAGES - 1);
+        const int n_mma = (min(TBN2, p.T - j * TBN2) + 15) & ~15;
+        for (int k = 0; k < n_mma / 16; ++k) {
+          const uint64_t vd = make_desc_mnmajor_sw128(sV + st * KV2_BYTES + k * 2048, 1024);
+          tc_mma_bf16_ts(tmem_base + COL_O, tmem_base + (uint32_t)((j & 1) * TBN2 + 8 * k), vd, idesc_o, k > 0 ? 1u : 0u);
+        }
+        tc_commit(kv_empty0 + 8 * st);
+        tc_commit(o_full);
+      }
+    }
+  } else {
+    // ---------------- softmax / accumulate: two threads per query row, 32 of the step's 64 keys each ----------------
+    const int quad = warp & 3, half = warp >> 2;
+    const int r = quad * 32 + lane;  // query row within the tile = TMEM lane
+    const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
+    constexpr int OH = THD / 2;  // output columns per thread
+    {
+      // this thread's half of its query row (32 bf16 = 16 packed columns) -> TMEM: the A operand of every S = Q K^T
+      const uint4* qp = reinterpret_cast<const uint4*>(qkv + (int64_t)(row_base + q0 + r) * (3 * p.d) + h * THD + half * 32);
+      uint32_t qr[16];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint4 u = __ldg(qp + i);
+        qr[4 * i] = u.x; qr[4 * i + 1] = u.y; qr[4 * i + 2] = u.z; qr[4 * i + 3] = u.w;
+      }
+      tmem_st_32x32b_x16(t_lane + COL_Q + half * 16, qr);
+      tc_wait_st();
+      tc_fence_before();
+      mbar_arrive(q_full);
+    }
+    const uint8_t* valid_g = p.key_valid ? p.key_valid + (int64_t)b * p.T : nullptr;
+    uint32_t* vwords = reinterpret_cast<uint32_t*>(valid_smem);  // [2 parities][2 words]: validity bit per key
+    const bool live = q0 + quad * 32 + 31 >= q_tile * TBM;  // see the first kernel
+    auto publish_valid = [&](int j) {  // threads r < 64 of half 0: validity bit of key j*64 + r
+      if (half == 0 && quad < 2) {
+        const int kidx = j * TBN2 + r;
+        bool ok = kidx < p.T;
+        if (ok && valid_g) ok = valid_g[kidx] != 0;
+        const uint32_t word = __ballot_sync(0xffffffffu, ok);
+        if (lane == 0) vwords[(j & 1) * 2 + quad] = word;
+      }
+    };
+    if (!live) {
+      for (int j = 0; j < n_kv; ++j) {
+        publish_valid(j);
+        mbar_wait(s_full0 + 8 * (j & 1), (j >> 1) & 1);
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (j > 0) mbar_wait(o_full, (j - 1) & 1);
+        mbar_arrive(p_ready0 + 8 * (j & 1));
+      }
+      mbar_wait(o_full, (n_kv - 1) & 1);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    } else {
+      float o[OH];
+#pragma unroll
+      for (int i = 0; i < OH; ++i) o[i] = 0.f;
+      float m_run = -INFINITY, l_run = 0.f, corr_prev = 1.f;
+      auto fold_o = [&](int jj, float corr) {  // o = o * corr + P.V tile of step jj (this thread's 32 columns)
+        mbar_wait(o_full, jj & 1);
+        tc_fence_after();
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(t_lane + COL_O + half * OH, v);
+        tc_wait_ld();
+#pragma unroll
+        for (int i = 0; i < OH; ++i) o[i] = fmaf(o[i], corr, __uint_as_float(v[i]));
+      };
+      for (int j = 0; j < n_kv; ++j) {
+        publish_valid(j);
+        mbar_wait(s_full0 + 8 * (j & 1), (j >> 1) & 1);
+        tc_fence_after();
+        uint32_t v[32];  // this thread's 32 scores of the step stay in registers for both passes
+        tmem_ld_32x32b_x32(t_lane + (uint32_t)((j & 1) * TBN2 + half * 32), v);
+        tc_wait_ld();
+        asm volatile("bar.sync 1, 256;" ::: "memory");  // validity words visible; every thread holds its scores
+        const uint32_t mw = vwords[(j & 1) * 2 + half];
+        float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        if (mw == 0xffffffffu) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(v[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            mx4[i & 3] = fmaxf(mx4[i & 3], ((mw >> i) & 1u) ? __uint_as_float(v[i]) : -INFINITY);
+        }
+        const __nv_bfloat16 mx_own_b = __float2bfloat16_ru(fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])));
+        xchg[half * TBM + r] = mx_own_b;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const float mx = fmaxf(__bfloat162float(mx_own_b), __bfloat162float(xchg[(half ^ 1) * TBM + r]));
+        const float m_new = fmaxf(m_run, mx);
+        const float corr = (m_new == -INFINITY) ? 1.f : exp2f((m_run - m_new) * p.scale_log2);
+        const float moff = (m_new == -INFINITY) ? 0.f : m_new * p.scale_log2;
+        // p = exp2(s*scale - moff) -> bf16 pairs -> TMEM columns [16*half, 16*half + 16) of this step's S buffer
+        // (all 256 threads passed the first bar.sync with their scores in registers, so the buffer is free to reuse)
+        float ls4[4] = {0.f, 0.f, 0.f, 0.f};
+        uint32_t packed[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float p0, p1;
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(fmaf(__uint_as_float(v[i]), p.scale_log2, -moff)));
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(fmaf(__uint_as_float(v[i + 1]), p.scale_log2, -moff)));
+          if (mw != 0xffffffffu) {
+            p0 = ((mw >> i) & 1u) ? p0 : 0.f;
+            p1 = ((mw >> (i + 1)) & 1u) ? p1 : 0.f;
+          }
+          ls4[(i >> 1) & 3] += p0 + p1;
+          if (ALU_PACK)
+            packed[i >> 1] = __byte_perm(__float_as_uint(p0) + 0x8000u, __float_as_uint(p1) + 0x8000u, 0x7632);
+          else
+            packed[i >> 1] = pack_bf16x2(p0, p1);
+        }
+        tmem_st_32x32b_x16(t_lane + (uint32_t)((j & 1) * TBN2 + half * 16), packed);
+        l_run = l_run * corr + ((ls4[0] + ls4[1]) + (ls4[2] + ls4[3]));
+        m_run = m_new;
+        // the P.V tile of the previous step (complete for about a step by now) must be folded in before P.V(j), which
+        // overwrites it, can be released
+        if (j > 0) fold_o(j - 1, corr_prev);
+        corr_prev = corr;
+        tc_wait_st();
+        tc_fence_before();
+        mbar_arrive(p_ready0 + 8 * (j & 1));
+      }
+      fold_o(n_kv - 1, corr_prev);
+      // ---- finalize: row sum = both halves ----
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      xchg_f[half * TBM + r] = l_run;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const float l_tot = l_run + xchg_f[(half ^ 1) * TBM + r];
+      const int qrow = q0 + r;
+      if (qrow < p.T && qrow >= q_tile * TBM) {  // rows below q_tile*TBM belong to the previous tile
+        const float inv = l_tot > 0.f ? 1.f / l_tot : 0.f;
+        bf16* op = p.o + (int64_t)(row_base + qrow) * p.o_rs + h * THD + half * OH;
+#pragma unroll
+        for (int c = 0; c < OH; c += 8) {
+          uint4 u;
+          u.x = pack_bf16x2(o[c] * inv, o[c + 1] * inv);
+          u.y = pack_bf16x2(o[c + 2] * inv, o[c + 3] * inv);
+          u.z = pack_bf16x2(o[c + 4] * inv, o[c + 5] * inv);
+          u.w = pack_bf16x2(o[c + 6] * inv, o[c + 7] * inv);
+          *reinterpret_cast<uint4*>(op + c) = u;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == SM_WARPS) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS_ATT);
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -587,16 +847,21 @@ int esm_attention_tc(const bf16* qkv, const uint8_t* key_valid, bf16* out, int B
   if (!attr_set) {
     PCY_CUDA(cudaFuncSetAttribute(esm_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
     PCY_CUDA(cudaFuncSetAttribute(esm_attention_tc64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC2_SMEM));
+    PCY_CUDA(cudaFuncSetAttribute(esm_attention_ts_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM));
+    PCY_CUDA(cudaFuncSetAttribute(esm_attention_ts_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM));
     attr_set = true;
   }
-  const bool steps64 = g_esm_attention_steps64;
+  const int kern = g_esm_attention_kernel;
+  const bool steps64 = kern != 0;
   CUtensorMap tmap;
   PCY_TRY(make_qkv_map(qkv, (int64_t)B * T, 3 * d, 3 * d, steps64 ? TBN2 : TBN, &tmap));
   TcAttnParams p;
   p.o = out; p.o_rs = d; p.key_valid = key_valid; p.B = B; p.H = n_heads; p.T = T; p.d = d; p.n_q_tiles = n_q_tiles;
   p.scale_log2 = scale * 1.4426950408889634f;
   dim3 grid(n_q_tiles, n_heads, B);
-  if (steps64) esm_attention_tc64_kernel<<<grid, TC_THREADS, TC2_SMEM, stream>>>(tmap, p);
+  if (kern == 3) esm_attention_ts_kernel<true><<<grid, TC_THREADS, TS_SMEM, stream>>>(tmap, p, qkv);
+  else if (kern == 2) esm_attention_ts_kernel<false><<<grid, TC_THREADS, TS_SMEM, stream>>>(tmap, p, qkv);
+  else if (kern == 1) esm_attention_tc64_kernel<<<grid, TC_THREADS, TC2_SMEM, stream>>>(tmap, p);
   else esm_attention_tc_kernel<<<grid, TC_THREADS, TC_SMEM, stream>>>(tmap, p);
   PCY_LAUNCH_CHECK();
   *rows_done = T;

@@ -26,7 +26,7 @@ void count_launch(int n = 1);
 extern bool g_fused_rope;
 extern bool g_gemm_cluster;
 extern int g_gemm_pair_mma;
-extern bool g_esm_attention_steps64;
+extern int g_esm_attention_kernel;
 extern bool g_skinny_mma;
 
 #define PCY_CUDA(expr)                                                     \
@@ -252,6 +252,26 @@ __device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t cta_mask) {
       ::"r"(bar), "h"(cta_mask)
       : "memory");
 }
+
+// A operand from TMEM (lane = row, two consecutive 16-bit K elements per 32-bit column), B from shared memory
+__device__ __forceinline__ void tc_mma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// registers -> TMEM: thread i of the warp writes 16 consecutive 32-bit columns of lane base + i
+__device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // ---- cta_group::2: the two CTAs of a cluster pair run ONE MMA of M = 256; each holds its 128 rows of A, half of B's
 // rows and its 128 rows of the accumulator in its own shared memory / TMEM, and only the even-ranked CTA issues ----

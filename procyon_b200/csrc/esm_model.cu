@@ -81,8 +81,9 @@ int pcy_set_esm_tc_attention(int enabled) {
   return 0;
 }
 
-int pcy_set_esm_attention_steps64(int enabled) {
-  pcy::g_esm_attention_steps64 = enabled != 0;
+int pcy_set_esm_attention_kernel(int kernel) {
+  PCY_REQUIRE(kernel >= 0 && kernel <= 3, "set_esm_attention_kernel: %d not in {0, 1, 2, 3}", kernel);
+  pcy::g_esm_attention_kernel = kernel;
   return 0;
 }
 

@@ -65,12 +65,12 @@ def main():
         torch.cuda.synchronize()
         return a.elapsed_time(b) / n
 
-    for budget in (64 * 1024, 128 * 1024, 256 * 1024):
+    for budget in (256 * 1024,):
         m.max_tokens_per_pass = budget
         ms = run()
         print(json.dumps({"max_tokens_per_pass": budget, "ms": round(ms, 2), "proteins_per_s": round(N / ms * 1e3, 1),
                           "tflops": round(flops / ms / 1e9, 1)}), flush=True)
-    m.max_tokens_per_pass = 128 * 1024
+    m.max_tokens_per_pass = 256 * 1024
 
     # clocks / power under a 3 s encode loop
     stop, samples = threading.Event(), []
@@ -88,8 +88,8 @@ def main():
                           "power_w_max": max(s[1] for s in samples), "reasons": sorted({s[2] for s in samples})}), flush=True)
 
     # per-class breakdown (events between kernels; adds a sync per encode, so the total is a little above `ms`)
-    for steps64 in (1, 0):
-        lib.pcy_set_esm_attention_steps64(steps64)
+    for steps64 in (3, 2, 1, 0):
+        lib.pcy_set_esm_attention_kernel(steps64)
         ms = run(n=3, warm=1)
         lib.pcy_esm_profile(1)
         reps = 3
@@ -103,11 +103,11 @@ def main():
         gemm_fl = {"qkv": 6, "out_proj": 2, "fc1": 8, "fc2": 8}
         tf = {k: round(N * T * layers * v * d * d / per[k] / 1e9, 1) for k, v in gemm_fl.items() if per[k] > 0}
         tf["attention"] = round(N * T * layers * 4 * T * d / per["attention"] / 1e9, 1) if per["attention"] > 0 else None
-        print(json.dumps({"attention_kernel": "64-key steps, double-buffered" if steps64 else "128-key steps",
+        print(json.dumps({"attention_kernel": ["128-key steps", "64-key steps, double-buffered", "64-key steps, Q and P in TMEM", "64-key steps, Q and P in TMEM, ALU pack"][steps64],
                           "ms_untraced": round(ms, 2), "proteins_per_s": round(N / ms * 1e3, 1), "ms_per_class": per,
                           "sum_ms": round(tot, 2), "share": {k: round(v / tot, 3) for k, v in per.items()},
                           "tflops_per_class": tf}), flush=True)
-    lib.pcy_set_esm_attention_steps64(1)
+    lib.pcy_set_esm_attention_kernel(2)
 
 
 if __name__ == "__main__":

@@ -89,8 +89,8 @@ def test_esm_empty_batch(cuda_device):
 
 @pytest.mark.parametrize("lengths", [[298, 131, 260], [512, 300, 130, 64]])
 def test_esm_tcgen05_attention_matches_mma_sync_and_oracle(cuda_device, lengths):
-    """head_dim 64: both tcgen05 kernels (64-key steps with double-buffered S / P / P.V, and 128-key steps) against
-    the mma.sync kernel and the oracle, with padded and un-padded rows, key tiles that end mid-tile (T = 300: 44 keys
+    """head_dim 64: the three tcgen05 kernels (64-key steps with Q and P in TMEM; 64-key steps with double-buffered
+    S / P / P.V; 128-key steps) against the mma.sync kernel and the oracle, with padded and un-padded rows, key tiles that end mid-tile (T = 300: 44 keys
     in the last step; T = 514: 2 keys) and the shifted last query tile whose repeated rows are skipped."""
     from oracle import esm2 as O
     from procyon_b200 import _lib
@@ -102,9 +102,9 @@ def test_esm_tcgen05_attention_matches_mma_sync_and_oracle(cuda_device, lengths)
     lib = _lib.load()
     outs = {}
     try:
-        for steps64 in (1, 0):
+        for steps64 in (3, 2, 1, 0):
             lib.pcy_set_esm_tc_attention(1)
-            lib.pcy_set_esm_attention_steps64(steps64)
+            lib.pcy_set_esm_attention_kernel(steps64)
             lib.pcy_set_fused_rope(1 if steps64 == 0 else 0)
             outs[steps64] = m.encode_tokens(toks.cuda()).float().cpu()
             again = m.encode_tokens(toks.cuda()).float().cpu()
@@ -114,7 +114,7 @@ def test_esm_tcgen05_attention_matches_mma_sync_and_oracle(cuda_device, lengths)
         b = m.encode_tokens(toks.cuda()).float().cpu()
     finally:
         lib.pcy_set_esm_tc_attention(1)
-        lib.pcy_set_esm_attention_steps64(1)
+        lib.pcy_set_esm_attention_kernel(2)
         lib.pcy_set_fused_rope(0)
     nonpad = toks != O.PAD_IDX
     ref = O.esm2_forward(sd, toks, L, H, act_round="bf16")
