@@ -102,9 +102,29 @@ class UnifiedProCyon(nn.Module):
         # ---- protein side ----
         if config.use_aaseq_embeddings:
             self.protein_seq_encoder = None
+            if protein_embeddings is None and getattr(config, "protein_seq_embeddings_path", None) \
+                    and os.environ.get("DATA_DIR"):
+                # the reference's own files (model_unified.py:189-211): embeddings in id-map order -> table order
+                from ..data.data_utils import load_aaseq_embeddings
+
+                node = os.path.join(os.environ["DATA_DIR"], "generated_data/node_embeddings")
+                protein_embeddings = load_aaseq_embeddings(
+                    config.protein_seq_embeddings_path,
+                    getattr(config, "protein_embeddings_idmap_path", None)
+                    or os.path.join(node, "protein/protein_esm2-3b_mean.pkl"), "protein")
+                if domain_embeddings is None and getattr(config, "domain_embeddings_path", None):
+                    domain_embeddings = load_aaseq_embeddings(
+                        config.domain_embeddings_path,
+                        getattr(config, "domain_embeddings_idmap_path", None)
+                        or os.path.join(node, "domain/domain_esm2-3b_mean.pkl"), "domain")
+                if peptide_embeddings is None and getattr(config, "peptide_embeddings_path", None):
+                    assert config.peptide_embeddings_idmap_path is not None
+                    peptide_embeddings = load_aaseq_embeddings(config.peptide_embeddings_path,
+                                                               config.peptide_embeddings_idmap_path, "peptide")
             if protein_embeddings is None:
                 raise ValueError("use_aaseq_embeddings=True needs the pre-computed embedding tables "
-                                 "(protein_embeddings=..., domain_embeddings=...)")
+                                 "(protein_embeddings=..., domain_embeddings=..., or config.*_embeddings_path with "
+                                 "DATA_DIR set)")
             self.protein_seq_embeddings = nn.Embedding.from_pretrained(protein_embeddings, freeze=True)
             if domain_embeddings is not None:
                 self.domain_embeddings = nn.Embedding.from_pretrained(domain_embeddings, freeze=True)
@@ -130,8 +150,13 @@ class UnifiedProCyon(nn.Module):
             "aaseq": create_mlp(config.num_layers_token_projector, self.protein_embed_dim, d_txt,
                                 config.hidden_size_token_projector)})
         if config.use_protein_struct:
+            if protein_struct_embeddings is None and getattr(config, "protein_struct_embeddings_path", None):
+                from ..data.data_utils import load_protein_struct_embeddings  # reference :271
+
+                protein_struct_embeddings = load_protein_struct_embeddings(config.protein_struct_embeddings_path)
             if protein_struct_embeddings is None:
-                raise ValueError("use_protein_struct=True needs protein_struct_embeddings=...")
+                raise ValueError("use_protein_struct=True needs protein_struct_embeddings=... or "
+                                 "config.protein_struct_embeddings_path")
             self.protein_struct_embeddings = nn.Embedding.from_pretrained(protein_struct_embeddings, freeze=True)
             self.protein_struct_embed_dim = protein_struct_embeddings.shape[1]
             self.token_projectors.update({"prot_structure": create_mlp(
@@ -140,8 +165,13 @@ class UnifiedProCyon(nn.Module):
         else:
             self.protein_struct_embeddings = None
         if config.use_drug_embeddings:
+            if drug_embeddings is None and getattr(config, "drug_struct_embeddings_path", None):
+                from ..data.data_utils import load_drug_structure_embeddings  # reference :286
+
+                drug_embeddings = load_drug_structure_embeddings(config.drug_struct_embeddings_path)
             if drug_embeddings is None:
-                raise ValueError("use_drug_embeddings=True needs drug_embeddings=...")
+                raise ValueError("use_drug_embeddings=True needs drug_embeddings=... or "
+                                 "config.drug_struct_embeddings_path")
             self.drug_structure_embeddings = nn.Embedding.from_pretrained(drug_embeddings, freeze=True)
             self.drug_embed_dim = drug_embeddings.shape[1]
             self.token_projectors.update({"drug": create_mlp(

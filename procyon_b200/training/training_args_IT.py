@@ -36,6 +36,8 @@ class ModelArgs:
     protein_seq_embeddings_path: Optional[str] = None
     domain_embeddings_path: Optional[str] = None
     peptide_embeddings_path: Optional[str] = None
+    protein_embeddings_idmap_path: Optional[str] = None  # default: DATA_DIR/generated_data/node_embeddings/protein/...
+    domain_embeddings_idmap_path: Optional[str] = None
     peptide_embeddings_idmap_path: Optional[str] = None
     # ---- structure / drug soft tokens ----
     use_protein_struct: bool = False

@@ -386,8 +386,46 @@ def golden_hf_llama():
                              hidden_last=o.hidden_states[-1], loss=o.loss, decode_logits=o2.logits))
 
 
+def golden_aaseq_embedding_tables():
+    """load_aaseq_embeddings (procyon/data/data_utils.py:365-386) on a synthetic DATA_DIR: info table in shuffled id
+    order, id map with descriptions after the id, embeddings in id-map order."""
+    import pickle
+    import tempfile
+
+    import pandas as pd
+
+    ref_du = ref_import.import_reference("procyon.data.data_utils")
+    g = torch.Generator().manual_seed(7)
+    n, d = 11, 6
+    ids = [f"P{1000 + 7 * i}" for i in range(n)]
+    table_index = torch.randperm(n, generator=g).tolist()  # `index` column of the info table for ids[i]
+    id_map_order = torch.randperm(n, generator=g).tolist()  # embedding row r belongs to ids[id_map_order[r]]
+    emb = torch.randn(n, d, generator=g)
+    with tempfile.TemporaryDirectory() as tmp:
+        os.makedirs(os.path.join(tmp, "integrated_data/v1/protein"))
+        info = pd.DataFrame({"index": table_index, "protein_id": ids, "name": [f"n{i}" for i in range(n)]})
+        info = info.sample(frac=1.0, random_state=3).reset_index(drop=True)
+        info.to_pickle(os.path.join(tmp, "integrated_data/v1/protein/protein_info_filtered.pkl"))
+        id_map = [f"{ids[k]} some description {k}" for k in id_map_order]
+        with open(os.path.join(tmp, "map.pkl"), "wb") as fh:
+            pickle.dump(id_map, fh)
+        torch.save(emb, os.path.join(tmp, "emb.pt"))
+        old = ref_du.DATA_DIR
+        ref_du.DATA_DIR = tmp
+        try:
+            out = ref_du.load_aaseq_embeddings(os.path.join(tmp, "emb.pt"), os.path.join(tmp, "map.pkl"), "protein")
+        finally:
+            ref_du.DATA_DIR = old
+    save("aaseq_embedding_tables.pt", dict(ids=ids, table_index=table_index, id_map=id_map, emb=emb, out=out,
+                                           info_order=info["protein_id"].tolist()))
+
+
 if __name__ == "__main__":
     torch.set_num_threads(4)
+    if len(sys.argv) > 1:  # regenerate only the named goldens, e.g. `make_golden.py golden_aaseq_embedding_tables`
+        for name in sys.argv[1:]:
+            globals()[name]()
+        sys.exit(0)
     golden_pooler()
     golden_split()
     golden_mlp()
@@ -399,3 +437,4 @@ if __name__ == "__main__":
     golden_hf_esm()
     golden_hf_esm_lm_head()
     golden_hf_llama()
+    golden_aaseq_embedding_tables()
