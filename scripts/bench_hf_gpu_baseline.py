@@ -78,6 +78,38 @@ def generate(esm, llama, proj, protein, prompt_ids, soft_pos, gen):
     return toks
 
 
+@torch.no_grad()
+def esm_batch(esm, proj, n_prot, n_res, device, steps, warmup, micro=32):
+    """Batch encode the way the reference's evaluation loop does it (evaluate/framework/procyon.py:296-321): fixed-size
+    batches through the encoder, mean pool, projector; returns proteins/s."""
+    g = torch.Generator().manual_seed(1234)
+    toks = torch.full((n_prot, n_res + 2), 1, dtype=torch.int64)
+    toks[:, 0] = 0
+    toks[:, 1:n_res + 1] = torch.randint(4, 24, (n_prot, n_res), generator=g)
+    toks[:, n_res + 1] = 2
+    toks = toks.to(device)
+
+    def run():
+        outs = []
+        for i in range(0, n_prot, micro):
+            t = toks[i:i + micro]
+            z = esm(input_ids=t, attention_mask=torch.ones_like(t)).last_hidden_state
+            outs.append(proj(z.mean(dim=1)).float().cpu())
+        return torch.cat(outs)
+
+    for _ in range(warmup):
+        run()
+    if device.type == "cuda":
+        torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        out = run()
+    if device.type == "cuda":
+        torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / steps
+    return n_prot / dt, dt * 1e3, tuple(out.shape)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=3)
@@ -111,6 +143,13 @@ def main():
                       "config": {"workload": f"HF EsmModel ({n_res} residues) + projector + HF LlamaForCausalLM eager: "
                                              f"prefill S={n_prompt} + {gen} greedy tokens, reference loop semantics",
                                  "tiny": args.tiny}, "n_generated": len(toks)}))
+    n_prot, n_res2 = (8, 30) if args.tiny else (256, 512)
+    pps, ms, shape = esm_batch(esm, proj, n_prot, n_res2, device, args.steps, args.warmup, micro=4 if args.tiny else 32)
+    print(json.dumps({"impl": "hf_eager_gpu_reference" if cuda else "hf_eager_cpu_tiny_check",
+                      "metric": "esm2_encode_proteins_per_s", "value": pps, "unit": "proteins/s", "ms_per_step": ms,
+                      "dtype": str(dtype), "config": {"workload": f"HF EsmModel eager, {n_prot} proteins x {n_res2} "
+                                                                  "residues in batches, mean pool + projector",
+                                                      "tiny": args.tiny}, "out_shape": list(shape)}))
 
 
 if __name__ == "__main__":
