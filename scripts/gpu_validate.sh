@@ -9,6 +9,7 @@ timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/bench.json 2> gpur
 tail -3 gpurun_out/bench.err
 timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "ref rc=$?"
 timeout 600 python scripts/bench_hf_gpu_baseline.py --steps 2 --warmup 1 > gpurun_out/hf_gpu_baseline.json 2> gpurun_out/hf_gpu_baseline.err; echo "hf gpu baseline rc=$?"; cat gpurun_out/hf_gpu_baseline.json
+timeout 300 python scripts/bench_retrieval.py > gpurun_out/retrieval.log 2>&1; echo "retrieval rc=$?"; tail -3 gpurun_out/retrieval.log
 timeout 300 python scripts/profile_esm_breakdown.py > gpurun_out/esm_breakdown.log 2>&1; echo "breakdown rc=$?"
 timeout 300 python scripts/profile_decode_phases.py > gpurun_out/decode_phases.log 2>&1
 timeout 300 python scripts/bench_gemm_shapes.py > gpurun_out/gemm_shapes_pair.log 2>&1
