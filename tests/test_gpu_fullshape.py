@@ -1,0 +1,174 @@
+"""Parity at the REAL shapes of BASELINE configs 2 and 3 (the shapes bench.py times), against the CPU oracle.
+
+  * Llama-3-8B width: one decoder layer with d = 4096, 32 / 8 heads, f = 14336 and the V = 128263 LM head — prefill
+    (tcgen05 GEMMs at N = 6144 / 4096 / 28672 / 128263, causal attention with head_dim 128 and GQA 4), then
+    teacher-forced decode steps through `llama_decode_megakernel<1,4>` (1 row), `<2,4>` (2 rows) and the one-launch-
+    per-op tensor-core weight-streaming path (10 rows = the evaluation default beam count).
+  * ESM2-650M at full size: L = 33, d = 1280, 20 heads, 4 proteins of up to 512 residues incl. padded ones, pooled.
+
+The oracle runs the same weights in fp32 on the CPU with bf16 rounding at the CUDA path's store points
+(`act_round="bf16"`); tolerances are the ones DESIGN.md §4 states. Token ids: exact arg-max wherever the oracle's own
+top-2 margin exceeds 0.05 (bf16 noise floor of a 4096-term dot product with O(1) logits).
+"""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+LOGIT_ATOL = 4e-2
+MARGIN = 0.05
+
+
+@pytest.fixture(scope="module")
+def llama8b_layer(cuda_device):
+    from oracle.llama import LlamaCfg, random_llama_state_dict
+    from procyon_b200.model.pmc_llama import LlamaConfig, LlamaPostTokenization
+
+    oc = LlamaCfg(d_model=4096, n_layers=1, n_heads=32, n_kv_heads=8, ffn_dim=14336, vocab=128263, max_pos=512)
+    pc = LlamaConfig(hidden_size=4096, intermediate_size=14336, num_hidden_layers=1, num_attention_heads=32,
+                     num_key_value_heads=8, vocab_size=128263, max_position_embeddings=512)
+    sd = random_llama_state_dict(oc, seed=17)
+    m = LlamaPostTokenization(config=pc, dtype=torch.bfloat16)
+    m.model.load_state_dict(sd, strict=True)
+    return oc, sd, m.cuda()
+
+
+def _prompt(oc, sd, B, S, seed, pad_left=0):
+    g = torch.Generator().manual_seed(seed)
+    ids = torch.randint(0, oc.vocab, (B, S), generator=g)
+    emb = sd["model.embed_tokens.weight"][ids].clone()
+    emb[:, 5] = (torch.randn(B, oc.d_model, generator=g) * 0.5).bfloat16()  # a spliced soft protein token
+    mask = torch.ones(B, S)
+    if pad_left and B > 1:
+        mask[1, :pad_left] = 0
+    return ids, emb, mask
+
+
+def _assert_argmax(ours, ref, what):
+    top2 = ref.topk(2, dim=-1).values
+    clear = (top2[..., 0] - top2[..., 1]) > MARGIN
+    assert clear.any(), f"{what}: no row with a clear top-2 margin — the test would be vacuous"
+    assert torch.equal(ours.argmax(-1)[clear], ref.argmax(-1)[clear]), f"{what}: arg-max token ids differ"
+
+
+def test_llama8b_width_prefill_hidden_logits_loss(llama8b_layer):
+    """Full-sequence forward at Llama-3-8B width incl. the LM head on every position (M = 96, N = 128263) + LM loss."""
+    from oracle.llama import llama_forward
+
+    oc, sd, m = llama8b_layer
+    ids, emb, mask = _prompt(oc, sd, 2, 48, seed=1, pad_left=7)
+    labels = ids.clone()
+    labels[:, :12] = -100
+    ref = llama_forward(sd, oc, inputs_embeds=emb.float(), attention_mask=mask, labels=labels, act_round="bf16")
+    out = m(input_embeds=emb.cuda(), attn_masks=mask.cuda(), full_labels=labels.cuda())
+    keep = mask.bool()
+    h = out.hidden_states[-1].float().cpu()
+    torch.testing.assert_close(h[keep], ref["hidden_states"][-1][keep], rtol=3e-2, atol=3e-2)
+    logits = out.logits.cpu()
+    torch.testing.assert_close(logits[keep], ref["logits"][keep], rtol=3e-2, atol=LOGIT_ATOL)
+    _assert_argmax(logits[keep], ref["logits"][keep], "prefill")
+    assert abs(out.loss.item() - ref["loss"].item()) < 2e-2
+
+
+@pytest.mark.parametrize("rows,path", [(1, "megakernel<1,4>"), (2, "megakernel<2,4>"), (4, "megakernel<4,4>"),
+                                       (10, "per-op, tensor-core GEMV"), (16, "per-op, tensor-core GEMV")])
+def test_llama8b_width_teacher_forced_decode(llama8b_layer, rows, path):
+    """Prefill + 4 teacher-forced KV-cache decode steps at full width: every step's (rows, 128263) logits against the
+    oracle, and exact arg-max ids where the oracle's margin is clear. rows selects the decode kernel that bench.py
+    times: the persistent single-launch step (1, 2, 4 rows) or the per-op path with the mma.sync weight streaming
+    (10 rows = evaluation-default beam count, 16 = the maximum)."""
+    from oracle.llama import llama_forward
+    from procyon_b200 import _lib
+
+    oc, sd, m = llama8b_layer
+    S, steps = 40, 4
+    ids, emb, mask = _prompt(oc, sd, rows, S, seed=100 + rows, pad_left=6)
+    use_mask = rows > 1
+    forced = torch.randint(0, oc.vocab, (rows, steps), generator=torch.Generator().manual_seed(rows))
+    lib = _lib.load()
+    lib.pcy_set_decode_megakernel(4)
+    try:
+        n0 = lib.pcy_launch_count()
+        out = m(input_embeds=emb.cuda(), attn_masks=mask.cuda() if use_mask else None, use_cache=True)
+        sess = out.past_key_values
+        ours = [sess.logits_cur.clone().cpu()]
+        n1 = lib.pcy_launch_count()
+        for i in range(steps):
+            o = m(input_ids=forced[:, i:i + 1].cuda(), past_key_values=sess)
+            ours.append(o.logits[:, 0].cpu())
+        per_step = (lib.pcy_launch_count() - n1) / steps
+    finally:
+        lib.pcy_set_decode_megakernel(2)
+    # the kernel under test really ran: the persistent step is ONE launch, the per-op path ~8 per layer
+    if rows <= 4:
+        assert per_step == 1, f"{path}: expected one launch per decode step, saw {per_step}"
+    else:
+        assert per_step > 4, f"{path}: expected the per-op path, saw {per_step} launches per step"
+
+    r = llama_forward(sd, oc, inputs_embeds=emb.float(), attention_mask=mask if use_mask else None, act_round="bf16")
+    refs = [r["logits"][:, -1]]
+    am = mask
+    for i in range(steps):
+        am = torch.cat([am, torch.ones(rows, 1)], dim=1)
+        r = llama_forward(sd, oc, input_ids=forced[:, i:i + 1], past=r["past"],
+                          attention_mask=am if use_mask else None, act_round="bf16")
+        refs.append(r["logits"][:, -1])
+    for s, (a, b) in enumerate(zip(ours, refs)):
+        assert torch.isfinite(a).all()
+        torch.testing.assert_close(a, b, rtol=3e-2, atol=LOGIT_ATOL, msg=lambda t: f"{path} step {s}: {t}")
+        _assert_argmax(a, b, f"{path} step {s}")
+
+
+def _esm650(sd):
+    from procyon_b200.model.esm import ESM_PLM
+
+    enc = ESM_PLM(num_params="650m", pooling_method="mean", protein_pooling_correction_option=False,
+                  max_protein_len=1024)
+    enc.model.load_state_dict(sd, strict=True)
+    return enc.cuda().eval()
+
+
+def test_esm2_650m_full_size_pooled(cuda_device):
+    """ESM2-650M at its real size (33 layers, d 1280, 20 heads of 64, ffn 5120): 8 proteins of up to 512 residues in
+    one padded batch (three shorter ones) -> mean-pooled embeddings, against the fp32 CPU oracle with bf16 rounding at
+    the store points.  M = 8 * 514 = 4112 token rows = 33 row blocks: qkv / fc1 are >= 3 waves of 128x256 tiles, so the
+    default heuristic takes the 2-CTA pair-MMA GEMM (cta_group::2) for them and the one-CTA kernel for out_proj; the
+    run is repeated with the pair MMA forced on everywhere and forced off — all three against the same oracle result.
+    The tcgen05 attention kernel sees ragged key masks."""
+    from oracle import esm2 as OE
+
+    L, d, H = OE.ESM_SIZES["650m"]
+    sd = OE.random_esm_state_dict(L, d, seed=5, dtype=torch.bfloat16)
+    from procyon_b200 import _lib
+
+    toks = OE.random_protein_tokens(8, 512, seed=21, lengths=[512, 512, 300, 77, 512, 512, 511, 512])
+    enc = _esm650(sd)
+    ref = OE.esm_plm_forward(sd, toks, L, H, pooling="mean", act_round="bf16")
+    lib = _lib.load()
+    try:
+        for mode in (1, 2, 0):  # default heuristic, pair MMA wherever legal, never
+            lib.pcy_set_gemm_pair_mma(mode)
+            pooled, _ = enc(toks.cuda(), aggregate=True)
+            assert pooled.shape == (8, d)
+            got = pooled.float().cpu()
+            assert torch.isfinite(got).all()
+            # 33 layers of bf16 stores: a few bf16 ulps of O(1) post-LayerNorm activations; pooling averages them down
+            torch.testing.assert_close(got, ref, rtol=3e-2, atol=3e-2, msg=lambda t: f"pair-MMA mode {mode}: {t}")
+            cos = torch.nn.functional.cosine_similarity(got, ref, dim=-1)
+            assert (cos > 0.999).all(), (mode, cos)
+    finally:
+        lib.pcy_set_gemm_pair_mma(1)
+
+
+def test_esm2_650m_full_size_residue_states(cuda_device):
+    """Same encoder, per-residue states of one 512-residue protein and one padded 130-residue protein (no pooling)."""
+    from oracle import esm2 as OE
+
+    L, d, H = OE.ESM_SIZES["650m"]
+    sd = OE.random_esm_state_dict(L, d, seed=6, dtype=torch.bfloat16)
+    toks = OE.random_protein_tokens(2, 512, seed=22, lengths=[512, 130])
+    enc = _esm650(sd)
+    states = enc.encode_tokens(toks.cuda()).float().cpu()
+    ref = OE.esm2_forward(sd, toks, L, H, act_round="bf16")
+    keep = toks != 1
+    torch.testing.assert_close(states[keep], ref[keep], rtol=4e-2, atol=4e-2)
