@@ -225,6 +225,15 @@ int pcy_llama_decode_forward(void* handle, const pcy_decode_buffers* b, void* st
 int pcy_decode_select(void* handle, const pcy_decode_buffers* b, int mode, int group_size, float diversity_penalty,
                       int eos_id, int stop_on_all_eos, void* stream);
 
+/* Same for a batch split over several decode sessions (<= 16 beam rows each) that step in lock-step on one stream:
+ * the reference stops the WHOLE batch at the first step where every beam of every input holds an EOS
+ * (procyon/model/model_unified.py:833). group_state: device int32 [4] shared by the sessions, zeroed by the caller
+ * except [3] = total number of inputs; [1] = finished, [2] = the step at which that happened (they replace state[2] /
+ * state[3]); group_last = 1 for the session that runs last within a step. */
+int pcy_decode_select_group(void* handle, const pcy_decode_buffers* b, int mode, int group_size,
+                            float diversity_penalty, int eos_id, int stop_on_all_eos, int32_t* group_state,
+                            int group_last, void* stream);
+
 /* ---- losses and retrieval scoring -------------------------------------------------------------------------
  * Row-wise cross-entropy of fp32 logits [rows, V] (row stride ld) against int32 labels: acc[0] += sum_i
  * (logsumexp(x_i) - x_i[label_i]), acc[1] += rows. HF LlamaForCausalLM loss (procyon/model/pmc_llama.py:576) is

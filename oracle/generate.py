@@ -29,10 +29,53 @@ def _step(sd, cfg, i, embeds, attn_mask, out, past, mask_pads_in_decode, **kw):
     return r["logits"][:, -1, :], r["past"]
 
 
+def beam_select_step(log_probs, out, cur, i, n, beam_size, beam_group_size, diversity_penalty, margins=None):
+    """One step of the selection of `_generate_beam_search` (procyon/model/model_unified.py:783-828) on
+    `log_probs` [n*beams, V] (= LogSoftmax(logits) + running scores; penalised IN PLACE like the reference's view).
+    Updates `out` (token histories, reordered) and `cur` (scores) in place and returns `parents` [n*beams]: the flat
+    row every new beam extends, i.e. the gather index the reference applies group by group to the logits history
+    and to every layer's K / V (:827-832).  Group-by-group in-place gathers compose to one gather here because a
+    group only ever reads rows of its own group (`orig_candidate_idxs` in [group_start, check_end))."""
+    V = log_probs.shape[1]
+    groups = beam_size // beam_group_size
+    parents = torch.arange(n * beam_size)
+    for inp in range(n):
+        b0 = inp * beam_size
+        for g in range(groups):
+            inc = 1 if i == 0 else beam_group_size
+            gs = b0 + g * beam_group_size
+            ge = gs + beam_group_size
+            lp = log_probs[gs : gs + inc]
+            if g != 0:
+                prev = out[b0:gs, i]
+                lp -= diversity_penalty * torch.bincount(prev, minlength=V)  # in place on the view
+            vals, idx = lp.ravel().topk(beam_group_size)
+            if margins is not None:
+                top = lp.ravel().topk(min(beam_group_size + 1, lp.numel())).values
+                margins.extend((top[:-1] - top[1:]).tolist())
+            toks = idx % V
+            src = (idx // V) + gs
+            out[gs:ge] = out[src]
+            out[torch.arange(gs, ge), i] = toks
+            cur[gs:ge] = vals
+            parents[gs:ge] = src
+    return parents
+
+
 @torch.no_grad()
 def generate_beam_search(sd, cfg: LlamaCfg, input_embeds, attn_mask, *, max_len=64, beam_size=5, beam_group_size=5,
-                         diversity_penalty=0.8, eos_id: int = 2, mask_pads_in_decode: bool = False, **kw):
-    """Returns (out [n, beams, max_len] int64, log_probs [n, beams], logits [n, beams, steps, V])."""
+                         diversity_penalty=0.8, eos_id: int = 2, mask_pads_in_decode: bool = False,
+                         margins: Optional[List[float]] = None, trace: Optional[list] = None, **kw):
+    """Returns (out [n, beams, max_len] int64, log_probs [n, beams], logits [n, beams, steps, V]).
+
+    `trace` (test aid): if a list is passed, every step appends dict(logits [n*beams, V] as the model produced them
+    for the beam rows BEFORE the selection, parents [n*beams], tokens [n*beams], scores [n*beams], margin = the
+    smallest decision gap of the step).
+
+    `margins` (test aid, not in the reference): if a list is passed, every group selection appends the gaps between
+    consecutive entries of its top-(k+1) candidate scores — the k-1 gaps that fix the ORDER of the selected beams and
+    the gap to the first rejected candidate. Their minimum is the numerical head-room of the whole search: an
+    implementation whose scores deviate by less than half of it must reproduce every beam exactly."""
     n = input_embeds.shape[0]
     bb = n * beam_size
     V = cfg.vocab
@@ -51,26 +94,18 @@ def generate_beam_search(sd, cfg: LlamaCfg, input_embeds, attn_mask, *, max_len=
         it = logits.clone().unsqueeze(1)
         output_logits = it if output_logits is None else torch.cat([output_logits, it], dim=1)
         log_probs = torch.log_softmax(logits, dim=-1) + cur[:, None]
-        for inp in range(n):
-            b0 = inp * beam_size
-            for g in range(groups):
-                inc = 1 if i == 0 else beam_group_size
-                gs = b0 + g * beam_group_size
-                ge = gs + beam_group_size
-                lp = log_probs[gs : gs + inc]
-                if g != 0:
-                    prev = out[b0:gs, i]
-                    lp -= diversity_penalty * torch.bincount(prev, minlength=V)  # in place on the view
-                vals, idx = lp.ravel().topk(beam_group_size)
-                toks = idx % V
-                src = (idx // V) + gs
-                out[gs:ge] = out[src]
-                out[torch.arange(gs, ge), i] = toks
-                cur[gs:ge] = vals
-                output_logits[gs:ge] = output_logits[src]
-                for l in range(len(past)):
-                    past[l][0][gs:ge] = past[l][0][src]
-                    past[l][1][gs:ge] = past[l][1][src]
+        step_margins = [] if (trace is not None or margins is not None) else None
+        parents = beam_select_step(log_probs, out, cur, i, n, beam_size, beam_group_size, diversity_penalty,
+                                   step_margins)
+        if margins is not None:
+            margins.extend(step_margins)
+        if trace is not None:
+            trace.append(dict(logits=logits.clone(), parents=parents.clone(), tokens=out[:, i].clone(),
+                              scores=cur.clone(), margin=min(step_margins)))
+        output_logits = output_logits[parents]
+        for l in range(len(past)):
+            past[l][0] = past[l][0][parents]
+            past[l][1] = past[l][1][parents]
         if torch.all((out == eos_id).any(dim=1)).item():
             break
     return (out.unflatten(0, (n, beam_size)), cur.unflatten(0, (n, beam_size)),

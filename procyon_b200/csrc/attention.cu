@@ -284,11 +284,9 @@ flash_attn_kernel(const AttnParams p) {
 template <int HD, bool CAUSAL>
 int launch_attn(const AttnParams& p, cudaStream_t stream) {
   constexpr int SMEM = 5 * 64 * HD * 2;
-  static bool attr_set = false;
-  if (!attr_set && SMEM > 48 * 1024) {
+  static SmemOptIn opt;
+  if (SMEM > 48 * 1024 && opt.need(SMEM))
     PCY_CUDA(cudaFuncSetAttribute(flash_attn_kernel<HD, CAUSAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    attr_set = true;
-  }
   dim3 grid(ceil_div(p.Tq, ATT_BM), p.H, p.B);
   flash_attn_kernel<HD, CAUSAL><<<grid, ATT_THREADS, SMEM, stream>>>(p);
   PCY_LAUNCH_CHECK();

@@ -843,13 +843,12 @@ int esm_attention_tc(const bf16* qkv, const uint8_t* key_valid, bf16* out, int B
   *rows_done = 0;
   if (T < TBM || d / n_heads != THD) return 0;
   const int n_q_tiles = (T + TBM - 1) / TBM;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static SmemOptIn opt;
+  if (opt.need(1)) {
     PCY_CUDA(cudaFuncSetAttribute(esm_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
     PCY_CUDA(cudaFuncSetAttribute(esm_attention_tc64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC2_SMEM));
     PCY_CUDA(cudaFuncSetAttribute(esm_attention_ts_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM));
     PCY_CUDA(cudaFuncSetAttribute(esm_attention_ts_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM));
-    attr_set = true;
   }
   const int kern = g_esm_attention_kernel;
   const bool steps64 = kern != 0;

@@ -11,6 +11,21 @@
 
 #include "../../include/procyon_b200.h"
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute of a kernel: remember, per call site and per
+// device ordinal, the largest size already opted into (one process may drive several GPUs; racing threads at worst set
+// the attribute twice, which is harmless).
+struct SmemOptIn {
+  size_t set[64] = {};
+  bool need(size_t bytes) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    size_t& cur = set[dev & 63];
+    if (bytes <= cur) return false;
+    cur = bytes;
+    return true;
+  }
+};
+
 namespace pcy {
 
 // ---------------------------------------------------------------------------------------------

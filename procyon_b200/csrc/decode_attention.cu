@@ -501,12 +501,10 @@ int decode_attention(const DecodeAttnArgs& a, cudaStream_t stream) {
   if (a.beams > 1 && gq == 4 && a.beams * gq <= SP_MAXR && g_skinny_mma) {
     const int n_shared = a.S / SP_KEYS;
     if (n_shared > 0) {
-      static bool attr_set = false;
-      if (!attr_set) {
+      static SmemOptIn opt;
+      if (opt.need(SP_SMEM))
         PCY_CUDA(cudaFuncSetAttribute(decode_attn_shared_prompt_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       SP_SMEM));
-        attr_set = true;
-      }
       dim3 sgrid(n_shared, a.KVH, a.rows / a.beams);
       decode_attn_shared_prompt_kernel<4><<<sgrid, SP_THREADS, SP_SMEM, stream>>>(p);
       PCY_LAUNCH_CHECK();

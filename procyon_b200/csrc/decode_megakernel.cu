@@ -1069,12 +1069,9 @@ int decode_megakernel(const pcy_llama_config& c, const LlamaLayerPtrs* layers_de
   if (mt == 1) fn = (void*)llama_decode_megakernel<1, 4>;
   else if (mt == 2) fn = (void*)llama_decode_megakernel<2, 4>;
   else fn = (void*)llama_decode_megakernel<4, 4>;
-  static size_t smem_set[3] = {0, 0, 0};
+  static SmemOptIn opt[3];
   const int slot = mt == 1 ? 0 : mt == 2 ? 1 : 2;
-  if (smem > smem_set[slot]) {
-    PCY_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set[slot] = smem;
-  }
+  if (opt[slot].need(smem)) PCY_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   void* args[] = {(void*)&p};
   // cooperative launch: guarantees that all CTAs are co-resident (the grid barrier needs it)
   PCY_CUDA(cudaLaunchCooperativeKernel(fn, dim3(num_sms()), dim3(MK_BLOCK), args, smem, stream));

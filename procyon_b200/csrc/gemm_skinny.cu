@@ -206,12 +206,10 @@ gemm_skinny_kernel(const SkinnyParams p) {
 template <int MT, int RPW, int KU, bool ASMEM>
 int launch_skinny(SkinnyParams p, cudaStream_t stream) {
   const size_t smem = ASMEM ? (size_t)MT * p.K * sizeof(bf16) : 0;
-  static size_t smem_set = 0;
-  if (smem > 48 * 1024 && smem > smem_set) {
+  static SmemOptIn opt;
+  if (smem > 48 * 1024 && opt.need(smem))
     PCY_CUDA(cudaFuncSetAttribute(gemm_skinny_kernel<MT, RPW, KU, ASMEM>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set = smem;
-  }
   p.num_units = (p.act == ACT_SWIGLU) ? p.N / RPW : ceil_div(p.N, RPW);
   int grid = ceil_div(p.num_units, SK_WARPS);
   const int max_grid = num_sms() * 8;
@@ -364,12 +362,10 @@ template <bool SWIGLU, int STG>
 int launch_skinny_mma(const SkinnyParams& p, cudaStream_t stream) {
   constexpr int WT = SWIGLU ? 2 : 1;
   constexpr size_t smem = (size_t)T_WARPS * STG * (WT + 1) * 2048 + (size_t)T_WARPS * 32 * 8 * WT * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static SmemOptIn opt;
+  if (opt.need(smem))
     PCY_CUDA(cudaFuncSetAttribute(gemm_skinny_mma_kernel<SWIGLU, STG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem));
-    attr_set = true;
-  }
   const int n_tiles = ceil_div(p.N, 16 * WT);
   const int grid = std::min(n_tiles, num_sms() * 8);
   gemm_skinny_mma_kernel<SWIGLU, STG><<<grid, T_THREADS, smem, stream>>>(p);

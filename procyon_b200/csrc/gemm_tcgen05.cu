@@ -603,12 +603,10 @@ int get_tensor_map(const bf16* ptr, int64_t rows, int64_t cols, int64_t ld, int 
 template <int BN, bool ROPE, int CL, bool U2 = false>
 int launch(const GemmArgs& a, cudaStream_t stream) {
   using Cfg = TileCfg<BN, U2>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static SmemOptIn opt;
+  if (opt.need(Cfg::SMEM_BYTES))
     PCY_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, ROPE, CL, U2>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_set = true;
-  }
   CUtensorMap ta, tb;
   PCY_TRY(get_tensor_map(a.A, a.M, a.K, a.lda, BM, &ta));
   PCY_TRY(get_tensor_map(a.W, a.N, a.K, a.ldw, BN / CL, &tb));  // CL = 2: each CTA loads half of the W tile

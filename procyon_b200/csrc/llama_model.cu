@@ -437,12 +437,11 @@ int pcy_decode_reset(void* handle, const pcy_decode_buffers* b, const float* pre
 }
 
 // token selection for the step whose logits are in logits_cur; advances state[0]
-int pcy_decode_select(void* handle, const pcy_decode_buffers* b, int mode, int group_size, float diversity_penalty,
-                      int eos_id, int stop_on_all_eos, void* stream_) {
+int pcy_decode_select_group(void* handle, const pcy_decode_buffers* b, int mode, int group_size, float diversity_penalty,
+                            int eos_id, int stop_on_all_eos, int32_t* group_state, int group_last, void* stream_) {
   PCY_REQUIRE(handle && b, "decode_select: null argument");
   LlamaModel* m = reinterpret_cast<LlamaModel*>(handle);
   const int rows = b->n_inputs * b->beams;
-  const int H = m->cfg.n_heads, KVH = m->cfg.n_kv_heads, d = m->cfg.d_model;
   // the top-k scratch sits after the forward-pass buffers in the shared workspace
   uint8_t* p = reinterpret_cast<uint8_t*>(round_up(reinterpret_cast<int64_t>(b->workspace), 256));
   float* tk = carve<float>(p, topk_workspace_floats(rows));
@@ -451,7 +450,14 @@ int pcy_decode_select(void* handle, const pcy_decode_buffers* b, int mode, int g
   a.logprobs = b->logprobs; a.state = b->state; a.workspace = tk; a.n_inputs = b->n_inputs; a.beams = b->beams;
   a.group = group_size; a.max_gen = b->max_gen; a.vocab = m->cfg.vocab; a.eos_id = eos_id;
   a.diversity_penalty = diversity_penalty; a.greedy = (mode == PCY_SELECT_GREEDY); a.stop_on_all_eos = stop_on_all_eos;
+  a.group_state = group_state; a.group_last = group_last;
   return decode_select(a, (cudaStream_t)stream_);
+}
+
+int pcy_decode_select(void* handle, const pcy_decode_buffers* b, int mode, int group_size, float diversity_penalty,
+                      int eos_id, int stop_on_all_eos, void* stream_) {
+  return pcy_decode_select_group(handle, b, mode, group_size, diversity_penalty, eos_id, stop_on_all_eos, nullptr, 1,
+                                 stream_);
 }
 
 }  // extern "C"

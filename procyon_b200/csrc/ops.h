@@ -123,6 +123,8 @@ struct DecodeSelectArgs {
   float diversity_penalty = 0.f;
   int greedy = 0;
   int stop_on_all_eos = 0;
+  int32_t* group_state = nullptr;  // int32 [4] shared by a lock-step group of sessions (see sampling.cu) or null
+  int group_last = 1;
 };
 int decode_select(const DecodeSelectArgs& a, cudaStream_t stream);
 int topk_workspace_floats(int rows);

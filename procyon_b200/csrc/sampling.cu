@@ -15,6 +15,7 @@ namespace {
 constexpr int TK_THREADS = 512;
 constexpr int TK_SEG = 8;      // segments per row (CTAs per row)
 constexpr int TK_MAXK = 16;    // max candidates kept per segment
+constexpr int SEL_MAX_CAND = 16 * TK_SEG * TK_MAXK;  // beam_group_size = beam_size = 16 (vanilla beam search)
 
 struct Cand {
   float v;
@@ -115,6 +116,7 @@ struct SelectParams {
   int32_t* slots;   // [rows][max_gen]
   float* logprobs;  // [rows]
   int32_t* state;   // [0]=t, [2]=finished, [3]=finish step
+  int32_t* gstate;  // lock-step session group (or null): [0]=inputs whose beams all hold EOS this step, [1]=finished
   int beams, group, max_gen, K, eos_id;
   float penalty;
   int greedy;
@@ -125,9 +127,9 @@ __global__ void __launch_bounds__(256)
 select_kernel(const SelectParams p) {
   extern __shared__ int32_t s_hist[];  // [beams][t] tokens then [beams][t] slots
   __shared__ float s_lse[32];
-  __shared__ float s_cv[32 * TK_SEG * TK_MAXK / 4];  // candidate values of the rows of one group (<= 8 rows x 8 x 16)
-  __shared__ int s_ct[32 * TK_SEG * TK_MAXK / 4];
-  __shared__ int s_cr[32 * TK_SEG * TK_MAXK / 4];
+  __shared__ float s_cv[SEL_MAX_CAND];  // candidate values of the rows of one group (<= 16 rows x 8 segments x 16)
+  __shared__ int s_ct[SEL_MAX_CAND];
+  __shared__ int s_cr[SEL_MAX_CAND];
   __shared__ Cand s_red[8];
   __shared__ int s_sel_tok[32], s_sel_par[32];
   __shared__ float s_sel_val[32];
@@ -135,7 +137,8 @@ select_kernel(const SelectParams p) {
 
   const int input = blockIdx.x;
   const int t = p.state[0];
-  if (p.state[2] != 0) return;  // generation already finished (all beams hit EOS): later steps are no-ops
+  // generation already finished (all beams of all inputs hit EOS): later steps are no-ops
+  if ((p.gstate ? p.gstate[1] : p.state[2]) != 0) return;
   const int beams = p.beams, G = p.group;
   const int r0 = input * beams;
   const int tid = threadIdx.x;
@@ -223,13 +226,29 @@ select_kernel(const SelectParams p) {
   }
   __syncthreads();
   if (tid == 0 && p.eos_id >= 0) {
-    // state[4] counts inputs whose beams all contain EOS at this step
-    if (s_all_eos) atomicAdd(&p.state[4], 1);
+    // counts the inputs whose beams all contain EOS at this step (across every session of a lock-step group)
+    if (s_all_eos) atomicAdd(p.gstate ? &p.gstate[0] : &p.state[4], 1);
   }
 }
 
-__global__ void advance_kernel(int32_t* state, int n_inputs, int check_eos) {
+// gstate (nullable): shared by the sessions that split one batch (<= 16 beam rows each) and step in lock-step on one
+// stream — the reference stops the WHOLE batch at the first step where every beam of every input holds an EOS
+// (procyon/model/model_unified.py:833), so the count is accumulated over the group and evaluated by its last session.
+__global__ void advance_kernel(int32_t* state, int32_t* gstate, int n_inputs, int check_eos, int group_last) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
+    if (gstate != nullptr) {
+      if (gstate[1] == 0) {
+        if (group_last) {
+          if (check_eos && gstate[0] == gstate[3]) {
+            gstate[1] = 1;
+            gstate[2] = state[0];
+          }
+          gstate[0] = 0;
+        }
+        state[0] += 1;
+      }
+      return;
+    }
     if (state[2] == 0) {
       if (check_eos && state[4] == n_inputs) {
         state[2] = 1;
@@ -251,7 +270,7 @@ int decode_select(const DecodeSelectArgs& a, cudaStream_t stream) {
               a.beams, a.group);
   const int K = a.greedy ? 1 : a.beams;
   PCY_REQUIRE(K <= TK_MAXK, "select: beams=%d exceeds the per-segment candidate limit %d", a.beams, TK_MAXK);
-  PCY_REQUIRE(a.group * TK_SEG * K <= 32 * TK_SEG * TK_MAXK / 4, "select: group too large");
+  PCY_REQUIRE(a.group * TK_SEG * K <= SEL_MAX_CAND, "select: group too large");
   const int rows = a.n_inputs * a.beams;
   float* seg_max = a.workspace;
   float* seg_sum = seg_max + rows * TK_SEG;
@@ -263,19 +282,17 @@ int decode_select(const DecodeSelectArgs& a, cudaStream_t stream) {
   PCY_LAUNCH_CHECK();
   SelectParams p;
   p.seg_max = seg_max; p.seg_sum = seg_sum; p.cand_val = cand_val; p.cand_idx = cand_idx;
-  p.tokens = a.tokens; p.slots = a.slots; p.logprobs = a.logprobs; p.state = a.state;
+  p.tokens = a.tokens; p.slots = a.slots; p.logprobs = a.logprobs; p.state = a.state; p.gstate = a.group_state;
   p.beams = a.beams; p.group = a.greedy ? 1 : a.group; p.max_gen = a.max_gen; p.K = K; p.eos_id = a.eos_id;
   p.penalty = a.diversity_penalty; p.greedy = a.greedy;
   const size_t smem = (size_t)2 * a.beams * a.max_gen * sizeof(int32_t);
   PCY_REQUIRE(smem <= 160 * 1024, "select: beams*max_gen too large for shared memory");
-  static size_t smem_set = 0;
-  if (smem > 40 * 1024 && smem > smem_set) {
+  static SmemOptIn opt;
+  if (smem > 16 * 1024 && opt.need(smem))
     PCY_CUDA(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set = smem;
-  }
   select_kernel<<<a.n_inputs, 256, smem, stream>>>(p);
   PCY_LAUNCH_CHECK();
-  advance_kernel<<<1, 32, 0, stream>>>(a.state, a.n_inputs, a.stop_on_all_eos);
+  advance_kernel<<<1, 32, 0, stream>>>(a.state, a.group_state, a.n_inputs, a.stop_on_all_eos, a.group_last);
   PCY_LAUNCH_CHECK();
   return 0;
 }

@@ -263,6 +263,9 @@ class ESM_PLM(nn.Module):
 
             def put(kind, layer, t, dtype):
                 t = t.detach().to(device=device, dtype=dtype).contiguous()
+                # the library copies with a blocking cudaMemcpy on the legacy stream, which does NOT order itself after
+                # a non-default (non-blocking) torch stream: finish the conversions that produced `t` first
+                torch.cuda.current_stream(device).synchronize()
                 check(lib.pcy_esm_load_tensor(handle, c_int(_KIND[kind]), c_int(layer), ptr(t),
                                               c_i64(t.numel() * t.element_size())), f"pcy_esm_load_tensor({kind})")
 

@@ -33,7 +33,9 @@ from .generation import generate_beam_search, generate_greedy
 from .model_utils import compute_conflict_matrix, create_mlp, left_pad_tensors
 from .pmc_llama import SELECT_GREEDY, LlamaConfig, LlamaPostTokenization
 
-DATASET_ID_PROTEIN = 0  # procyon/data/constants.py DATASET_ID["protein"]
+from ..training.trainIT import DATASET_ID as _DATASET_ID  # noqa: E402
+
+DATASET_ID_PROTEIN = _DATASET_ID["protein"]  # procyon/data/constants.py:666-671 (= 4)
 # procyon/model/model_unified.py:33 (`f'{DATA_DIR}/model_weights/'`); None when DATA_DIR is not configured
 DEFAULT_PRETRAINED_WEIGHTS_DIR = (os.path.join(os.environ["DATA_DIR"], "model_weights") + os.sep
                                   if os.environ.get("DATA_DIR") else None)
@@ -107,16 +109,16 @@ class UnifiedProCyon(nn.Module):
                 # the reference's own files (model_unified.py:189-211): embeddings in id-map order -> table order
                 from ..data.data_utils import load_aaseq_embeddings
 
+                # the id maps are ALWAYS taken from the current DATA_DIR, whatever the checkpoint's config says
+                # (reference :197-198 overwrites both fields unconditionally)
                 node = os.path.join(os.environ["DATA_DIR"], "generated_data/node_embeddings")
-                protein_embeddings = load_aaseq_embeddings(
-                    config.protein_seq_embeddings_path,
-                    getattr(config, "protein_embeddings_idmap_path", None)
-                    or os.path.join(node, "protein/protein_esm2-3b_mean.pkl"), "protein")
+                config.protein_embeddings_idmap_path = os.path.join(node, "protein/protein_esm2-3b_mean.pkl")
+                config.domain_embeddings_idmap_path = os.path.join(node, "domain/domain_esm2-3b_mean.pkl")
+                protein_embeddings = load_aaseq_embeddings(config.protein_seq_embeddings_path,
+                                                           config.protein_embeddings_idmap_path, "protein")
                 if domain_embeddings is None and getattr(config, "domain_embeddings_path", None):
-                    domain_embeddings = load_aaseq_embeddings(
-                        config.domain_embeddings_path,
-                        getattr(config, "domain_embeddings_idmap_path", None)
-                        or os.path.join(node, "domain/domain_esm2-3b_mean.pkl"), "domain")
+                    domain_embeddings = load_aaseq_embeddings(config.domain_embeddings_path,
+                                                              config.domain_embeddings_idmap_path, "domain")
                 if peptide_embeddings is None and getattr(config, "peptide_embeddings_path", None):
                     assert config.peptide_embeddings_idmap_path is not None
                     peptide_embeddings = load_aaseq_embeddings(config.peptide_embeddings_path,
@@ -504,26 +506,13 @@ class UnifiedProCyon(nn.Module):
     @torch.no_grad()
     def _generate_beam_search(self, input_embeds, attn_mask, max_len=64, beam_size=5, beam_group_size=5,
                               diversity_penalty=0.8, return_logits=True):
-        """model_unified.py:701-842 — runs on the device (procyon_b200.model.generation)."""
-        n = input_embeds.shape[0]
-        per_call = max(1, 16 // beam_size)  # a decode session holds <= 16 beam rows
-        outs, lps, lgs = [], [], []
+        """model_unified.py:701-842 — runs on the device (procyon_b200.model.generation); batches of more than 16
+        beam rows step through several lock-step sessions that share the reference's whole-batch stop condition."""
         any_pad = attn_mask is not None and bool((attn_mask == 0).any())
-        for i0 in range(0, n, per_call):
-            sl = slice(i0, min(n, i0 + per_call))
-            o, lp, lg = generate_beam_search(
-                self.text_encoder, input_embeds[sl], attn_mask[sl] if any_pad else None, max_len=max_len,
-                beam_size=beam_size, beam_group_size=beam_group_size, diversity_penalty=diversity_penalty,
-                eos_token_id=self.tokenizer.eos_token_id, return_logits=return_logits)
-            outs.append(o), lps.append(lp), lgs.append(lg)
-        if len(outs) > 1:
-            # the reference stops the WHOLE batch when every beam of every input has an EOS; with several sessions
-            # each one stops on its own — tokens after an input's stop stay zero either way.
-            steps = max(l.shape[2] for l in lgs) if return_logits else None
-            if return_logits:
-                lgs = [torch.nn.functional.pad(l, (0, 0, 0, steps - l.shape[2])) for l in lgs]
-        logits = torch.cat(lgs, 0) if return_logits else None
-        return torch.cat(outs, 0), torch.cat(lps, 0), logits
+        return generate_beam_search(
+            self.text_encoder, input_embeds, attn_mask if any_pad else None, max_len=max_len, beam_size=beam_size,
+            beam_group_size=beam_group_size, diversity_penalty=diversity_penalty,
+            eos_token_id=self.tokenizer.eos_token_id, return_logits=return_logits)
 
     def _get_nucleus_mask(self, probs, nucleus_prob):
         """model_unified.py:844-858."""
@@ -568,23 +557,23 @@ class UnifiedProCyon(nn.Module):
         return out_tokens, log_probs, out_logits
 
     def _sample_loop(self, input_embeds, attn_masks, max_len, temperature, nucleus_prob, return_logits):
+        """Temperature / nucleus sampling (model_unified.py:885-911): logits stay on the device, torch.multinomial draws
+        there; any batch size (rows beyond 16 go through further decode sessions)."""
+        from .pmc_llama import SessionGroup
+
         te = self.text_encoder
         n, S, _ = input_embeds.shape
-        if n > 16:
-            raise _lib.ProcyonB200Error("sampling supports at most 16 inputs per call")
         dev = input_embeds.device
         sel = torch.arange(n, device=dev, dtype=torch.int32) * S + (S - 1)
-        sess = te.get_session(n, 1, S, max_len, dev, attn_masks is not None, False)
-        _, _, logits, valid = te.prefill(input_embeds, attn_masks, want_cache=True, want_hidden=False, sel_rows=sel,
-                                         kv_out=sess.kv_prompt)
-        if attn_masks is not None:
-            sess.prompt_valid.copy_(valid)
-        sess.reset(logits)
+        kv, _, logits, valid = te.prefill(input_embeds, attn_masks, want_cache=True, want_hidden=False, sel_rows=sel)
+        sess = te.sessions_from_prefill(kv, valid if attn_masks is not None else None, logits, max_len)
+        if not isinstance(sess, SessionGroup):
+            sess = SessionGroup([sess])
+        del kv
         total = torch.zeros(n, device=dev)
         all_logits, toks = [], []
-        rows = torch.arange(n, device=dev, dtype=torch.int32)
+        cur = sess.logits()
         for i in range(max_len):
-            cur = sess.logits_cur.clone()
             if return_logits:
                 all_logits.append(cur)
             lp = torch.log_softmax(cur, dim=-1)
@@ -597,12 +586,9 @@ class UnifiedProCyon(nn.Module):
             total += lp[torch.arange(n, device=dev), nxt.squeeze(-1)]
             toks.append(nxt)
             if i + 1 < max_len:
-                sess.tokens[:, i] = nxt.squeeze(-1).to(torch.int32)
-                sess.slots[:, i] = rows
-                sess.state[0] = i + 1
-                sess.forward()
+                cur = sess.step(nxt.squeeze(-1))
         out = torch.cat(toks, dim=-1).cpu()
-        return out, total.cpu(), (torch.stack(all_logits, 1) if return_logits else None)
+        return out, total.cpu(), (torch.stack(all_logits, 1).cpu() if return_logits else None)
 
     @torch.no_grad()
     def generate(self, inputs, max_len=64, aaseq_type="protein", method="sampling", temperature=1.0, greedy=False,
@@ -705,6 +691,13 @@ class UnifiedProCyon(nn.Module):
                                     "(deepspeed is not a dependency of this build)")
         state_dict = torch.load(path, map_location="cpu", weights_only=False)
         if model is None:
+            # stale DATA_DIR prefixes of the training machine -> the current DATA_DIR (reference :1372)
+            data_args_path = os.path.join(checkpoint_dir, "data_args.pt")
+            if os.path.exists(data_args_path):
+                from ..training.training_args_IT import update_model_args_data_dir
+
+                data_args = torch.load(data_args_path, weights_only=False)
+                update_model_args_data_dir(config, prev_data_dir=getattr(data_args, "data_dir", None))
             model = UnifiedProCyon(pretrained_weights_dir=pretrained_weights_dir, config=config,
                                    for_pretraining=False, **model_kwargs)
             model.load_state_dict(state_dict, strict=strict_load)

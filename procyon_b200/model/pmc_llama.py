@@ -256,10 +256,14 @@ class DecodeSession:
         check(_lib.load().pcy_llama_decode_forward(self.owner._handle, ctypes.byref(self.c), stream_ptr(self.device)),
               "pcy_llama_decode_forward")
 
-    def select(self, mode: int, group: int = 1, penalty: float = 0.0, eos_id: int = -1, stop_on_all_eos: bool = False):
-        check(_lib.load().pcy_decode_select(self.owner._handle, ctypes.byref(self.c), c_int(mode), c_int(group),
-                                            c_float(penalty), c_int(eos_id), c_int(1 if stop_on_all_eos else 0),
-                                            stream_ptr(self.device)), "pcy_decode_select")
+    def select(self, mode: int, group: int = 1, penalty: float = 0.0, eos_id: int = -1, stop_on_all_eos: bool = False,
+               group_state: Optional[torch.Tensor] = None, group_last: bool = True):
+        """`group_state` (int32 [4] on the device, [3] = total inputs): shared by the sessions that split one batch and
+        step in lock-step, so that the all-EOS stop is taken over the WHOLE batch like the reference's (:833)."""
+        check(_lib.load().pcy_decode_select_group(self.owner._handle, ctypes.byref(self.c), c_int(mode), c_int(group),
+                                                  c_float(penalty), c_int(eos_id), c_int(1 if stop_on_all_eos else 0),
+                                                  ptr(group_state), c_int(1 if group_last else 0),
+                                                  stream_ptr(self.device)), "pcy_decode_select_group")
 
     def step_graph(self, mode, group, penalty, eos_id, stop_on_all_eos):
         """CUDA graph of one (forward, select) step; the step index lives in device memory so it replays as is."""
@@ -279,6 +283,33 @@ class DecodeSession:
         self.graph_launches = lib.pcy_launch_count() - n0  # kernels replayed by every g.replay()
         self._graph, self._graph_key = g, key
         return g
+
+
+class SessionGroup:
+    """More than 16 rows of token-by-token decoding (`forward(use_cache=True)` on a large batch, sampling loops): the
+    rows are split over DecodeSessions of <= 16 rows that are stepped one after the other.  Presents the few members
+    the stepping code uses (`rows`, `device`, `step(tokens)`, `logits()`)."""
+
+    def __init__(self, sessions):
+        self.sessions = sessions
+        self.rows = sum(s.rows for s in sessions)
+        self.device = sessions[0].device
+        self.t = 0  # tokens fed so far (host-side copy of state[0]; the sessions advance together)
+
+    def logits(self) -> torch.Tensor:
+        return torch.cat([s.logits_cur for s in self.sessions], 0)
+
+    def step(self, tokens: torch.Tensor) -> torch.Tensor:
+        """Feeds one token per row (int tensor [rows]) and returns the next-token logits fp32 [rows, V]."""
+        r0 = 0
+        for s in self.sessions:
+            s.tokens[:, self.t] = tokens[r0:r0 + s.rows].to(s.tokens.dtype)
+            s.slots[:, self.t] = torch.arange(s.rows, device=s.device, dtype=torch.int32)
+            s.state[0] = self.t + 1
+            s.forward()
+            r0 += s.rows
+        self.t += 1
+        return self.logits()
 
 
 class LlamaPostTokenization(nn.Module):
@@ -344,6 +375,9 @@ class LlamaPostTokenization(nn.Module):
 
             def put(kind, layer, t):
                 t = t.detach().to(device=device, dtype=bf).contiguous()
+                # the library copies with a blocking cudaMemcpy on the legacy stream, which does NOT order itself after
+                # a non-default (non-blocking) torch stream: finish the cat / pack kernels that produced `t` first
+                torch.cuda.current_stream(device).synchronize()
                 check(lib.pcy_llama_load_tensor(h, c_int(_KIND[kind]), c_int(layer), ptr(t),
                                                 c_i64(t.numel() * 2)), f"pcy_llama_load_tensor({kind})")
 
@@ -520,6 +554,12 @@ class LlamaPostTokenization(nn.Module):
         torch.cuda.synchronize(dev)
         return shares if ok else None
 
+    def new_session(self, n_inputs, beams, S, max_gen, device, masked, keep_logits) -> DecodeSession:
+        """An uncached session (batches split over several lock-step sessions need distinct ones of the same shape)."""
+        self._ensure_packed(torch.device(device))
+        self._ensure_rope(S + max_gen, device)
+        return DecodeSession(self, n_inputs, beams, S, max_gen, device, masked, keep_logits)
+
     def get_session(self, n_inputs, beams, S, max_gen, device, masked, keep_logits) -> DecodeSession:
         """Decode sessions (KV caches, tables, captured step graph) are cached per shape and reused across calls."""
         self._ensure_packed(torch.device(device))
@@ -539,6 +579,23 @@ class LlamaPostTokenization(nn.Module):
             cache[key] = DecodeSession(self, n_inputs, beams, S, max_gen, device, masked, keep_logits)
         return cache[key]
 
+    def sessions_from_prefill(self, kv, valid, sel_logits, max_gen):
+        """Token-by-token decode state after a prefill of B prompts (kv [L, 2, B, S, kvd], last-position logits
+        [B, V]): one DecodeSession for B <= 16, else a SessionGroup of <= 16-row sessions."""
+        L, _, B, S, _ = kv.shape
+        dev = kv.device
+        self._ensure_rope(S + max_gen, dev)
+        out = []
+        for r0 in range(0, B, 16):
+            r1 = min(B, r0 + 16)
+            sess = DecodeSession(self, r1 - r0, 1, S, max_gen, dev, valid is not None, keep_logits=False)
+            sess.kv_prompt.copy_(kv[:, :, r0:r1])
+            if valid is not None:
+                sess.prompt_valid.copy_(valid[r0:r1])
+            sess.reset(sel_logits[r0:r1].contiguous())
+            out.append(sess)
+        return out[0] if len(out) == 1 else SessionGroup(out)
+
     # ---- reference-facing forward -------------------------------------------------------------------------------
     def forward(self, input_embeds=None, input_ids=None, attn_masks=None, full_labels=None, past_key_values=None,
                 use_cache=False, output_attentions=None, sum_hidden_rows=None):
@@ -551,8 +608,11 @@ class LlamaPostTokenization(nn.Module):
         n_layers = self.model.config.num_hidden_layers
         if past_key_values is not None:
             # single decode step on an existing session (greedy-style stepping: one row per input)
-            sess: DecodeSession = past_key_values
             assert input_ids is not None and input_ids.shape[1] == 1
+            if isinstance(past_key_values, SessionGroup):
+                logits = past_key_values.step(input_ids[:, 0].to(past_key_values.device))
+                return CausalLMOutput(self, None, n_layers, logits=logits.unsqueeze(1), past=past_key_values)
+            sess: DecodeSession = past_key_values
             t = int(sess.state[0].item())
             sess.tokens[:, t] = input_ids[:, 0].to(sess.tokens.dtype)
             sess.slots[:, t] = torch.arange(sess.rows, device=sess.device, dtype=torch.int32)
@@ -579,12 +639,7 @@ class LlamaPostTokenization(nn.Module):
             loss = lm_loss(self, hidden, full_labels)
         past = None
         if use_cache:
-            past = DecodeSession(self, B, 1, S, 256, dev, attn_masks is not None, keep_logits=False)
-            self._ensure_rope(S + 256, dev)
-            past.kv_prompt.copy_(kv)
-            if attn_masks is not None:
-                past.prompt_valid.copy_(valid)
-            past.reset(sel_logits)
+            past = self.sessions_from_prefill(kv, valid if attn_masks is not None else None, sel_logits, 256)
         out = CausalLMOutput(self, hidden, n_layers, loss=loss, past=past)
         out.hidden_sum = self.last_hidden_sum if sum_hidden_rows is not None else None
         return out

@@ -98,5 +98,35 @@ class DataArgs:
     data_dir = None
 
 
+def _current_data_dir():
+    import os
+
+    return os.environ.get("DATA_DIR")
+
+
+def update_model_args_data_dir(model_args: ModelArgs, prev_data_dir: str):
+    """procyon/training/training_args_IT.py:1787-1801: a checkpoint's `model_args.pt` stores every `*_path` field under
+    the DATA_DIR of the machine it was trained on; swap that prefix for the current DATA_DIR.  Works on the instance
+    `__dict__` (an unpickled reference ModelArgs carries ~90 fields this mirror class does not declare)."""
+    if not isinstance(model_args, ModelArgs):
+        raise ValueError(f"expected ModelArgs, got: {type(model_args)}")
+    data_dir = _current_data_dir()
+    if data_dir is None or prev_data_dir is None or data_dir == prev_data_dir:
+        return
+    import os
+
+    for name, cur in list(vars(model_args).items()):
+        if name.endswith("path") and isinstance(cur, str) and cur.startswith(prev_data_dir):
+            suffix = cur.replace(prev_data_dir, "").lstrip("/")
+            setattr(model_args, name, os.path.join(data_dir, suffix))
+
+
+def update_data_args_data_dir(data_args):
+    """procyon/training/training_args_IT.py:1803-1811."""
+    data_dir = _current_data_dir()
+    if data_dir is not None and getattr(data_args, "data_dir", None) != data_dir:
+        data_args.data_dir = data_dir
+
+
 class TrainArgs:
     """Placeholder so pickled `training_args.pt` from reference checkpoints can be loaded."""

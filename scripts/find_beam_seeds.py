@@ -1,0 +1,38 @@
+"""Seed search for tests/test_gpu_beam_strict.py part (C): for every parametrisation, find a prompt seed for which the
+ORACLE's smallest beam-decision margin over the whole generation is >= MARGIN, and print the E2E_CASES list.
+CPU only (the oracle).  The model is the test's own `_tiny(..., structured_head=True)`."""
+import sys
+
+import torch
+
+sys.path.insert(0, ".")
+sys.path.insert(0, "tests")
+from oracle.generate import generate_beam_search  # noqa: E402
+from test_gpu_beam_strict import MARGIN, _inputs, _tiny_state  # noqa: E402
+
+CASES = [  # kind, n, beams, group, pad, S, max_len
+    ("gq2", 2, 4, 2, 0, 24, 8), ("gq2", 1, 4, 4, 0, 24, 8), ("gq2", 1, 6, 1, 0, 24, 8), ("gq2", 2, 4, 2, 5, 24, 6),
+    ("gq4", 1, 4, 2, 0, 24, 10), ("gq4", 2, 2, 1, 3, 24, 10), ("gq4", 1, 10, 2, 0, 300, 5), ("gq4", 2, 6, 3, 9, 260, 4),
+    ("gq4", 1, 16, 4, 0, 129, 4), ("gq4", 1, 5, 5, 0, 256, 6),
+]
+
+if __name__ == "__main__":
+    models = {}
+    for (kind, n, beams, group, pad, S, max_len) in CASES:
+        if kind not in models:
+            models[kind] = _tiny_state(kind)
+        oc, sd = models[kind]
+        best = (-1.0, None)
+        for seed in range(2000, 2000 + int(sys.argv[1]) if len(sys.argv) > 1 else 2400):
+            ids, emb, mask = _inputs(oc, sd, n, S, seed, pad)
+            trace = []
+            generate_beam_search(sd, oc, emb.float(), mask, max_len=max_len, beam_size=beams, beam_group_size=group,
+                                 diversity_penalty=0.8, eos_id=-5, act_round="bf16", mask_pads_in_decode=True,
+                                 trace=trace)
+            mg = min(t["margin"] for t in trace)
+            if mg > best[0]:
+                best = (mg, seed)
+            if mg >= 1.3 * MARGIN:
+                break
+        print(f'    ("{kind}", {n}, {beams}, {group}, {pad}, {S}, {max_len}, {best[1]}),  # oracle margin {best[0]:.3f}',
+              flush=True)

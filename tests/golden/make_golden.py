@@ -420,6 +420,46 @@ def golden_aaseq_embedding_tables():
                                            info_order=info["protein_id"].tolist()))
 
 
+def golden_checkpoint_args():
+    """`model_args.pt` / `data_args.pt` as a reference training run writes them: pickles of the REAL
+    `procyon.training.training_args_IT.ModelArgs` / `DataArgs` dataclasses (1821-line module, 90+ fields), filled like
+    configs/llama3-full.yml, with every `*_path` under the DATA_DIR of a (fictional) training cluster.  The test loads
+    them through `procyon_b200.compat` (no reference package present) and through `from_pretrained`."""
+    ref_args = ref_import.import_reference("procyon.training.training_args_IT")
+    old_dd = "/n/holylfs06/LABS/mzitnik_lab/Lab/PLM"  # stale prefix, as in a checkpoint trained elsewhere
+    ma = ref_args.ModelArgs()
+    full = dict(protein_encoder_num_params="3b", use_aaseq_embeddings=True, freeze_aaseq_embeddings=True,
+                protein_pooling_opt="mean", freeze_protein_encoder="all", text_encoder_fname="llama-3-8b",
+                max_text_len=2048, num_layers_token_projector=3, hidden_size_token_projector=2560,
+                num_layers_shared_projector=3, hidden_size_shared_projector=2560, num_layers_lm_projector=3,
+                hidden_size_lm_projector=2560, ret_token_access="last", train_qa_full_lm=False, roll_num=0,
+                context_crop_sampling=False, use_protein_struct=True, use_drug_embeddings=True,
+                protein_struct_dropout=0.0, contrastive_global=True, filter_negatives_by_id_contrastive=True,
+                cl_method="infonce", use_projection_cl=False)
+    for k, v in full.items():
+        assert hasattr(ma, k), k
+        setattr(ma, k, v)
+    cur = os.environ["DATA_DIR"]
+    n_paths = 0
+    for k, v in list(vars(ma).items()):
+        if k.endswith("path") and isinstance(v, str) and v.startswith(cur):
+            setattr(ma, k, old_dd + v[len(cur):])
+            n_paths += 1
+    da = ref_args.DataArgs()
+    da.data_dir = old_dd
+    out = os.path.join(HERE, "ckpt_args")
+    os.makedirs(out, exist_ok=True)
+    torch.save(ma, os.path.join(out, "model_args.pt"))
+    torch.save(da, os.path.join(out, "data_args.pt"))
+    save("ckpt_args/expected.pt", dict(n_model_fields=len(vars(ma)), n_path_fields=n_paths, old_data_dir=old_dd,
+                                       model_fields={k: v for k, v in vars(ma).items()
+                                                     if isinstance(v, (str, int, float, bool, type(None)))},
+                                       data_fields={k: v for k, v in vars(da).items()
+                                                    if isinstance(v, (str, int, float, bool, type(None)))}))
+    print(f"wrote ckpt_args/: ModelArgs with {len(vars(ma))} fields ({n_paths} stale paths), DataArgs with "
+          f"{len(vars(da))} fields")
+
+
 if __name__ == "__main__":
     torch.set_num_threads(4)
     if len(sys.argv) > 1:  # regenerate only the named goldens, e.g. `make_golden.py golden_aaseq_embedding_tables`
@@ -438,3 +478,4 @@ if __name__ == "__main__":
     golden_hf_esm_lm_head()
     golden_hf_llama()
     golden_aaseq_embedding_tables()
+    golden_checkpoint_args()

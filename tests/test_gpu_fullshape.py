@@ -171,4 +171,13 @@ def test_esm2_650m_full_size_residue_states(cuda_device):
     states = enc.encode_tokens(toks.cuda()).float().cpu()
     ref = OE.esm2_forward(sd, toks, L, H, act_round="bf16")
     keep = toks != 1
-    torch.testing.assert_close(states[keep], ref[keep], rtol=4e-2, atol=4e-2)
+    a, b = states[keep], ref[keep]
+    assert torch.isfinite(a).all()
+    # 826 880 values after 33 layers x 2 bf16 residual-stream stores, |values| up to ~5 (one bf16 ulp there = 0.03):
+    # the tolerance band of DESIGN §4 (3e-2 + 3e-2 |ref|) must hold for all but a 1e-4 tail, nothing may be off by more
+    # than 3 ulps of the largest values, and the mean error must sit at the rounding floor
+    err = (a - b).abs()
+    band = 3e-2 + 3e-2 * b.abs()
+    assert (err > band).float().mean().item() < 1e-4, (err > band).float().mean().item()
+    assert err.max().item() < 0.1, err.max().item()
+    assert err.mean().item() < 4e-3, err.mean().item()

@@ -114,25 +114,44 @@ def test_greedy_generation(llama):
                 torch.testing.assert_close(logits[b].cpu(), rlogits[b], rtol=3e-2, atol=5e-2)
 
 
+BEAM_MARGIN = 0.12  # twice the worst log-prob deviation of the bf16 forward measured on B200 (test_gpu_beam_strict.py)
+
+
+def _clear_steps(trace, margin=BEAM_MARGIN):
+    """Number of leading steps whose every beam decision has a margin >= `margin` in the oracle: up to there a
+    forward pass that is right to half the margin MUST reproduce every beam exactly."""
+    n = 0
+    for t in trace:
+        if t["margin"] < margin:
+            break
+        n += 1
+    return n
+
+
 @pytest.mark.parametrize("n,beams,group,pad", [(2, 4, 2, 0), (2, 4, 4, 0), (2, 6, 1, 0), (2, 4, 2, 5), (1, 4, 2, 0),
                                                 (2, 2, 1, 3)])
 def test_beam_search(llama, n, beams, group, pad):
+    """Random-weight model (flat logits, top-k gaps of ~0.3): EVERY beam must equal the oracle's on every step before
+    the first decision the oracle itself takes with a margin inside the forward noise; nothing is asserted after it
+    here — tests/test_gpu_beam_strict.py verifies every later decision one by one."""
     from oracle.generate import generate_beam_search as oracle_beam
     from procyon_b200.model.generation import generate_beam_search
 
     oc, sd, m = llama
     ids, emb, mask = _inputs(oc, sd, n, 24, seed=beams * 10 + group, pad_left=pad)
     am = mask if pad else None
+    trace = []
     ro, rlp, rlogits = oracle_beam(sd, oc, emb.float(), mask if pad else torch.ones_like(mask), max_len=8,
                                    beam_size=beams, beam_group_size=group, diversity_penalty=0.8, eos_id=-5,
-                                   act_round="bf16", mask_pads_in_decode=True)
+                                   act_round="bf16", mask_pads_in_decode=True, trace=trace)
     out, lp, logits = generate_beam_search(m, emb.cuda(), am.cuda() if am is not None else None, max_len=8,
                                            beam_size=beams, beam_group_size=group, diversity_penalty=0.8,
                                            eos_token_id=-5)
     assert out.shape == ro.shape == (n, beams, 8)
+    clear = _clear_steps(trace)
+    assert torch.equal(out[..., :clear], ro[..., :clear]), f"beams differ within the {clear} clear-margin steps"
     same = (out == ro).all(dim=-1)
     # beams whose whole token history agrees must agree on score and on the gathered per-step logits
-    assert same.float().mean() >= 0.5, f"only {same.float().mean():.2f} of beams match the oracle"
     torch.testing.assert_close(lp[same], rlp[same], rtol=1e-2, atol=6e-2)
     torch.testing.assert_close(logits.cpu()[same], rlogits[same], rtol=3e-2, atol=6e-2)
 
@@ -147,63 +166,98 @@ def test_beam_search_stops_on_eos(llama):
     out, lp, logits = generate_beam_search(m, emb.cuda(), None, max_len=10, beam_size=2, beam_group_size=2,
                                            eos_token_id=-5)
     eos = int(out[0, 0, 1])  # a token the best beam emits at step 1
+    trace = []
     ro, rlp, rlogits = oracle_beam(sd, oc, emb.float(), torch.ones(1, 16), max_len=10, beam_size=2, beam_group_size=2,
-                                   diversity_penalty=0.8, eos_id=eos, act_round="bf16")
+                                   diversity_penalty=0.8, eos_id=eos, act_round="bf16", trace=trace)
     out2, lp2, logits2 = generate_beam_search(m, emb.cuda(), None, max_len=10, beam_size=2, beam_group_size=2,
                                               eos_token_id=eos)
     steps_ref = rlogits.shape[2]
-    if torch.equal(out2[..., :steps_ref], ro[..., :steps_ref]):
+    clear = _clear_steps(trace)
+    assert torch.equal(out2[..., :clear], ro[..., :clear])
+    if clear == steps_ref:  # every decision up to the oracle's stop was clear: the device must stop at the same step
         assert logits2.shape[2] == steps_ref
         assert int(out2[..., steps_ref:].abs().sum()) == 0
         torch.testing.assert_close(lp2, rlp, rtol=1e-2, atol=6e-2)
+    # whatever the margins: once stopped, nothing is written after the stop step
+    assert int(out2[..., logits2.shape[2]:].abs().sum()) == 0
+
+
+def _forced_decode(m, emb, mask, forced, max_rows):
+    """Prefill + teacher-forced decode steps; returns the logits of every step [rows, steps + 1, V] (cpu)."""
+    from procyon_b200 import _lib
+
+    lib = _lib.load()
+    lib.pcy_set_decode_megakernel(max_rows)
+    try:
+        out = m(input_embeds=emb.cuda(), attn_masks=mask.cuda() if mask is not None else None, use_cache=True)
+        sess = out.past_key_values
+        logs = [sess.logits_cur.clone().cpu()]
+        for i in range(forced.shape[1]):
+            o = m(input_ids=forced[:, i:i + 1].cuda(), past_key_values=sess)
+            logs.append(o.logits[:, 0].cpu())
+    finally:
+        lib.pcy_set_decode_megakernel(2)
+    return torch.stack(logs, 1)
+
+
+def _forced_oracle(sd, oc, emb, mask, forced):
+    from oracle.llama import llama_forward
+
+    r = llama_forward(sd, oc, inputs_embeds=emb.float(), attention_mask=mask, act_round="bf16")
+    logs = [r["logits"][:, -1]]
+    am = mask
+    for i in range(forced.shape[1]):
+        if am is not None:
+            am = torch.cat([am, torch.ones(am.shape[0], 1)], dim=1)
+        r = llama_forward(sd, oc, input_ids=forced[:, i:i + 1], past=r["past"], attention_mask=am, act_round="bf16")
+        logs.append(r["logits"][:, -1])
+    return torch.stack(logs, 1)
+
+
+def _assert_argmax_where_clear(ours, ref, tol=0.05):
+    top2 = ref.topk(2, dim=-1).values
+    clear = (top2[..., 0] - top2[..., 1]) > tol
+    assert clear.any()
+    assert torch.equal(ours.argmax(-1)[clear], ref.argmax(-1)[clear]), "arg-max token ids differ at a clear margin"
 
 
 @pytest.mark.parametrize("kind,rows", [("gq4", 3), ("gq4wide", 1), ("gq4wide", 2), ("gq4wide", 4)])
-def test_persistent_and_per_op_decode_agree(cuda_device, kind, rows):
-    """The single-launch decode step and the one-launch-per-op path implement the same math."""
+def test_persistent_and_per_op_decode_match_oracle(cuda_device, kind, rows):
+    """The single-launch decode step and the one-launch-per-op path, teacher-forced with the same tokens: the logits
+    of every step of BOTH against the oracle, and exact arg-max ids wherever the oracle's margin is clear."""
     from oracle.llama import random_llama_state_dict
-    from procyon_b200 import _lib
-    from procyon_b200.model.generation import generate_greedy
 
     oc, pc = _cfgs(kind)
     sd = random_llama_state_dict(oc, seed=3)
     m = _build(sd, pc)
     ids, emb, mask = _inputs(oc, sd, rows, 50, seed=7, pad_left=4)
-    lib = _lib.load()
-    try:
-        lib.pcy_set_decode_megakernel(4)
-        o1, lp1, lg1 = generate_greedy(m, emb.cuda(), mask.cuda(), max_len=10)
-        lib.pcy_set_decode_megakernel(0)
-        o2, lp2, lg2 = generate_greedy(m, emb.cuda(), mask.cuda(), max_len=10, use_graph=False)
-    finally:
-        lib.pcy_set_decode_megakernel(2)
-    torch.testing.assert_close(lg1[:, 1], lg2[:, 1], rtol=2e-2, atol=3e-2)  # first decode step: same inputs
-    agree = (o1 == o2).float().mean().item()
-    assert agree > 0.7, agree
+    forced = torch.randint(0, oc.vocab, (rows, 9), generator=torch.Generator().manual_seed(rows))
+    ref = _forced_oracle(sd, oc, emb, mask, forced)
+    for max_rows in (4, 0):
+        got = _forced_decode(m, emb, mask, forced, max_rows)
+        assert torch.isfinite(got).all()
+        torch.testing.assert_close(got, ref, rtol=3e-2, atol=4e-2, msg=lambda t: f"megakernel max_rows={max_rows}: {t}")
+        _assert_argmax_where_clear(got, ref)
 
 
 @pytest.mark.parametrize("rows,S", [(1, 1300), (4, 1800)])
 def test_persistent_decode_long_context(cuda_device, rows, S):
     """Long prompts in the single-launch decode step: more than 12 KV splits per head (two-pass merge of the split
-    partials) and, with 4 rows x 2 kv heads x 19 splits, more attention work items than CTAs (several per CTA)."""
+    partials) and, with 4 rows x 2 kv heads x 19 splits, more attention work items than CTAs (several per CTA).
+    Teacher-forced, every step against the oracle (and the per-op path against it too)."""
     from oracle.llama import random_llama_state_dict
-    from procyon_b200 import _lib
-    from procyon_b200.model.generation import generate_greedy
 
     oc, pc = _cfgs("gq4", max_pos=2048)
     sd = random_llama_state_dict(oc, seed=5)
     m = _build(sd, pc)
     ids, emb, mask = _inputs(oc, sd, rows, S, seed=11, pad_left=7)
-    lib = _lib.load()
-    try:
-        lib.pcy_set_decode_megakernel(4)
-        o1, lp1, lg1 = generate_greedy(m, emb.cuda(), mask.cuda(), max_len=6)
-        lib.pcy_set_decode_megakernel(0)
-        o2, lp2, lg2 = generate_greedy(m, emb.cuda(), mask.cuda(), max_len=6, use_graph=False)
-    finally:
-        lib.pcy_set_decode_megakernel(2)
-    torch.testing.assert_close(lg1[:, 1], lg2[:, 1], rtol=2e-2, atol=3e-2)  # first decode step: same inputs
-    assert (o1 == o2).float().mean().item() > 0.7
+    forced = torch.randint(0, oc.vocab, (rows, 5), generator=torch.Generator().manual_seed(S))
+    ref = _forced_oracle(sd, oc, emb, mask, forced)
+    for max_rows in (4, 0):
+        got = _forced_decode(m, emb, mask, forced, max_rows)
+        assert torch.isfinite(got).all()
+        torch.testing.assert_close(got, ref, rtol=3e-2, atol=4e-2, msg=lambda t: f"megakernel max_rows={max_rows}: {t}")
+        _assert_argmax_where_clear(got, ref)
 
 
 @pytest.mark.parametrize("n,beams,S,pad", [(1, 10, 300, 0), (2, 6, 260, 9), (1, 16, 129, 0), (1, 5, 256, 0)])
@@ -251,14 +305,17 @@ def test_beam_search_shared_prompt_attention(cuda_device, n, beams, S, pad):
     ro, rlp, rlogits = oracle_beam(sd, oc, emb.float(), mask if pad else torch.ones_like(mask), max_len=5,
                                    beam_size=beams, beam_group_size=group, diversity_penalty=0.8, eos_id=-5,
                                    act_round="bf16", mask_pads_in_decode=True)
-    # with many beams near-ties reorder the final beams: compare as sets of token sequences, and the scores of the
-    # sequences both found
-    for i in range(n):
+    # every beam identical to the oracle's on all steps before the first sub-noise decision margin
+    tr = []
+    oracle_beam(sd, oc, emb.float(), mask if pad else torch.ones_like(mask), max_len=5, beam_size=beams,
+                beam_group_size=group, diversity_penalty=0.8, eos_id=-5, act_round="bf16", mask_pads_in_decode=True,
+                trace=tr)
+    clear = _clear_steps(tr)
+    assert torch.equal(o1[..., :clear], ro[..., :clear]), f"beams differ within the {clear} clear-margin steps"
+    for i in range(n):  # sequences both searches found must carry the same score
         ours = {tuple(o1[i, b].tolist()): float(lp1[i, b]) for b in range(beams)}
         ref = {tuple(ro[i, b].tolist()): float(rlp[i, b]) for b in range(beams)}
-        common = set(ours) & set(ref)
-        assert len(common) >= 0.5 * len(ref), f"only {len(common)} of {len(ref)} oracle beams found"
-        for k in common:
+        for k in set(ours) & set(ref):
             assert abs(ours[k] - ref[k]) < 6e-2 + 1e-2 * abs(ref[k])
 
 
@@ -293,3 +350,7 @@ def test_persistent_decode_crosses_key_split_boundaries(cuda_device, rows, S, st
         lib.pcy_set_decode_megakernel(2)
     assert torch.isfinite(a).all()
     torch.testing.assert_close(a, b, rtol=3e-2, atol=4e-2)
+    ref = _forced_oracle(sd, oc, emb, None, forced.cpu())[:, 1:]
+    torch.testing.assert_close(a.cpu(), ref, rtol=3e-2, atol=4e-2)
+    torch.testing.assert_close(b.cpu(), ref, rtol=3e-2, atol=4e-2)
+    _assert_argmax_where_clear(a.cpu(), ref)

@@ -161,11 +161,21 @@ def test_generate_beam_matches_oracle(cuda_device):
     (_, ids, am, _, _, _) = m._preprocessing(inputs, crop_off=True, no_pad=True, left_pad=True)
     sd, pooled, z, ret = _oracle_embeds(m, inputs, ids)
     oc, lsd = _llama_cfg_sd(m, sd)
+    trace = []
     ro, rlp, rlogits = o_beam(lsd, oc, z, am.cpu(), max_len=6, beam_size=4, beam_group_size=2, diversity_penalty=0.8,
-                              eos_id=m.tokenizer.eos_token_id, act_round="bf16", mask_pads_in_decode=True)
+                              eos_id=m.tokenizer.eos_token_id, act_round="bf16", mask_pads_in_decode=True, trace=trace)
     steps = rlogits.shape[2]
+    # EVERY beam equals the oracle's on all steps before the first decision whose margin in the oracle is inside the
+    # forward noise (0.12 = twice the worst measured log-prob deviation; tests/test_gpu_beam_strict.py checks every
+    # later decision one by one)
+    clear = 0
+    for t in trace:
+        if t["margin"] < 0.12:
+            break
+        clear += 1
+    assert clear >= 1, "pick another seed: the very first decision is a numerical tie"
+    assert torch.equal(toks[..., :clear], ro[..., :clear]), f"beams differ within the {clear} clear-margin steps"
     same = (toks[..., :steps] == ro[..., :steps]).all(dim=-1)
-    assert same.float().mean() >= 0.5
     torch.testing.assert_close(lp[same], rlp[same], rtol=2e-2, atol=8e-2)
 
 
