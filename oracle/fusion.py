@@ -86,5 +86,27 @@ def infonce(zs, zt, temperature=0.07, all_s=None, all_t=None, mask=None, rank=0)
     return (F.cross_entropy(sim_st, tgt) + F.cross_entropy(sim_ts, tgt)) / 2.0
 
 
+def conflict_matrix(text_ids, prot_ids, aaseq_code=0, dset_ids=None, protein_dataset_id=4):
+    """`negatives_mask` of a retrieval batch, procyon/model/model_unified.py:596-684, on the (already all-gathered) id
+    vectors: True = usable negative.  A pair conflicts when it shares the text id but not the protein id, or (same
+    amino-acid-sequence type) shares the protein id but not the text id; with `dataset_id`s, text conflicts only count
+    inside one dataset — and the reference then clears them for every pair whose two samples are both PPI or both
+    non-PPI (`ppi_dset_matrix` compares the two PPI flags for EQUALITY, :670-678), a quirk kept here."""
+    n = prot_ids.shape[0]
+    code = torch.full((n,), aaseq_code)
+    same_type = code[None, :] == code[:, None]
+
+    def conflict(a, b):
+        return (a[None, :] == a[:, None]) & ~(b[None, :] == b[:, None])
+
+    text_c = conflict(text_ids, prot_ids)
+    prot_c = same_type & conflict(prot_ids, text_ids)
+    if dset_ids is not None:
+        text_c = (dset_ids[None, :] == dset_ids[:, None]) & text_c
+        ppi = dset_ids == protein_dataset_id
+        text_c[ppi[None, :] == ppi[:, None]] = False
+    return ~(text_c | prot_c)
+
+
 def cosine_scores(q, db):
     return F.normalize(q.float(), dim=-1) @ F.normalize(db.float(), dim=-1).t()

@@ -128,3 +128,22 @@ def generate_greedy(sd, cfg: LlamaCfg, input_embeds, attn_mask, *, max_len=64, m
         total += lp[torch.arange(n), nxt.squeeze(-1)]
         out = nxt if out is None else torch.cat([out, nxt], dim=-1)
     return out, total, torch.stack(logits_all, 1)
+
+
+def structured_lm_head(embed: torch.Tensor, seed: int, J: int = 12) -> torch.Tensor:
+    """Test aid (not in the reference): a margin-controlled LM head for beam-search parity tests.  Random head rows
+    give ~N(0,1) logits whose top-k gaps (~0.3) are only ~10x the bf16 forward noise, so some of the ~100 decisions of
+    a beam search always fall inside the noise.  Here token v gets J graded successor tokens,
+    lm_head[succ_j(v)] += c_j(v) * embed[v] / |embed[v]| with c_j in [0.55, 1]: with embeddings that dominate the
+    residual stream the candidates that matter are ~10 logits above the rest and ~0.5 apart, while the forward noise
+    stays ~3e-2 — decisions become numerically unambiguous, yet every kernel still runs on dense random data."""
+    g = torch.Generator().manual_seed(seed)
+    vocab, d = embed.shape
+    E = embed.float()
+    E = E / E.norm(dim=1, keepdim=True).clamp_min(1e-6)
+    head = torch.zeros(vocab, d)
+    for j in range(J):
+        succ = torch.randperm(vocab, generator=g)
+        c = 0.55 + 0.45 * torch.rand(vocab, generator=g)
+        head.index_add_(0, succ, c[:, None] * E)
+    return head.to(torch.bfloat16)

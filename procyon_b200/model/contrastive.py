@@ -56,14 +56,26 @@ class InfoNCEInBatch(nn.Module):
                 # the reference dereferences an undefined local here (contrastive.py:186): masks need the gathered path
                 raise RuntimeError("negatives_mask requires all_gather_version with an initialised process group")
             all_s, all_t, G, off = zs, zt, b, 0
-        mask = None
-        if negatives_mask is not None:
-            mask = negatives_mask.to(device=zs.device, dtype=torch.uint8).contiguous()
-            if mask.shape != (G, G):
-                raise ValueError(f"negatives_mask must be {(G, G)}, got {tuple(mask.shape)}")
-        scratch = torch.empty(2 * b * G, device=zs.device, dtype=torch.float32)
-        loss = torch.empty(1, device=zs.device, dtype=torch.float32)
-        check(lib.pcy_infonce_loss(ptr(zs), ptr(zt), ptr(all_s), ptr(all_t), ptr(mask), ptr(scratch), ptr(loss),
-                                   c_int(b), c_int(G), c_int(d), c_int(off), c_float(float(self.temperature.detach())),
-                                   stream_ptr(zs.device)), "pcy_infonce_loss")
-        return loss[0]
+        return infonce_loss(zs, zt, all_s, all_t, negatives_mask, off, float(self.temperature.detach()))
+
+
+def infonce_loss(zs, zt, all_s, all_t, negatives_mask, rank_off: int, temperature: float) -> torch.Tensor:
+    """One rank's loss on L2-normalised fp32 embeddings: zs / zt [b, d] local, all_s / all_t [G, d] the rank-ordered
+    all-gather, negatives_mask [G, G] (0/1, multiplied into this rank's rows of the logits like the reference does,
+    contrastive.py:195-196) or None, targets rank_off + i.  One launch sequence in libprocyon_b200.so
+    (`pcy_infonce_loss`)."""
+    lib = _lib.load()
+    _lib.require_cuda(zs, zt, all_s, all_t)
+    b, d = zs.shape
+    G = all_s.shape[0]
+    mask = None
+    if negatives_mask is not None:
+        mask = negatives_mask.to(device=zs.device, dtype=torch.uint8).contiguous()
+        if mask.shape != (G, G):
+            raise ValueError(f"negatives_mask must be {(G, G)}, got {tuple(mask.shape)}")
+    scratch = torch.empty(2 * b * G, device=zs.device, dtype=torch.float32)
+    loss = torch.empty(1, device=zs.device, dtype=torch.float32)
+    check(lib.pcy_infonce_loss(ptr(zs), ptr(zt), ptr(all_s.contiguous()), ptr(all_t.contiguous()), ptr(mask),
+                               ptr(scratch), ptr(loss), c_int(b), c_int(G), c_int(d), c_int(rank_off),
+                               c_float(temperature), stream_ptr(zs.device)), "pcy_infonce_loss")
+    return loss[0]

@@ -271,31 +271,29 @@ class UnifiedProCyon(nn.Module):
 
         text_inputs = [[inputs["data"]["text"][i] for i in inp_list] for inp_list in inputs["input"]["text"]]
         instruction_list = list(inputs["instructions"])
+        # Structure soft tokens (reference :409-460): every instruction that survives the structure dropout gets one
+        # <|struct|> placeholder after each <|protein|>, filled with the projected GearNet embedding of that protein.
+        # One entry per instruction: a [k, d] tensor, or [] for an instruction whose structure was dropped.
         protein_struct_tokens = []
         if (not exclude_protein_structure) and self.config.use_protein_struct and inputs["input"]["seq"]:
-            include_mask = torch.bernoulli(torch.full((len(instruction_list),), 1 - self.struct_dropout_prob))
-            all_row_indices = []
-            for i in include_mask.nonzero(as_tuple=True)[0].tolist():
-                instruction_list[i] = instruction_list[i].replace("<|protein|>", "<|protein|> <|struct|>")
-                row_index = torch.cat([inputs["data"]["seq_idx"][j].unsqueeze(0) for j in inputs["input"]["seq"][i]])
-                all_row_indices.append(row_index)
-            if all_row_indices:
-                all_row_indices = torch.stack(all_row_indices, dim=0)
-                ari_unique, ari_inverse = all_row_indices.unique(return_inverse=True)
+            n_instr = len(instruction_list)
+            keep = torch.bernoulli(torch.full((n_instr,), 1 - self.struct_dropout_prob)).bool().tolist()
+            table_rows = []  # per kept instruction: rows of the structure table, one per input protein
+            for i in range(n_instr):
+                if keep[i]:
+                    instruction_list[i] = instruction_list[i].replace("<|protein|>", "<|protein|> <|struct|>")
+                    table_rows.append(torch.stack([torch.as_tensor(inputs["data"]["seq_idx"][j]).reshape(())
+                                                   for j in inputs["input"]["seq"][i]]))
+            if table_rows:
+                table_rows = torch.stack(table_rows, dim=0)  # [kept, proteins per instruction]
+                distinct, where = table_rows.unique(return_inverse=True)  # project every distinct protein once
                 if aaseq_type == "protein":
-                    struct_z = self.protein_struct_embeddings(ari_unique.to(dev))
-                else:
-                    struct_z = torch.zeros((ari_unique.shape[0], self.protein_struct_embed_dim), device=dev,
-                                           dtype=self.protein_struct_embeddings.weight.dtype)
-                struct_token_z = self.token_projectors["prot_structure"](struct_z)
-                token_z_expand = struct_token_z[ari_inverse.to(dev)]
-                k = 0
-                for val in include_mask:
-                    if val:
-                        protein_struct_tokens.append(token_z_expand[k])
-                        k += 1
-                    else:
-                        protein_struct_tokens.append([])
+                    z = self.protein_struct_embeddings(distinct.to(dev))
+                else:  # domains / peptides have no structure table: a zero embedding goes through the projector
+                    z = torch.zeros((distinct.shape[0], self.protein_struct_embed_dim), device=dev,
+                                    dtype=self.protein_struct_embeddings.weight.dtype)
+                per_instruction = iter(self.token_projectors["prot_structure"](z)[where.to(dev)])
+                protein_struct_tokens = [next(per_instruction) if k else [] for k in keep]
 
         input_ids, attn_masks = self._prepare_text_inputs_and_tokenize(
             instruction_list, text_inputs, crop_off=crop_off, retrieval=retrieval, no_pad=no_pad, left_pad=left_pad)

@@ -81,11 +81,11 @@ def create_mlp(n_layers, in_features, out_features, hidden_features=256, dropout
 
 
 def compute_conflict_matrix(id1, id2):
-    id1_r0 = id1.repeat(id1.shape[0], 1)
-    id1_r1 = id1.unsqueeze(1).repeat(1, id1.shape[0])
-    id2_r0 = id2.repeat(id2.shape[0], 1)
-    id2_r1 = id2.unsqueeze(1).repeat(1, id2.shape[0])
-    return (id1_r0 == id1_r1) & (~(id2_r0 == id2_r1))
+    """[i, j] is True when samples i and j share their first id but not their second: a false negative of in-batch
+    contrastive learning (procyon/model/model_utils.py:135-146)."""
+    same_first = id1[:, None] == id1[None, :]
+    same_second = id2[:, None] == id2[None, :]
+    return same_first & ~same_second
 
 
 def left_pad_tensors(tensors: List[torch.Tensor], pad_value=0):

@@ -11,9 +11,7 @@ from oracle.generate import generate_beam_search  # noqa: E402
 from test_gpu_beam_strict import MARGIN, _inputs, _tiny_state  # noqa: E402
 
 CASES = [  # kind, n, beams, group, pad, S, max_len
-    ("gq2", 2, 4, 2, 0, 24, 8), ("gq2", 1, 4, 4, 0, 24, 8), ("gq2", 1, 6, 1, 0, 24, 8), ("gq2", 2, 4, 2, 5, 24, 6),
-    ("gq4", 1, 4, 2, 0, 24, 10), ("gq4", 2, 2, 1, 3, 24, 10), ("gq4", 1, 10, 2, 0, 300, 5), ("gq4", 2, 6, 3, 9, 260, 4),
-    ("gq4", 1, 16, 4, 0, 129, 4), ("gq4", 1, 5, 5, 0, 256, 6),
+    ("gq2", 3, 6, 2, 0, 24, 5), ("gq2", 5, 4, 2, 6, 24, 5), ("gq4", 2, 10, 2, 0, 140, 4),
 ]
 
 if __name__ == "__main__":

@@ -99,6 +99,54 @@ def golden_infonce():
     save("infonce.pt", cases)
 
 
+def _infonce_rank(rank, world, port, case, q):
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(1)
+    b = case["b"]
+    head = ref_con.InfoNCEInBatch(input_embed_dim=case["zs"].shape[1], use_projection=False, all_gather_version=True)
+    with torch.no_grad():
+        head.temperature.fill_(case["temperature"])
+        loss = head({"positive": {"sequence": case["zs"][rank * b:(rank + 1) * b],
+                                  "text": case["zt"][rank * b:(rank + 1) * b]}}, negatives_mask=case["mask"])
+    q.put((rank, float(loss)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def golden_infonce_gathered():
+    """The branch ProCyon-Full trains with (`contrastive_global` + `filter_negatives_by_id_contrastive`): the
+    UNMODIFIED `InfoNCEInBatch.forward` (procyon/model/contrastive.py:141-204) inside real gloo process groups of 2 and
+    3 ranks, all-gathered embeddings, rank-offset targets and a 0/1 `negatives_mask` MULTIPLIED into the logits
+    (:195-196).  Stores the global inputs and every rank's loss."""
+    import multiprocessing as mp
+
+    ctx = mp.get_context("fork")
+    cases = []
+    for ci, (world, b, d, temp, with_mask) in enumerate([(2, 4, 32, 0.07, True), (3, 3, 16, 0.2, True),
+                                                         (2, 5, 24, 0.07, False)]):
+        g = torch.Generator().manual_seed(100 + ci)
+        G = world * b
+        zs, zt = torch.randn(G, d, generator=g), torch.randn(G, d, generator=g)
+        mask = None
+        if with_mask:
+            mask = torch.rand(G, G, generator=g) > 0.25
+            mask |= torch.eye(G, dtype=torch.bool)  # a sample never conflicts with itself
+        case = dict(world=world, b=b, zs=zs, zt=zt, mask=mask, temperature=temp)
+        q = ctx.Queue()
+        procs = [ctx.Process(target=_infonce_rank, args=(r, world, 29610 + ci, case, q)) for r in range(world)]
+        [p.start() for p in procs]
+        got = dict(q.get(timeout=120) for _ in range(world))
+        [p.join(timeout=60) for p in procs]
+        case["loss_per_rank"] = [got[r] for r in range(world)]
+        print(f"infonce gathered: world {world} b {b} mask {with_mask}: {case['loss_per_rank']}")
+        cases.append(case)
+    save("infonce_gathered.pt", cases)
+
+
 def golden_host_utils():
     out = {}
     ids1, ids2 = torch.tensor([3, 3, 5, 7, 5]), torch.tensor([1, 2, 2, 4, 4])
@@ -470,6 +518,7 @@ if __name__ == "__main__":
     golden_split()
     golden_mlp()
     golden_infonce()
+    golden_infonce_gathered()
     golden_host_utils()
     golden_qa_retrieval_metrics()
     golden_prompt_and_labels()

@@ -26,6 +26,8 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
+from oracle.generate import structured_lm_head  # noqa: E402
+
 EMBED_GAIN = 4.0
 MARGIN = 0.12  # > 2 x the measured worst log-prob deviation of the bf16 forward on the top candidates (0.056)
 
@@ -45,18 +47,9 @@ def _tiny_state(kind="gq4", max_pos=1024, vocab=1003, seed=3, structured_head=Tr
                   ffn_dim=f, vocab=vocab, max_pos=max_pos)
     sd = random_llama_state_dict(oc, seed=seed)
     if structured_head and kind != "sel":
-        g = torch.Generator().manual_seed(seed + 1000)
         # embeddings 4x larger than the sub-layer outputs: the last token's embedding dominates the residual stream
         sd["model.embed_tokens.weight"] = (sd["model.embed_tokens.weight"].float() * EMBED_GAIN).to(torch.bfloat16)
-        E = sd["model.embed_tokens.weight"].float()
-        E = E / E.norm(dim=1, keepdim=True)
-        J = 12
-        head = torch.zeros(vocab, d)
-        for j in range(J):
-            succ = torch.randperm(vocab, generator=g)
-            c = 0.55 + 0.45 * torch.rand(vocab, generator=g)
-            head.index_add_(0, succ, c[:, None] * E)
-        sd["lm_head.weight"] = head.to(torch.bfloat16)
+        sd["lm_head.weight"] = structured_lm_head(sd["model.embed_tokens.weight"], seed + 1000)
     return oc, sd
 
 
@@ -138,6 +131,69 @@ def test_selection_is_bit_exact(cuda_device, V, n, beams, group, steps, eos_boos
         assert int(st[2]) == 1 and int(st[3]) == stopped_at, (st.tolist(), stopped_at)
     if eos_boost:
         assert stopped_at is not None, "the EOS case never stopped: raise eos_boost"
+
+
+@pytest.mark.parametrize("n,beams,group,steps,per", [(5, 4, 2, 14, 2), (3, 10, 2, 12, 1), (7, 2, 1, 14, 3)])
+def test_lockstep_sessions_share_the_whole_batch_stop(cuda_device, n, beams, group, steps, per):
+    """A batch of more than 16 beam rows is split over several decode sessions.  The reference stops the WHOLE batch
+    at the first step where every beam of every input holds an EOS, and inputs that finish early keep extending and
+    re-ranking until then (model_unified.py:833): the sessions step in lock-step and share a device-side group state.
+    Same logits into `pcy_decode_select_group` and the oracle's step — identical tokens / scores at every step for
+    every input, and the same stop step."""
+    from oracle.generate import beam_select_step
+    from procyon_b200.model.pmc_llama import SELECT_BEAM
+
+    V, eos = 1003, 17
+    oc, sd, m = _tiny("sel", vocab=V, seed=1)
+    dev = torch.device("cuda")
+    chunks = [(i0, min(n, i0 + per)) for i0 in range(0, n, per)]
+    sessions = [m.new_session(b - a, beams, 8, steps, dev, False, False) for a, b in chunks]
+    for s_ in sessions:
+        s_.reset(None)
+    gstate = torch.zeros(4, device=dev, dtype=torch.int32)
+    gstate[3] = n
+    bb = n * beams
+    g = torch.Generator().manual_seed(n * 100 + beams)
+    out = torch.zeros(bb, steps, dtype=torch.int64)
+    cur = torch.zeros(bb)
+    stopped_at = None
+    finish_of_input = {}
+    for i in range(steps):
+        logits = torch.randn(bb, V, generator=g) * 3.0
+        if i >= 2:  # inputs are pushed towards EOS one after the other: they finish at different steps
+            hot = (torch.arange(bb) // beams) < (i - 1) * max(1, n // 4)
+            logits[hot, eos] += 30.0
+        if i == 0:
+            logits = logits.view(n, beams, V)[:, :1].expand(n, beams, V).reshape(bb, V).contiguous()
+        for k, ((a, b), s_) in enumerate(zip(chunks, sessions)):
+            s_.logits_cur.copy_(logits[a * beams:b * beams])
+            s_.select(SELECT_BEAM, group, 0.8, eos, True, gstate, k == len(sessions) - 1)
+        lp = torch.log_softmax(logits, dim=-1) + cur[:, None]
+        mg = []
+        beam_select_step(lp, out, cur, i, n, beams, group, 0.8, mg)
+        assert min(mg) > 1e-4
+        torch.cuda.synchronize()
+        got = torch.cat([s_.tokens[:, : i + 1].cpu().long() for s_ in sessions], 0)
+        assert torch.equal(got, out[:, : i + 1]), f"token histories differ at step {i}"
+        torch.testing.assert_close(torch.cat([s_.logprobs.cpu() for s_ in sessions]), cur, rtol=1e-5, atol=2e-4)
+        has = (out == eos).any(dim=1).view(n, beams).all(dim=1)
+        for j in range(n):
+            if bool(has[j]) and j not in finish_of_input:
+                finish_of_input[j] = i
+        if bool(has.all()):
+            stopped_at = i
+            break
+        assert int(gstate[1].item()) == 0, f"stopped at step {i} although inputs {(~has).nonzero().flatten().tolist()} go on"
+    assert stopped_at is not None and len(set(finish_of_input.values())) > 1, "inputs should finish at different steps"
+    gs = gstate.cpu()
+    assert int(gs[1]) == 1 and int(gs[2]) == stopped_at, (gs.tolist(), stopped_at)
+    # one more step after the stop is a no-op for every session
+    before = [s_.tokens.clone() for s_ in sessions]
+    for k, s_ in enumerate(sessions):
+        s_.select(SELECT_BEAM, group, 0.8, eos, True, gstate, k == len(sessions) - 1)
+    torch.cuda.synchronize()
+    assert all(torch.equal(a, s_.tokens) for a, s_ in zip(before, sessions))
+    assert all(int(s_.state[0].item()) == stopped_at + 1 for s_ in sessions)
 
 
 # ------------------------------------------------------------------------------------------------ (B) forward
@@ -285,7 +341,14 @@ def test_every_device_beam_decision_is_the_oracles(cuda_device, kind, n, beams, 
 # (kind, n, beams, group, pad, S, max_len, seed): seeds from scripts/find_beam_seeds.py — the oracle's smallest decision
 # margin over the whole generation is >= MARGIN for each of them (re-checked below, so a stale seed fails loudly)
 E2E_CASES = [
-    # __E2E_CASES__
+    ("gq2", 1, 4, 4, 0, 24, 8, 2061),    # oracle margin 0.141
+    ("gq2", 1, 6, 1, 0, 24, 8, 2315),    # oracle margin 0.188
+    ("gq2", 2, 4, 2, 5, 24, 6, 2032),    # oracle margin 0.130 (left-padded second prompt)
+    ("gq4", 1, 4, 2, 0, 24, 10, 2078),   # oracle margin 0.238 (4 rows: persistent decode kernel)
+    ("gq4", 2, 2, 1, 3, 24, 10, 2075),   # oracle margin 0.298
+    ("gq4", 1, 10, 2, 0, 300, 5, 2593),  # oracle margin 0.164 (evaluation default: 10 beams in groups of 2)
+    ("gq4", 2, 6, 3, 9, 260, 4, 2104),   # oracle margin 0.125
+    # __MORE_E2E_CASES__
 ]
 
 

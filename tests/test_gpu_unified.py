@@ -150,33 +150,43 @@ def test_forward_sequences_and_retrieval_scores(cuda_device):
 
 
 def test_generate_beam_matches_oracle(cuda_device):
+    """`UnifiedProCyon.generate(method="beam")` end to end (ESM2 -> pool -> projector -> splice -> prefill -> diverse
+    beam search) against the oracle pipeline: EVERY beam identical, token for token.  The LM head is the margin-
+    controlled one of tests/test_gpu_beam_strict.py and its seed is chosen HERE, by the oracle, as the first whose
+    smallest decision margin over the whole generation exceeds 0.12 (twice the worst measured forward deviation)."""
     from oracle.generate import generate_beam_search as o_beam
+    from oracle.generate import structured_lm_head
+
+    EMBED_GAIN, MARGIN = 4.0, 0.12  # as in tests/test_gpu_beam_strict.py
 
     m = _tiny_model()
+    te = m.text_encoder.model
+    te.model.embed_tokens.weight.data.mul_(EMBED_GAIN)
     inputs = _inputs()
-    toks, lp, logits, texts = m.generate(inputs, max_len=6, method="beam", beam_size=4, beam_group_size=2,
-                                         diversity_penalty=0.8)
-    assert toks.shape == (2, 4, 6) and len(texts) == 2 and len(texts[0]) == 4
-    # oracle on the same spliced, left-padded prompt
     (_, ids, am, _, _, _) = m._preprocessing(inputs, crop_off=True, no_pad=True, left_pad=True)
     sd, pooled, z, ret = _oracle_embeds(m, inputs, ids)
     oc, lsd = _llama_cfg_sd(m, sd)
-    trace = []
-    ro, rlp, rlogits = o_beam(lsd, oc, z, am.cpu(), max_len=6, beam_size=4, beam_group_size=2, diversity_penalty=0.8,
-                              eos_id=m.tokenizer.eos_token_id, act_round="bf16", mask_pads_in_decode=True, trace=trace)
-    steps = rlogits.shape[2]
-    # EVERY beam equals the oracle's on all steps before the first decision whose margin in the oracle is inside the
-    # forward noise (0.12 = twice the worst measured log-prob deviation; tests/test_gpu_beam_strict.py checks every
-    # later decision one by one)
-    clear = 0
-    for t in trace:
-        if t["margin"] < 0.12:
+    kw = dict(max_len=5, beam_size=4, beam_group_size=2, diversity_penalty=0.8)
+    best = None
+    for head_seed in range(1234, 1234 + 300):
+        head = structured_lm_head(sd["input_embeddings.weight"], seed=head_seed)
+        lsd["lm_head.weight"] = head
+        trace = []
+        ro, rlp, rlogits = o_beam(lsd, oc, z, am.cpu(), eos_id=m.tokenizer.eos_token_id, act_round="bf16",
+                                  mask_pads_in_decode=True, trace=trace, **kw)
+        margin = min(t["margin"] for t in trace)
+        if best is None or margin > best[0]:
+            best = (margin, head_seed, head, ro, rlp, rlogits)
+        if margin >= MARGIN:
             break
-        clear += 1
-    assert clear >= 1, "pick another seed: the very first decision is a numerical tie"
-    assert torch.equal(toks[..., :clear], ro[..., :clear]), f"beams differ within the {clear} clear-margin steps"
-    same = (toks[..., :steps] == ro[..., :steps]).all(dim=-1)
-    torch.testing.assert_close(lp[same], rlp[same], rtol=2e-2, atol=8e-2)
+    margin, head_seed, head, ro, rlp, rlogits = best
+    assert margin >= MARGIN, f"no head seed with clear margins found (best {margin:.3f})"
+    te.lm_head.weight.data.copy_(head)
+    toks, lp, logits, texts = m.generate(inputs, **kw)
+    assert toks.shape == (2, 4, 5) and len(texts) == 2 and len(texts[0]) == 4
+    assert torch.equal(toks, ro), f"beams differ from the oracle (head seed {head_seed}, smallest margin {margin:.3f})"
+    torch.testing.assert_close(lp, rlp, rtol=2e-2, atol=8e-2)
+    torch.testing.assert_close(logits, rlogits, rtol=3e-2, atol=8e-2)
 
 
 def test_generate_greedy_and_sampling_run(cuda_device):
@@ -202,6 +212,44 @@ def test_infonce_matches_reference_golden(cuda_device):
         head = InfoNCEInBatch(c["zs"].shape[1], use_projection=False).cuda()
         loss = head({"positive": {"sequence": c["zs"].cuda(), "text": c["zt"].cuda()}})
         torch.testing.assert_close(loss.cpu(), c["loss"], rtol=1e-4, atol=1e-5)
+
+
+def test_infonce_gathered_masked_matches_reference_golden(cuda_device):
+    """`pcy_infonce_loss` on the branch ProCyon-Full uses — G = W*b gathered rows, targets offset by rank*b, a
+    non-trivial 0/1 `negatives_mask` multiplied into the logits: every rank's loss against the unmodified reference
+    run in real 2- and 3-rank process groups (tests/golden/infonce_gathered.pt), one GPU playing each rank in turn."""
+    import os
+
+    import torch.nn.functional as F
+
+    from oracle.fusion import infonce
+    from procyon_b200.model.contrastive import _normalize, infonce_loss
+
+    cases = torch.load(os.path.join(os.path.dirname(__file__), "golden", "infonce_gathered.pt"), weights_only=False)
+    assert any(c["mask"] is not None and not bool(c["mask"].all()) for c in cases)
+    for c in cases:
+        b, W = c["b"], c["world"]
+        all_s, all_t = _normalize(c["zs"].cuda()), _normalize(c["zt"].cuda())
+        torch.testing.assert_close(all_s.cpu(), F.normalize(c["zs"], dim=-1), rtol=1e-6, atol=1e-6)
+        for r in range(W):
+            zs, zt = all_s[r * b:(r + 1) * b].contiguous(), all_t[r * b:(r + 1) * b].contiguous()
+            loss = infonce_loss(zs, zt, all_s, all_t, c["mask"], r * b, c["temperature"])
+            assert abs(float(loss) - c["loss_per_rank"][r]) < 2e-4 * max(1.0, abs(c["loss_per_rank"][r])), \
+                (W, r, float(loss), c["loss_per_rank"][r])
+    # a larger, ProCyon-Full-shaped case (8 ranks x 8 pairs, d = 2560) against the oracle
+    g = torch.Generator().manual_seed(5)
+    W, b, d = 8, 8, 2560
+    zs, zt = torch.randn(W * b, d, generator=g), torch.randn(W * b, d, generator=g)
+    zt = zt + 0.5 * zs  # correlated pairs, like trained embeddings
+    mask = torch.rand(W * b, W * b, generator=g) > 0.1
+    mask |= torch.eye(W * b, dtype=torch.bool)
+    all_s, all_t = _normalize(zs.cuda()), _normalize(zt.cuda())
+    for r in (0, 3, 7):
+        loss = infonce_loss(all_s[r * b:(r + 1) * b].contiguous(), all_t[r * b:(r + 1) * b].contiguous(), all_s, all_t,
+                            mask, r * b, 0.07)
+        ref = infonce(zs[r * b:(r + 1) * b], zt[r * b:(r + 1) * b], temperature=0.07, all_s=all_s.cpu(),
+                      all_t=all_t.cpu(), mask=mask, rank=r)
+        assert abs(float(loss) - float(ref)) < 1e-3, (r, float(loss), float(ref))
 
 
 def test_pooler_and_mlp_match_reference_goldens(cuda_device):
