@@ -246,6 +246,22 @@ int pcy_cross_entropy_rows(const float* logits, const int32_t* labels, int rows,
 int pcy_cosine_scores(const float* queries, const void* db, int db_is_bf16, float* out, int n_queries, int n_db,
                       int d, int64_t ld_out, void* stream);
 
+/* The same scores plus the ranking get_proteins_from_embedding takes from them (procyon/data/inference_utils.py:964-
+ * 970: full argsort, then the first top_k), in ONE launch: the CTA that finishes last selects the k <= 32 best rows of
+ * every query from the scores (still in L2).  scores fp32 [n_queries, ld_scores] is written as by pcy_cosine_scores;
+ * top_val fp32 / top_idx int32 [n_queries, k] = the k largest scores in descending order (ties: smaller row first)
+ * and their row numbers + index_base (the first global row of a database shard, so that per-shard results of a
+ * row-sharded database merge by value); missing entries (n_db < k) are (-inf, -1).  ticket: one device int32 that is
+ * zero on entry (the kernel leaves it zero).  k = 0 skips the ranking. */
+int pcy_retrieval_scores_topk(const float* queries, const void* db, int db_is_bf16, float* scores, int n_queries,
+                              int n_db, int d, int64_t ld_scores, int k, int index_base, float* top_val,
+                              int32_t* top_idx, int32_t* ticket, void* stream);
+
+/* Merge of per-shard top-k candidates of a row-sharded database (the all-gather of every rank's top_val / top_idx):
+ * cand_val fp32 / cand_idx int32 [n_queries, m] (idx < 0 = padding) -> the k <= 32 best per query, same order. */
+int pcy_topk_merge(const float* cand_val, const int32_t* cand_idx, int n_queries, int m, int k, float* out_val,
+                   int32_t* out_idx, void* stream);
+
 /* F.normalize(x, dim=-1) on fp32 rows */
 int pcy_normalize_rows(const float* x, float* out, int rows, int d, void* stream);
 /* InfoNCEInBatch.forward (procyon/model/contrastive.py:120-204) on L2-normalised fp32 embeddings:

@@ -151,6 +151,8 @@ int normalize_rows(const float* x, float* out, int rows, int d, cudaStream_t str
 int infonce_loss(const float* zs, const float* zt, const float* all_s, const float* all_t, const uint8_t* mask,
                  float* sims_scratch, float* loss, int b, int G, int d, int rank_off, float temperature,
                  cudaStream_t stream);
+int retrieval_scores_topk(const float* Q, const void* D, int db_bf16, float* scores, int nq, int N, int d, int64_t lds,
+                          int k, int index_base, float* top_val, int32_t* top_idx, int* ticket, cudaStream_t stream);
 int cosine_scores(const float* Q, const void* D, int db_bf16, float* out, int nq, int N, int d, int64_t ldo,
                   cudaStream_t stream);
 

@@ -36,6 +36,44 @@ def cosine_scores(query_embeddings: torch.Tensor, protein_embeds: torch.Tensor,
     return out
 
 
+FUSED_TOPK_MAX = 32  # pcy_retrieval_scores_topk ranks inside the scoring launch up to this k
+_tickets = {}
+
+
+def _ticket(dev: torch.device) -> torch.Tensor:
+    """One zero-initialised int32 per device: the 'last CTA' counter of the fused ranking (the kernel re-zeroes it)."""
+    key = str(dev)
+    if key not in _tickets:
+        _tickets[key] = torch.zeros(1, device=dev, dtype=torch.int32)
+    return _tickets[key]
+
+
+def retrieval_scores_topk(query_embeddings: torch.Tensor, protein_embeds: torch.Tensor, k: int, index_base: int = 0,
+                          scores_out: Optional[torch.Tensor] = None):
+    """Cosine scores (Q, N) AND their k <= 32 best rows per query in one launch (`pcy_retrieval_scores_topk`).
+    Returns (scores fp32 [Q, N], top_val fp32 [Q, k], top_idx int32 [Q, k] = row + index_base, -1 where N < k)."""
+    lib = _lib.load()
+    dev = protein_embeds.device if protein_embeds.is_cuda else query_embeddings.device
+    if dev.type != "cuda":
+        raise _lib.ProcyonB200Error("retrieval scoring needs the database or the query on a CUDA device")
+    if not 1 <= k <= FUSED_TOPK_MAX:
+        raise ValueError(f"fused top-k supports 1 <= k <= {FUSED_TOPK_MAX}, got {k}")
+    db = protein_embeds.to(dev)
+    if db.dtype not in (torch.float32, torch.bfloat16):
+        db = db.float()
+    db = db.contiguous()
+    q = query_embeddings.detach().to(device=dev, dtype=torch.float32).reshape(-1, db.shape[1]).contiguous()
+    Q, N, d = q.shape[0], db.shape[0], db.shape[1]
+    scores = scores_out if scores_out is not None else torch.empty((Q, N), device=dev, dtype=torch.float32)
+    top_val = torch.empty((Q, k), device=dev, dtype=torch.float32)
+    top_idx = torch.empty((Q, k), device=dev, dtype=torch.int32)
+    check(lib.pcy_retrieval_scores_topk(ptr(q), ptr(db), c_int(1 if db.dtype == torch.bfloat16 else 0), ptr(scores),
+                                        c_int(Q), c_int(N), c_int(d), c_i64(scores.stride(0)), c_int(k),
+                                        c_int(index_base), ptr(top_val), ptr(top_idx), ptr(_ticket(dev)),
+                                        stream_ptr(dev)), "pcy_retrieval_scores_topk")
+    return scores, top_val, top_idx
+
+
 def get_proteins_from_embedding(protein_embeds: torch.Tensor, model_out: Optional[Dict] = None,
                                 query_embeddings: Optional[torch.Tensor] = None, protein_ids=None, top_k: int = 20):
     """Returns a DataFrame (uniprot_id, name, sim_score) of the top_k hits (all proteins when top_k is None)."""
@@ -45,12 +83,19 @@ def get_proteins_from_embedding(protein_embeds: torch.Tensor, model_out: Optiona
     if model_out is not None:
         assert query_embeddings is None
         query_embeddings = model_out["contrastive_out"]["positive"]["text"][0, :].unsqueeze(0).detach()
-    sims = cosine_scores(query_embeddings, protein_embeds)[0]
-    sort_inds = torch.argsort(sims, descending=True)
-    if top_k is not None:
-        sort_inds = sort_inds[:top_k]
-    top = sort_inds.cpu().tolist()
-    sim_sub = sims[sort_inds].cpu().tolist()
+    if top_k is not None and top_k <= FUSED_TOPK_MAX:
+        # scores + ranking in one launch; only 2 * top_k numbers come back to the host
+        _, top_val, top_idx = retrieval_scores_topk(query_embeddings, protein_embeds, top_k)
+        keep = (top_idx[0] >= 0).cpu()
+        top = top_idx[0].cpu()[keep].tolist()
+        sim_sub = top_val[0].cpu()[keep].tolist()
+    else:  # whole ranking (top_k=None) or more hits than the fused ranking holds: library sort of the device scores
+        sims = cosine_scores(query_embeddings, protein_embeds)[0]
+        sort_inds = torch.argsort(sims, descending=True)
+        if top_k is not None:
+            sort_inds = sort_inds[:top_k]
+        top = sort_inds.cpu().tolist()
+        sim_sub = sims[sort_inds].cpu().tolist()
     if protein_ids is None:
         return pd.DataFrame({"index": top, "sim_score": sim_sub})
     return pd.DataFrame({"uniprot_id": protein_ids["protein_id"].iloc[top], "name": protein_ids["name"].iloc[top],
@@ -101,8 +146,34 @@ class ShardedProteinIndex:
         return gathered.view(self.W, Q, self.per).permute(1, 0, 2).reshape(Q, self.W * self.per)[:, : self.N]
 
     def topk(self, query_embeddings: torch.Tensor, k: int = 20):
-        s = self.scores(query_embeddings)
-        return torch.topk(s, min(k, self.N), dim=-1)
+        """(values [Q, k], global row indices [Q, k]) of the k best database rows per query.  Every rank ranks its own
+        shard inside the scoring launch and only the k candidates per rank are exchanged (2 * W * k numbers per query
+        instead of N scores), then merged by value (`pcy_topk_merge`)."""
+        import torch.distributed as dist
+
+        k = min(k, self.N)
+        if k > FUSED_TOPK_MAX:
+            return torch.topk(self.scores(query_embeddings), k, dim=-1)
+        q = query_embeddings.reshape(-1, self.d)
+        Q = q.shape[0]
+        if self.local.shape[0] > 0:
+            _, val, idx = retrieval_scores_topk(q, self.local, k, index_base=self.rank * self.per)
+        else:
+            val = torch.full((Q, k), float("-inf"), device=self.device)
+            idx = torch.full((Q, k), -1, device=self.device, dtype=torch.int32)
+        if self.W == 1:
+            return val, idx.to(torch.int64)
+        all_val = torch.empty((self.W, Q, k), device=self.device, dtype=torch.float32)
+        all_idx = torch.empty((self.W, Q, k), device=self.device, dtype=torch.int32)
+        dist.all_gather_into_tensor(all_val, val.contiguous(), group=self.group)
+        dist.all_gather_into_tensor(all_idx, idx.contiguous(), group=self.group)
+        cand_val = all_val.permute(1, 0, 2).reshape(Q, self.W * k).contiguous()
+        cand_idx = all_idx.permute(1, 0, 2).reshape(Q, self.W * k).contiguous()
+        out_val = torch.empty((Q, k), device=self.device, dtype=torch.float32)
+        out_idx = torch.empty((Q, k), device=self.device, dtype=torch.int32)
+        check(_lib.load().pcy_topk_merge(ptr(cand_val), ptr(cand_idx), c_int(Q), c_int(self.W * k), c_int(k),
+                                         ptr(out_val), ptr(out_idx), stream_ptr(self.device)), "pcy_topk_merge")
+        return out_val, out_idx.to(torch.int64)
 
 
 # ---- QA inference (procyon/data/inference_utils.py:581-655) --------------------------------------------------------

@@ -11,7 +11,7 @@ from oracle.generate import generate_beam_search  # noqa: E402
 from test_gpu_beam_strict import MARGIN, _inputs, _tiny_state  # noqa: E402
 
 CASES = [  # kind, n, beams, group, pad, S, max_len
-    ("gq2", 3, 6, 2, 0, 24, 5), ("gq2", 5, 4, 2, 6, 24, 5), ("gq4", 2, 10, 2, 0, 140, 4),
+    ("gq2", 3, 6, 2, 0, 24, 4), ("gq4", 2, 10, 2, 0, 140, 3), ("gq2", 5, 4, 2, 6, 24, 4),
 ]
 
 if __name__ == "__main__":

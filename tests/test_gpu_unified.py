@@ -182,7 +182,7 @@ def test_generate_beam_matches_oracle(cuda_device):
     margin, head_seed, head, ro, rlp, rlogits = best
     assert margin >= MARGIN, f"no head seed with clear margins found (best {margin:.3f})"
     te.lm_head.weight.data.copy_(head)
-    toks, lp, logits, texts = m.generate(inputs, **kw)
+    toks, lp, logits, texts = m.generate(inputs, method="beam", **kw)
     assert toks.shape == (2, 4, 5) and len(texts) == 2 and len(texts[0]) == 4
     assert torch.equal(toks, ro), f"beams differ from the oracle (head seed {head_seed}, smallest margin {margin:.3f})"
     torch.testing.assert_close(lp, rlp, rtol=2e-2, atol=8e-2)
