@@ -52,9 +52,9 @@ class InfoNCEInBatch(nn.Module):
             dist.all_gather_into_tensor(all_t, zt)
             G, off = W * b, rank * b
         else:
-            if negatives_mask is not None:
-                # the reference dereferences an undefined local here (contrastive.py:186): masks need the gathered path
-                raise RuntimeError("negatives_mask requires all_gather_version with an initialised process group")
+            # one rank: G = b, offset 0.  (With a mask the reference dereferences a local that only the gathered branch
+            # defines, contrastive.py:186, and raises NameError; the loss is well defined — rows of the (b, b) mask
+            # multiplied into the logits — so it is computed instead of failing.  Listed in DESIGN.md.)
             all_s, all_t, G, off = zs, zt, b, 0
         return infonce_loss(zs, zt, all_s, all_t, negatives_mask, off, float(self.temperature.detach()))
 

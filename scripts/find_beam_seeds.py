@@ -11,7 +11,7 @@ from oracle.generate import generate_beam_search  # noqa: E402
 from test_gpu_beam_strict import MARGIN, _inputs, _tiny_state  # noqa: E402
 
 CASES = [  # kind, n, beams, group, pad, S, max_len
-    ("gq2", 3, 6, 2, 0, 24, 4), ("gq4", 2, 10, 2, 0, 140, 3), ("gq2", 5, 4, 2, 6, 24, 4),
+    ("gq2", 3, 6, 2, 0, 24, 3), ("gq4", 2, 10, 2, 0, 140, 3), ("gq2", 5, 4, 2, 6, 24, 3),
 ]
 
 if __name__ == "__main__":
@@ -21,7 +21,7 @@ if __name__ == "__main__":
             models[kind] = _tiny_state(kind)
         oc, sd = models[kind]
         best = (-1.0, None)
-        for seed in range(2000, 2000 + int(sys.argv[1]) if len(sys.argv) > 1 else 2400):
+        for seed in range(3000, 3000 + int(sys.argv[1]) if len(sys.argv) > 1 else 3400):
             ids, emb, mask = _inputs(oc, sd, n, S, seed, pad)
             trace = []
             generate_beam_search(sd, oc, emb.float(), mask, max_len=max_len, beam_size=beams, beam_group_size=group,

@@ -13,7 +13,7 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "l1tex__t_bytes.sum", "sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed"]
 
 
-def main(path):
+def main(path, json_out=None, kernel_filter=None):
     out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr, units = rows[0], rows[1]
@@ -35,9 +35,22 @@ def main(path):
                 return v * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1}.get(u[k], 1)
             tr = b("dram__bytes_read.sum") + b("dram__bytes_write.sum")
             print(f"   dram traffic {tr/1e6:.1f} MB -> {tr/t_us/1e3:.1f} GB/s over {t_us:.1f} us")
+            if json_out and (kernel_filter is None or kernel_filter in d["Kernel Name"]):
+                import json
+
+                with open(json_out, "w") as f:  # the first matching launch: what bench.py reads as roofline.traffic
+                    json.dump({"kernel": d["Kernel Name"][:160], "grid": d["Grid Size"], "block": d["Block Size"],
+                               "duration_us_under_ncu": t_us, "dram_bytes_read": b("dram__bytes_read.sum"),
+                               "dram_bytes_write": b("dram__bytes_write.sum"), "source_report": path,
+                               "how": "ncu --set full --clock-control none, one launch"}, f, indent=1)
+                json_out = None
         except Exception as e:  # noqa
             print("   (traffic n/a)", e)
 
 
 if __name__ == "__main__":
-    main(sys.argv[1])
+    # ncu_summary.py report.ncu-rep [--json out.json [--kernel substring]]
+    a = sys.argv[1:]
+    jo = a[a.index("--json") + 1] if "--json" in a else None
+    kf = a[a.index("--kernel") + 1] if "--kernel" in a else None
+    main(a[0], jo, kf)
