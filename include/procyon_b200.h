@@ -99,10 +99,14 @@ enum {
 /* head_dim-64 encoders run attention on tcgen05 by default; 0 selects the mma.sync kernel for every row (tests) */
 int pcy_set_esm_tc_attention(int enabled);
 /* tcgen05 ESM attention kernel: 0 = 128-key steps, MMAs and softmax of a CTA taking turns; 1 = 64-key steps with the
-   S, P and P.V tiles double-buffered so that the MMAs of step j+1 run under the softmax of step j; 2 (default) = the
+   S, P and P.V tiles double-buffered so that the MMAs of step j+1 run under the softmax of step j; 2 = the
    same schedule with both A operands in TMEM (Q written once per CTA, P written over the scores it came from); 3 = as
-   2 with the bf16 pairs of P built on the ALU pipe (round half up) instead of the XU pipe's F2FP */
+   2 with the bf16 pairs of P built on the ALU pipe (round half up) instead of the XU pipe's F2FP; 4 = as 2 with one
+   64-thread named barrier per step between the two warps of a row pair instead of two CTA-wide bar.sync */
 int pcy_set_esm_attention_kernel(int kernel);
+/* 1: attention kernels 2 / 3 / 4 apply RoPE to Q while they move it into TMEM and the RoPE pass only rotates K;
+   0 (default; measured faster overall on B200): the RoPE pass rotates Q and K in place before the attention kernel */
+int pcy_set_esm_attention_q_rope(int enabled);
 /* 1: apply RoPE in the QKV GEMM epilogue (head_dim 64/128, tensor-core path); 0 (default): separate vectorised pass */
 int pcy_set_fused_rope(int enabled);
 /* 1: tcgen05 GEMMs with >= 2 row-blocks run as 2-CTA clusters sharing the weight tile by TMA multicast;

@@ -16,8 +16,13 @@ namespace pcy {
 
 // pcy_set_esm_attention_kernel: 0 = 128-key steps (esm_attention_tc_kernel), 1 = 64-key steps with double-buffered
 // S / P / P.V (esm_attention_tc64_kernel), 2 = 64-key steps with Q and P in TMEM (esm_attention_ts_kernel), 3 = the
-// same with P packed on the ALU pipe
-int g_esm_attention_kernel = 2;
+// same with P packed on the ALU pipe, 4 = kernel 2 with pair barriers instead of CTA-wide bar.sync
+int g_esm_attention_kernel = 4;
+// pcy_set_esm_attention_q_rope(1): kernels 2 / 3 / 4 rotate Q on its way into TMEM and the RoPE pass only covers K.
+// Measured on B200 (profiles/r02_esm_breakdown.log): the RoPE pass drops 8.3 -> 4.3 ms per 256-protein step, but the
+// attention kernel's prologue (cos / sin loads + 4 FMAs per element in front of the first MMA, on the critical path of
+// every CTA) costs 51.5 -> 65.4 ms: off by default.
+bool g_esm_attention_q_rope = false;
 
 namespace {
 
@@ -33,6 +38,15 @@ constexpr int TC_SMEM = Q_BYTES + 2 * 2 * KV_BYTES + P_BYTES + 2 * TBM * 2 /*row
 static_assert(2 * (TC_SMEM + 1024) <= 228 * 1024, "two CTAs per SM must fit");
 constexpr int TMEM_COLS_ATT = 256;  // S: [0,128), O_tile: [128,192)
 
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                    pack_bf16x2(f[6], f[7]));
+}
+
 struct TcAttnParams {
   bf16* o;
   int64_t o_rs;  // output row stride (elements)
@@ -40,6 +54,7 @@ struct TcAttnParams {
   int B, H, T, d;
   int n_q_tiles;
   float scale_log2;
+  const float* q_rope;  // fp32 [T][32][2] (cos, sin) or null: rotate-half RoPE applied to Q on its way into TMEM
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 2)
@@ -562,12 +577,18 @@ esm_attention_tc64_kernel(const __grid_constant__ CUtensorMap tmap, const TcAttn
 // tcgen05.st per thread) and consumed from there by P.V — no P tile in shared memory, no async-proxy fence.
 // TMEM columns: S/P buffers at 0 and 64, the P.V tile at 128, Q at 192 (32 columns).
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int TS_SMEM = 2 * KV2_STAGES * KV2_BYTES + 2 * TBM * 2 /*row max exchange*/ + 2 * TBM * 4 /*row sums*/ +
+constexpr int TS_SMEM = 2 * KV2_STAGES * KV2_BYTES + 4 * TBM * 2 /*row max exchange, 2 parities*/ + 2 * TBM * 4 /*row sums*/ +
                         16 /*valid words*/ + 144 /*barriers*/;
 
 // ALU_PACK: the bf16 pairs of P are built with two integer adds (round half up) and one byte permute instead of
 // F2FP.BF16.PACK_AB, which shares the quarter-rate XU pipe with MUFU.EX2 (ncu: XU 43 % busy, 1.5 XU ops per score).
-template <bool ALU_PACK>
+// PAIR: the only data two warps ever exchange is the row maximum between the two threads of a row, i.e. between warps w
+// and w + 4 (same TMEM lane quadrant, same SM sub-partition).  Instead of two 256-thread bar.sync per step (18 % of the
+// warp samples of the plain kernel sit there: eight warps on four sub-partitions drift apart) every warp takes the
+// validity bits of its own 32 keys with one ballot, the pair meets at ONE 64-thread named barrier per step (row-max
+// slots double-buffered by step parity), and the masked / unmasked forms of the exponential pass are separate loops
+// (as one loop the compiler predicates 66 LOP3 / FSEL into every step, masked or not).
+template <bool ALU_PACK, bool PAIR = false>
 __global__ void __launch_bounds__(TC_THREADS, 2)
 esm_attention_ts_kernel(const __grid_constant__ CUtensorMap tmap, const TcAttnParams p, const bf16* __restrict__ qkv) {
   extern __shared__ uint8_t smem_raw[];
@@ -576,7 +597,7 @@ esm_attention_ts_kernel(const __grid_constant__ CUtensorMap tmap, const TcAttnPa
   const uint32_t sK = base;                             // KV2_STAGES stages
   const uint32_t sV = sK + KV2_STAGES * KV2_BYTES;      // KV2_STAGES stages
   const uint32_t sXchg = sV + KV2_STAGES * KV2_BYTES;   // bf16 [2 halves][128 rows]
-  const uint32_t sSum = sXchg + 2 * TBM * 2;            // float [2 halves][128 rows]
+  const uint32_t sSum = sXchg + 4 * TBM * 2;            // float [2 halves][128 rows]
   const uint32_t sValid = sSum + 2 * TBM * 4;           // [2 parities][2 words]
   const uint32_t bars = sValid + 16;
   const uint32_t q_full = bars, kv_full0 = bars + 8, kv_empty0 = kv_full0 + 8 * KV2_STAGES,
@@ -674,12 +695,38 @@ esm_attention_ts_kernel(const __grid_constant__ CUtensorMap tmap, const TcAttnPa
     constexpr int OH = THD / 2;  // output columns per thread
     {
       // this thread's half of its query row (32 bf16 = 16 packed columns) -> TMEM: the A operand of every S = Q K^T
-      const uint4* qp = reinterpret_cast<const uint4*>(qkv + (int64_t)(row_base + q0 + r) * (3 * p.d) + h * THD + half * 32);
+      const bf16* qrow_p = qkv + (int64_t)(row_base + q0 + r) * (3 * p.d) + h * THD;
       uint32_t qr[16];
+      if (p.q_rope == nullptr) {
+        const uint4* qp = reinterpret_cast<const uint4*>(qrow_p + half * 32);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const uint4 u = __ldg(qp + i);
-        qr[4 * i] = u.x; qr[4 * i + 1] = u.y; qr[4 * i + 2] = u.z; qr[4 * i + 3] = u.w;
+        for (int i = 0; i < 4; ++i) {
+          const uint4 u = __ldg(qp + i);
+          qr[4 * i] = u.x; qr[4 * i + 1] = u.y; qr[4 * i + 2] = u.z; qr[4 * i + 3] = u.w;
+        }
+      } else {
+        // Q arrives un-rotated (the RoPE pass then only touches K: a third less HBM traffic for it); same arithmetic
+        // as rope_kernel: out[i] = x[i] cos_i - x[i+32] sin_i, out[i+32] = x[i+32] cos_i + x[i] sin_i, one rounding
+        const float4* cs = reinterpret_cast<const float4*>(p.q_rope + (int64_t)(q0 + r) * THD);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float lo[8], hi[8], out[8];
+          unpack8(__ldg(reinterpret_cast<const uint4*>(qrow_p + 8 * c)), lo);
+          unpack8(__ldg(reinterpret_cast<const uint4*>(qrow_p + 32 + 8 * c)), hi);
+#pragma unroll
+          for (int j = 0; j < 8; j += 2) {
+            const float4 t = __ldg(cs + 4 * c + (j >> 1));  // (cos_j, sin_j, cos_j+1, sin_j+1)
+            if (half == 0) {
+              out[j] = lo[j] * t.x - hi[j] * t.y;
+              out[j + 1] = lo[j + 1] * t.z - hi[j + 1] * t.w;
+            } else {
+              out[j] = hi[j] * t.x + lo[j] * t.y;
+              out[j + 1] = hi[j + 1] * t.z + lo[j + 1] * t.w;
+            }
+          }
+          const uint4 u = pack8(out);
+          qr[4 * c] = u.x; qr[4 * c + 1] = u.y; qr[4 * c + 2] = u.z; qr[4 * c + 3] = u.w;
+        }
       }
       tmem_st_32x32b_x16(t_lane + COL_Q + half * 16, qr);
       tc_wait_st();
@@ -698,18 +745,36 @@ esm_attention_ts_kernel(const __grid_constant__ CUtensorMap tmap, const TcAttnPa
         if (lane == 0) vwords[(j & 1) * 2 + quad] = word;
       }
     };
+    auto pair_sync = [&]() {  // warps quad and quad + 4; literal ids so that ptxas reserves 5 barriers, not all 16
+      if (quad == 0) asm volatile("bar.sync 1, 64;" ::: "memory");
+      else if (quad == 1) asm volatile("bar.sync 2, 64;" ::: "memory");
+      else if (quad == 2) asm volatile("bar.sync 3, 64;" ::: "memory");
+      else asm volatile("bar.sync 4, 64;" ::: "memory");
+    };
+    auto own_mask = [&](int j) -> uint32_t {  // PAIR: validity bits of this warp's own 32 keys of step j
+      const int kidx = j * TBN2 + half * 32 + lane;
+      bool ok = kidx < p.T;
+      if (ok && valid_g) ok = valid_g[kidx] != 0;
+      return __ballot_sync(0xffffffffu, ok);
+    };
     if (!live) {
+      // (PAIR: both warps of a pair are dead together and nobody else waits for them at a bar.sync; the mbarrier
+      // waits alone keep their arrivals one per phase)
       for (int j = 0; j < n_kv; ++j) {
-        publish_valid(j);
+        if (!PAIR) publish_valid(j);
         mbar_wait(s_full0 + 8 * (j & 1), (j >> 1) & 1);
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (!PAIR) {
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+        }
         if (j > 0) mbar_wait(o_full, (j - 1) & 1);
         mbar_arrive(p_ready0 + 8 * (j & 1));
       }
       mbar_wait(o_full, (n_kv - 1) & 1);
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (!PAIR) {
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
     } else {
       float o[OH];
 #pragma unroll
@@ -725,14 +790,18 @@ esm_attention_ts_kernel(const __grid_constant__ CUtensorMap tmap, const TcAttnPa
         for (int i = 0; i < OH; ++i) o[i] = fmaf(o[i], corr, __uint_as_float(v[i]));
       };
       for (int j = 0; j < n_kv; ++j) {
-        publish_valid(j);
+        uint32_t mw;
+        if (PAIR) mw = own_mask(j);
+        else publish_valid(j);
         mbar_wait(s_full0 + 8 * (j & 1), (j >> 1) & 1);
         tc_fence_after();
         uint32_t v[32];  // this thread's 32 scores of the step stay in registers for both passes
         tmem_ld_32x32b_x32(t_lane + (uint32_t)((j & 1) * TBN2 + half * 32), v);
         tc_wait_ld();
-        asm volatile("bar.sync 1, 256;" ::: "memory");  // validity words visible; every thread holds its scores
-        const uint32_t mw = vwords[(j & 1) * 2 + half];
+        if (!PAIR) {
+          asm volatile("bar.sync 1, 256;" ::: "memory");  // validity words visible; every thread holds its scores
+          mw = vwords[(j & 1) * 2 + half];
+        }
         float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
         if (mw == 0xffffffffu) {
 #pragma unroll
@@ -743,9 +812,14 @@ esm_attention_ts_kernel(const __grid_constant__ CUtensorMap tmap, const TcAttnPa
             mx4[i & 3] = fmaxf(mx4[i & 3], ((mw >> i) & 1u) ? __uint_as_float(v[i]) : -INFINITY);
         }
         const __nv_bfloat16 mx_own_b = __float2bfloat16_ru(fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])));
-        xchg[half * TBM + r] = mx_own_b;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        const float mx = fmaxf(__bfloat162float(mx_own_b), __bfloat162float(xchg[(half ^ 1) * TBM + r]));
+        // (PAIR: slots double-buffered by step parity — the partner may read this step's value after this thread has
+        // gone on to the next step; the barrier also tells each thread that its partner holds its scores, whose
+        // TMEM columns the two P stores below overwrite)
+        const int xo = PAIR ? (j & 1) * 2 * TBM : 0;
+        xchg[xo + half * TBM + r] = mx_own_b;
+        if (PAIR) pair_sync();
+        else asm volatile("bar.sync 1, 256;" ::: "memory");
+        const float mx = fmaxf(__bfloat162float(mx_own_b), __bfloat162float(xchg[xo + (half ^ 1) * TBM + r]));
         const float m_new = fmaxf(m_run, mx);
         const float corr = (m_new == -INFINITY) ? 1.f : exp2f((m_run - m_new) * p.scale_log2);
         const float moff = (m_new == -INFINITY) ? 0.f : m_new * p.scale_log2;
@@ -753,6 +827,16 @@ esm_attention_ts_kernel(const __grid_constant__ CUtensorMap tmap, const TcAttnPa
         // (all 256 threads passed the first bar.sync with their scores in registers, so the buffer is free to reuse)
         float ls4[4] = {0.f, 0.f, 0.f, 0.f};
         uint32_t packed[16];
+        if (PAIR && mw == 0xffffffffu) {  // every key of this warp's 32 is valid: no select per score
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            float p0, p1;
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(fmaf(__uint_as_float(v[i]), p.scale_log2, -moff)));
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(fmaf(__uint_as_float(v[i + 1]), p.scale_log2, -moff)));
+            ls4[(i >> 1) & 3] += p0 + p1;
+            packed[i >> 1] = pack_bf16x2(p0, p1);
+          }
+        } else
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
           float p0, p1;
@@ -781,9 +865,11 @@ esm_attention_ts_kernel(const __grid_constant__ CUtensorMap tmap, const TcAttnPa
       }
       fold_o(n_kv - 1, corr_prev);
       // ---- finalize: row sum = both halves ----
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (PAIR) pair_sync();
+      else asm volatile("bar.sync 1, 256;" ::: "memory");
       xchg_f[half * TBM + r] = l_run;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (PAIR) pair_sync();
+      else asm volatile("bar.sync 1, 256;" ::: "memory");
       const float l_tot = l_run + xchg_f[(half ^ 1) * TBM + r];
       const int qrow = q0 + r;
       if (qrow < p.T && qrow >= q_tile * TBM) {  // rows below q_tile*TBM belong to the previous tile
@@ -838,8 +924,13 @@ int make_qkv_map(const bf16* qkv, int64_t rows, int64_t cols, int64_t ld, int bo
 
 // qkv bf16 [B*T, 3d] (q pre-scaled, RoPE applied), out bf16 [B*T, d]; covers all T query rows of every sequence when
 // T >= 128 and head_dim == 64 (*rows_done = T), otherwise does nothing (*rows_done = 0).
+bool esm_attention_tc_ropes_q(int T, int n_heads, int d) {
+  return g_esm_attention_kernel >= 2 && g_esm_attention_q_rope && T >= TBM && d / n_heads == THD;
+}
+
+// q_rope: RoPE table for Q when the caller left Q un-rotated (only if esm_attention_tc_ropes_q() said so), else null
 int esm_attention_tc(const bf16* qkv, const uint8_t* key_valid, bf16* out, int B, int T, int n_heads, int d,
-                     float scale, int* rows_done, cudaStream_t stream) {
+                     float scale, const float* q_rope, int* rows_done, cudaStream_t stream) {
   *rows_done = 0;
   if (T < TBM || d / n_heads != THD) return 0;
   const int n_q_tiles = (T + TBM - 1) / TBM;
@@ -849,6 +940,8 @@ int esm_attention_tc(const bf16* qkv, const uint8_t* key_valid, bf16* out, int B
     PCY_CUDA(cudaFuncSetAttribute(esm_attention_tc64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC2_SMEM));
     PCY_CUDA(cudaFuncSetAttribute(esm_attention_ts_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM));
     PCY_CUDA(cudaFuncSetAttribute(esm_attention_ts_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM));
+    PCY_CUDA(cudaFuncSetAttribute(esm_attention_ts_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  TS_SMEM));
   }
   const int kern = g_esm_attention_kernel;
   const bool steps64 = kern != 0;
@@ -857,8 +950,11 @@ int esm_attention_tc(const bf16* qkv, const uint8_t* key_valid, bf16* out, int B
   TcAttnParams p;
   p.o = out; p.o_rs = d; p.key_valid = key_valid; p.B = B; p.H = n_heads; p.T = T; p.d = d; p.n_q_tiles = n_q_tiles;
   p.scale_log2 = scale * 1.4426950408889634f;
+  p.q_rope = q_rope;
+  PCY_REQUIRE(q_rope == nullptr || kern >= 2, "esm_attention_tc: only the TMEM-operand kernels rotate Q themselves");
   dim3 grid(n_q_tiles, n_heads, B);
-  if (kern == 3) esm_attention_ts_kernel<true><<<grid, TC_THREADS, TS_SMEM, stream>>>(tmap, p, qkv);
+  if (kern == 4) esm_attention_ts_kernel<false, true><<<grid, TC_THREADS, TS_SMEM, stream>>>(tmap, p, qkv);
+  else if (kern == 3) esm_attention_ts_kernel<true><<<grid, TC_THREADS, TS_SMEM, stream>>>(tmap, p, qkv);
   else if (kern == 2) esm_attention_ts_kernel<false><<<grid, TC_THREADS, TS_SMEM, stream>>>(tmap, p, qkv);
   else if (kern == 1) esm_attention_tc64_kernel<<<grid, TC_THREADS, TC2_SMEM, stream>>>(tmap, p);
   else esm_attention_tc_kernel<<<grid, TC_THREADS, TC_SMEM, stream>>>(tmap, p);

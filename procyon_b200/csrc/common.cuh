@@ -42,6 +42,7 @@ extern bool g_fused_rope;
 extern bool g_gemm_cluster;
 extern int g_gemm_pair_mma;
 extern int g_esm_attention_kernel;
+extern bool g_esm_attention_q_rope;
 extern bool g_skinny_mma;
 
 #define PCY_CUDA(expr)                                                     \

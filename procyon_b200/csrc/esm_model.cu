@@ -82,8 +82,13 @@ int pcy_set_esm_tc_attention(int enabled) {
 }
 
 int pcy_set_esm_attention_kernel(int kernel) {
-  PCY_REQUIRE(kernel >= 0 && kernel <= 3, "set_esm_attention_kernel: %d not in {0, 1, 2, 3}", kernel);
+  PCY_REQUIRE(kernel >= 0 && kernel <= 4, "set_esm_attention_kernel: %d not in {0, 1, 2, 3, 4}", kernel);
   pcy::g_esm_attention_kernel = kernel;
+  return 0;
+}
+
+int pcy_set_esm_attention_q_rope(int enabled) {
+  pcy::g_esm_attention_q_rope = enabled != 0;
   return 0;
 }
 
@@ -269,10 +274,14 @@ int pcy_esm_encode(void* handle, const int32_t* tokens, int B, int T, void* out_
     if (fuse_rope) { g.rope = m->rope; g.rope_hd = hd; g.rope_T = T; g.rope_ncols = 2 * d; }  // q and k heads
     PCY_TRY(gemm_bf16(g, stream));
     g_prof.mark(PC_QKV, stream);
-    if (!fuse_rope) PCY_TRY(rope_inplace(big, n, T, 2 * H, hd, 3 * d, 0, m->rope, nullptr, 0, stream));
+    // the TMEM-operand attention kernels rotate Q while they move it into TMEM: the RoPE pass then only covers K
+    const bool q_in_attn = !fuse_rope && g_esm_tc_attention && esm_attention_tc_ropes_q(T, H, d);
+    if (q_in_attn) PCY_TRY(rope_inplace(big, n, T, H, hd, 3 * d, d, m->rope, nullptr, 0, stream));
+    else if (!fuse_rope) PCY_TRY(rope_inplace(big, n, T, 2 * H, hd, 3 * d, 0, m->rope, nullptr, 0, stream));
     g_prof.mark(PC_ROPE, stream);
     int rows_done = 0;
-    if (g_esm_tc_attention) PCY_TRY(esm_attention_tc(big, valid, h, B, T, H, d, 1.0f, &rows_done, stream));
+    if (g_esm_tc_attention)
+      PCY_TRY(esm_attention_tc(big, valid, h, B, T, H, d, 1.0f, q_in_attn ? m->rope : nullptr, &rows_done, stream));
     AttnArgs a;
     a.q = big + (int64_t)rows_done * 3 * d; a.k = big + d; a.v = big + 2 * d; a.o = h + (int64_t)rows_done * d;
     a.q_bs = a.k_bs = a.v_bs = (int64_t)T * 3 * d; a.q_rs = a.k_rs = a.v_rs = 3 * d;

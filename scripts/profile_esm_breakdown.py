@@ -88,7 +88,10 @@ def main():
                           "power_w_max": max(s[1] for s in samples), "reasons": sorted({s[2] for s in samples})}), flush=True)
 
     # per-class breakdown (events between kernels; adds a sync per encode, so the total is a little above `ms`)
-    for steps64 in (3, 2, 1, 0):
+    for steps64 in (4, -4, 2, 1, 0):
+        lib.pcy_set_esm_attention_q_rope(0 if steps64 < 0 else 1)
+        qr = steps64 > 0
+        steps64 = abs(steps64)
         lib.pcy_set_esm_attention_kernel(steps64)
         ms = run(n=3, warm=1)
         lib.pcy_esm_profile(1)
@@ -103,11 +106,12 @@ def main():
         gemm_fl = {"qkv": 6, "out_proj": 2, "fc1": 8, "fc2": 8}
         tf = {k: round(N * T * layers * v * d * d / per[k] / 1e9, 1) for k, v in gemm_fl.items() if per[k] > 0}
         tf["attention"] = round(N * T * layers * 4 * T * d / per["attention"] / 1e9, 1) if per["attention"] > 0 else None
-        print(json.dumps({"attention_kernel": ["128-key steps", "64-key steps, double-buffered", "64-key steps, Q and P in TMEM", "64-key steps, Q and P in TMEM, ALU pack"][steps64],
+        print(json.dumps({"q_rope_in_attention": bool(steps64 >= 2 and qr), "attention_kernel": ["128-key steps", "64-key steps, double-buffered", "64-key steps, Q and P in TMEM", "64-key steps, Q and P in TMEM, ALU pack", "64-key steps, Q and P in TMEM, pair barriers"][steps64],
                           "ms_untraced": round(ms, 2), "proteins_per_s": round(N / ms * 1e3, 1), "ms_per_class": per,
                           "sum_ms": round(tot, 2), "share": {k: round(v / tot, 3) for k, v in per.items()},
                           "tflops_per_class": tf}), flush=True)
-    lib.pcy_set_esm_attention_kernel(2)
+    lib.pcy_set_esm_attention_kernel(4)
+    lib.pcy_set_esm_attention_q_rope(0)
 
 
 if __name__ == "__main__":
