@@ -120,6 +120,11 @@ int pcy_set_gemm_pair_mma(int mode);
 /* 1 (default): linears with 5..16 activation rows and no fused norm stream the weights through mma.sync (tensor
    cores); 0: the scalar-FMA weight-streaming kernel for every M <= 16 */
 int pcy_set_skinny_mma(int enabled);
+/* 1 (default): the kernels of the one-launch-per-op decode step (RMSNorm, weight-streaming GEMV, decode attention,
+   token embedding) are launched with the programmatic-dependent-launch attribute: each may become resident while its
+   predecessor drains and prefetches its first weight stages before `griddepcontrol.wait` (see csrc/common.cuh).
+   Results are identical to 0 (plain stream edges); tests compare both. */
+int pcy_set_pdl(int enabled);
 /* Profiling aid: pcy_esm_profile(1) makes every pcy_esm_encode record CUDA events between its kernels and sync at
    the end; pcy_esm_profile_read returns the milliseconds accumulated since, per kernel class
    [embed, layernorm, qkv, rope, attention, out_proj, fc1, fc2] (n >= 8). pcy_esm_profile(0) turns it off. */
@@ -255,11 +260,13 @@ int pcy_cosine_scores(const float* queries, const void* db, int db_is_bf16, floa
  * every query from the scores (still in L2).  scores fp32 [n_queries, ld_scores] is written as by pcy_cosine_scores;
  * top_val fp32 / top_idx int32 [n_queries, k] = the k largest scores in descending order (ties: smaller row first)
  * and their row numbers + index_base (the first global row of a database shard, so that per-shard results of a
- * row-sharded database merge by value); missing entries (n_db < k) are (-inf, -1).  ticket: one device int32 that is
- * zero on entry (the kernel leaves it zero).  k = 0 skips the ranking. */
+ * row-sharded database merge by value); missing entries (n_db < k) are (-inf, -1).  workspace: device memory of
+ * pcy_retrieval_workspace_bytes() bytes whose first word is zero on entry (the kernel leaves it zero; the rest holds
+ * the per-CTA candidate lists).  k = 0 skips the ranking (workspace may be NULL). */
 int pcy_retrieval_scores_topk(const float* queries, const void* db, int db_is_bf16, float* scores, int n_queries,
                               int n_db, int d, int64_t ld_scores, int k, int index_base, float* top_val,
-                              int32_t* top_idx, int32_t* ticket, void* stream);
+                              int32_t* top_idx, int32_t* workspace, void* stream);
+int64_t pcy_retrieval_workspace_bytes(void);
 
 /* Merge of per-shard top-k candidates of a row-sharded database (the all-gather of every rank's top_val / top_idx):
  * cand_val fp32 / cand_idx int32 [n_queries, m] (idx < 0 = padding) -> the k <= 32 best per query, same order. */

@@ -44,6 +44,7 @@ extern int g_gemm_pair_mma;
 extern int g_esm_attention_kernel;
 extern bool g_esm_attention_q_rope;
 extern bool g_skinny_mma;
+extern bool g_pdl;  // pcy_set_pdl: programmatic dependent launch for the one-launch-per-op decode chain (default on)
 
 #define PCY_CUDA(expr)                                                     \
   do {                                                                     \
@@ -73,6 +74,30 @@ static inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * 
 static inline int ceil_div(int64_t x, int64_t m) { return (int)((x + m - 1) / m); }
 
 #ifdef __CUDACC__
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------------------------
+// The one-launch-per-op decode step is a chain of ~260 short kernels; a plain stream (or graph) edge lets kernel n + 1
+// start only when kernel n has drained, so every link costs a launch ramp during which HBM idles.  With the
+// programmatic-serialization launch attribute kernel n + 1 may become resident as soon as every CTA of kernel n has
+// executed pdl_launch_dependents() (first statement of every kernel in the chain) and runs until its own pdl_wait():
+// the weight-streaming kernels put the prefetch of their first weight stages BEFORE the wait (weights depend on
+// nothing), i.e. the next op's HBM stream starts under the previous op's tail - what the persistent kernel's producer
+// warp does inside one launch.  pdl_wait() returns when the preceding grid has completed and flushed, so everything
+// that is read or written after it is ordered exactly as with a normal edge; only immutable data (weights, RoPE /
+// norm tables) may be touched before it.  Both instructions are no-ops in a launch without the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = ::pcy::g_pdl ? 1 : 0;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 // ---------------------------------------------------------------------------------------------
 // Small device utilities
 // ---------------------------------------------------------------------------------------------

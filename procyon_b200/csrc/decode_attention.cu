@@ -97,6 +97,8 @@ decode_attn_kernel(const DecAttnParams p) {
 
   const int split = blockIdx.x + p.split0, kvh = blockIdx.y, row = blockIdx.z;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  pdl_launch_dependents();
+  pdl_wait();  // qkv, the step state and the partial buffers belong to the preceding kernels
   const int t = p.state[0];
   const int g_cur = t - 1;           // generation slot written by this step
   const int pos_cur = p.S + g_cur;   // its position
@@ -300,6 +302,7 @@ decode_attn_shared_prompt_kernel(const DecAttnParams p) {
 
   const int split = blockIdx.x, kvh = blockIdx.y, input = blockIdx.z;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  pdl_launch_dependents();
   const int R = p.beams * GQ;             // live query rows
   const int m_tiles = (R + 15) / 16;
   const int t = p.state[0];
@@ -321,6 +324,9 @@ decode_attn_shared_prompt_kernel(const DecAttnParams p) {
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   }
+  // (the prompt's K / V rows were written by the prefill and never change during decoding: they are requested above,
+  // before the dependency wait; qkv and the step state come from the preceding kernels)
+  pdl_wait();
   // ---- Q: RoPE (rotate-half, rounded to bf16 like the stored k) of the beams' GQ heads; rows >= R are zero ----
   {
     const float2* cs = reinterpret_cast<const float2*>(p.cos_sin) + (int64_t)pos_cur * (HD / 2);
@@ -506,16 +512,16 @@ int decode_attention(const DecodeAttnArgs& a, cudaStream_t stream) {
         PCY_CUDA(cudaFuncSetAttribute(decode_attn_shared_prompt_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       SP_SMEM));
       dim3 sgrid(n_shared, a.KVH, a.rows / a.beams);
-      decode_attn_shared_prompt_kernel<4><<<sgrid, SP_THREADS, SP_SMEM, stream>>>(p);
+      PCY_CUDA(launch_pdl(decode_attn_shared_prompt_kernel<4>, sgrid, dim3(SP_THREADS), (size_t)SP_SMEM, stream, p));
       PCY_LAUNCH_CHECK();
       p.split0 = n_shared;
     }
   }
   dim3 grid(p.n_splits - p.split0, a.KVH, a.rows);
-  if (gq == 4) decode_attn_kernel<4><<<grid, DA_THREADS, 0, stream>>>(p);
-  else if (gq == 1) decode_attn_kernel<1><<<grid, DA_THREADS, 0, stream>>>(p);
-  else if (gq == 2) decode_attn_kernel<2><<<grid, DA_THREADS, 0, stream>>>(p);
-  else if (gq == 8) decode_attn_kernel<8><<<grid, DA_THREADS, 0, stream>>>(p);
+  if (gq == 4) PCY_CUDA(launch_pdl(decode_attn_kernel<4>, grid, dim3(DA_THREADS), 0, stream, p));
+  else if (gq == 1) PCY_CUDA(launch_pdl(decode_attn_kernel<1>, grid, dim3(DA_THREADS), 0, stream, p));
+  else if (gq == 2) PCY_CUDA(launch_pdl(decode_attn_kernel<2>, grid, dim3(DA_THREADS), 0, stream, p));
+  else if (gq == 8) PCY_CUDA(launch_pdl(decode_attn_kernel<8>, grid, dim3(DA_THREADS), 0, stream, p));
   else return set_error(PCY_ERR_UNSUPPORTED, "decode attention: H/KVH=%d unsupported (1,2,4,8)", gq);
   PCY_LAUNCH_CHECK();
   return 0;

@@ -30,6 +30,8 @@ norm_kernel(const bf16* __restrict__ x, const bf16* __restrict__ gamma, const bf
             bf16* __restrict__ y, int64_t rows, int d, float eps) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * ROW_WARPS + warp;
+  pdl_launch_dependents();
+  pdl_wait();  // x is the preceding kernel's output
   if (row >= rows) return;
   const bf16* xr = x + row * d;
   uint4 v[NV];
@@ -98,7 +100,7 @@ int launch_norm(const bf16* x, const bf16* gamma, const bf16* beta, bf16* y, int
   const int grid = ceil_div(rows, ROW_WARPS);
   const int nv = ceil_div(d, 256);
 #define PCY_NORM_CASE(NV)                                                                          \
-  norm_kernel<NV, RMS><<<grid, ROW_THREADS, 0, stream>>>(x, gamma, beta, y, rows, d, eps)
+  launch_pdl(norm_kernel<NV, RMS>, dim3(grid), dim3(ROW_THREADS), 0, stream, x, gamma, beta, y, rows, d, eps)
   if (nv <= 2) PCY_NORM_CASE(2);
   else if (nv <= 5) PCY_NORM_CASE(5);
   else if (nv <= 10) PCY_NORM_CASE(10);

@@ -97,6 +97,10 @@ int pcy_set_fused_rope(int enabled) {
   return 0;
 }
 
+int pcy_set_pdl(int enabled) {
+  pcy::g_pdl = enabled != 0;
+  return 0;
+}
 int pcy_set_skinny_mma(int enabled) {
   pcy::g_skinny_mma = enabled != 0;
   return 0;

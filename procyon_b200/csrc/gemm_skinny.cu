@@ -14,6 +14,7 @@
 
 namespace pcy {
 
+bool g_pdl = true;
 bool g_skinny_mma = true;  // pcy_set_skinny_mma(0): scalar-FMA kernel for every M <= 16 (A/B measurements, tests)
 int skinny_mma_min_rows() {  // rows from which the tensor-core kernel is used (tuning knob)
   static const int v = [] { const char* e = getenv("PCY_SKINNY_MMA_MIN_M"); return e ? atoi(e) : 3; }();
@@ -262,34 +263,56 @@ gemm_skinny_mma_kernel(const SkinnyParams p) {
   const int k_blocks = p.K / TK;
   const int my_blocks = (k_blocks - warp + T_WARPS - 1) / T_WARPS;  // k-blocks warp, warp + 4, ...
 
+  pdl_launch_dependents();  // the next op of the chain may start ITS weight prefetch under this kernel's tail
+  bool dep_pending = true;  // the activations (and C / residual) belong to the preceding kernel until pdl_wait()
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int row0 = tile * 16 * WT;
-    auto issue = [&](int i) {  // k-block warp + 4 i of this tile -> ring slot i % STG
+    auto issue_w = [&](int i) {  // weights of k-block warp + 4 i of this tile -> ring slot i % STG
       const int k0 = (warp + i * T_WARPS) * TK;
       const uint32_t st = ring + (i % STG) * STAGE_BYTES;
 #pragma unroll
-      for (int j = 0; j < 4 * WT; ++j) {  // weights: 16 WT rows x 8 chunks of 16 B
+      for (int j = 0; j < 4 * WT; ++j) {  // 16 WT rows x 8 chunks of 16 B
         const int c = lane + 32 * j, r = c >> 3, ch = c & 7;
         const int row = min(row0 + r, p.N - 1);  // (rows past N are computed and dropped)
         cp_async16(st + r * 128 + ((ch ^ (r & 7)) << 4), p.W + (int64_t)row * p.ldw + k0 + ch * 8, true);
       }
+    };
+    auto issue_a = [&](int i) {  // the matching slice of the <= 16 activation rows (zero past M)
+      const int k0 = (warp + i * T_WARPS) * TK;
+      const uint32_t st = ring + (i % STG) * STAGE_BYTES;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {       // activations: 16 rows (zero past M) x 8 chunks
+      for (int j = 0; j < 4; ++j) {
         const int c = lane + 32 * j, r = c >> 3, ch = c & 7;
         const bool ok = r < p.M;
         cp_async16(st + WT * 2048 + r * 128 + ((ch ^ (r & 7)) << 4), p.A + (int64_t)(ok ? r : 0) * p.lda + k0 + ch * 8,
                    ok);
       }
     };
+    auto issue = [&](int i) { issue_w(i); issue_a(i); };
     float acc[WT][2][4];
 #pragma unroll
     for (int t = 0; t < WT; ++t)
 #pragma unroll
       for (int n = 0; n < 2; ++n) acc[t][n][0] = acc[t][n][1] = acc[t][n][2] = acc[t][n][3] = 0.f;
+    if (dep_pending) {
+      // first tile: the weights of the whole prologue go out before the dependency wait (group 0 then holds every
+      // prologue weight stage plus activation stage 0: a group is complete only when all of them have landed)
 #pragma unroll
-    for (int i = 0; i < STG - 1; ++i) {
-      if (i < my_blocks) issue(i);
-      cp_async_commit();
+      for (int i = 0; i < STG - 1; ++i)
+        if (i < my_blocks) issue_w(i);
+      pdl_wait();
+      dep_pending = false;
+#pragma unroll
+      for (int i = 0; i < STG - 1; ++i) {
+        if (i < my_blocks) issue_a(i);
+        cp_async_commit();
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < STG - 1; ++i) {
+        if (i < my_blocks) issue(i);
+        cp_async_commit();
+      }
     }
     for (int i = 0; i < my_blocks; ++i) {
       cp_async_wait<STG - 2>();
@@ -356,6 +379,7 @@ gemm_skinny_mma_kernel(const SkinnyParams p) {
     }
     __syncthreads();  // red is reused by the next tile
   }
+  if (dep_pending) pdl_wait();  // (a CTA without a tile: keep the chain's ordering anyway)
 }
 
 template <bool SWIGLU, int STG>
@@ -368,7 +392,7 @@ int launch_skinny_mma(const SkinnyParams& p, cudaStream_t stream) {
                                   (int)smem));
   const int n_tiles = ceil_div(p.N, 16 * WT);
   const int grid = std::min(n_tiles, num_sms() * 8);
-  gemm_skinny_mma_kernel<SWIGLU, STG><<<grid, T_THREADS, smem, stream>>>(p);
+  PCY_CUDA(launch_pdl(gemm_skinny_mma_kernel<SWIGLU, STG>, dim3(grid), dim3(T_THREADS), smem, stream, p));
   PCY_LAUNCH_CHECK();
   return 0;
 }

@@ -55,6 +55,8 @@ int alloc_bf16(LlamaModel* m, bf16** dst, int64_t n) {
 __global__ void embed_last_token_kernel(const int32_t* __restrict__ tokens, const int32_t* __restrict__ state,
                                         const bf16* __restrict__ table, bf16* __restrict__ x, int max_gen, int d) {
   const int row = blockIdx.x;
+  pdl_launch_dependents();
+  pdl_wait();  // tokens / state: written by the selection kernels of the previous step
   const int t = state[0];
   const int tok = tokens[(int64_t)row * max_gen + (t - 1)];
   const uint4* src = reinterpret_cast<const uint4*>(table + (int64_t)tok * d);
@@ -369,7 +371,8 @@ int pcy_llama_decode_forward(void* handle, const pcy_decode_buffers* b, void* st
     return decode_megakernel(c, m->layers_dev, m->embed, m->lm_head, m->norm, m->rope, b, p, stream);
   }
 
-  embed_last_token_kernel<<<rows, 128, 0, stream>>>(b->tokens, b->state, m->embed, x, b->max_gen, d);
+  PCY_CUDA(launch_pdl(embed_last_token_kernel, dim3(rows), dim3(128), 0, stream, (const int32_t*)b->tokens,
+                      (const int32_t*)b->state, (const bf16*)m->embed, x, b->max_gen, d));
   PCY_LAUNCH_CHECK();
   const int64_t n_prompt = (int64_t)b->n_inputs * b->S;
   const int64_t n_gen = (int64_t)rows * b->max_gen;

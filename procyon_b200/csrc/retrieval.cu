@@ -5,8 +5,9 @@
 // the host, upload, matmul, full argsort, slice) and ProcyonRetrievalEval's cosine scores
 // (procyon/evaluate/framework/procyon.py:400-406).  HBM-bound: the database (N*d*4 bytes, 102 MB at N = 20 000,
 // d = 1280) is read exactly once, row norms and dot products come out of the same pass; the query lives in registers.
-// The top-k is taken by the CTA that finishes last (ticket), from the N scores that are still in L2: every warp keeps
-// a sorted list of 32 (score, row) pairs spread over its lanes and only touches it for scores that beat its 32nd.
+// The top-k costs no second pass: every warp keeps a sorted list of its 32 best (score, row) pairs spread over its
+// lanes (one insertion per row that beats the list's last entry); lists meet by bitonic merges in a tree: the 8 warps
+// of a CTA, then the 16 CTAs of a group, then the 19 groups - at each level the CTA that arrives last (ticket) merges.
 #include <algorithm>
 #include <vector>
 
@@ -20,6 +21,7 @@ namespace {
 constexpr int RT_THREADS = 256;  // 8 warps, two CTAs per SM; every warp owns ROWS database rows per step
 constexpr int RT_WARPS = RT_THREADS / 32;
 constexpr int RT_MAXK = 32;
+constexpr int RT_GROUP = 16;  // CTAs per group of the ranking tree
 
 // order of the ranking: larger score first; equal scores: smaller row index first
 __device__ __forceinline__ bool ranks_before(float v, int i, float w, int j) { return v > w || (v == w && i < j); }
@@ -46,6 +48,22 @@ __device__ __forceinline__ void warp_topk_offer(float& tv, int& ti, float s, int
   }
 }
 
+// top-32 of the union of two sorted lists (each spread over the lanes, best first): reverse one, take the better of
+// each pair -> a bitonic sequence holding exactly the 32 best -> 5 compare-exchange stages sort it.  ~40 instructions.
+__device__ __forceinline__ void warp_topk_merge(float& tv, int& ti, float ov, int oi, int lane) {
+  const float rv = __shfl_sync(0xffffffffu, ov, 31 - lane);
+  const int ri = __shfl_sync(0xffffffffu, oi, 31 - lane);
+  if (ranks_before(rv, ri, tv, ti)) { tv = rv; ti = ri; }
+#pragma unroll
+  for (int stride = 16; stride > 0; stride >>= 1) {
+    const float pv = __shfl_xor_sync(0xffffffffu, tv, stride);
+    const int pi = __shfl_xor_sync(0xffffffffu, ti, stride);
+    const bool keep_better = (lane & stride) == 0;
+    const bool partner_better = ranks_before(pv, pi, tv, ti);
+    if (partner_better == keep_better) { tv = pv; ti = pi; }
+  }
+}
+
 template <typename DT>
 __device__ __forceinline__ void load4(const DT* row, int k, float (&r)[4]) {
   if constexpr (sizeof(DT) == 4) {
@@ -67,7 +85,7 @@ template <int QT, int NV, int ROWS, typename DT>
 __global__ void __launch_bounds__(RT_THREADS, 2)
 retrieval_scores_topk_kernel(const float* __restrict__ Q, const DT* __restrict__ D, float* __restrict__ scores, int nq,
                              int N, int d, int64_t lds, int k, int index_base, float* __restrict__ top_val,
-                             int32_t* __restrict__ top_idx, int* __restrict__ ticket) {
+                             int32_t* __restrict__ top_idx, int* __restrict__ ws) {
   extern __shared__ float s_q[];  // [QT][d] queries, then [QT] inverse norms
   float* s_inv = s_q + (size_t)QT * d;
   __shared__ float s_tv[RT_WARPS][RT_MAXK];
@@ -101,6 +119,11 @@ retrieval_scores_topk_kernel(const float* __restrict__ Q, const DT* __restrict__
     if (lane == 0) s_inv[q] = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
   }
   __syncthreads();
+  // every warp ranks the rows it scores as it goes: QT sorted lists of 32 (score, row), lane l holding the l-th best
+  float tv[QT];
+  int ti[QT];
+#pragma unroll
+  for (int q = 0; q < QT; ++q) { tv[q] = -INFINITY; ti[q] = 0x7fffffff; }
   for (; n0 < N; n0 += rows_per_step) {
     float dot[ROWS][QT], nn[ROWS];
 #pragma unroll
@@ -153,49 +176,87 @@ retrieval_scores_topk_kernel(const float* __restrict__ Q, const DT* __restrict__
       const float inv_n = 1.0f / fmaxf(sqrtf(warp_sum(nn[r])), 1e-12f);
 #pragma unroll
       for (int q = 0; q < QT; ++q) {
-        const float v = warp_sum(dot[r][q]);
-        if (lane == 0 && q < nq && n0 + r < N) scores[(int64_t)q * lds + n0 + r] = v * s_inv[q] * inv_n;
+        float v = warp_sum(dot[r][q]) * s_inv[q] * inv_n;
+        if (lane == 0 && q < nq && n0 + r < N) scores[(int64_t)q * lds + n0 + r] = v;
+        if (k > 0 && n0 + r < N) {  // (warp-uniform) one insertion, only if the row beats the list's last entry
+          if (!(v == v)) v = -INFINITY;  // a NaN in the inputs ranks last
+          const float kv = __shfl_sync(0xffffffffu, tv[q], 31);
+          const int ki = __shfl_sync(0xffffffffu, ti[q], 31);
+          if (ranks_before(v, n0 + r, kv, ki)) warp_topk_insert(tv[q], ti[q], v, n0 + r, lane);
+        }
       }
     }
   }
   if (k <= 0) return;
 
-  // ---- ranking by the CTA that finishes last --------------------------------------------------------------------
-  __threadfence();  // this CTA's scores are visible device-wide before its ticket is
+  // ---- ranking: warps -> CTA -> group of 16 CTAs -> all groups; whoever arrives last at a level merges it ----------
+  // ws: [0] global ticket, [1 + g] ticket of group g, then (from word 64) the CTA lists [gridDim.x][QT] and the group
+  // lists [n_groups][QT], each a sorted list of 32 scores followed by their 32 rows
+  const int n_groups = ((int)gridDim.x + RT_GROUP - 1) / RT_GROUP;
+  float* cta_lists = reinterpret_cast<float*>(ws + 64);
+  float* grp_lists = cta_lists + (size_t)gridDim.x * QT * 64;
+  // the 8 warp lists of this CTA -> warp 0, as a tree of bitonic merges (3 levels)
+  auto cta_merge = [&](float& mv, int& mi) {
+#pragma unroll
+    for (int half = RT_WARPS / 2; half >= 1; half >>= 1) {
+      s_tv[warp][lane] = mv;
+      s_ti[warp][lane] = mi;
+      __syncthreads();
+      if (warp < half) warp_topk_merge(mv, mi, s_tv[warp + half][lane], s_ti[warp + half][lane], lane);
+      __syncthreads();
+    }
+  };
+  auto store_list = [&](float* dst, float mv, int mi) {
+    dst[lane] = mv;
+    reinterpret_cast<int*>(dst)[32 + lane] = mi;
+  };
+  auto load_merge = [&](const float* src, bool in, float& mv, int& mi) {
+    const float lv = in ? __ldcg(src + lane) : -INFINITY;  // L2: written by other SMs
+    const int li = in ? __ldcg(reinterpret_cast<const int*>(src) + 32 + lane) : 0x7fffffff;
+    warp_topk_merge(mv, mi, lv, li, lane);
+  };
+#pragma unroll
+  for (int q = 0; q < QT; ++q) {
+    cta_merge(tv[q], ti[q]);
+    if (warp == 0) store_list(cta_lists + ((size_t)blockIdx.x * QT + q) * 64, tv[q], ti[q]);
+  }
+  const int grp = blockIdx.x / RT_GROUP;
+  const int grp_size = min(RT_GROUP, (int)gridDim.x - grp * RT_GROUP);
+  __threadfence();  // this CTA's lists are visible device-wide before its ticket is
   __syncthreads();
-  if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1) == (int)gridDim.x - 1);
+  if (threadIdx.x == 0) s_last = (atomicAdd(ws + 1 + grp, 1) == grp_size - 1);
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  for (int q = 0; q < nq; ++q) {
-    float tv = -INFINITY;
-    int ti = 0x7fffffff;
-    const float* sc = scores + (int64_t)q * lds;
-    for (int base = warp * 32; base < N; base += RT_THREADS) {
-      const int n = base + lane;
-      float s = -INFINITY;
-      int idx = 0x7fffffff;
-      if (n < N) { s = __ldcg(sc + n); idx = n; }  // L2: written by other SMs
-      // NaN scores (a NaN in the inputs) rank last, like -inf
-      if (!(s == s)) s = -INFINITY;
-      warp_topk_offer(tv, ti, s, idx, lane);
+  for (int q = 0; q < nq; ++q) {  // the group's 16 CTA lists: two per warp
+    float mv = -INFINITY;
+    int mi = 0x7fffffff;
+#pragma unroll
+    for (int u = 0; u < RT_GROUP / RT_WARPS; ++u) {
+      const int c = warp + u * RT_WARPS;
+      load_merge(cta_lists + ((size_t)(grp * RT_GROUP + c) * QT + q) * 64, c < grp_size, mv, mi);
     }
-    s_tv[warp][lane] = tv;
-    s_ti[warp][lane] = ti;
-    __syncthreads();
-    if (warp == 0) {
-      float mv = s_tv[0][lane];
-      int mi = s_ti[0][lane];
-      for (int w = 1; w < RT_WARPS; ++w) warp_topk_offer(mv, mi, s_tv[w][lane], s_ti[w][lane], lane);
-      if (lane < k) {
-        const bool real = mi != 0x7fffffff;  // fewer than k rows in the database: pad with (-inf, -1)
-        top_val[(int64_t)q * k + lane] = real ? mv : -INFINITY;
-        top_idx[(int64_t)q * k + lane] = real ? mi + index_base : -1;
-      }
-    }
-    __syncthreads();
+    cta_merge(mv, mi);
+    if (warp == 0) store_list(grp_lists + ((size_t)grp * QT + q) * 64, mv, mi);
   }
-  if (threadIdx.x == 0) *ticket = 0;  // ready for the next launch
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(ws, 1) == n_groups - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (int q = 0; q < nq; ++q) {  // the <= 19 group lists
+    float mv = -INFINITY;
+    int mi = 0x7fffffff;
+    for (int g0 = warp; g0 < n_groups; g0 += RT_WARPS) load_merge(grp_lists + ((size_t)g0 * QT + q) * 64, true, mv, mi);
+    cta_merge(mv, mi);
+    if (warp == 0 && lane < k) {
+      const bool real = mi != 0x7fffffff;  // fewer than k rows in the database: pad with (-inf, -1)
+      top_val[(int64_t)q * k + lane] = real ? mv : -INFINITY;
+      top_idx[(int64_t)q * k + lane] = real ? mi + index_base : -1;
+    }
+  }
+  if (threadIdx.x <= n_groups) ws[threadIdx.x] = 0;  // every ticket back to zero: ready for the next launch
 }
 
 // Final merge of per-shard candidates (row-sharded database, one shard per rank): out = the k best of m (value,
@@ -227,7 +288,7 @@ topk_merge_kernel(const float* __restrict__ cand_val, const int32_t* __restrict_
 
 template <int QT, typename DT>
 int launch_retrieval(const float* Q, const DT* D, float* scores, int nq, int N, int d, int64_t lds, int k,
-                     int index_base, float* top_val, int32_t* top_idx, int* ticket, cudaStream_t stream) {
+                     int index_base, float* top_val, int32_t* top_idx, int* ws, cudaStream_t stream) {
   const size_t smem = ((size_t)QT * d + QT) * sizeof(float);
   PCY_REQUIRE(smem <= 200 * 1024, "retrieval_scores: d=%d too large", d);
   // enough CTAs for every SM to keep >= 64 KB of row data in flight, never more rows than the database has
@@ -238,7 +299,7 @@ int launch_retrieval(const float* Q, const DT* D, float* scores, int nq, int N, 
     static SmemOptIn opt;                                                                                         \
     if (smem > 48 * 1024 && opt.need(smem))                                                                       \
       PCY_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));               \
-    kern<<<grid, RT_THREADS, smem, stream>>>(Q, D, scores, nq, N, d, lds, k, index_base, top_val, top_idx, ticket); \
+    kern<<<grid, RT_THREADS, smem, stream>>>(Q, D, scores, nq, N, d, lds, k, index_base, top_val, top_idx, ws);         \
   } while (0)
   if (d == 1280) PCY_RT_LAUNCH(10, 2);
   else if (d == 2560) PCY_RT_LAUNCH(20, 1);
@@ -252,11 +313,11 @@ int launch_retrieval(const float* Q, const DT* D, float* scores, int nq, int N, 
 }  // namespace
 
 int retrieval_scores_topk(const float* Q, const void* D, int db_bf16, float* scores, int nq, int N, int d, int64_t lds,
-                          int k, int index_base, float* top_val, int32_t* top_idx, int* ticket, cudaStream_t stream) {
+                          int k, int index_base, float* top_val, int32_t* top_idx, int* ws, cudaStream_t stream) {
   PCY_REQUIRE(d % 4 == 0, "retrieval_scores: d %% 4 != 0");
   PCY_REQUIRE(k >= 0 && k <= RT_MAXK, "retrieval_scores: top-k of %d > %d is not fused (rank the scores instead)", k,
               RT_MAXK);
-  PCY_REQUIRE(k == 0 || (top_val && top_idx && ticket), "retrieval_scores: top-k outputs / ticket missing");
+  PCY_REQUIRE(k == 0 || (top_val && top_idx && ws), "retrieval_scores: top-k outputs / workspace missing");
   if (nq == 0) return 0;
   if (N == 0) {
     if (k > 0) {  // empty shard: nothing to rank
@@ -279,10 +340,10 @@ int retrieval_scores_topk(const float* Q, const void* D, int db_bf16, float* sco
 #define PCY_RT_QT(QT_)                                                                                              \
   do {                                                                                                              \
     if (db_bf16)                                                                                                    \
-      PCY_TRY((launch_retrieval<QT_, bf16>(q, (const bf16*)D, sc, cnt, N, d, lds, k, index_base, tv, ti, ticket,   \
+      PCY_TRY((launch_retrieval<QT_, bf16>(q, (const bf16*)D, sc, cnt, N, d, lds, k, index_base, tv, ti, ws,       \
                                            stream)));                                                              \
     else                                                                                                            \
-      PCY_TRY((launch_retrieval<QT_, float>(q, (const float*)D, sc, cnt, N, d, lds, k, index_base, tv, ti, ticket, \
+      PCY_TRY((launch_retrieval<QT_, float>(q, (const float*)D, sc, cnt, N, d, lds, k, index_base, tv, ti, ws,     \
                                             stream)));                                                             \
   } while (0)
     if (cnt == 1) PCY_RT_QT(1);
@@ -320,9 +381,14 @@ int pcy_cosine_scores(const float* queries, const void* db, int db_is_bf16, floa
 
 int pcy_retrieval_scores_topk(const float* queries, const void* db, int db_is_bf16, float* scores, int n_queries,
                               int n_db, int d, int64_t ld_scores, int k, int index_base, float* top_val,
-                              int32_t* top_idx, int32_t* ticket, void* stream) {
+                              int32_t* top_idx, int32_t* workspace, void* stream) {
   return retrieval_scores_topk(queries, db, db_is_bf16, scores, n_queries, n_db, d, ld_scores, k, index_base, top_val,
-                               top_idx, ticket, (cudaStream_t)stream);
+                               top_idx, workspace, (cudaStream_t)stream);
+}
+
+int64_t pcy_retrieval_workspace_bytes(void) {
+  const int64_t grid = 2 * num_sms();
+  return 256 + (grid + (grid + 15) / 16) * 4 * 64 * 4;
 }
 
 int pcy_topk_merge(const float* cand_val, const int32_t* cand_idx, int n_queries, int m, int k, float* out_val,

@@ -41,10 +41,16 @@ _tickets = {}
 
 
 def _ticket(dev: torch.device) -> torch.Tensor:
-    """One zero-initialised int32 per device: the 'last CTA' counter of the fused ranking (the kernel re-zeroes it)."""
+    """Per-device workspace of the fused ranking: the 'last CTA' counter (zero on entry, re-zeroed by the kernel) and
+    the per-CTA candidate lists."""
     key = str(dev)
     if key not in _tickets:
-        _tickets[key] = torch.zeros(1, device=dev, dtype=torch.int32)
+        import ctypes
+
+        f = _lib.load().pcy_retrieval_workspace_bytes
+        f.restype = ctypes.c_int64
+        with torch.cuda.device(dev):
+            _tickets[key] = torch.zeros(int(f()) // 4 + 1, device=dev, dtype=torch.int32)
     return _tickets[key]
 
 

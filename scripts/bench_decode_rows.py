@@ -22,22 +22,30 @@ def main():
         _, _, logits, _ = te.prefill(x, None, want_cache=True, want_hidden=False, sel_rows=sel, kv_out=sess.kv_prompt)
         mode = SELECT_GREEDY if beams == 1 else SELECT_BEAM
         group = 1 if beams == 1 else (beams // 2 if beams % 2 == 0 else beams)
-        sess.reset(logits)
-        sess.select(mode, group, 0.8, -1, False)
-        g = sess.step_graph(mode, group, 0.8, -1, False)
-        for _ in range(5):
-            g.replay()
-        torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        n = 60
-        a.record()
-        for _ in range(n):
-            g.replay()
-        b.record()
-        torch.cuda.synchronize()
-        ms = a.elapsed_time(b) / n
-        print(json.dumps({"beams": beams, "ms_per_step": ms, "tokens_per_s_aggregate": beams / ms * 1e3,
-                          "weights_gb_per_s": 15.01 / ms * 1e3}), flush=True)
+        from procyon_b200 import _lib
+
+        lib = _lib.load()
+        for pdl in ((1, 0) if beams > 2 else (1,)):  # (rows <= 2: persistent kernel, no launch chain)
+            lib.pcy_set_pdl(pdl)
+            sess.reset(logits)
+            sess.select(mode, group, 0.8, -1, False)
+            sess._graph = None
+            g = sess.step_graph(mode, group, 0.8, -1, False)
+            for _ in range(5):
+                g.replay()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n = 60
+            a.record()
+            for _ in range(n):
+                g.replay()
+            b.record()
+            torch.cuda.synchronize()
+            ms = a.elapsed_time(b) / n
+            print(json.dumps({"beams": beams, "programmatic_dependent_launch": bool(pdl), "ms_per_step": ms,
+                              "tokens_per_s_aggregate": beams / ms * 1e3, "weights_gb_per_s": 15.01 / ms * 1e3}),
+                  flush=True)
+        lib.pcy_set_pdl(1)
 
 
 if __name__ == "__main__":

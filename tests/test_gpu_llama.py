@@ -354,3 +354,41 @@ def test_persistent_decode_crosses_key_split_boundaries(cuda_device, rows, S, st
     torch.testing.assert_close(a.cpu(), ref, rtol=3e-2, atol=4e-2)
     torch.testing.assert_close(b.cpu(), ref, rtol=3e-2, atol=4e-2)
     _assert_argmax_where_clear(a.cpu(), ref)
+
+
+@pytest.mark.parametrize("rows", [6, 10, 16])
+def test_programmatic_dependent_launch_changes_nothing(cuda_device, rows):
+    """The per-op decode chain launched with the programmatic-dependent-launch attribute (each kernel may become
+    resident while its predecessor drains and prefetches weights before `griddepcontrol.wait`) against plain stream
+    edges: bit-identical logits, eagerly and through CUDA-graph replays, and both against the oracle."""
+    from oracle.llama import random_llama_state_dict
+    from procyon_b200 import _lib
+    from procyon_b200.model.generation import generate_beam_search
+
+    oc, pc = _cfgs("gq4", max_pos=512)
+    sd = random_llama_state_dict(oc, seed=31)
+    m = _build(sd, pc)
+    ids, emb, mask = _inputs(oc, sd, rows, 150, seed=rows, pad_left=5)
+    forced = torch.randint(0, oc.vocab, (rows, 6), generator=torch.Generator().manual_seed(rows))
+    lib = _lib.load()
+    try:
+        lib.pcy_set_pdl(1)
+        a = _forced_decode(m, emb, mask, forced, 0)
+        lib.pcy_set_pdl(0)
+        b = _forced_decode(m, emb, mask, forced, 0)
+    finally:
+        lib.pcy_set_pdl(1)
+    assert torch.equal(a, b)
+    ref = _forced_oracle(sd, oc, emb, mask, forced)
+    torch.testing.assert_close(a, ref, rtol=3e-2, atol=4e-2)
+    if rows <= 16:
+        i1, e1, m1 = _inputs(oc, sd, 1, 150, seed=rows)
+        kw = dict(max_len=12, beam_size=rows, beam_group_size=rows // 2, diversity_penalty=0.8, eos_token_id=-5)
+        try:
+            lib.pcy_set_pdl(1)
+            o1, lp1, lg1 = generate_beam_search(m, e1.cuda(), None, **kw)   # CUDA-graph replays
+            lib.pcy_set_pdl(0)
+            o2, lp2, lg2 = generate_beam_search(m, e1.cuda(), None, **kw)
+        finally:
+            lib.pcy_set_pdl(1)
+        assert torch.equal(o1, o2) and torch.equal(lp1, lp2) and torch.equal(lg1, lg2)
