@@ -19,6 +19,7 @@
 // procyon/model/pmc_llama.py:571) and of create_mlp (procyon/model/model_utils.py:13-41).
 #include <algorithm>
 #include <mutex>
+#include <cstdlib>
 #include <unordered_map>
 
 #include "common.cuh"
@@ -659,20 +660,31 @@ int gemm_bf16_tc(const GemmArgs& a, cudaStream_t stream) {
   const int sms = num_sms();
   const int tiles256 = ceil_div(a.M, BM) * ceil_div(a.N, 256);
   const int tiles128 = ceil_div(a.M, BM) * ceil_div(a.N, 128);
-  bool use128 = (a.N <= 128) || (tiles256 < sms && tiles128 > tiles256);
+  // (a single, nearly full wave of 128x256 tiles beats two waves of 128x128 tiles: measured on B200 at M = 1024,
+  // N = 4096: K = 14336 1188 vs 964 TFLOP/s, K = 4096 854 vs 794 - the wider tile halves the shared-memory traffic per
+  // flop, which is what limits the narrow one)
+  bool use128 = (a.N <= 128) || (tiles256 * 10 < sms * 7 && tiles128 > tiles256);
   if (!use128) {
     // wave quantisation: prefer the tile size with the better SM-time efficiency
     const double w256 = (double)tiles256 / (double)(ceil_div(tiles256, sms) * sms);
     const double w128 = (double)tiles128 / (double)(ceil_div(tiles128, sms) * sms);
     if (w128 > w256 * 1.15) use128 = true;
   }
+  {
+    static const int force = [] { const char* e = getenv("PCY_GEMM_FORCE_TILE"); return e ? atoi(e) : 0; }();  // tuning
+    if (force == 128) use128 = true;
+    if (force == 256 && a.N > 128) use128 = false;
+  }
   // two or more row-blocks: cluster pairs share the W tile — as one cta_group::2 MMA, or through TMA multicast
   // Measured on B200 (profiles/r01_gemm_shapes_pair.log): +5..12 % on the ESM2 shapes (M = 32 896) and on the Llama
   // gate/up GEMM, i.e. at or above cuBLAS, but -5 % on problems of one or two waves (Llama q/k/v/o at M = 1024), where
   // pairing halves the number of schedulable units.
   const int tiles = use128 ? tiles128 : tiles256;
+  // ... and on single-wave problems with an even number of row blocks and a long K loop, where a pair occupies the two
+  // SMs two single tiles would have occupied anyway (M = 1024, N = 4096, K = 14336: 1355 vs 1188 TFLOP/s, cuBLAS 1341)
+  const bool single_wave_pair = !use128 && tiles256 <= sms && ceil_div(a.M, BM) % 2 == 0 && a.K >= 8192;
   if (ceil_div(a.M, BM) >= 2 && a.N > 128 && a.rope == nullptr &&
-      (g_gemm_pair_mma == 2 || (g_gemm_pair_mma == 1 && tiles >= 3 * sms)))
+      (g_gemm_pair_mma == 2 || (g_gemm_pair_mma == 1 && (tiles >= 3 * sms || single_wave_pair))))
     return use128 ? launch<128, false, 2, true>(a, stream) : launch<256, false, 2, true>(a, stream);
   const bool pair = g_gemm_cluster && ceil_div(a.M, BM) >= 2;
   if (a.rope != nullptr) {
