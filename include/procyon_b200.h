@@ -169,6 +169,9 @@ enum {
   PCY_LLAMA_WDOWN = 8    /* bf16 [d,F]            down_proj.weight */
 };
 
+/* 1 (default): prefill attention of prompts with >= 128 positions and head_dim 128 runs on tcgen05 (causal, GQA,
+   left-pad key mask; csrc/attention_tc_causal.cu); 0: the mma.sync kernel for every prefill (tests, A/B) */
+int pcy_set_llama_tc_attention(int enabled);
 int pcy_llama_create(const pcy_llama_config* cfg, void** handle);
 int pcy_llama_destroy(void* handle);
 int pcy_llama_load_tensor(void* handle, int kind, int layer, const void* src, int64_t nbytes);

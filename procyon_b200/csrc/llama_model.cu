@@ -291,7 +291,9 @@ int pcy_llama_prefill_ex(void* handle, const void* input_embeds, const uint8_t* 
     a.o_bs = (int64_t)S * d; a.o_rs = d; a.o_hs = hd;
     a.B = B; a.H = H; a.KVH = KVH; a.Tq = S; a.Tk = S; a.head_dim = hd;
     a.key_valid = key_valid; a.key_valid_bs = S; a.scale = 1.0f / sqrtf((float)hd); a.causal = 1;
-    PCY_TRY(flash_attention(a, stream));
+    int tc_done = 0;  // prompts of >= 128 positions, head_dim 128: tcgen05 kernel (attention_tc_causal.cu)
+    PCY_TRY(llama_attention_tc(qkv, qkv_dim, key_valid, h, d, B, S, H, KVH, hd, a.scale, &tc_done, stream));
+    if (!tc_done) PCY_TRY(flash_attention(a, stream));
     GemmArgs o;
     o.A = h; o.lda = d; o.W = y.wo; o.ldw = H * hd; o.C = x; o.ldc = d; o.M = (int)n; o.N = d; o.K = H * hd;
     o.residual = x; o.ldr = d;

@@ -111,6 +111,9 @@ int decode_attention(const DecodeAttnArgs& a, cudaStream_t stream);
 int decode_attention_splits(int S, int max_gen);
 int64_t decode_attention_partial_floats(int rows, int H, int KVH, int S, int max_gen);
 
+int llama_attention_tc(const bf16* qkv, int64_t qkv_ld, const uint8_t* key_valid, bf16* out, int64_t o_rs, int B, int S,
+                       int H, int KVH, int head_dim, float scale, int* done, cudaStream_t stream);
+
 // ---- decode-step token selection ---------------------------------------------------------------------
 struct DecodeSelectArgs {
   const float* logits = nullptr;  // [rows][vocab]

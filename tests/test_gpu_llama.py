@@ -392,3 +392,52 @@ def test_programmatic_dependent_launch_changes_nothing(cuda_device, rows):
         finally:
             lib.pcy_set_pdl(1)
         assert torch.equal(o1, o2) and torch.equal(lp1, lp2) and torch.equal(lg1, lg2)
+
+
+@pytest.mark.parametrize("kind,B,S,pad", [("gq4", 2, 128, 0), ("gq4", 2, 200, 37), ("gq4", 1, 333, 0), ("gq4", 3, 257, 130),
+                                          ("gq2", 2, 192, 5), ("gq4", 1, 1024, 0)])
+def test_prefill_tcgen05_causal_attention_matches_oracle_and_mma_sync(cuda_device, kind, B, S, pad):
+    """Prefill attention on tcgen05 (prompts of >= 128 positions, head_dim 128: causal mask inside the diagonal key
+    steps, GQA, left-pad key mask, shifted last query tile when S % 128 != 0, key steps that end mid-tile) against the
+    mma.sync kernel it replaces and against the oracle: hidden states, last-position logits and the KV cache it leaves
+    for decoding."""
+    from oracle.llama import llama_forward, random_llama_state_dict
+    from procyon_b200 import _lib
+
+    oc, pc = _cfgs(kind, max_pos=1024)
+    sd = random_llama_state_dict(oc, seed=61)
+    m = _build(sd, pc)
+    ids, emb, mask = _inputs(oc, sd, B, S, seed=S + B, pad_left=pad)
+    am = mask.cuda() if pad else None
+    lib = _lib.load()
+    outs = {}
+    try:
+        for tc in (1, 0):
+            lib.pcy_set_llama_tc_attention(tc)
+            n0 = lib.pcy_launch_count()
+            o = m(input_embeds=emb.cuda(), attn_masks=am)
+            outs[tc] = (o.hidden_states[-1].float().cpu(), lib.pcy_launch_count() - n0)
+            again = m(input_embeds=emb.cuda(), attn_masks=am).hidden_states[-1].float().cpu()
+            assert torch.equal(outs[tc][0], again)  # deterministic
+    finally:
+        lib.pcy_set_llama_tc_attention(1)
+    keep = mask.bool()
+    assert torch.isfinite(outs[1][0][keep]).all()
+
+    def close(a, b, what):
+        # two bf16 pipelines: the DESIGN tolerance band (3e-2 + 3e-2 |ref|) for all but a 1e-3 tail of single-ulp flips
+        # of the larger values, nothing off by more than 0.1
+        err = (a - b).abs()
+        band = 3e-2 + 3e-2 * b.abs()
+        assert (err > band).float().mean().item() < 1e-3, (what, (err > band).float().mean().item())
+        assert err.max().item() < 0.1, (what, err.max().item())
+
+    close(outs[1][0][keep], outs[0][0][keep], "tcgen05 vs mma.sync")
+    ref = llama_forward(sd, oc, inputs_embeds=emb.float(), attention_mask=mask if pad else None, act_round="bf16")
+    close(outs[1][0][keep], ref["hidden_states"][-1][keep], "tcgen05 vs oracle")
+    close(outs[0][0][keep], ref["hidden_states"][-1][keep], "mma.sync vs oracle")
+    # decoding from the cache the tcgen05 prefill left behind
+    forced = torch.randint(0, oc.vocab, (B, 3), generator=torch.Generator().manual_seed(S))
+    got = _forced_decode(m, emb, mask if pad else None, forced, 4)
+    want = _forced_oracle(sd, oc, emb, mask if pad else None, forced)
+    torch.testing.assert_close(got, want, rtol=3e-2, atol=4e-2)
