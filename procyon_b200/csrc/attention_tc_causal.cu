@@ -5,7 +5,7 @@
 // positions; shorter prompts keep the mma.sync kernel in attention.cu.
 //
 // One CTA = 128 queries of one (sequence, query head); 64 keys per step; two CTAs per SM (112 KB of shared memory and
-// 256 TMEM columns each), so that one CTA's softmax runs under the other's MMAs.
+// 256 TMEM columns each: two S buffers + O), so that one CTA's softmax runs under the other's MMAs.
 //   warp 8, one thread   TMA loads (Q once: two 64-dim blocks of [128 x 128 B], 128B swizzle; K / V per step: two blocks of
 //                        [64 x 128 B] each, 2 stages) and tcgen05.mma issue:  S = Q K^T  (M 128, N 64, K 128 = 8 UMMA_K
 //                        over the two dim blocks)  and  O += P V  (M 128, N 2 x 64, K 64 keys; V consumed in place as an
@@ -44,7 +44,7 @@ constexpr int C_SMEM = Q_BYTES_C + 2 * C_STAGES * KV_BYTES_C + P_BYTES_C + 2 * C
                        128 /*barriers*/;
 static_assert(2 * CBM * 4 <= P_BYTES_C, "the final row-sum exchange reuses the P region");
 static_assert(2 * (C_SMEM + 1024) <= 228 * 1024, "two CTAs per SM must fit");
-constexpr int C_TMEM_COLS = 256;  // S: [0, 64), O: [64, 192)
+constexpr int C_TMEM_COLS = 256;  // S (two buffers): [0, 64) and [64, 128), O: [128, 256)
 
 struct CausalParams {
   bf16* o;
@@ -66,8 +66,8 @@ llama_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
   const uint32_t sP = sV + C_STAGES * KV_BYTES_C;
   const uint32_t sX = sP + P_BYTES_C;                   // bf16 [2 halves][128 rows]
   const uint32_t bars = sX + 2 * CBM * 2;
-  const uint32_t q_full = bars, kv_full0 = bars + 8, kv_empty0 = bars + 24, s_full = bars + 40, p_ready = bars + 48,
-                 o_full = bars + 56, tmem_slot = bars + 64;
+  const uint32_t q_full = bars, kv_full0 = bars + 8, kv_empty0 = bars + 24, s_full0 = bars + 40, p_ready = bars + 56,
+                 o_full = bars + 64, tmem_slot = bars + 72;
   __nv_bfloat16* xchg = reinterpret_cast<__nv_bfloat16*>(smem_raw + (sX - base));
   float* xchg_f = reinterpret_cast<float*>(smem_raw + (sP - base));  // P region, free after the last P V
 
@@ -88,7 +88,8 @@ llama_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
     mbar_init(kv_full0 + 8, 1);
     mbar_init(kv_empty0, 1);
     mbar_init(kv_empty0 + 8, 1);
-    mbar_init(s_full, 1);
+    mbar_init(s_full0, 1);
+    mbar_init(s_full0 + 8, 1);
     mbar_init(p_ready, C_SM_WARPS * 32);
     mbar_init(o_full, 1);
     fence_barrier_init();
@@ -119,9 +120,10 @@ llama_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
         tma_load_2d(sV + st * KV_BYTES_C, &tmap_kv, bar, col_v, r0);
         tma_load_2d(sV + st * KV_BYTES_C + KVBLK, &tmap_kv, bar, col_v + 64, r0);
       };
-      load_kv(0);
-      mbar_wait(q_full, 0);
-      for (int j = 0; j < n_kv; ++j) {
+      // S is double-buffered in TMEM: S(j + 1) is issued BEFORE the wait for softmax(j), so the softmax of consecutive
+      // steps runs back to back and the MMAs / TMA loads hide under it (with one S buffer a step was the serial chain
+      // S -> softmax -> P V, 2.9 us per step; the longest tile of S = 1024 has 16 steps)
+      auto issue_s = [&](int j) {
         const int st = j & 1;
         mbar_wait(kv_full0 + 8 * st, (j >> 1) & 1);
         tc_fence_after();
@@ -132,27 +134,38 @@ llama_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
         for (int k = 0; k < CHD / 16; ++k) {
           const uint64_t qd = make_desc_kmajor_sw128(sQ + (k >> 2) * QBLK) + 2 * (k & 3);
           const uint64_t kd = make_desc_kmajor_sw128(sK + st * KV_BYTES_C + (k >> 2) * KVBLK) + 2 * (k & 3);
-          tc_mma_bf16(tmem_base, qd, kd, idesc_s, k > 0 ? 1u : 0u);
+          tc_mma_bf16(tmem_base + st * CBN, qd, kd, idesc_s, k > 0 ? 1u : 0u);
         }
-        tc_commit(s_full);
-        if (j + 1 < n_kv) {  // next K/V tile into the other stage once its previous user (P V of j - 1) is done
-          if (j + 1 >= 2) mbar_wait(kv_empty0 + 8 * ((j + 1) & 1), (((j + 1) >> 1) - 1) & 1);
-          load_kv(j + 1);
-        }
+        tc_commit(s_full0 + 8 * st);
+      };
+      load_kv(0);
+      if (n_kv > 1) load_kv(1);
+      mbar_wait(q_full, 0);
+      issue_s(0);
+      for (int j = 0; j < n_kv; ++j) {
+        const int st = j & 1;
+        // (S buffer (j + 1) & 1 was last read by softmax(j - 1), whose p_ready this thread has already waited for)
+        if (j + 1 < n_kv) issue_s(j + 1);
         // O += P V : M = 128, N = 64 per dim block, K = n_mma keys; A = P (K-major), B = V (MN-major)
         mbar_wait(p_ready, j & 1);
         tc_fence_after();
+        const int keys = min(CBN, p.S - j * CBN);
+        const int n_mma = (keys + 15) & ~15;
         const uint32_t idesc_o = make_idesc_bf16(CBM, 64, 0, 1);
         for (int k = 0; k < n_mma / 16; ++k) {
           const uint64_t pd = make_desc_kmajor_sw128(sP) + 2 * k;
 #pragma unroll
           for (int nb = 0; nb < 2; ++nb) {
             const uint64_t vd = make_desc_mnmajor_sw128(sV + st * KV_BYTES_C + nb * KVBLK + k * 2048, 1024);
-            tc_mma_bf16(tmem_base + CBN + nb * 64, pd, vd, idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+            tc_mma_bf16(tmem_base + 2 * CBN + nb * 64, pd, vd, idesc_o, (j > 0 || k > 0) ? 1u : 0u);
           }
         }
         tc_commit(kv_empty0 + 8 * st);
         tc_commit(o_full);
+        if (j + 2 < n_kv) {  // K / V of step j + 2 into this stage as soon as P V (j) has retired
+          mbar_wait(kv_empty0 + 8 * st, (j >> 1) & 1);
+          load_kv(j + 2);
+        }
       }
     }
   } else {
@@ -171,10 +184,10 @@ llama_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
       uint32_t mw = __ballot_sync(0xffffffffu, ok);
       const int n_vis = q_pos - k_lo + 1;  // keys k_lo .. k_lo + n_vis - 1 are not in this query's future
       mw &= n_vis >= 32 ? 0xffffffffu : (n_vis <= 0 ? 0u : ((1u << n_vis) - 1u));
-      mbar_wait(s_full, j & 1);
+      mbar_wait(s_full0 + 8 * (j & 1), (j >> 1) & 1);
       tc_fence_after();
       uint32_t v[32];
-      tmem_ld_32x32b_x32(t_lane + half * 32, v);
+      tmem_ld_32x32b_x32(t_lane + (j & 1) * CBN + half * 32, v);
       tc_wait_ld();
       float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
       if (mw == 0xffffffffu) {
@@ -201,7 +214,7 @@ llama_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
 #pragma unroll
           for (int c = 0; c < 64; c += 32) {
             uint32_t o[32];
-            tmem_ld_32x32b_x32(t_lane + CBN + half * 64 + c, o);
+            tmem_ld_32x32b_x32(t_lane + 2 * CBN + half * 64 + c, o);
             tc_wait_ld();
             uint32_t lo[16], hi[16];
 #pragma unroll
@@ -209,8 +222,8 @@ llama_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
               lo[i] = __float_as_uint(__uint_as_float(o[i]) * corr);
               hi[i] = __float_as_uint(__uint_as_float(o[16 + i]) * corr);
             }
-            tmem_st_32x32b_x16(t_lane + CBN + half * 64 + c, lo);
-            tmem_st_32x32b_x16(t_lane + CBN + half * 64 + c + 16, hi);
+            tmem_st_32x32b_x16(t_lane + 2 * CBN + half * 64 + c, lo);
+            tmem_st_32x32b_x16(t_lane + 2 * CBN + half * 64 + c + 16, hi);
           }
           tc_wait_st();
         }
@@ -255,7 +268,7 @@ llama_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
 #pragma unroll
     for (int c = 0; c < 64; c += 32) {
       uint32_t o[32];
-      tmem_ld_32x32b_x32(t_lane + CBN + half * 64 + c, o);
+      tmem_ld_32x32b_x32(t_lane + 2 * CBN + half * 64 + c, o);
       tc_wait_ld();
       if (write) {
 #pragma unroll
