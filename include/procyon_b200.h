@@ -117,6 +117,9 @@ int pcy_set_gemm_cluster(int enabled);
    at least three waves of tiles, two or more row-blocks and N > 128; 2: whenever there are two row-blocks and N > 128
    (tests). Same chain of k-steps per output element as the one-CTA kernel: results are bit-identical (tests) */
 int pcy_set_gemm_pair_mma(int mode);
+/* tile width of the one-CTA tcgen05 GEMM: 0 (default) = heuristic over 128x256 / 128x192 / 128x128 by wave efficiency,
+   128 / 192 / 256 = that width whenever legal (tests, A/B) */
+int pcy_set_gemm_tile(int width);
 /* 1 (default): linears with 5..16 activation rows and no fused norm stream the weights through mma.sync (tensor
    cores); 0: the scalar-FMA weight-streaming kernel for every M <= 16 */
 int pcy_set_skinny_mma(int enabled);

@@ -41,6 +41,7 @@ void count_launch(int n = 1);
 extern bool g_fused_rope;
 extern bool g_gemm_cluster;
 extern int g_gemm_pair_mma;
+extern int g_gemm_force_tile;
 extern int g_esm_attention_kernel;
 extern bool g_esm_attention_q_rope;
 extern bool g_skinny_mma;

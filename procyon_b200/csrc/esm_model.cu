@@ -97,6 +97,10 @@ int pcy_set_fused_rope(int enabled) {
   return 0;
 }
 
+int pcy_set_gemm_tile(int width) {
+  pcy::g_gemm_force_tile = (width == 128 || width == 192 || width == 256) ? width : 0;
+  return 0;
+}
 int pcy_set_pdl(int enabled) {
   pcy::g_pdl = enabled != 0;
   return 0;

@@ -27,6 +27,7 @@
 
 namespace pcy {
 
+int g_gemm_force_tile = [] { const char* e = getenv("PCY_GEMM_FORCE_TILE"); return e ? atoi(e) : 0; }();
 bool g_gemm_cluster = false;  // pcy_set_gemm_cluster(1): 2-CTA clusters sharing the W tile by TMA multicast (measured: no gain)
 // pcy_set_gemm_pair_mma: 2-CTA clusters issuing cta_group::2 MMAs (M = 256 per pair).  0 = never, 1 = when the problem
 // has at least three waves of tiles (default), 2 = whenever there are two row-blocks (tests)
@@ -42,11 +43,12 @@ constexpr int NUM_THREADS = 64 + NUM_EPI_WARPS * 32;
 
 template <int BN, bool U2 = false>
 struct TileCfg {
-  static constexpr int STAGES = U2 ? ((BN == 256) ? 6 : 8) : ((BN == 256) ? 4 : 6);
+  static constexpr int STAGES = U2 ? ((BN == 256) ? 6 : 8) : ((BN >= 192) ? 4 : 6);
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = (U2 ? BN / 2 : BN) * BK * 2;  // U2: this CTA's half of the W tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int TMEM_COLS = 2 * BN;  // two accumulator buffers (256 or 512 columns: powers of two)
+  // two accumulator buffers at columns 0 and BN; the allocation must be a power of two (BN = 192: 384 -> 512)
+  static constexpr int TMEM_COLS = 2 * BN <= 256 ? 256 : 512;
   static constexpr int STAGING_BYTES = NUM_EPI_WARPS * 32 * 128;  // per warp: 32 rows x 64 bf16 columns
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
@@ -337,7 +339,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           }
           continue;
         }
-        if (fast_store && (c & 1) == 0 && col0 + 64 <= p.N) {
+        if (fast_store && (c & 1) == 0 && c + 1 < (chalf + 1) * C_PER && col0 + 64 <= p.N) {
           // ---- coalesced path: 64 columns (two chunks) of this warp's 32 rows go through a swizzled smem block so
           // that every global load / store instruction moves four full 128-byte row segments ----
           const uint32_t stg = staging_base + (uint32_t)(warp - 2) * (32 * 128);
@@ -670,11 +672,9 @@ int gemm_bf16_tc(const GemmArgs& a, cudaStream_t stream) {
     const double w128 = (double)tiles128 / (double)(ceil_div(tiles128, sms) * sms);
     if (w128 > w256 * 1.15) use128 = true;
   }
-  {
-    static const int force = [] { const char* e = getenv("PCY_GEMM_FORCE_TILE"); return e ? atoi(e) : 0; }();  // tuning
-    if (force == 128) use128 = true;
-    if (force == 256 && a.N > 128) use128 = false;
-  }
+  const int force = g_gemm_force_tile;  // pcy_set_gemm_tile: 0 = heuristic, 128 / 192 / 256 = that tile width (tests)
+  if (force == 128) use128 = true;
+  if ((force == 256 || force == 192) && a.N > 128) use128 = false;
   // two or more row-blocks: cluster pairs share the W tile — as one cta_group::2 MMA, or through TMA multicast
   // Measured on B200 (profiles/r01_gemm_shapes_pair.log): +5..12 % on the ESM2 shapes (M = 32 896) and on the Llama
   // gate/up GEMM, i.e. at or above cuBLAS, but -5 % on problems of one or two waves (Llama q/k/v/o at M = 1024), where
@@ -692,6 +692,19 @@ int gemm_bf16_tc(const GemmArgs& a, cudaStream_t stream) {
     return use128 ? launch<128, true, 1>(a, stream) : launch<256, true, 1>(a, stream);
   }
   if (pair) return use128 ? launch<128, false, 2>(a, stream) : launch<256, false, 2>(a, stream);
+  {
+    // 128x192 tiles when they fill the waves better than both other sizes (Llama q/k/v at M = 1024: N = 6144 is 192
+    // tiles of 128x256 = 1.3 waves, 384 of 128x128 = 2.6 waves, but 256 of 128x192 = 1.73 waves with 93 % of the wide
+    // tile's per-tile rate); relative per-tile rates measured on B200: 1.0 / 0.93 / 0.75
+    const int tiles192 = ceil_div(a.M, BM) * ceil_div(a.N, 192);
+    auto eff = [&](int tiles, double rate, int bn) {
+      const double waste = (double)a.N / ((double)ceil_div(a.N, bn) * bn);  // columns of the last tile past N
+      return (double)tiles / (double)(ceil_div(tiles, sms) * sms) * rate * waste;
+    };
+    const double e192 = eff(tiles192, 0.93, 192), e256 = eff(tiles256, 1.0, 256), e128 = eff(tiles128, 0.75, 128);
+    if (force == 192 || (force == 0 && a.N >= 192 && e192 > 1.08 * (use128 ? e128 : e256)))
+      return launch<192, false, 1>(a, stream);
+  }
   return use128 ? launch<128, false, 1>(a, stream) : launch<256, false, 1>(a, stream);
 }
 

@@ -216,3 +216,42 @@ def test_attention_parity(cuda_device, hd, H, KVH, Tq, Tk, causal, masked):
     got = o.float().cpu()
     rows_ok = ~mask.all(dim=-1).permute(0, 2, 1)  # fully masked query rows are undefined in the reference
     torch.testing.assert_close(got[rows_ok], ref[rows_ok], rtol=2e-2, atol=2e-2)
+
+
+@pytest.mark.parametrize("M,N,K", [(1024, 6144, 4096), (300, 1000, 200), (129, 192, 64), (514, 3840, 1280), (257, 520, 1288),
+                                   (1024, 4096, 512)])
+@pytest.mark.parametrize("epi", ["plain", "bias_gelu", "bias_res_scale", "swiglu"])
+def test_gemm_tile_widths_agree(cuda_device, M, N, K, epi):
+    """The one-CTA tcgen05 GEMM with 128x128, 128x192 and 128x256 tiles (`pcy_set_gemm_tile`): the same chain of k-steps
+    per output element, so bf16 / fp32 results must be bit-identical across tile widths, and right against fp32 torch.
+    (1024, 6144, 4096) is the Llama-3-8B q/k/v projection of a 1024-token prefill, where the heuristic picks 192.)"""
+    from procyon_b200 import _lib, ops
+
+    g = torch.Generator().manual_seed(M + 13 * N + 7 * K)
+    if epi == "swiglu":
+        N = (N // 32) * 32
+    a = (torch.randn(M, K, generator=g) * 0.5).bfloat16().cuda()
+    w = (torch.randn(N, K, generator=g) / math.sqrt(K)).bfloat16().cuda()
+    bias = torch.randn(N, generator=g).cuda() if epi in ("bias_gelu", "bias_res_scale") else None
+    res = torch.randn(M, N, generator=g).bfloat16().cuda() if epi == "bias_res_scale" else None
+    act = {"bias_gelu": 1, "swiglu": 2}.get(epi, 0)
+    sc = 64 if epi == "bias_res_scale" else 0
+    lib = _lib.load()
+    outs = {}
+    try:
+        lib.pcy_set_gemm_pair_mma(0)
+        for width in (256, 192, 128, 0):
+            lib.pcy_set_gemm_tile(width)
+            outs[width] = (ops.linear(a, w, bias, residual=res, act=act, scale=0.125, scale_ncols=sc, force="tc"),
+                           ops.linear(a, w, bias, residual=res, act=act, scale=0.125, scale_ncols=sc, force="tc",
+                                      out_fp32=True) if epi != "swiglu" else None)
+    finally:
+        lib.pcy_set_gemm_tile(0)
+        lib.pcy_set_gemm_pair_mma(1)
+    for width in (192, 128, 0):
+        assert torch.equal(outs[width][0], outs[256][0]), f"tile {width} differs from 256"
+        if outs[width][1] is not None:
+            assert torch.equal(outs[width][1], outs[256][1])
+    ref = _cpu_linear(a.cpu(), w.cpu(), bias.cpu() if bias is not None else None, res.cpu() if res is not None else None,
+                      act, 0.125, sc)
+    torch.testing.assert_close(outs[192][0].float().cpu(), ref, rtol=1e-2, atol=1e-2 * ref.abs().max().item())
