@@ -548,6 +548,11 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device — procyon_b200 has no CPU path (use --impl reference for the CPU port)")
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
+    # stdout carries exactly ONE line (the JSON): libraries that print there (NCCL's version banner at the first
+    # collective) are sent to stderr for the duration of the run
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     lib = _lib.load(build_if_missing=False)
@@ -697,7 +702,8 @@ def run_ours(args):
             "decode_beam10": beam, "e2e_beam10": beam_e2e, "cpu_baseline": cpu_base, "gpu_reference": gpu_ref,
             "vs_gpu_reference": vs_gpu_ref,
         }
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
