@@ -492,7 +492,8 @@ def time_beam_e2e(model, inputs, device, steps=2):
     signature, `method="beam"`, 10 beams in groups of 2, 128 tokens — including the (1, 10, 128, V) fp32 logits history
     returned on the HOST like the reference's (model_unified.py:773-781, 842)."""
     kw = dict(max_len=GEN_LEN, method="beam", beam_size=10, beam_group_size=2, truncate_on_eos=True)
-    out = model.generate(inputs, **kw)
+    for _ in range(2):  # (two calls: the page-locked logits buffers of consecutive results alternate)
+        out = model.generate(inputs, **kw)
     torch.cuda.synchronize(device)
     t0 = time.perf_counter()
     for _ in range(steps):
