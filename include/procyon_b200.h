@@ -220,6 +220,16 @@ typedef struct {
 /* Decode steps with up to `max_rows` rows (inputs x beams) run as ONE persistent kernel; default 2 (measured faster
    than the one-launch-per-op path there), supported up to 4, 0 selects the per-op path for every row count. */
 int pcy_set_decode_megakernel(int max_rows);
+/* Decode steps with more rows than that (beam search: rows = inputs x beam_size, the reference's evaluation default is
+   beam_size 10, procyon/evaluate/framework/procyon.py:71-76) also run as ONE persistent kernel - weight tiles of 16
+   rows x 256 k streamed by TMA into a shared-memory ring, mma.sync against up to 16 staged activation rows, stream-K
+   work split, attention over the union of the beams' keys (csrc/decode_rows_megakernel.cu).  1 (default) enables it,
+   0 selects the one-launch-per-op path (A/B measurements, tests).  Shapes it does not support (head_dim != 128,
+   H != 4 KVH, d_model or ffn_dim not a multiple of 256) always take the per-op path. */
+int pcy_set_decode_rows_megakernel(int enabled);
+/* profiling aid for that kernel: device uint64 buffer (zeroed, >= 64 + 40 * n_layers words) that receives %globaltimer
+   at every phase boundary of CTA 0 (NULL disables) */
+int pcy_set_decode_rows_timing_buffer(void* dev_u64);
 /* profiling aid: device uint64 buffer of >= 4096 words (zeroed) that receives %globaltimer at every phase boundary of
  * the persistent decode kernel: 24 stamps per layer + 4, written by CTA 0 (NULL disables).  If word 4095 holds the tag
  * 0x534B4557 the buffer must have 4096 + (4 L + 1) * n_sms * 2 words, and every CTA also records (time, SM id) when it

@@ -10,6 +10,7 @@
 //            as a CUDA graph.
 // Semantics: HF transformers 4.31 LlamaForCausalLM as wrapped by LlamaPostTokenization.forward
 // (procyon/model/pmc_llama.py:546-596, :287-406): positions arange(past, past+S), fp32 softmax, RMSNorm in fp32.
+#include <algorithm>
 #include <cstdlib>
 #include <vector>
 
@@ -30,6 +31,7 @@ struct LlamaModel {
   float* rope = nullptr;
   int rope_pos = 0;
   LlamaLayerPtrs* layers_dev = nullptr;
+  void* rows_maps = nullptr;  // device array of tensor maps for the 3..16-row persistent decode kernel (or null)
   int qkv_dim() const { return (cfg.n_heads + 2 * cfg.n_kv_heads) * cfg.head_dim; }
   int kv_dim() const { return cfg.n_kv_heads * cfg.head_dim; }
 };
@@ -91,6 +93,15 @@ using namespace pcy;
 // B200 (scripts/bench_decode_rows.py) it wins only up to 2 rows: 3.1 / 4.6 ms against 6.1 / 6.5 ms at 3 / 4 rows, where
 // the one-launch-per-op path with the tensor-core GEMV and the shared-prompt attention takes 5.3 ms.
 static int g_megakernel_max_rows = 2;
+// 3..16 rows (beam search): the tile-streaming persistent kernel of decode_rows_megakernel.cu (1), or the
+// one-launch-per-op path (0: A/B measurements, tests)
+static int g_rows_megakernel = 1;
+static bool use_rows_megakernel(const LlamaModel* m, int rows, int beams) {
+  static const bool force_multi = getenv("PCY_DECODE_MULTIKERNEL") != nullptr;
+  // (pcy_set_decode_megakernel(0) selects the per-op path for EVERY row count, as documented)
+  return !force_multi && g_rows_megakernel != 0 && g_megakernel_max_rows > 0 && rows > g_megakernel_max_rows &&
+         m->rows_maps != nullptr && decode_rows_megakernel_supported(m->cfg, rows, beams);
+}
 
 extern "C" {
 
@@ -100,6 +111,16 @@ int pcy_set_decode_timing_buffer(void* dev_u64) {
 }
 
 int pcy_set_decode_sm_shares(const float* shares, int n) { return decode_megakernel_set_shares(shares, n); }
+
+int pcy_set_decode_rows_megakernel(int enabled) {
+  g_rows_megakernel = enabled != 0;
+  return 0;
+}
+
+int pcy_set_decode_rows_timing_buffer(void* dev_u64) {
+  decode_rows_megakernel_set_timing(reinterpret_cast<unsigned long long*>(dev_u64));
+  return 0;
+}
 
 int pcy_set_decode_megakernel(int max_rows) {
   g_megakernel_max_rows = max_rows < 0 ? 0 : (max_rows > 4 ? 4 : max_rows);
@@ -144,6 +165,10 @@ int pcy_llama_create(const pcy_llama_config* cfg, void** handle) {
     m->slabs.push_back(p);
     PCY_CUDA(cudaMemcpy(p, host.data(), sizeof(LlamaLayerPtrs) * cfg->n_layers, cudaMemcpyHostToDevice));
     m->layers_dev = reinterpret_cast<LlamaLayerPtrs*>(p);
+    // tensor maps of the weights for the 3..16-row persistent decode kernel (they hold addresses and shapes only);
+    // a failure just leaves that kernel unavailable
+    if (decode_rows_build_maps(*cfg, host.data(), m->lm_head, &m->rows_maps) == 0) m->slabs.push_back(m->rows_maps);
+    else m->rows_maps = nullptr;
   }
   *handle = m;
   return 0;
@@ -342,6 +367,14 @@ int64_t pcy_llama_decode_workspace_bytes(void* handle, int rows, int S, int max_
   b += round_up((int64_t)rows * m->cfg.n_kv_heads * 4, 256);
   b += round_up((int64_t)topk_workspace_floats(rows) * 4, 256);
   if (decode_megakernel_supported(m->cfg, rows)) b += decode_megakernel_scratch_bytes(m->cfg, rows, S, max_gen) + 256;
+  // (the beam count is not known here: size for the worst case over the divisors of rows)
+  if (m->rows_maps != nullptr) {
+    int64_t extra = 0;
+    for (int beams = 1; beams <= rows; ++beams)
+      if (rows % beams == 0 && decode_rows_megakernel_supported(m->cfg, rows, beams))
+        extra = std::max(extra, decode_rows_megakernel_scratch_bytes(m->cfg, rows, beams, S, max_gen));
+    b += extra + 256;
+  }
   return b + 4096;
 }
 
@@ -371,6 +404,10 @@ int pcy_llama_decode_forward(void* handle, const pcy_decode_buffers* b, void* st
   if (!force_multi && rows <= g_megakernel_max_rows && decode_megakernel_supported(c, rows)) {
     // persistent single-launch step: see decode_megakernel.cu
     return decode_megakernel(c, m->layers_dev, m->embed, m->lm_head, m->norm, m->rope, b, p, stream);
+  }
+  if (use_rows_megakernel(m, rows, b->beams)) {
+    if (decode_megakernel_supported(c, rows)) p += round_up(decode_megakernel_scratch_bytes(c, rows, b->S, b->max_gen) + 256, 256);
+    return decode_rows_megakernel(c, m->layers_dev, m->rows_maps, m->embed, m->norm, m->rope, b, p, stream);
   }
 
   PCY_CUDA(launch_pdl(embed_last_token_kernel, dim3(rows), dim3(128), 0, stream, (const int32_t*)b->tokens,

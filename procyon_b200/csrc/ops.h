@@ -148,6 +148,16 @@ int decode_megakernel(const pcy_llama_config& c, const LlamaLayerPtrs* layers_de
                       const bf16* lm_head, const bf16* norm, const float* rope, const pcy_decode_buffers* b,
                       void* scratch, cudaStream_t stream);
 
+// ---- persistent decode-step kernel for 3..16 rows (beam search), decode_rows_megakernel.cu ------------------------
+void decode_rows_megakernel_set_timing(unsigned long long* dev_buf);
+int decode_rows_build_maps(const pcy_llama_config& c, const LlamaLayerPtrs* layers_host, const bf16* lm_head,
+                           void** maps_dev);
+bool decode_rows_megakernel_supported(const pcy_llama_config& c, int rows, int beams);
+int64_t decode_rows_megakernel_scratch_bytes(const pcy_llama_config& c, int rows, int beams, int S, int max_gen);
+int decode_rows_megakernel(const pcy_llama_config& c, const LlamaLayerPtrs* layers_dev, const void* maps_dev,
+                           const bf16* embed, const bf16* norm, const float* rope, const pcy_decode_buffers* b,
+                           void* scratch, cudaStream_t stream);
+
 // ---- losses / scoring -----------------------------------------------------------------------------------
 int cross_entropy_rows(const float* logits, const int32_t* labels, int rows, int V, int64_t ld, float* acc,
                        cudaStream_t stream);

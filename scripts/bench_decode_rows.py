@@ -25,8 +25,10 @@ def main():
         from procyon_b200 import _lib
 
         lib = _lib.load()
-        for pdl in ((1, 0) if beams > 2 else (1,)):  # (rows <= 2: persistent kernel, no launch chain)
+        # rows <= 2: the greedy persistent kernel; more rows: the persistent beam kernel, then the per-op chain
+        for rows_kernel, pdl in (((1, 1), (0, 1)) if beams > 2 else ((1, 1),)):
             lib.pcy_set_pdl(pdl)
+            lib.pcy_set_decode_rows_megakernel(rows_kernel)
             sess.reset(logits)
             sess.select(mode, group, 0.8, -1, False)
             sess._graph = None
@@ -42,10 +44,12 @@ def main():
             b.record()
             torch.cuda.synchronize()
             ms = a.elapsed_time(b) / n
-            print(json.dumps({"beams": beams, "programmatic_dependent_launch": bool(pdl), "ms_per_step": ms,
+            print(json.dumps({"beams": beams, "persistent_kernel": bool(rows_kernel) or beams <= 2,
+                              "programmatic_dependent_launch": bool(pdl), "ms_per_step": ms,
                               "tokens_per_s_aggregate": beams / ms * 1e3, "weights_gb_per_s": 15.01 / ms * 1e3}),
                   flush=True)
         lib.pcy_set_pdl(1)
+        lib.pcy_set_decode_rows_megakernel(1)
 
 
 if __name__ == "__main__":

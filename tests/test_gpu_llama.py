@@ -289,16 +289,22 @@ def test_beam_search_shared_prompt_attention(cuda_device, n, beams, S, pad):
     group = max(1, beams // 2) if beams % 2 == 0 else beams
     sess.select(SELECT_BEAM, group, 0.8, -5, False)
     try:
+        lib.pcy_set_decode_rows_megakernel(0)  # this part compares the two one-launch-per-op variants
         lib.pcy_set_skinny_mma(1)
         sess.forward()
         la = sess.logits_cur.clone()
         lib.pcy_set_skinny_mma(0)
         sess.forward()
         lb = sess.logits_cur.clone()
+        lib.pcy_set_decode_rows_megakernel(1)  # ... and the persistent beam kernel on the same state against both
+        sess.forward()
+        lc = sess.logits_cur.clone()
     finally:
         lib.pcy_set_skinny_mma(1)
-    assert torch.isfinite(la).all()
+        lib.pcy_set_decode_rows_megakernel(1)
+    assert torch.isfinite(la).all() and torch.isfinite(lc).all()
     torch.testing.assert_close(la, lb, rtol=3e-2, atol=4e-2)
+    torch.testing.assert_close(lc, la, rtol=3e-2, atol=4e-2)
     # ---- whole generations ----
     kw = dict(max_len=5, beam_size=beams, beam_group_size=group, diversity_penalty=0.8, eos_token_id=-5)
     o1, lp1, lg1 = generate_beam_search(m, emb.cuda(), am, **kw)
@@ -385,12 +391,15 @@ def test_programmatic_dependent_launch_changes_nothing(cuda_device, rows):
         i1, e1, m1 = _inputs(oc, sd, 1, 150, seed=rows)
         kw = dict(max_len=12, beam_size=rows, beam_group_size=rows // 2, diversity_penalty=0.8, eos_token_id=-5)
         try:
+            lib.pcy_set_decode_rows_megakernel(0)  # the per-op chain is what the attribute applies to
             lib.pcy_set_pdl(1)
             o1, lp1, lg1 = generate_beam_search(m, e1.cuda(), None, **kw)   # CUDA-graph replays
             lib.pcy_set_pdl(0)
+            m.__dict__.pop("_sessions", None)  # (the cached session holds the step graph captured with the attribute)
             o2, lp2, lg2 = generate_beam_search(m, e1.cuda(), None, **kw)
         finally:
             lib.pcy_set_pdl(1)
+            lib.pcy_set_decode_rows_megakernel(1)
         assert torch.equal(o1, o2) and torch.equal(lp1, lp2) and torch.equal(lg1, lg2)
 
 
