@@ -1,9 +1,10 @@
 // One persistent kernel per Llama decode step for 3..16 rows (inputs x beams): the beam-search path, which is what
 // every shipped caller of the reference runs (procyon/evaluate/framework/procyon.py:71-76, beam_size = 2 x captions).
 //
-// Same skeleton as decode_megakernel.cu (one CTA per SM, a producer warp that streams the CTA's share of all 4 L + 1
-// weight matrices through a shared-memory ring ahead of the grid barriers, phases separated by grid-wide barriers),
-// but built for up to 16 activation rows:
+// Same skeleton as decode_megakernel.cu (one CTA per SM, the CTA's share of all 4 L + 1 weight matrices streamed through
+// a shared-memory ring that runs ahead of the grid barriers, phases separated by grid-wide barriers), but built for
+// up to 16 activation rows and without a producer warp (8 warps = 255 registers per thread; each warp refills the
+// ring slots it owns right after it has drained them):
 //   * a ring slot is a TILE of 16 weight rows x 256 k (4 TMA boxes of 16 x 64, 128-byte swizzle), so that one
 //     ldmatrix.x4 of weights (A) and one of activations (B) feed two real mma.sync.m16n8k16 (16 weight rows x 16 rows);
 //   * work is cut stream-K style: the chunk sequence (k-part, row group, k-chunk) of a matrix is split evenly over the
@@ -36,7 +37,7 @@ namespace {
 
 constexpr int RW = 8;             // consumer warps
 constexpr int RT = RW * 32;       // consumer threads
-constexpr int RBLOCK = RT + 32;   // + one producer warp (warp 8)
+constexpr int RBLOCK = RT;        // no producer warp: every warp refills its own ring slots (255 registers per thread)
 constexpr int TR = 16;            // weight rows per tile
 constexpr int TK = 256;           // k per tile
 constexpr int SLOT_BYTES = TR * TK * 2;
@@ -52,7 +53,7 @@ constexpr int KV_ISSUERS = 2 * SUBK;  // threads that fetch K / V rows of an ite
 // misc block of shared memory: [0, 96) row group of every pool tile | [128, 192) tokens | [256, ...) mbarriers (full /
 // empty per ring slot + one for the attention tiles) | [MISC_LN, ...) two RMSNorm weight pointers per layer
 constexpr int MAX_SLOTS = 40;
-constexpr int MISC_TOK = 128, MISC_BARS = 256, MISC_LN = MISC_BARS + 8 * (2 * MAX_SLOTS + 1) + 8;
+constexpr int MISC_TOK = 128, MISC_BARS = 256, MISC_LN = MISC_BARS + 8 * (MAX_SLOTS + 1) + 8;
 
 enum : int { EPI_BF16 = 0, EPI_RESIDUAL = 1, EPI_SWIGLU = 2, EPI_FP32 = 3 };
 enum : int { STAGE_PLAIN = 0, STAGE_RMS = 1 };
@@ -168,16 +169,6 @@ __host__ __device__ inline int range_lo(int T, int i, int nb) {
   return (int)((unsigned int)T * (unsigned int)i / (unsigned int)nb);
 }
 
-struct RingGeom {
-  int ns;
-  uint32_t magic;  // ceil(2^32 / ns)
-  __device__ __forceinline__ void locate(uint32_t g, uint32_t& slot, uint32_t& par) const {
-    const uint32_t q = __umulhi(g, magic);
-    slot = g - q * (uint32_t)ns;
-    par = q & 1u;
-  }
-};
-
 struct RowsParams {
   pcy_llama_config cfg;
   const bf16* embed;
@@ -200,13 +191,12 @@ struct RowsParams {
   unsigned int* tickets;  // [max output groups], zero between phases
   unsigned int* barrier;
   int ring_slots;
-  uint32_t ring_magic;
   int kcap;      // activation columns the staging area holds per row (multiple of 256)
   int maxcp;     // piece slots per segment in `pieces`
-  int window;    // weight tiles in flight per SM (multiple of 8, < ring slots) or 0 = as many as the ring holds
   int off_pool;  // byte offsets inside the work area (after ring + barrier block)
   int off_misc;
   unsigned long long* timing;
+  int timing_cta;
 };
 
 struct PhaseDesc {
@@ -253,96 +243,108 @@ __device__ __forceinline__ PhaseDesc phase_desc(const RowsParams& p, const bf16*
   return z;
 }
 
-// ---- producer: every weight tile of this CTA, in phase order --------------------------------------------------------
-// Ring position g0 + 8 j + w belongs to consumer warp w (slot = position mod ns, ns a multiple of 8: one consumer per
-// mbarrier).  Within a run (the CTA's chunks of one k-part) warp w owns a contiguous span of the chunks; round j
-// carries the j-th chunk of every span, lane w of the producer warp issues for warp w.  Spans differ by at most one
-// chunk: the missing entries of the last round are completed without data so that positions stay aligned.
-__device__ __forceinline__ void produce_all(const RowsParams& p, uint32_t ring, uint32_t bars, RingGeom rg) {
-  const int lane = threadIdx.x & 31;
+// ---- the weight tiles of one warp, in consumption order ----------------------------------------------------------------
+// There is no producer warp (a ninth warp would cap every thread at 168 registers): each warp owns ring_slots / 8 slots
+// of the ring and refills a slot itself, right after it has consumed it, with the tile it will need ring-depth tiles
+// later - whatever phase that tile belongs to, so weights keep streaming across grid barriers, staging and attention.
+// The cursor walks the warp's tiles: phases -> runs (the CTA's chunks of one k-part) -> the warp's span of the run.
+__device__ __forceinline__ void phase_shape(const RowsParams& p, int ph, int& N, int& K) {
   const pcy_llama_config& c = p.cfg;
-  const int d = c.d_model, f = c.ffn_dim, H = c.n_heads, KVH = c.n_kv_heads;
-  const int nb = gridDim.x, bid = blockIdx.x;
-  const uint64_t pol = l2_evict_first_policy();
   const int n_phases = 4 * c.n_layers + 1;
-  uint32_t g0 = 0;
-  for (int ph = 0; ph < n_phases; ++ph) {
+  if (ph == n_phases - 1) { N = c.vocab; K = c.d_model; }
+  else if ((ph & 3) == 0) { N = (c.n_heads + 2 * c.n_kv_heads) * HD; K = c.d_model; }
+  else if ((ph & 3) == 1) { N = c.d_model; K = c.n_heads * HD; }
+  else if ((ph & 3) == 2) { N = 2 * c.ffn_dim; K = c.d_model; }
+  else { N = c.d_model; K = c.ffn_dim; }
+}
+
+struct Cursor {
+  int ph;              // phase of the next tile (n_phases = exhausted)
+  int hi, b;           // end of the CTA's range in the phase, end of the current run
+  int c, c_hi;         // next chunk / end of this warp's span in the run
+  int q, len, qbase;   // run constants: k-part, chunks per (row group, part), first chunk of the part
+  int ckq;
+  int n_rg, ck, KQ, per, T;
+
+  __device__ __forceinline__ void begin_run(int a, int warp) {
+    q = min(a / per, KQ - 1);
+    b = min(hi, q == KQ - 1 ? T : (q + 1) * per);
+    len = q == KQ - 1 ? ck - q * ckq : ckq;
+    qbase = q * per;
+    const int C = b - a;
+    c = a + C * warp / RW;
+    c_hi = a + C * (warp + 1) / RW;
+  }
+  __device__ __forceinline__ void begin_phase(const RowsParams& p, int warp) {
     int N, K;
-    if (ph == n_phases - 1) { N = c.vocab; K = d; }
-    else if ((ph & 3) == 0) { N = (H + 2 * KVH) * HD; K = d; }
-    else if ((ph & 3) == 1) { N = d; K = H * HD; }
-    else if ((ph & 3) == 2) { N = 2 * f; K = d; }
-    else { N = d; K = f; }
+    phase_shape(p, ph, N, K);
     const Geom g = make_geom(N, K, p.kcap);
-    const CUtensorMap* map = p.maps + ph;
-    const int lo = range_lo(g.T, bid, nb), hi = range_lo(g.T, bid + 1, nb);
-    for (int a = lo; a < hi;) {
-      const int q = min(a / g.per, g.KQ - 1);
-      const int b = min(hi, q == g.KQ - 1 ? g.T : (q + 1) * g.per);
-      const int len = part_len(g, q), qbase = q * g.per;
-      const int C = b - a, L = (C + RW - 1) / RW;
-      const int w = lane & (RW - 1);
-      const int w_lo = a + C * w / RW, w_hi = a + C * (w + 1) / RW;
-      for (int j = 0; j < L; ++j) {
-        uint32_t slot, par;
-        const uint32_t pos = g0 + (uint32_t)(j * RW + w);
-        rg.locate(pos, slot, par);
-        if (lane < RW) {
-          if (p.window > 0 && pos >= (uint32_t)p.window) {
-            // bound the copies in flight: the lane's chunk `window` positions back must have landed (same slot
-            // class; window < ring slots, so that slot cannot have been re-armed since)
-            uint32_t wslot, wpar;
-            rg.locate(pos - (uint32_t)p.window, wslot, wpar);
-            mbar_wait(bars + 8u * wslot, wpar);
-          }
-          uint64_t t0 = 0;
-          for (uint32_t it = 0; !mbar_try_wait(bars + 8u * (rg.ns + slot), par ^ 1u); ++it) {  // slot drained
-            if ((it & 0xfffu) == 0xfffu) {
-              const uint64_t now = globaltimer_ns();
-              if (t0 == 0) t0 = now;
-              else if (now - t0 > 4000000000ull) __trap();
-            }
-          }
-          const int cc = w_lo + j;
-          if (cc < w_hi) {
-            const int rem = cc - qbase;
-            const int rgi = rem / len, kc = q * g.ckq + (rem - rgi * len);
-            mbar_arrive_expect_tx(bars + 8u * slot, SLOT_BYTES);
-            const uint32_t dst = ring + slot * SLOT_BYTES;
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-              tma_load_2d_hint(dst + i * 2048, map, bars + 8u * slot, kc * TK + i * 64, rgi * TR, pol);
-          } else {
-            mbar_arrive(bars + 8u * slot);  // empty entry: completes the phase of the slot without data
-          }
-        }
-        __syncwarp();
+    n_rg = g.n_rg; ck = g.ck; KQ = g.KQ; ckq = g.ckq; per = g.per; T = g.T;
+    const int lo = range_lo(T, blockIdx.x, gridDim.x);
+    hi = range_lo(T, blockIdx.x + 1, gridDim.x);
+    b = lo;
+    c = c_hi = 0;
+  }
+  // the next tile: tensor map index, first weight row, first k element; false when every phase is exhausted
+  __device__ __forceinline__ bool next(const RowsParams& p, int warp, int n_phases, int& map, int& row0, int& k0) {
+    while (true) {
+      if (ph >= n_phases) return false;
+      if (c < c_hi) {
+        const int rem = c - qbase;
+        const int rgi = rem / len;
+        map = ph;
+        row0 = rgi * TR;
+        k0 = (q * ckq + (rem - rgi * len)) * TK;
+        ++c;
+        return true;
       }
-      g0 += (uint32_t)(L * RW);
-      a = b;
+      if (b < hi) {
+        begin_run(b, warp);
+      } else {
+        ++ph;
+        if (ph < n_phases) begin_phase(p, warp);
+      }
     }
   }
-}
+};
 
 // ---- consumer side ---------------------------------------------------------------------------------------------------
 struct Ctx {
-  uint32_t ring, bars;
-  RingGeom rg;
-  uint32_t chunk0;     // ring positions consumed so far
+  uint32_t ring, bars;  // this WARP's slots: slot i at ring + i * SLOT_BYTES, its mbarrier at bars + 8 i
+  int depth;            // slots per warp
+  uint32_t n_used;      // tiles consumed so far by this warp (tile e lives in slot e % depth, parity (e / depth) & 1)
+  Cursor fill;          // the next tile to request
+  int n_phases;
   uint32_t act;        // staged activations: row m at act + m * pitch
   uint32_t pitch;      // kcap * 2 + 16 bytes
   float* pool;         // [RW * PW][16][rs] partial tiles
   int rs;              // activation rows rounded up to an even number: columns of a partial tile
   int* prg;            // [RW * PW] row group of every pool tile (-1 = free)
   unsigned long long* tbuf;
-  int tix;
+  int tix, tcta;
   __device__ __forceinline__ void stamp() {
     if (tbuf != nullptr) {
-      if (blockIdx.x == 0 && threadIdx.x == 0) tbuf[tix] = globaltimer_ns();
+      if (blockIdx.x == tcta && threadIdx.x == 0) tbuf[tix] = globaltimer_ns();
       ++tix;
     }
   }
 };
+
+// Request the warp's next tile into ring slot `slot` (just drained by this warp, or still untouched).
+__device__ __forceinline__ void refill(const RowsParams& p, Ctx& cx, uint32_t slot) {
+  int map, row0, k0;
+  const int warp = threadIdx.x >> 5;
+  if (!cx.fill.next(p, warp, cx.n_phases, map, row0, k0)) return;
+  if ((threadIdx.x & 31) == 0) {
+    fence_proxy_async_smem();  // the warp's ldmatrix reads of the slot are ordered before the bulk write
+    const uint32_t bar = cx.bars + 8u * slot;
+    mbar_arrive_expect_tx(bar, SLOT_BYTES);
+    const uint32_t dst = cx.ring + slot * SLOT_BYTES;
+    const uint64_t pol = l2_evict_first_policy();  // weights are read once per step: keep L2 for KV / activations
+#pragma unroll
+    for (int i = 0; i < 4; ++i) tma_load_2d_hint(dst + i * 2048, p.maps + map, bar, k0 + i * 64, row0, pol);
+  }
+}
 
 // one tile (16 weight rows x 256 k) against the staged activations: 16 k-steps of ldmatrix(A) + ldmatrix(B) + NT mma
 template <int NT>
@@ -477,9 +479,12 @@ __device__ __forceinline__ void weight_phase(const RowsParams& p, Ctx& cx, const
                   uint32_t oo[4];
 #pragma unroll
                   for (int e = 0; e < 4; ++e) {
+                    // two elements at a time: bf16(x * rstd) by one packed conversion, times the weight by one
+                    // packed bf16 multiply (the product of two bf16 is exact in fp32, so rounding it once is what
+                    // the fp32 form w * bf16_round(x * rstd) -> bf16 gives)
                     const float2 xv = unpack_bf16x2(uu[e]);
-                    const float2 wv = unpack_bf16x2(gg[e]);
-                    oo[e] = pack_bf16x2(wv.x * bf16_round(xv.x * rstd), wv.y * bf16_round(xv.y * rstd));
+                    const uint32_t t = pack_bf16x2(xv.x * rstd, xv.y * rstd);
+                    asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(oo[e]) : "r"(gg[e]), "r"(t));
                   }
                   sts_v4(cx.act + m * cx.pitch + (h == 0 ? pc0 : pc1) * 16, make_uint4(oo[0], oo[1], oo[2], oo[3]));
                 }
@@ -493,7 +498,7 @@ __device__ __forceinline__ void weight_phase(const RowsParams& p, Ctx& cx, const
     cx.stamp();
 
     // ---- consume the ring: this warp's span of the run ----
-    const int C = b - a, L = (C + RW - 1) / RW;
+    const int C = b - a;
     const int w_lo = a + C * warp / RW, w_hi = a + C * (warp + 1) / RW;
     int np = 0, cur_rg = -1, cnt = 0;
     float acc[NT][4];
@@ -532,29 +537,25 @@ __device__ __forceinline__ void weight_phase(const RowsParams& p, Ctx& cx, const
       }
     };
 
-    for (int j = 0; j < L; ++j) {
-      uint32_t slot, par;
-      cx.rg.locate(cx.chunk0 + (uint32_t)(j * RW + warp), slot, par);
-      mbar_wait(cx.bars + 8u * slot, par);
-      const int cc = w_lo + j;
-      if (cc < w_hi) {
-        const int rem = cc - qbase;
-        const int rgi = rem / len, kl = rem - rgi * len;
-        if (rgi != cur_rg) {
-          if (cur_rg >= 0) flush();
-          cur_rg = rgi;
-          cnt = 0;
+    for (int cc = w_lo; cc < w_hi; ++cc) {
+      const uint32_t e = cx.n_used++;
+      const uint32_t lap = e / (uint32_t)cx.depth, slot = e - lap * (uint32_t)cx.depth;
+      mbar_wait(cx.bars + 8u * slot, lap & 1u);
+      const int rem = cc - qbase;
+      const int rgi = rem / len, kl = rem - rgi * len;
+      if (rgi != cur_rg) {
+        if (cur_rg >= 0) flush();
+        cur_rg = rgi;
+        cnt = 0;
 #pragma unroll
-          for (int nt = 0; nt < NT; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
-        }
-        mma_tile<NT>(cx.ring + slot * SLOT_BYTES, a_lane0 + kl * (TK * 2), acc);
-        ++cnt;
+        for (int nt = 0; nt < NT; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
       }
+      mma_tile<NT>(cx.ring + slot * SLOT_BYTES, a_lane0 + kl * (TK * 2), acc);
+      ++cnt;
       __syncwarp();
-      if (lane == 0) mbar_arrive(cx.bars + 8u * (cx.rg.ns + slot));  // slot free
+      refill(p, cx, slot);  // the slot is free: request the tile this warp needs `depth` tiles from now
     }
     if (cur_rg >= 0) flush();
-    cx.chunk0 += (uint32_t)(L * RW);
     consumer_sync();
     cx.stamp();
 
@@ -881,8 +882,10 @@ __device__ __forceinline__ void attention_phase(const RowsParams& p, Ctx& cx, Gr
     }
     if (tid < SUBK) s.kbits[tid] = bits;
     consumer_sync();
+    if (item == it_lo) cx.stamp();
     mbar_wait(kvbar, kv_par);
     kv_par ^= 1u;
+    if (item == it_lo) cx.stamp();
 
     // ---- S = Q K^T: warp w owns keys 8 w .. 8 w + 7 ----
     float sc[4][4];
@@ -947,6 +950,7 @@ __device__ __forceinline__ void attention_phase(const RowsParams& p, Ctx& cx, Gr
       }
     }
     consumer_sync();
+    if (item == it_lo) cx.stamp();
     // ---- O = P V: warp w owns output dims 16 w .. 16 w + 15 ----
     float oc[4][2][4];
 #pragma unroll
@@ -998,6 +1002,7 @@ __device__ __forceinline__ void attention_phase(const RowsParams& p, Ctx& cx, Gr
       part[HD + 1] = sm;
     }
   }
+  if (it_lo >= it_hi) { cx.stamp(); cx.stamp(); cx.stamp(); }  // (same number of stamps with and without items)
   cx.stamp();
   bar.sync();  // every partial of the layer is in L2
   cx.stamp();
@@ -1073,29 +1078,32 @@ llama_decode_rows_megakernel(const RowsParams p) {
   uint8_t* work = base + (size_t)ns * SLOT_BYTES;
   uint8_t* misc = work + p.off_misc;
   const uint32_t bars = smem_u32(misc + MISC_BARS);
-  const uint32_t kvbar = bars + 8u * (2 * ns);
+  const uint32_t kvbar = bars + 8u * ns;
   // RMSNorm weight pointers of every layer, copied once so that no phase starts with a dependent global load
   const bf16** s_ln = reinterpret_cast<const bf16**>(misc + MISC_LN);
   for (int i = threadIdx.x; i < 2 * c.n_layers; i += RBLOCK)
     s_ln[i] = (i & 1) ? p.layers[i >> 1].ln2 : p.layers[i >> 1].ln1;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < ns; ++i) {
-      mbar_init(bars + 8u * i, 1);         // full: the producer's arrive(.expect_tx) (+ the copies' bytes)
-      mbar_init(bars + 8u * (ns + i), 1);  // empty: lane 0 of the consuming warp
-    }
+    for (int i = 0; i < ns; ++i) mbar_init(bars + 8u * i, 1);  // one arrive.expect_tx by the refilling warp + the bytes
     mbar_init(kvbar, KV_ISSUERS);
     fence_barrier_init();
   }
-  __syncthreads();  // the only CTA-wide barrier: after it the producer warp goes its own way
-
-  if (threadIdx.x >= RT) {
-    produce_all(p, ring, bars, RingGeom{ns, p.ring_magic});
-    return;
-  }
+  __syncthreads();
 
   const int tid = threadIdx.x;
+  const int n_phases = 4 * c.n_layers + 1;
   Ctx cx;
-  cx.ring = ring; cx.bars = bars; cx.rg = RingGeom{ns, p.ring_magic}; cx.chunk0 = 0;
+  {
+    const int warp = tid >> 5;
+    cx.depth = ns / RW;
+    cx.ring = ring + (uint32_t)(warp * cx.depth) * SLOT_BYTES;
+    cx.bars = bars + 8u * (uint32_t)(warp * cx.depth);
+    cx.n_used = 0;
+    cx.n_phases = n_phases;
+    cx.fill.ph = 0;
+    cx.fill.begin_phase(p, warp);
+    for (int i = 0; i < cx.depth; ++i) refill(p, cx, (uint32_t)i);  // the warp's first tiles
+  }
   cx.act = smem_u32(work);
   cx.pitch = (uint32_t)p.kcap * 2u + 16u;
   cx.pool = reinterpret_cast<float*>(work + p.off_pool);
@@ -1103,6 +1111,7 @@ llama_decode_rows_megakernel(const RowsParams p) {
   cx.prg = reinterpret_cast<int*>(misc);
   cx.tbuf = p.timing;
   cx.tix = 0;
+  cx.tcta = p.timing_cta;
   AttLayout al;
   {
     const int QR = (p.beams * GQ + 15) & ~15;
@@ -1135,7 +1144,6 @@ llama_decode_rows_megakernel(const RowsParams p) {
     }
   }
 
-  const int n_phases = 4 * c.n_layers + 1;
   for (int ph = 0; ph < n_phases; ++ph) {
     const int kind = ph == n_phases - 1 ? 4 : (ph & 3);
     const PhaseDesc z = phase_desc(p, s_ln, ph);
@@ -1356,15 +1364,13 @@ int decode_rows_megakernel(const pcy_llama_config& c, const LlamaLayerPtrs* laye
   p.part = reinterpret_cast<float*>(carve((int64_t)rows * c.n_kv_heads * p.max_splits * GQ * PSTR * 4));
   p.pieces = reinterpret_cast<float*>(s);
   p.ring_slots = pl.ring_slots;
-  p.ring_magic = (uint32_t)(((1ull << 32) + pl.ring_slots - 1) / pl.ring_slots);
   p.kcap = pl.kcap; p.maxcp = pl.maxcp; p.off_pool = pl.off_pool; p.off_misc = pl.off_misc;
   p.timing = g_rows_timing;
-  static const int window_env = [] {
-    const char* e = getenv("PCY_ROWS_WINDOW");  // tuning knob: weight tiles (8 KB) in flight per SM
+  static const int timing_cta = [] {
+    const char* e = getenv("PCY_ROWS_TIMING_CTA");  // which CTA writes the profiling stamps (default 0)
     return e ? atoi(e) : 0;
   }();
-  p.window = window_env / RW * RW;
-  if (p.window >= pl.ring_slots) p.window = 0;
+  p.timing_cta = std::min(std::max(timing_cta, 0), num_sms() - 1);
   PCY_CUDA(cudaMemsetAsync(p.barrier, 0, 512, stream));  // grid barrier counter (tickets reset themselves)
   void* fn = pl.nt == 1 ? (void*)llama_decode_rows_megakernel<1> : (void*)llama_decode_rows_megakernel<2>;
   static SmemOptIn opt[2];

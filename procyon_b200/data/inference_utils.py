@@ -231,3 +231,146 @@ def merge_model_input_dicts(dict_list):
             mega["input"][k] += [[val + shift for val in v[0]]]
         mega["instructions"] += d["instructions"]
     return mega
+
+
+# ---- retrieval query builders (procyon/data/inference_utils.py:663-925) ---------------------------------------------
+# Host code: strings and index lists only.  Files are the reference's own: the task descriptions under
+# `$HOME_DIR/procyon/data/instruct_tune/tasks/<task_id>.json` and the text tables under
+# `$DATA_DIR/integrated_data/v1/<dataset>/<dataset>_info_filtered_composed.pkl`; both roots can also be passed in.
+
+# text columns a retrieval query may be drawn from, per `DataArgs.retrieval_subset_version` (the column names are the
+# contract with the reference's data files, procyon/data/constants.py:241-330); versions 2 and 5 differ from 1 only in
+# the entries listed
+_RETRIEVAL_COLUMNS_V1 = {
+    "go": ["description_name_type_def"],
+    "pfam": ["description_pfam", "description_interpro"],
+    "disgenet": ["description_" + s for s in ("air aot chv csp fma go hl7v3.0 hpo lnc mcm medlineplus msh nci pdq spn uwda "
+                                              "primekg_mondo primekg_orphanet").split()],
+    "reactome": ["description_name_description"],
+    "protein": [None],
+    "omim": ["description_" + s for s in "omim mondo umls orphanet mayo".split()],
+    "drugbank": ["moa", "indication"],
+    "drugbank:moa": ["moa"],
+    "drugbank:indication": ["indication"],
+    "gtop": ["description_name_" + s for s in "overview comments introduction".split()],
+    "ec": ["description_explorenz"],
+    "uniprot": ["function"],
+}
+RETRIEVAL_SUBSETS = {
+    1: _RETRIEVAL_COLUMNS_V1,
+    2: {**_RETRIEVAL_COLUMNS_V1, "disgenet": ["description_all_collapse"]},
+    5: {**_RETRIEVAL_COLUMNS_V1, "disgenet": ["description_all_collapse"], "go": ["go_def"], "reactome": ["description"],
+        "omim": ["omim_" + s + "_curated" for s in "def clinical molecular title".split()],
+        "gtop": ["target_family_overview", "target_family_comments"]},
+}
+
+
+def construct_task_id(aaseq_type: str, text_type: str, relation_type: str, task_type: str) -> str:
+    """procyon/data/it_collator.py:886-897"""
+    kind = aaseq_type.lower()
+    if kind == "domain":
+        return f"domain_{text_type}_{relation_type}_{task_type}"
+    if kind in ("protein", "peptide"):
+        return f"{text_type}_{relation_type}_{task_type}"
+    raise NotImplementedError(f"No dataset found for aaseq_type = {aaseq_type}")
+
+
+def _first_text(row) -> str:
+    """first non-null description among the candidate columns of one table row"""
+    vals = row[row.notna()].tolist()
+    return vals[0]
+
+
+def create_input_retrieval(input_description: str, data_args, instruction_source_dataset: str,
+                           drug_input_idx=None, task_definition: Optional[str] = None,
+                           instruction_source_relation: str = "all", aaseq_type: str = "protein",
+                           icl_example_number: int = 1, *, home_dir: Optional[str] = None,
+                           data_dir: Optional[str] = None, text_table=None, drug_mask=None) -> Dict:
+    """Model-input dict of ONE free-text retrieval query: the task's instruction with `icl_example_number` in-context
+    examples (their descriptions come from the dataset's text table, their proteins by index) followed by the query
+    text.  Same arguments and output layout as the reference; `home_dir` / `data_dir` / `text_table` / `drug_mask`
+    (keyword-only extensions) replace the environment roots and the files read from them."""
+    import json
+    import os
+
+    from .instruct_tune.instruct_constructor import get_prompt, get_prompt_open_def
+
+    dataset = instruction_source_dataset.lower()
+    home = home_dir or os.environ.get("HOME_DIR")
+    if home is None:
+        raise RuntimeError("HOME_DIR is not set (root of the checkout that holds procyon/data/instruct_tune/tasks)")
+    task_id = construct_task_id(aaseq_type, dataset, instruction_source_relation, "retrieval")
+    with open(os.path.join(home, "procyon", "data", "instruct_tune", "tasks", f"{task_id}.json")) as fh:
+        task = json.load(fh)
+    kw = dict(task=task, num_examples=icl_example_number, is_special_definition=False, is_ppi=(dataset == "protein"),
+              aaseq_type=aaseq_type)
+    if task_definition is None:
+        instruction, _, _, ex_text, ex_seq = get_prompt(**kw)
+    else:
+        instruction, _, _, _, ex_text, ex_seq = get_prompt_open_def(**kw)
+        instruction = instruction.format(definition=task_definition)
+
+    if text_table is None:
+        import pandas as pd
+
+        root = data_dir or os.environ.get("DATA_DIR")
+        if root is None:
+            raise RuntimeError("DATA_DIR is not set (root of integrated_data/v1/<dataset>/..._info_filtered_composed.pkl)")
+        text_table = pd.read_pickle(os.path.join(root, "integrated_data", "v1", dataset,
+                                                 f"{dataset}_info_filtered_composed.pkl"))
+    cols = RETRIEVAL_SUBSETS[data_args.retrieval_subset_version][dataset]
+    candidates = text_table[cols] if dataset != "protein" else None  # (get_text_sequences_compositions)
+    descriptions = [_first_text(candidates.iloc[i, :]) for i in ex_text]
+
+    # optional drug soft tokens: examples that have a structure embedding, then the query's own drug
+    slot_of_drug, drug_rows = None, None
+    if drug_input_idx is not None:
+        if drug_mask is None:
+            root = data_dir or os.environ.get("DATA_DIR")
+            drug_mask = torch.load(os.path.join(root, "integrated_data/v1/drugbank/drugbank_mask.pt"))
+        slot_of_drug, drug_rows = [], []
+        if dataset == "drugbank":
+            for i, tid in enumerate(ex_text):
+                if drug_mask[tid]:
+                    descriptions[i] += "\nDrug: <|drug|>"
+                    slot_of_drug.append(i)
+                    drug_rows.append(tid)
+        if bool(drug_mask[drug_input_idx]):
+            input_description = input_description + "\nDrug: <|drug|>"
+            slot_of_drug.append(len(slot_of_drug))
+            drug_rows.append(drug_input_idx)
+            slot_of_drug = torch.LongTensor(slot_of_drug).unsqueeze(0).tolist()
+            drug_rows = torch.LongTensor(drug_rows)
+        else:
+            print("WARNING: not inserting drug index because we don't have one in our database")
+            slot_of_drug, drug_rows = None, None
+
+    seq_ids = torch.LongTensor(ex_seq) if len(ex_seq) > 0 else None
+    texts = descriptions + [input_description]
+    if instruction.endswith("[EXT]"):
+        instruction = instruction[:-5]
+    instruction = instruction.replace("[CONTEXT]", "")
+    return {
+        "data": {"seq": seq_ids, "seq_idx": seq_ids, "text": texts, "drug": drug_rows},
+        "input": {"seq": [list(range(len(ex_seq)))] if seq_ids is not None else None,
+                  "text": [list(range(len(texts)))], "drug": slot_of_drug},
+        "target": {"seq": None, "text": None, "drug": None},
+        "instructions": [instruction],
+    }
+
+
+def create_batched_input_retrieval(input_descriptions, data_args, task_definitions=None,
+                                   instruction_source_dataset: Optional[str] = None,
+                                   instruction_source_relation: str = "all", aaseq_type: str = "protein",
+                                   icl_example_number: int = 1, **roots) -> Dict:
+    """One merged model-input dict for several queries (procyon/data/inference_utils.py:886-925)."""
+    n = len(input_descriptions)
+    if task_definitions is None:
+        task_definitions = [None] * n
+    assert len(task_definitions) == n
+    dicts = [create_input_retrieval(input_description=input_descriptions[i], data_args=data_args,
+                                    task_definition=task_definitions[i],
+                                    instruction_source_dataset=instruction_source_dataset,
+                                    instruction_source_relation=instruction_source_relation, aaseq_type=aaseq_type,
+                                    icl_example_number=icl_example_number, **roots) for i in range(n)]
+    return merge_model_input_dicts(dicts)

@@ -12,7 +12,8 @@ from procyon_b200 import _lib  # noqa: E402
 from procyon_b200.model.pmc_llama import SELECT_BEAM  # noqa: E402
 
 NAMES = ["qkv stage", "qkv stream", "qkv pieces/epilogue",
-         "att: K/V request", "att: barrier (qkv done)", "att: items (Q, S, softmax, PV)", "att: barrier (partials)",
+         "att: K/V request", "att: barrier (qkv done)", "att: item loads + Q/K RoPE",
+         "att: wait for the K/V tiles", "att: S, mask, softmax", "att: P.V + partials", "att: barrier (partials)",
          "att: merge", "att: barrier (attn done)",
          "o stage", "o stream", "o pieces/epilogue", "o barrier",
          "gate/up stage", "gate/up stream", "gate/up pieces/epilogue", "gate/up barrier",

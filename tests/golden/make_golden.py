@@ -508,6 +508,125 @@ def golden_checkpoint_args():
           f"{len(vars(da))} fields")
 
 
+
+def _ref_functions(rel_path, names, ns):
+    """Runs the named top-level functions of a reference file, unmodified, in the namespace `ns` (for modules that read
+    dataset files at import time)."""
+    import ast
+
+    path = os.path.join(ref_import.REFERENCE_ROOT, rel_path)
+    tree = ast.parse(open(path).read())
+    body = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in names]
+    assert len(body) == len(names), (names, [n.name for n in body])
+    exec(compile(ast.Module(body=body, type_ignores=[]), path, "exec"), ns)
+    return ns
+
+
+def golden_retrieval_inputs():
+    """create_input_retrieval / create_batched_input_retrieval (procyon/data/inference_utils.py:663-925) and the prompt
+    builder under them (procyon/data/instruct_tune/instruct_constructor.py) on SYNTHETIC task files and text tables
+    (written here, not taken from the reference), plus a digest of every prompt the reference builds from its own 66
+    task files (checked when /root/reference is present)."""
+    import glob
+    import hashlib
+    import json
+    import tempfile
+    import typing
+
+    import numpy as np
+    import pandas as pd
+
+    import procyon.data.constants as ref_const
+    import procyon.data.instruct_tune.instruct_constructor as ref_ic
+
+    def task(category, dataset, n_ex, ppi=False):
+        ex = ([{"aaseq_1": 10 + i, "aaseq_2": 20 + i, "output": "yes"} for i in range(n_ex)] if ppi else
+              [{"text": 1 + 2 * i, "aaseq": 30 + i, "output": "yes"} for i in range(n_ex)])
+        neg = ([{"aaseq_1": 40 + i, "aaseq_2": 50 + i, "output": "no"} for i in range(n_ex)] if ppi else
+               [{"text": 2 * i, "aaseq": 60 + i, "output": "no"} for i in range(n_ex)])
+        return {"Definition": "Given {Biological Summary}, find what is {Relationship Summary}. {Task-Specific Relationship}",
+                "DATASET_IDENTIFIER": dataset, "CATEGORY": category, "Relationship Summary": f"linked to it ({dataset})",
+                "Biological Summary": f"a synthetic {dataset} record", "Task-Specific Relationship": "Links are made up.",
+                "Positive Examples": ex, "Negative Examples": neg, "Instances": None}
+
+    tasks = {"go_process_retrieval": task("retrieval", "go", 2), "protein_homology_retrieval": task("retrieval", "protein", 2, ppi=True),
+             "drugbank_drug_target_retrieval": task("retrieval", "drugbank", 2), "domain_pfam_all_retrieval": task("retrieval", "pfam", 2),
+             "go_process_qa": task("qa", "go", 2), "protein_homology_qa": task("qa", "protein", 2, ppi=True),
+             "go_process_caption": task("caption", "go", 2)}
+    nan = float("nan")
+    tables = {"go": {"description_name_type_def": [f"go term {i}" for i in range(6)]},
+              "pfam": {"description_pfam": [nan, "pfam b", nan, "pfam d", "pfam e", nan],
+                       "description_interpro": ["ipr a", "ipr b", "ipr c", nan, "ipr e", "ipr f"]},
+              "drugbank": {"moa": [nan, "blocks x", "binds y", nan, "opens z", "cuts w"],
+                           "indication": ["for a", "for b", nan, "for d", "for e", nan]}}
+    drug_mask = torch.tensor([True, False, True, True, False, True])
+
+    prompts = {}
+    for name, t in tasks.items():
+        for n_ex in (0, 1, 2, None):
+            for kind in ("protein", "domain", "peptide", "other"):
+                ppi = t["DATASET_IDENTIFIER"] == "protein"
+                kw = dict(num_examples=n_ex, is_special_definition=False, is_ppi=ppi, aaseq_type=kind)
+                prompts[(name, n_ex, kind, "fixed")] = ref_ic.get_prompt(t, **kw)
+                prompts[(name, n_ex, kind, "open")] = ref_ic.get_prompt_open_def(t, **kw)
+        prompts[(name, 1, "protein", "special")] = ref_ic.get_prompt(t, num_examples=1, is_special_definition=True,
+                                                                   is_ppi=t["DATASET_IDENTIFIER"] == "protein",
+                                                                   aaseq_type="protein")
+
+    with tempfile.TemporaryDirectory() as home, tempfile.TemporaryDirectory() as data:
+        tdir = os.path.join(home, "procyon", "data", "instruct_tune", "tasks")
+        os.makedirs(tdir)
+        for name, t in tasks.items():
+            json.dump(t, open(os.path.join(tdir, name + ".json"), "w"))
+        for ds, cols in tables.items():
+            os.makedirs(os.path.join(data, "integrated_data", "v1", ds))
+            pd.DataFrame(cols).to_pickle(os.path.join(data, "integrated_data", "v1", ds, f"{ds}_info_filtered_composed.pkl"))
+        ns = {"os": os, "json": json, "pd": pd, "torch": torch, "np": np, "List": typing.List, "Dict": typing.Dict,
+              "Optional": typing.Optional, "DataArgs": object, "HOME_DIR": home, "DATA_DIR": data, "DRUGMASK": drug_mask,
+              "RETRIEVAL_SUBSETS": ref_const.RETRIEVAL_SUBSETS, "get_prompt": ref_ic.get_prompt,
+              "get_prompt_open_def": ref_ic.get_prompt_open_def}
+        _ref_functions("procyon/data/it_collator.py", ["construct_task_id"], ns)
+        _ref_functions("procyon/data/data_utils.py", ["get_text_sequences_compositions"], ns)
+        _ref_functions("procyon/data/inference_utils.py",
+                       ["create_input_retrieval", "merge_model_input_dicts", "create_batched_input_retrieval"], ns)
+        da = types.SimpleNamespace(retrieval_subset_version=1)
+        calls = [dict(input_description="binds ATP", instruction_source_dataset="GO", instruction_source_relation="process"),
+                 dict(input_description="binds ATP", instruction_source_dataset="go", instruction_source_relation="process",
+                      icl_example_number=2, task_definition="Find the proteins of this made-up process."),
+                 dict(input_description="binds ATP", instruction_source_dataset="go", instruction_source_relation="process",
+                      icl_example_number=0),
+                 dict(input_description="a repeat domain", instruction_source_dataset="pfam", aaseq_type="domain",
+                      icl_example_number=2),
+                 dict(input_description="an inhibitor", instruction_source_dataset="drugbank",
+                      instruction_source_relation="drug_target", drug_input_idx=3, icl_example_number=2),
+                 dict(input_description="an inhibitor", instruction_source_dataset="drugbank",
+                      instruction_source_relation="drug_target", drug_input_idx=4),
+                 dict(input_description="an inhibitor", instruction_source_dataset="drugbank",
+                      instruction_source_relation="drug_target")]
+        single = [ns["create_input_retrieval"](data_args=da, **kw) for kw in calls]
+        batched_kw = dict(input_descriptions=["binds ATP", "kinase", "membrane part"], instruction_source_dataset="go",
+                          instruction_source_relation="process", task_definitions=None, icl_example_number=1)
+        batched = ns["create_batched_input_retrieval"](data_args=da, **batched_kw)
+
+    # every prompt of the reference's own task files, as digests
+    digests = {}
+    for path in sorted(glob.glob(os.path.join(ref_import.REFERENCE_ROOT, "procyon/data/instruct_tune/tasks/*.json"))):
+        t = json.load(open(path))
+        name = os.path.basename(path)[:-5]
+        ppi = name.startswith("protein_") or name.startswith("domain_protein_")
+        for n_ex in (0, 1, 2):
+            for kind in ("protein", "domain"):
+                try:
+                    out = (ref_ic.get_prompt(t, num_examples=n_ex, is_ppi=ppi, aaseq_type=kind),
+                           ref_ic.get_prompt_open_def(t, num_examples=n_ex, is_ppi=ppi, aaseq_type=kind))
+                except Exception:  # (a caption task flagged PPI; task files whose CATEGORY is not one of the three)
+                    out = "error"
+                digests[f"{name}|{n_ex}|{kind}"] = hashlib.sha256(repr(out).encode()).hexdigest()
+    save("retrieval_inputs.pt", dict(tasks=tasks, tables=tables, drug_mask=drug_mask, prompts=prompts, calls=calls,
+                                     single=single, batched_kw=batched_kw, batched=batched, task_file_digests=digests))
+    print(f"wrote retrieval_inputs.pt: {len(prompts)} prompts, {len(single)} + 1 input dicts, {len(digests)} digests")
+
+
 if __name__ == "__main__":
     torch.set_num_threads(4)
     if len(sys.argv) > 1:  # regenerate only the named goldens, e.g. `make_golden.py golden_aaseq_embedding_tables`
@@ -528,3 +647,4 @@ if __name__ == "__main__":
     golden_hf_llama()
     golden_aaseq_embedding_tables()
     golden_checkpoint_args()
+    golden_retrieval_inputs()
