@@ -205,8 +205,8 @@ def test_forced_beam_ancestry_logits_match_oracle_every_step(cuda_device, kind, 
     """The oracle's beam decisions are forced into the device session (token tables + physical-KV-row tables, exactly
     what `select` would write) and the decode forward runs under them: the logits of EVERY beam row at EVERY step
     against the oracle's (which physically reorders its KV cache like the reference, model_unified.py:830-832).
-    Row counts 2 and 4 go through the persistent kernel, 6..16 through the per-op path with the shared-prompt
-    attention kernel."""
+    Row counts 2 and 4 go through the greedy persistent kernel, 6..16 through the persistent beam kernel (attention over the
+    union of the beams' keys with per-key beam masks)."""
     from oracle.generate import generate_beam_search as oracle_beam
     from procyon_b200 import _lib
 

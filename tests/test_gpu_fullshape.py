@@ -70,13 +70,16 @@ def test_llama8b_width_prefill_hidden_logits_loss(llama8b_layer):
     assert abs(out.loss.item() - ref["loss"].item()) < 2e-2
 
 
-@pytest.mark.parametrize("rows,path", [(1, "megakernel<1,4>"), (2, "megakernel<2,4>"), (4, "megakernel<4,4>"),
-                                       (10, "per-op, tensor-core GEMV"), (16, "per-op, tensor-core GEMV")])
-def test_llama8b_width_teacher_forced_decode(llama8b_layer, rows, path):
+@pytest.mark.parametrize("rows,path,max_rows,rows_kernel",
+                         [(1, "megakernel<1,4>", 4, 1), (2, "megakernel<2,4>", 4, 1), (4, "megakernel<4,4>", 4, 1),
+                          (4, "rows megakernel<1> (4 rows)", 2, 1), (10, "rows megakernel<2> (10 rows)", 2, 1),
+                          (16, "rows megakernel<2> (16 rows)", 2, 1), (10, "per-op, tensor-core GEMV", 2, 0),
+                          (16, "per-op, tensor-core GEMV", 2, 0)])
+def test_llama8b_width_teacher_forced_decode(llama8b_layer, rows, path, max_rows, rows_kernel):
     """Prefill + 4 teacher-forced KV-cache decode steps at full width: every step's (rows, 128263) logits against the
-    oracle, and exact arg-max ids where the oracle's margin is clear. rows selects the decode kernel that bench.py
-    times: the persistent single-launch step (1, 2, 4 rows) or the per-op path with the mma.sync weight streaming
-    (10 rows = evaluation-default beam count, 16 = the maximum)."""
+    oracle, and exact arg-max ids where the oracle's margin is clear. The parameters select the decode kernel that
+    bench.py times: the greedy persistent step (1, 2 rows; 4 on request), the persistent beam kernel (4, 10 = the
+    evaluation-default beam count, 16 = the maximum) or the per-op path with the mma.sync weight streaming."""
     from oracle.llama import llama_forward
     from procyon_b200 import _lib
 
@@ -86,7 +89,8 @@ def test_llama8b_width_teacher_forced_decode(llama8b_layer, rows, path):
     use_mask = rows > 1
     forced = torch.randint(0, oc.vocab, (rows, steps), generator=torch.Generator().manual_seed(rows))
     lib = _lib.load()
-    lib.pcy_set_decode_megakernel(4)
+    lib.pcy_set_decode_megakernel(max_rows)
+    lib.pcy_set_decode_rows_megakernel(rows_kernel)
     try:
         n0 = lib.pcy_launch_count()
         out = m(input_embeds=emb.cuda(), attn_masks=mask.cuda() if use_mask else None, use_cache=True)
@@ -99,8 +103,9 @@ def test_llama8b_width_teacher_forced_decode(llama8b_layer, rows, path):
         per_step = (lib.pcy_launch_count() - n1) / steps
     finally:
         lib.pcy_set_decode_megakernel(2)
+        lib.pcy_set_decode_rows_megakernel(1)
     # the kernel under test really ran: the persistent step is ONE launch, the per-op path ~8 per layer
-    if rows <= 4:
+    if "megakernel" in path:
         assert per_step == 1, f"{path}: expected one launch per decode step, saw {per_step}"
     else:
         assert per_step > 4, f"{path}: expected the per-op path, saw {per_step} launches per step"
