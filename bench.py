@@ -180,10 +180,23 @@ def time_decode_kernel(model, sess, device, iters=20):
     for _ in range(3):
         sess.forward()
     torch.cuda.synchronize(device)
+    # the kernel as the generate loop launches it: from a captured graph (the 256-byte memset of its barrier word +
+    # the cooperative launch), replayed back to back; state[0] is not advanced (no select): every launch does
+    # identical work.  (Eager launches through ctypes add a host-side gap per launch that is not kernel time.)
+    g = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream(device)
+    side.wait_stream(torch.cuda.current_stream(device))
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(g, stream=side):
+            sess.forward()
+    torch.cuda.current_stream(device).wait_stream(side)
+    for _ in range(3):
+        g.replay()
+    torch.cuda.synchronize(device)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(iters):
-        sess.forward()  # state[0] is not advanced (no select): every launch does identical work
+        g.replay()
     e1.record()
     torch.cuda.synchronize(device)
     ms = e0.elapsed_time(e1) / iters
@@ -196,8 +209,8 @@ def time_decode_kernel(model, sess, device, iters=20):
 
 def time_beam_decode(model, x, device, beams=10, iters=30):
     """ms per decode step (forward + diverse-beam selection, CUDA-graph replay) at the reference's evaluation default
-    beam_size = 10 (procyon/evaluate/framework/procyon.py:72-76): the one-launch-per-op path with the tensor-core
-    weight-streaming GEMM."""
+    beam_size = 10 (procyon/evaluate/framework/procyon.py:72-76): the persistent beam kernel
+    (csrc/decode_rows_megakernel.cu) + 3 selection kernels."""
     from procyon_b200.model.pmc_llama import SELECT_BEAM
 
     te = model.text_encoder
@@ -523,12 +536,12 @@ def gpu_reference(args):
         return {"impl": "hf-eager", "unavailable": f"{type(e).__name__}: {e}"}
 
 
-def ncu_traffic():
-    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from the committed summary of
-    an `ncu --set full` capture (profiles/*_ncu_decode_megakernel.json, written by scripts/ncu_summary.py --json)."""
+def ncu_traffic(name="decode_megakernel"):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of a kernel, from the committed summary of an
+    `ncu --set full` capture (profiles/*_ncu_<name>.json, written by scripts/ncu_summary.py --json)."""
     import glob
 
-    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_decode_megakernel.json")))
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", f"r*_ncu_{name}.json")))
     if not files:
         return None, None
     with open(files[-1]) as f:
@@ -649,6 +662,8 @@ def run_ours(args):
     beam = time_beam_decode(model, x, device) if rank == 0 else None
     if beam is not None:
         beam["frac_of_hbm_peak"] = beam["weight_stream_gbs"] / hbm_peak
+        beam["kernel"] = "llama_decode_rows_megakernel<2> (one launch per step for all 10 beams) + 3 selection kernels"
+        beam["traffic"], beam["traffic_source"] = ncu_traffic("decode_rows_megakernel")
     beam_e2e = time_beam_e2e(model, inputs, device) if rank == 0 and not args.quick else None
     esm = time_esm_encode(model, device, world, rank, steps=max(2, K // 2), warmup=2)
     esm["frac_of_bf16_peak"] = esm["tflops_per_gpu"] / tf_peak

@@ -217,8 +217,9 @@ typedef struct {
 #define PCY_SELECT_GREEDY 0
 #define PCY_SELECT_BEAM 1
 
-/* Decode steps with up to `max_rows` rows (inputs x beams) run as ONE persistent kernel; default 2 (measured faster
-   than the one-launch-per-op path there), supported up to 4, 0 selects the per-op path for every row count. */
+/* Decode steps with up to `max_rows` rows (inputs x beams) run as the greedy persistent kernel (one weight row per ring
+   slot); default 1 (measured fastest only there), supported up to 4; 0 selects the one-launch-per-op path for EVERY row
+   count (it also switches the persistent beam kernel below off). */
 int pcy_set_decode_megakernel(int max_rows);
 /* Decode steps with more rows than that (beam search: rows = inputs x beam_size, the reference's evaluation default is
    beam_size 10, procyon/evaluate/framework/procyon.py:71-76) also run as ONE persistent kernel - weight tiles of 16

@@ -66,11 +66,10 @@ __device__ __forceinline__ unsigned int ld_relaxed_u32(const unsigned int* p) {
 __device__ __forceinline__ void red_release_add(unsigned int* p, unsigned int v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ uint4 ld_relaxed_v4(const uint4* p) {
-  uint4 v;
-  asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];"
-               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
-  return v;
+__device__ __forceinline__ unsigned int atom_release_add(unsigned int* p, unsigned int v) {
+  unsigned int old;
+  asm volatile("atom.release.gpu.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+  return old;
 }
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(RT) : "memory"); }
 __device__ __forceinline__ uint64_t l2_evict_first_policy() {
@@ -147,8 +146,9 @@ struct GridBarrier {
 // CTA b takes chunks [T b / n, T (b + 1) / n).
 struct Geom {
   int n_rg, ck, KQ, ckq, per, T;
+  int unit;  // CTA ranges begin at multiples of `unit` chunks: 1 = anywhere (stream-K), ck = at row-group boundaries
 };
-__host__ __device__ inline Geom make_geom(int N, int K, int kcap) {
+__host__ __device__ inline Geom make_geom(int N, int K, int kcap, bool aligned = false) {
   Geom g;
   g.n_rg = (N + TR - 1) / TR;
   g.ck = K / TK;
@@ -157,7 +157,14 @@ __host__ __device__ inline Geom make_geom(int N, int K, int kcap) {
   g.KQ = (g.ck + g.ckq - 1) / g.ckq;
   g.per = g.n_rg * g.ckq;
   g.T = g.n_rg * g.ck;
+  g.unit = (aligned && g.KQ == 1) ? g.ck : 1;
   return g;
+}
+// Matrices whose phases are short (qkv, o_proj) are cut at row-group boundaries instead: the largest share grows by
+// up to one group (16 chunks of ~0.2 us), but no group is split between CTAs, and a split group costs its finisher
+// two L2 round trips (ticket, pieces) at the very end of the phase, when every other CTA waits at the grid barrier.
+__host__ __device__ inline int cta_lo(const Geom& g, int i, int nb) {
+  return (int)((unsigned int)(g.T / g.unit) * (unsigned int)i / (unsigned int)nb) * g.unit;
 }
 __host__ __device__ inline int part_len(const Geom& g, int q) { return q == g.KQ - 1 ? g.ck - q * g.ckq : g.ckq; }
 __host__ __device__ inline int seg_start(const Geom& g, int q, int rg) { return q * g.per + rg * part_len(g, q); }
@@ -168,15 +175,6 @@ __host__ __device__ inline int chunk_owner(int c, int T, int nb) {
 }
 __host__ __device__ inline int range_lo(int T, int i, int nb) {
   return (int)((unsigned int)T * (unsigned int)i / (unsigned int)nb);
-}
-
-// The CTA that finishes an output group (adds every piece and runs the epilogue): the owner of the group's first chunk
-// - its own share of the group then lies at the END of its range, while the other CTAs meet theirs at the START of
-// their ranges and have published it long before.  Matrices cut into k-parts: the parts of a group are spread over
-// distant CTAs that reach them at about the same time, so the duty rotates over the parts (group % KQ).
-__host__ __device__ inline int merger_of(const Geom& g, int og, bool swiglu, int nb) {
-  const int q = g.KQ > 1 ? og % g.KQ : 0;
-  return chunk_owner(seg_start(g, q, swiglu ? 2 * og : og), g.T, nb);
 }
 
 struct RowsParams {
@@ -197,19 +195,22 @@ struct RowsParams {
   bf16 *x, *qkv, *attn, *act;
   float* part;            // attention partials [rows][KVH][max_splits][GQ][PSTR]
   int max_splits;
-  uint4* pub;             // published pieces [(cta * 8 + warp) * PW + piece][32 lanes][2 NT] (value, flag, value, flag)
-  unsigned int* epoch;    // launch counter: the flag of a piece is (epoch, phase), so that no stale piece ever matches
+  float* pieces;          // cross-CTA partial tiles [(og * nseg + seg) * maxcp + piece][16 x 8 NT]
+  unsigned int* tickets;  // [max output groups], zero between phases
   unsigned int* barrier;
   int ring_slots;
   int kcap;      // activation columns the staging area holds per row (multiple of 256)
+  int maxcp;     // piece slots per segment in `pieces`
   int off_pool;  // byte offsets inside the work area (after ring + barrier block)
   int off_misc;
   unsigned long long* timing;
   int timing_cta;
+  int align_mask;  // bit k: phases of kind k (0 qkv, 1 o_proj, 2 gate/up, 4 LM head) are cut at row-group boundaries
 };
 
 struct PhaseDesc {
   int N, K, stage, epi, map;
+  bool aligned;
   const bf16* A;
   int64_t lda;
   const bf16* rms_w;
@@ -226,6 +227,7 @@ __device__ __forceinline__ PhaseDesc phase_desc(const RowsParams& p, const bf16*
   PhaseDesc z;
   z.rms_w = nullptr;
   z.map = ph;
+  z.aligned = (p.align_mask >> (ph == n_phases - 1 ? 4 : (ph & 3))) & 1;
   if (ph == n_phases - 1) {
     z.N = c.vocab; z.K = d; z.stage = STAGE_RMS; z.epi = EPI_FP32; z.A = p.x; z.lda = d; z.rms_w = p.norm;
     z.out = p.logits; z.ldo = c.vocab;
@@ -257,13 +259,15 @@ __device__ __forceinline__ PhaseDesc phase_desc(const RowsParams& p, const bf16*
 // of the ring and refills a slot itself, right after it has consumed it, with the tile it will need ring-depth tiles
 // later - whatever phase that tile belongs to, so weights keep streaming across grid barriers, staging and attention.
 // The cursor walks the warp's tiles: phases -> runs (the CTA's chunks of one k-part) -> the warp's span of the run.
-__device__ __forceinline__ void phase_shape(const RowsParams& p, int ph, int& N, int& K) {
+__device__ __forceinline__ void phase_shape(const RowsParams& p, int ph, int& N, int& K, bool& aligned) {
   const pcy_llama_config& c = p.cfg;
   const int n_phases = 4 * c.n_layers + 1;
-  if (ph == n_phases - 1) { N = c.vocab; K = c.d_model; }
-  else if ((ph & 3) == 0) { N = (c.n_heads + 2 * c.n_kv_heads) * HD; K = c.d_model; }
-  else if ((ph & 3) == 1) { N = c.d_model; K = c.n_heads * HD; }
-  else if ((ph & 3) == 2) { N = 2 * c.ffn_dim; K = c.d_model; }
+  const int kind = ph == n_phases - 1 ? 4 : (ph & 3);
+  aligned = (p.align_mask >> kind) & 1;
+  if (kind == 4) { N = c.vocab; K = c.d_model; }
+  else if (kind == 0) { N = (c.n_heads + 2 * c.n_kv_heads) * HD; K = c.d_model; }
+  else if (kind == 1) { N = c.d_model; K = c.n_heads * HD; }
+  else if (kind == 2) { N = 2 * c.ffn_dim; K = c.d_model; }
   else { N = c.d_model; K = c.ffn_dim; }
 }
 
@@ -286,11 +290,12 @@ struct Cursor {
   }
   __device__ __forceinline__ void begin_phase(const RowsParams& p, int warp) {
     int N, K;
-    phase_shape(p, ph, N, K);
-    const Geom g = make_geom(N, K, p.kcap);
+    bool aligned;
+    phase_shape(p, ph, N, K, aligned);
+    const Geom g = make_geom(N, K, p.kcap, aligned);
     n_rg = g.n_rg; ck = g.ck; KQ = g.KQ; ckq = g.ckq; per = g.per; T = g.T;
-    const int lo = range_lo(T, blockIdx.x, gridDim.x);
-    hi = range_lo(T, blockIdx.x + 1, gridDim.x);
+    const int lo = cta_lo(g, blockIdx.x, gridDim.x);
+    hi = cta_lo(g, blockIdx.x + 1, gridDim.x);
     b = lo;
     c = c_hi = 0;
   }
@@ -328,8 +333,6 @@ struct Ctx {
   uint32_t pitch;      // kcap * 2 + 16 bytes
   float* pool;         // [RW * PW][16][rs] partial tiles
   int rs;              // activation rows rounded up to an even number: columns of a partial tile
-  uint32_t flag;       // tag of the pieces published in the current phase: (launch epoch << 10) | (phase + 1)
-  uint32_t epoch;
   int* prg;            // [RW * PW] row group of every pool tile (-1 = free)
   unsigned long long* tbuf;
   int tix, tcta;
@@ -401,16 +404,14 @@ __device__ __forceinline__ void weight_phase(const RowsParams& p, Ctx& cx, const
   // partial tile: [16 weight rows][rs activation rows] fp32; when tiles are added, lane l owns weight row l / 2 and
   // the activation rows (l & 1) * rs / 2 ... of it
   constexpr int EPL = 4 * NT;       // upper bound of rs / 2
-  constexpr int NVEC = 2 * NT;      // 16-byte (value, flag, value, flag) vectors per lane of a published piece
-  constexpr int LLB = 6;            // published pieces fetched per batch of loads
   const int RS = cx.rs, TS = TR * RS, eh = RS >> 1;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nb = gridDim.x, bid = blockIdx.x;
   const int rows = p.rows;
-  const Geom g = make_geom(z.N, z.K, p.kcap);
+  const Geom g = make_geom(z.N, z.K, p.kcap, z.aligned);
   const bool swiglu = z.epi == EPI_SWIGLU;
   const int n_out = swiglu ? z.N / 2 : z.N;
-  const int lo = range_lo(g.T, bid, nb), hi = range_lo(g.T, bid + 1, nb);
+  const int lo = cta_lo(g, bid, nb), hi = cta_lo(g, bid + 1, nb);
   const int nseg = swiglu ? 2 : g.KQ;
   const unsigned int og_total = (unsigned int)(swiglu ? 2 * g.ck : g.ck);
 
@@ -536,6 +537,7 @@ __device__ __forceinline__ void weight_phase(const RowsParams& p, Ctx& cx, const
       } else {
         if (np >= PW) __trap();  // the host-side sizing guarantees this never happens
         const int ti = warp * PW + np;
+        ++np;
         float* tile = cx.pool + ti * TS;
         const int wr = lane >> 2, mc = (lane & 3) * 2;
 #pragma unroll
@@ -545,24 +547,7 @@ __device__ __forceinline__ void weight_phase(const RowsParams& p, Ctx& cx, const
             *reinterpret_cast<float2*>(tile + (wr + 8) * RS + nt * 8 + mc) = make_float2(acc[nt][2], acc[nt][3]);
           }
         }
-        const int og = swiglu ? cur_rg >> 1 : cur_rg;
-        if (merger_of(g, og, swiglu, nb) == bid) {
-          if (lane == 0) cx.prg[ti] = cur_rg;  // this CTA finishes the group: the piece waits in the pool
-        } else {
-          // another CTA finishes the group: hand the piece over right now, value and flag in the same 8 bytes (the
-          // reader needs no ticket and no fence, and usually finds the piece long before it asks for it)
-          __syncwarp();
-          const float* mine = tile + lane * eh;
-          uint4* dst = reinterpret_cast<uint4*>(p.pub) + ((int64_t)(bid * RW + warp) * PW + np) * (32 * NVEC) + lane * NVEC;
-#pragma unroll
-          for (int v = 0; v < NVEC; ++v) {
-            if (2 * v < eh) {
-              const float f0 = mine[2 * v], f1 = 2 * v + 1 < eh ? mine[2 * v + 1] : 0.f;
-              dst[v] = make_uint4(__float_as_uint(f0), cx.flag, __float_as_uint(f1), cx.flag);
-            }
-          }
-        }
-        ++np;
+        if (lane == 0) cx.prg[ti] = cur_rg;
       }
     };
 
@@ -588,7 +573,7 @@ __device__ __forceinline__ void weight_phase(const RowsParams& p, Ctx& cx, const
     consumer_sync();
     cx.stamp();
 
-    // ---- per output group this CTA finishes: add the warps' pieces and the pieces other CTAs published ----
+    // ---- per output group: add the warps' pieces; finish here or through the global ticket ----
     const int rg_first = (a - qbase) / len, rg_last = (b - 1 - qbase) / len;
     const int og_first = swiglu ? rg_first >> 1 : rg_first, og_last = swiglu ? rg_last >> 1 : rg_last;
     for (int og = og_first + warp; og <= og_last; og += RW) {
@@ -598,6 +583,8 @@ __device__ __forceinline__ void weight_phase(const RowsParams& p, Ctx& cx, const
 #pragma unroll
         for (int i = 0; i < EPL; ++i) sum[s][i] = 0.f;
       bool any = false;
+      int contrib = 0;
+      int seg_n[2] = {0, 0};
 #pragma unroll
       for (int s = 0; s < 2; ++s) {
         if (s == 1 && !swiglu) break;
@@ -613,106 +600,97 @@ __device__ __forceinline__ void weight_phase(const RowsParams& p, Ctx& cx, const
             if (i < eh) sum[s][i] += tile[i];
           any = true;
         }
+        const int s_lo = qbase + rgi * len;
+        seg_n[s] = max(0, min(b, s_lo + len) - max(a, s_lo));
+        contrib += seg_n[s];
       }
-      if (!any) continue;  // finished by the warp that held it, or another CTA finishes it
+      if (!any) continue;  // every piece of the group was finished by the warp that held it
       const int wr = lane >> 1, m0 = (lane & 1) * eh;
       const int col = og * TR + wr;
+      auto finish = [&]() {
+#pragma unroll
+        for (int i = 0; i < EPL; ++i) {
+          if (i >= eh) break;
+          const int m = m0 + i;
+          if (swiglu) {
+            if (m < rows && col < n_out)
+              reinterpret_cast<bf16*>(z.out)[(int64_t)m * z.ldo + col] = __float2bfloat16_rn(silu(sum[0][i]) * sum[1][i]);
+          } else {
+            store_out<NT>(z, rows, n_out, col, m, sum[0][i]);
+          }
+        }
+      };
       const int og_c0 = swiglu ? 2 * og * g.ck : og * g.ck;  // (KQ == 1) first chunk of the group
-      if (!(g.KQ == 1 && og_c0 >= lo && og_c0 + (int)og_total <= hi)) {
-        // pieces of other CTAs belong to the group: add them in a fixed order (k-part / gate-up, CTA, warp).  Lane
-        // (j, w) finds out whether warp w of the j-th CTA of a segment holds a piece of it and where it published it;
-        // the loads of up to LLB pieces are issued together and repeated until every flag carries this phase's tag.
-        for (int sidx = 0; sidx < nseg; ++sidx) {
-          const int qq = swiglu ? 0 : sidx;
-          const int rgi = swiglu ? 2 * og + sidx : og;
-          const int s_len = part_len(g, qq), s_lo = seg_start(g, qq, rgi), s_hi = s_lo + s_len;
-          const int q_base = qq * g.per, q_end = qq == g.KQ - 1 ? g.T : (qq + 1) * g.per;
-          const int first = chunk_owner(s_lo, g.T, nb), last = chunk_owner(s_hi - 1, g.T, nb);
-          for (int j0 = first; j0 <= last; j0 += 4) {
-            const int j = j0 + (lane >> 3), w = lane & 7;
-            int slot_ix = 0;
-            bool have = false;
-            if (j <= last && j != bid) {
-              const int ra = max(range_lo(g.T, j, nb), q_base), rb = min(range_lo(g.T, j + 1, nb), q_end);
-              const int C = rb - ra;
-              if (C > 0) {
-                const int w_lo = ra + C * w / RW, w_hi = ra + C * (w + 1) / RW;
-                if (max(w_lo, s_lo) < min(w_hi, s_hi)) {
-                  have = true;  // that warp's pieces are numbered by row group from the start of its span
-                  slot_ix = (j * RW + w) * PW + (rgi - (w_lo - q_base) / s_len);
-                }
-              }
+      if (g.KQ == 1 && og_c0 >= lo && og_c0 + (int)og_total <= hi) {
+        finish();
+        continue;
+      }
+      // pieces of other CTAs are missing: publish ours, the last contributor merges
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        if (s == 1 && !swiglu) break;
+        if (seg_n[s] == 0) continue;
+        const int rgi = swiglu ? 2 * og + s : og;
+        const int sidx = swiglu ? s : q;
+        const int pi = bid - chunk_owner(qbase + rgi * len, g.T, nb);
+        if (pi < 0 || pi >= p.maxcp) __trap();
+        float* dst = p.pieces + ((int64_t)(og * nseg + sidx) * p.maxcp + pi) * TS + lane * eh;
+#pragma unroll
+        for (int i = 0; i < EPL; ++i)
+          if (i < eh) dst[i] = sum[s][i];
+      }
+      __syncwarp();
+      unsigned int old = 0;
+      if (lane == 0) old = atom_release_add(p.tickets + og, (unsigned int)contrib);
+      old = __shfl_sync(0xffffffffu, old, 0);
+      if (old + (unsigned int)contrib != og_total) continue;
+      // last contributor: add all pieces in a fixed order (k-part / gate-up, then CTA order); the loads of a batch of
+      // pieces are issued together (one L2 round trip per batch, not per piece)
+#pragma unroll
+      for (int s = 0; s < 2; ++s)
+#pragma unroll
+        for (int i = 0; i < EPL; ++i) sum[s][i] = 0.f;
+      constexpr int FB = 8;
+      const int n_f = nseg * p.maxcp;
+      for (int f0 = 0; f0 < n_f; f0 += FB) {
+        float v[FB][EPL];
+        int tgt[FB];
+#pragma unroll
+        for (int j = 0; j < FB; ++j) {
+          const int f = f0 + j;
+          tgt[j] = -1;
+#pragma unroll
+          for (int i = 0; i < EPL; ++i) v[j][i] = 0.f;
+          if (f < n_f) {
+            const int sidx = f / p.maxcp, pi = f - sidx * p.maxcp;
+            const int qq = swiglu ? 0 : sidx;
+            const int rgi = swiglu ? 2 * og + sidx : og;
+            const int s_lo = seg_start(g, qq, rgi), s_len = part_len(g, qq);
+            const int first = chunk_owner(s_lo, g.T, nb), last = chunk_owner(s_lo + s_len - 1, g.T, nb);
+            bool valid = pi <= last - first;
+            if (valid && g.T < nb) valid = range_lo(g.T, first + pi + 1, nb) > range_lo(g.T, first + pi, nb);  // CTA without chunks
+            if (valid) {
+              tgt[j] = swiglu ? sidx : 0;
+              const float* src = p.pieces + ((int64_t)(og * nseg + sidx) * p.maxcp + pi) * TS + lane * eh;
+#pragma unroll
+              for (int i = 0; i < EPL; ++i)
+                if (i < eh) v[j][i] = __ldcg(src + i);
             }
-            unsigned int mask = __ballot_sync(0xffffffffu, have);
-            while (mask) {
-              uint4 v[LLB][NVEC];
-              int ix[LLB];
-              int n_b = 0;
+          }
+        }
 #pragma unroll
-              for (int i = 0; i < LLB; ++i) {
-                ix[i] = 0;
-                if (mask) {
-                  const int src = __ffs(mask) - 1;
-                  mask &= mask - 1;
-                  ++n_b;
-                  ix[i] = __shfl_sync(0xffffffffu, slot_ix, src);
-                }
-              }
-              uint64_t t0 = 0;
-              for (uint32_t it = 0;; ++it) {
+        for (int j = 0; j < FB; ++j) {
+          if (tgt[j] >= 0) {
 #pragma unroll
-                for (int i = 0; i < LLB; ++i) {
-                  if (i < n_b) {
-                    const uint4* pp = reinterpret_cast<const uint4*>(p.pub) + (int64_t)ix[i] * (32 * NVEC) + lane * NVEC;
-#pragma unroll
-                    for (int k = 0; k < NVEC; ++k)
-                      if (2 * k < eh) v[i][k] = ld_relaxed_v4(pp + k);
-                  }
-                }
-                bool ok = true;
-#pragma unroll
-                for (int i = 0; i < LLB; ++i) {
-                  if (i < n_b) {
-#pragma unroll
-                    for (int k = 0; k < NVEC; ++k)
-                      if (2 * k < eh) ok = ok && v[i][k].y == cx.flag && v[i][k].w == cx.flag;
-                  }
-                }
-                if (__all_sync(0xffffffffu, ok)) break;
-                if ((it & 0x3ffu) == 0x3ffu) {  // bounded: a protocol bug must trap, not hang the GPU
-                  const uint64_t now = globaltimer_ns();
-                  if (t0 == 0) t0 = now;
-                  else if (now - t0 > 4000000000ull) __trap();
-                }
-              }
-#pragma unroll
-              for (int i = 0; i < LLB; ++i) {
-                if (i < n_b) {
-#pragma unroll
-                  for (int k = 0; k < NVEC; ++k) {
-                    if (2 * k < eh) {
-                      const float f0 = __uint_as_float(v[i][k].x), f1 = __uint_as_float(v[i][k].z);
-                      if (swiglu && sidx == 1) { sum[1][2 * k] += f0; if (2 * k + 1 < EPL) sum[1][2 * k + 1] += f1; }
-                      else { sum[0][2 * k] += f0; if (2 * k + 1 < EPL) sum[0][2 * k + 1] += f1; }
-                    }
-                  }
-                }
-              }
+            for (int i = 0; i < EPL; ++i) {
+              if (tgt[j] == 0) sum[0][i] += v[j][i];
+              else sum[1][i] += v[j][i];
             }
           }
         }
       }
-#pragma unroll
-      for (int i = 0; i < EPL; ++i) {
-        if (i >= eh) break;
-        const int m = m0 + i;
-        if (swiglu) {
-          if (m < rows && col < n_out)
-            reinterpret_cast<bf16*>(z.out)[(int64_t)m * z.ldo + col] = __float2bfloat16_rn(silu(sum[0][i]) * sum[1][i]);
-        } else {
-          store_out<NT>(z, rows, n_out, col, m, sum[0][i]);
-        }
-      }
+      finish();
+      if (lane == 0) p.tickets[og] = 0;  // (the next phase that uses it starts after a grid barrier)
     }
     a = b;
     if (a < hi) consumer_sync();  // the next run restages the activations and reuses the pool
@@ -1227,7 +1205,9 @@ struct RowsPlan {
 // everything the kernel's bookkeeping needs to hold for one matrix: pool tiles per warp, piece slots per segment
 void plan_matrix(int N, int K, int kcap, bool swiglu, int nb, RowsPlan& pl) {
   const Geom g = make_geom(N, K, kcap);
-  const int cmax = (g.T + nb - 1) / nb;   // chunks of the largest CTA range
+  // chunks of the largest CTA range: stream-K cut, or (single-part matrices, tuning knob) cut at group boundaries
+  int cmax = (g.T + nb - 1) / nb;
+  if (g.KQ == 1) cmax = std::max(cmax, (g.n_rg + nb - 1) / nb * g.ck);
   const int span = (cmax + RW - 1) / RW;  // chunks of the largest warp span
   int len_min = g.ckq;
   for (int q = 0; q < g.KQ; ++q) len_min = std::min(len_min, part_len(g, q));
@@ -1407,6 +1387,11 @@ int decode_rows_megakernel(const pcy_llama_config& c, const LlamaLayerPtrs* laye
     return e ? atoi(e) : 0;
   }();
   p.timing_cta = std::min(std::max(timing_cta, 0), num_sms() - 1);
+  static const int align_env = [] {
+    const char* e = getenv("PCY_ROWS_ALIGN");  // tuning knob, see RowsParams::align_mask
+    return e ? atoi(e) : 3;
+  }();
+  p.align_mask = align_env;
   PCY_CUDA(cudaMemsetAsync(p.barrier, 0, 512, stream));  // grid barrier counter (tickets reset themselves)
   void* fn = pl.nt == 1 ? (void*)llama_decode_rows_megakernel<1> : (void*)llama_decode_rows_megakernel<2>;
   static SmemOptIn opt[2];

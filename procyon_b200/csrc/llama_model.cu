@@ -89,10 +89,11 @@ __global__ void broadcast_rows_kernel(const float* __restrict__ in, float* __res
 
 using namespace pcy;
 
-// rows (inputs x beams) up to which a decode step runs as the one persistent kernel.  It supports 4, but measured on
-// B200 (scripts/bench_decode_rows.py) it wins only up to 2 rows: 3.1 / 4.6 ms against 6.1 / 6.5 ms at 3 / 4 rows, where
-// the one-launch-per-op path with the tensor-core GEMV and the shared-prompt attention takes 5.3 ms.
-static int g_megakernel_max_rows = 2;
+// rows (inputs x beams) up to which a decode step runs as the GREEDY persistent kernel (decode_megakernel.cu: one weight
+// row per ring slot, dot products on the MMA diagonals).  It supports 4, but measured on B200
+// (scripts/bench_decode_rows.py) it wins only at 1 row: 3.07 ms, against 4.58 / 6.1 / 6.5 ms at 2 / 3 / 4 rows, where the
+// tile-streaming kernel of decode_rows_megakernel.cu takes 3.51 / 3.64 / 3.8 ms.
+static int g_megakernel_max_rows = 1;
 // 3..16 rows (beam search): the tile-streaming persistent kernel of decode_rows_megakernel.cu (1), or the
 // one-launch-per-op path (0: A/B measurements, tests)
 static int g_rows_megakernel = 1;

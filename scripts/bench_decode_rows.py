@@ -1,6 +1,7 @@
 """ms per decode step (forward + selection, CUDA graph replay) for several row counts: 1 (greedy), 4 (small beam:
 persistent kernel) and 10 (the reference's evaluation default, beam_size=10: one launch per op).  Run on the B200 box."""
 import json
+import os
 import sys
 
 import torch
@@ -25,6 +26,8 @@ def main():
         from procyon_b200 import _lib
 
         lib = _lib.load()
+        if os.environ.get("PCY_BENCH_MAX_ROWS"):  # rows up to which the GREEDY persistent kernel is used (default 2)
+            lib.pcy_set_decode_megakernel(int(os.environ["PCY_BENCH_MAX_ROWS"]))
         # rows <= 2: the greedy persistent kernel; more rows: the persistent beam kernel, then the per-op chain
         for rows_kernel, pdl in (((1, 1), (0, 1)) if beams > 2 else ((1, 1),)):
             lib.pcy_set_pdl(pdl)

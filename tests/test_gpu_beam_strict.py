@@ -249,7 +249,7 @@ def test_forced_beam_ancestry_logits_match_oracle_every_step(cuda_device, kind, 
             sess.state[0] = i + 1
             sess.forward()
     finally:
-        lib.pcy_set_decode_megakernel(2)
+        lib.pcy_set_decode_megakernel(1)
     print(f"forced-ancestry decode: worst |logit error| {worst:.4f} (logits are O(20) with the structured head)")
 
 

@@ -27,7 +27,7 @@ def _forced(m, emb, mask, forced, rows_kernel):
     return torch.stack(logs, 1)
 
 
-@pytest.mark.parametrize("kind,rows,S,pad", [("gq4", 3, 50, 4), ("gq4", 5, 70, 0), ("gq4", 8, 33, 3), ("gq4", 9, 64, 0),
+@pytest.mark.parametrize("kind,rows,S,pad", [("gq4", 2, 90, 0), ("gq4", 3, 50, 4), ("gq4", 5, 70, 0), ("gq4", 8, 33, 3), ("gq4", 9, 64, 0),
                                              ("gq4", 16, 40, 5), ("gq4wide", 10, 50, 4), ("gq4wide", 4, 130, 0)])
 def test_rows_kernel_teacher_forced_matches_oracle_and_per_op(cuda_device, kind, rows, S, pad):
     """Independent rows (beams = 1, every row its own prompt): k-parts of the down projection (gq4wide: 9 parts, the

@@ -72,7 +72,7 @@ def test_llama8b_width_prefill_hidden_logits_loss(llama8b_layer):
 
 @pytest.mark.parametrize("rows,path,max_rows,rows_kernel",
                          [(1, "megakernel<1,4>", 4, 1), (2, "megakernel<2,4>", 4, 1), (4, "megakernel<4,4>", 4, 1),
-                          (4, "rows megakernel<1> (4 rows)", 2, 1), (10, "rows megakernel<2> (10 rows)", 2, 1),
+                          (2, "rows megakernel<1> (2 rows)", 1, 1), (4, "rows megakernel<1> (4 rows)", 2, 1), (10, "rows megakernel<2> (10 rows)", 2, 1),
                           (16, "rows megakernel<2> (16 rows)", 2, 1), (10, "per-op, tensor-core GEMV", 2, 0),
                           (16, "per-op, tensor-core GEMV", 2, 0)])
 def test_llama8b_width_teacher_forced_decode(llama8b_layer, rows, path, max_rows, rows_kernel):
@@ -102,7 +102,7 @@ def test_llama8b_width_teacher_forced_decode(llama8b_layer, rows, path, max_rows
             ours.append(o.logits[:, 0].cpu())
         per_step = (lib.pcy_launch_count() - n1) / steps
     finally:
-        lib.pcy_set_decode_megakernel(2)
+        lib.pcy_set_decode_megakernel(1)
         lib.pcy_set_decode_rows_megakernel(1)
     # the kernel under test really ran: the persistent step is ONE launch, the per-op path ~8 per layer
     if "megakernel" in path:

@@ -196,7 +196,7 @@ def _forced_decode(m, emb, mask, forced, max_rows):
             o = m(input_ids=forced[:, i:i + 1].cuda(), past_key_values=sess)
             logs.append(o.logits[:, 0].cpu())
     finally:
-        lib.pcy_set_decode_megakernel(2)
+        lib.pcy_set_decode_megakernel(1)
     return torch.stack(logs, 1)
 
 
@@ -353,7 +353,7 @@ def test_persistent_decode_crosses_key_split_boundaries(cuda_device, rows, S, st
         a = run(4)
         b = run(0)
     finally:
-        lib.pcy_set_decode_megakernel(2)
+        lib.pcy_set_decode_megakernel(1)
     assert torch.isfinite(a).all()
     torch.testing.assert_close(a, b, rtol=3e-2, atol=4e-2)
     ref = _forced_oracle(sd, oc, emb, None, forced.cpu())[:, 1:]
