@@ -374,3 +374,149 @@ def create_batched_input_retrieval(input_descriptions, data_args, task_definitio
                                     instruction_source_relation=instruction_source_relation, aaseq_type=aaseq_type,
                                     icl_example_number=icl_example_number, **roots) for i in range(n)]
     return merge_model_input_dicts(dicts)
+
+
+# ---- caption / QA query builders (procyon/data/inference_utils.py:67-420) -----------------------------------------
+_V5 = {"disgenet": ["description_all_collapse"], "go": ["go_def"], "reactome": ["description"],
+       "omim": ["omim_" + s + "_curated" for s in "def clinical molecular title".split()],
+       "gtop": ["target_family_overview", "target_family_comments"]}
+_DRUG_QA = {"drugbank": ["indication", "moa"]}
+# (procyon/data/constants.py: QA_SUBSETS, CAPTION_SUBSETS - column names of the reference's data files)
+QA_SUBSETS = {
+    1: {**_RETRIEVAL_COLUMNS_V1, **_DRUG_QA},
+    5: {**_RETRIEVAL_COLUMNS_V1, **_V5},
+    "ProtLLM": {**_RETRIEVAL_COLUMNS_V1, **_DRUG_QA, "disgenet": ["description_all_collapse"]},
+    "ProtLLM_name": {**_RETRIEVAL_COLUMNS_V1, **_DRUG_QA, "disgenet": ["description_all_collapse"], "go": ["go_name"],
+                     "ec": ["explorenz_accepted_name"]},
+}
+_CAP_COMMON = {"omim": ["description_omim"], "gtop": ["description_name_overview", "description_name_comments"]}
+_CAP_2 = {**_RETRIEVAL_COLUMNS_V1, **_CAP_COMMON, "go": ["go_def"], "reactome": ["description"], "disgenet": ["allDescriptions"]}
+CAPTION_SUBSETS = {
+    1: {**_RETRIEVAL_COLUMNS_V1, **_CAP_COMMON, "disgenet": ["allDescriptions"], "ec": []},
+    2: _CAP_2,
+    3: {**_CAP_2, "disgenet": ["description_all_collapse"]},
+    4: {**_CAP_2, "disgenet": ["description_all_collapse"]},
+    5: {**_RETRIEVAL_COLUMNS_V1, **_V5},
+}
+
+
+def _instruction_and_examples(dataset, relation, aaseq_type, task_type, icl_example_number, task_definition, home_dir):
+    """(instruction, example text ids, example sequence ids) of `<task_id>.json` under the task directory"""
+    import json
+    import os
+
+    from .instruct_tune.instruct_constructor import get_prompt, get_prompt_open_def
+
+    home = home_dir or os.environ.get("HOME_DIR")
+    if home is None:
+        raise RuntimeError("HOME_DIR is not set (root of the checkout that holds procyon/data/instruct_tune/tasks)")
+    task_id = construct_task_id(aaseq_type, dataset, relation, task_type)
+    with open(os.path.join(home, "procyon", "data", "instruct_tune", "tasks", f"{task_id}.json")) as fh:
+        task = json.load(fh)
+    kw = dict(task=task, num_examples=icl_example_number, is_special_definition=False, is_ppi=(dataset == "protein"),
+              aaseq_type=aaseq_type)
+    if task_definition is None:
+        instruction, _, _, ex_text, ex_seq = get_prompt(**kw)
+    else:
+        instruction, _, _, _, ex_text, ex_seq = get_prompt_open_def(**kw)
+        instruction = instruction.format(definition=task_definition)
+    return instruction, ex_text, ex_seq
+
+
+def _text_candidates(dataset, columns, data_dir, text_table):
+    import os
+
+    if text_table is None:
+        import pandas as pd
+
+        root = data_dir or os.environ.get("DATA_DIR")
+        if root is None:
+            raise RuntimeError("DATA_DIR is not set (root of integrated_data/v1/<dataset>/..._info_filtered_composed.pkl)")
+        text_table = pd.read_pickle(os.path.join(root, "integrated_data", "v1", dataset,
+                                                 f"{dataset}_info_filtered_composed.pkl"))
+    if dataset == "protein":
+        return None
+    if columns is None:
+        raise NotImplementedError("default description columns (ENTITY_DESCRIPTION_NAMES) are not mirrored: "
+                                  "set the subset version in DataArgs")
+    return text_table[columns[dataset]]
+
+
+def _sequence_query_dict(instruction, descriptions, seq_ids, device, qa, disease_context_augmentation,
+                         functional_descriptions):
+    if instruction.endswith("[EXT]"):
+        instruction = instruction[:-5]
+    seq = torch.LongTensor(seq_ids).to(device)
+    if disease_context_augmentation:
+        if functional_descriptions is None:
+            raise RuntimeError("disease_context_augmentation needs the protein function table "
+                               "(integrated_data/v1/protein/uniprot_functional_descriptions.pkl): pass functional_descriptions=")
+        instruction = instruction.replace("[CONTEXT]", "[EXT]")
+        contexts = functional_descriptions.iloc[seq.cpu().numpy()].tolist()
+        mixed = []
+        if qa:  # description, then its protein's context
+            for c, d in zip(contexts, descriptions):
+                mixed += [d, f"Context: {c}"]
+        else:   # context first; the query protein's context closes the list
+            for i, c in enumerate(contexts):
+                mixed.append(f"Context: {c}")
+                if i != len(contexts) - 1:
+                    mixed.append(descriptions[i])
+        descriptions = mixed
+    else:
+        instruction = instruction.replace("[CONTEXT]", "")
+    if qa:
+        instruction = instruction.format(answer="null")
+    return {
+        "data": {"seq": seq, "seq_idx": seq, "text": descriptions, "drug": None},
+        "input": {"seq": [list(range(len(seq_ids)))], "text": [list(range(len(descriptions)))], "drug": None},
+        "target": {"seq": None, "text": None, "drug": None},
+        "instructions": [instruction],
+    }
+
+
+def create_caption_input_simple(input_aaseq_ids, data_args, input_description=None, drug_inputs=None,
+                                task_definition=None, instruction_source_dataset=None,
+                                instruction_source_relation="all", aaseq_type="protein", task_type="caption",
+                                icl_example_number=1, device=None, disease_context_augmentation=False, *,
+                                home_dir=None, data_dir=None, text_table=None, functional_descriptions=None) -> Dict:
+    """Model-input dict that asks for a description of the sequences `input_aaseq_ids` (indices into the model's
+    protein / domain table): the caption task's instruction with its in-context examples, then the query sequences.
+    Same arguments and output as the reference (:67-244); keyword-only extensions replace the environment roots."""
+    assert drug_inputs is None
+    if instruction_source_dataset is None:
+        raise NotImplementedError
+    dataset = instruction_source_dataset.lower()
+    instruction, ex_text, ex_seq = _instruction_and_examples(dataset, instruction_source_relation, aaseq_type, "caption",
+                                                             icl_example_number, task_definition, home_dir)
+    columns = None
+    if task_type == "qa" and data_args.qa_subset_version is not None:
+        columns = QA_SUBSETS[data_args.qa_subset_version]
+    elif task_type == "caption" and data_args.caption_subset_version is not None:
+        columns = CAPTION_SUBSETS[data_args.caption_subset_version]
+    cand = _text_candidates(dataset, columns, data_dir, text_table)
+    descriptions = cand.iloc[ex_text, 0].tolist()  # (first candidate column, whatever it holds)
+    if input_description is not None:
+        descriptions = descriptions + [input_description]
+    return _sequence_query_dict(instruction, descriptions, list(ex_seq) + list(input_aaseq_ids), device, False,
+                                disease_context_augmentation, functional_descriptions)
+
+
+def create_qa_input_simple(input_aaseq_ids, data_args, input_description, drug_inputs=None, task_definition=None,
+                           instruction_source_dataset=None, instruction_source_relation="all", aaseq_type="protein",
+                           icl_example_number=1, device=None, disease_context_augmentation=False, *,
+                           home_dir=None, data_dir=None, text_table=None, functional_descriptions=None) -> Dict:
+    """Model-input dict of a yes/no question "is `input_description` true of the sequences `input_aaseq_ids`?" (:247-
+    420): the QA task's instruction with positive and negative in-context examples, answer slot filled with "null"."""
+    assert drug_inputs is None
+    if instruction_source_dataset is None:
+        raise NotImplementedError
+    dataset = instruction_source_dataset.lower()
+    instruction, ex_text, ex_seq = _instruction_and_examples(dataset, instruction_source_relation, aaseq_type, "qa",
+                                                             icl_example_number, task_definition, home_dir)
+    cand = _text_candidates(dataset, QA_SUBSETS[data_args.qa_subset_version], data_dir, text_table)
+    descriptions = [_first_text(cand.iloc[i, :]) for i in ex_text]
+    if input_description is not None:
+        descriptions = descriptions + [input_description]
+    return _sequence_query_dict(instruction, descriptions, list(ex_seq) + list(input_aaseq_ids), device, True,
+                                disease_context_augmentation, functional_descriptions)

@@ -557,6 +557,7 @@ def golden_retrieval_inputs():
     tables = {"go": {"description_name_type_def": [f"go term {i}" for i in range(6)]},
               "pfam": {"description_pfam": [nan, "pfam b", nan, "pfam d", "pfam e", nan],
                        "description_interpro": ["ipr a", "ipr b", "ipr c", nan, "ipr e", "ipr f"]},
+              "protein": {"name": [f"protein {i}" for i in range(6)]},
               "drugbank": {"moa": [nan, "blocks x", "binds y", nan, "opens z", "cuts w"],
                            "indication": ["for a", "for b", nan, "for d", "for e", nan]}}
     drug_mask = torch.tensor([True, False, True, True, False, True])
@@ -583,12 +584,15 @@ def golden_retrieval_inputs():
             pd.DataFrame(cols).to_pickle(os.path.join(data, "integrated_data", "v1", ds, f"{ds}_info_filtered_composed.pkl"))
         ns = {"os": os, "json": json, "pd": pd, "torch": torch, "np": np, "List": typing.List, "Dict": typing.Dict,
               "Optional": typing.Optional, "DataArgs": object, "HOME_DIR": home, "DATA_DIR": data, "DRUGMASK": drug_mask,
-              "RETRIEVAL_SUBSETS": ref_const.RETRIEVAL_SUBSETS, "get_prompt": ref_ic.get_prompt,
-              "get_prompt_open_def": ref_ic.get_prompt_open_def}
+              "RETRIEVAL_SUBSETS": ref_const.RETRIEVAL_SUBSETS, "QA_SUBSETS": ref_const.QA_SUBSETS,
+              "CAPTION_SUBSETS": ref_const.CAPTION_SUBSETS, "get_prompt": ref_ic.get_prompt,
+              "get_prompt_open_def": ref_ic.get_prompt_open_def,
+              "functional_descriptions": pd.Series([f"function of sequence {i}" for i in range(80)])}
         _ref_functions("procyon/data/it_collator.py", ["construct_task_id"], ns)
         _ref_functions("procyon/data/data_utils.py", ["get_text_sequences_compositions"], ns)
         _ref_functions("procyon/data/inference_utils.py",
-                       ["create_input_retrieval", "merge_model_input_dicts", "create_batched_input_retrieval"], ns)
+                       ["create_input_retrieval", "merge_model_input_dicts", "create_batched_input_retrieval",
+                        "create_caption_input_simple", "create_qa_input_simple"], ns)
         da = types.SimpleNamespace(retrieval_subset_version=1)
         calls = [dict(input_description="binds ATP", instruction_source_dataset="GO", instruction_source_relation="process"),
                  dict(input_description="binds ATP", instruction_source_dataset="go", instruction_source_relation="process",
@@ -607,6 +611,26 @@ def golden_retrieval_inputs():
         batched_kw = dict(input_descriptions=["binds ATP", "kinase", "membrane part"], instruction_source_dataset="go",
                           instruction_source_relation="process", task_definitions=None, icl_example_number=1)
         batched = ns["create_batched_input_retrieval"](data_args=da, **batched_kw)
+        da2 = types.SimpleNamespace(qa_subset_version=1, caption_subset_version=1)
+        cap_calls = [dict(input_aaseq_ids=[7], instruction_source_dataset="GO", instruction_source_relation="process"),
+                     dict(input_aaseq_ids=[7, 9], instruction_source_dataset="go", instruction_source_relation="process",
+                          icl_example_number=2, task_definition="Describe the made-up process of this protein."),
+                     dict(input_aaseq_ids=[3], instruction_source_dataset="go", instruction_source_relation="process",
+                          icl_example_number=0, input_description="extra text"),
+                     dict(input_aaseq_ids=[5], instruction_source_dataset="go", instruction_source_relation="process",
+                          icl_example_number=2, disease_context_augmentation=True)]
+        qa_calls = [dict(input_aaseq_ids=[7], input_description="binds ATP", instruction_source_dataset="go",
+                         instruction_source_relation="process"),
+                    # (task_definition= cannot be used with the QA builder upstream: its prompt still holds the
+                    # "{answer}" slot when the definition is formatted in, :335 -> KeyError)
+                    dict(input_aaseq_ids=[7], input_description="binds ATP", instruction_source_dataset="go",
+                         instruction_source_relation="process", icl_example_number=2),
+                    dict(input_aaseq_ids=[11, 12], input_description=None, instruction_source_dataset="protein",
+                         instruction_source_relation="homology"),
+                    dict(input_aaseq_ids=[7], input_description="binds ATP", instruction_source_dataset="go",
+                         instruction_source_relation="process", icl_example_number=1, disease_context_augmentation=True)]
+        caption = [ns["create_caption_input_simple"](data_args=da2, **kw) for kw in cap_calls]
+        qa = [ns["create_qa_input_simple"](data_args=da2, **kw) for kw in qa_calls]
 
     # every prompt of the reference's own task files, as digests
     digests = {}
@@ -623,7 +647,10 @@ def golden_retrieval_inputs():
                     out = "error"
                 digests[f"{name}|{n_ex}|{kind}"] = hashlib.sha256(repr(out).encode()).hexdigest()
     save("retrieval_inputs.pt", dict(tasks=tasks, tables=tables, drug_mask=drug_mask, prompts=prompts, calls=calls,
-                                     single=single, batched_kw=batched_kw, batched=batched, task_file_digests=digests))
+                                     single=single, batched_kw=batched_kw, batched=batched, task_file_digests=digests,
+                                     cap_calls=cap_calls, caption=caption, qa_calls=qa_calls, qa=qa,
+                                     subsets=dict(retrieval=ref_const.RETRIEVAL_SUBSETS, qa=ref_const.QA_SUBSETS,
+                                                  caption=ref_const.CAPTION_SUBSETS)))
     print(f"wrote retrieval_inputs.pt: {len(prompts)} prompts, {len(single)} + 1 input dicts, {len(digests)} digests")
 
 
