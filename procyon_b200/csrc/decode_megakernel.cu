@@ -161,6 +161,12 @@ struct Smem {
   RingGeom rg;
   uint32_t chunk0;  // ring chunks consumed by the phases before the current one (same count in the producer)
   Share share;      // this CTA's slice of every phase
+  // self-refill mode (no producer warp): the next chunk THIS warp will request - always ring_slots positions ahead of
+  // the chunk it consumes, whatever phase that falls into
+  int f_ph, f_c, f_n, f_cpr, f_lo, f_K, f_epi;
+  uint32_t f_pos;
+  const bf16* f_W;
+  int64_t f_ldw;
   unsigned long long* tbuf;  // profiling stamps (CTA 0, thread 0) or null
   int tix;
   int phase_ix;  // weight phases finished so far (profiling: per-CTA stream-end times at tbuf[4096 + ...])
@@ -240,12 +246,63 @@ __device__ __noinline__ void produce_phase(uint32_t ring, uint32_t bars, RingGeo
   g += (uint32_t)n_chunks;
 }
 
+// ---- self-refill mode ------------------------------------------------------------------------------------------------
+// Without the producer warp the block is 12 warps = 3 per scheduler partition = 168 registers per thread instead of 128
+// (13 warps round up to 4 per partition), which removes the kernel's local-memory frame: spilled values come back
+// through L2 at phase boundaries, ~28 KB of L1 being all that is left beside the ring.  Ring position g belongs to warp
+// g % 12 as before; after consuming the chunk at position g a warp requests the chunk at position g + ring_slots
+// itself (same slot, and again its own), so every warp always has ring_slots / 12 copies in flight and the empty
+// barriers disappear.
+struct MegaParams;
+struct PhaseW {
+  const bf16* W;
+  int64_t ldw;
+  int n_out, K, epi;
+};
+__device__ __forceinline__ PhaseW phase_weights(const MegaParams& p, const LlamaLayerPtrs* s_layers, int ph);
+
+__device__ __forceinline__ void fill_load_phase(Smem& sm, const MegaParams& p, const LlamaLayerPtrs* s_layers) {
+  const PhaseW w = phase_weights(p, s_layers, sm.f_ph);
+  int lo, hi;
+  cta_range(sm.share, w.n_out, lo, hi);
+  sm.f_cpr = (w.K + CH - 1) / CH;
+  sm.f_n = (hi - lo) * (w.epi == EPI_SWIGLU ? 2 : 1) * sm.f_cpr;
+  sm.f_lo = lo; sm.f_K = w.K; sm.f_epi = w.epi; sm.f_W = w.W; sm.f_ldw = w.ldw;
+}
+__device__ __forceinline__ void fill_normalise(Smem& sm, const MegaParams& p, const LlamaLayerPtrs* s_layers,
+                                               int n_phases) {
+  while (sm.f_ph < n_phases && sm.f_c >= sm.f_n) {
+    sm.f_c -= sm.f_n;
+    ++sm.f_ph;
+    if (sm.f_ph < n_phases) fill_load_phase(sm, p, s_layers);
+  }
+}
+// request this warp's next chunk (it lands in the slot the warp has just drained, or in a still untouched one)
+__device__ __forceinline__ void fill_next(Smem& sm, const MegaParams& p, const LlamaLayerPtrs* s_layers, int n_phases,
+                                          uint64_t pol) {
+  if (sm.f_ph >= n_phases) return;
+  if ((threadIdx.x & 31) == 0) {
+    const int r = sm.f_c / sm.f_cpr, kc = sm.f_c - r * sm.f_cpr;
+    uint32_t slot, par;
+    sm.rg.locate(sm.f_pos, slot, par);
+    const bf16* src = sm.f_W + (int64_t)weight_row(sm.f_epi, sm.f_lo, r) * sm.f_ldw + kc * CH;
+    const uint32_t bytes = (uint32_t)min(CH, sm.f_K - kc * CH) * 2u;
+    fence_proxy_async_smem();  // the warp's reads of the slot are ordered before the bulk write
+    mbar_arrive_expect_tx(sm.bars + 8u * slot, bytes);
+    bulk_g2s(sm.ring + slot * SLOT_BYTES, src, bytes, sm.bars + 8u * slot, pol);
+  }
+  sm.f_c += MK_WARPS;
+  sm.f_pos += MK_WARPS;
+  fill_normalise(sm, p, s_layers, n_phases);
+}
+
 // out = epi(W[n_out(x2), K] . A[MT, K]).  The CTA's slice of W arrives through the ring in chunks of <= CH elements
 // of one row.
 // `hook` runs once per warp right after its first chunk (or after the loop if it has none): work that only has to be
 // ISSUED during the phase (the attention K / V requests) goes there, where the warp would otherwise wait for HBM.
-template <int MT, class Hook>
-__device__ __forceinline__ void gemv_phase(Smem& sm, int n_out, int K, int stage, const bf16* A, int64_t lda, int rows,
+template <int MT, bool SELF, class Hook>
+__device__ __forceinline__ void gemv_phase(Smem& sm, const MegaParams& p, const LlamaLayerPtrs* s_layers, int n_phases,
+                                        uint64_t pol, int n_out, int K, int stage, const bf16* A, int64_t lda, int rows,
                                         const bf16* __restrict__ rms_w, float eps, int epi, void* out, int64_t ldo,
                                         Hook&& hook) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -386,7 +443,8 @@ __device__ __forceinline__ void gemv_phase(Smem& sm, int n_out, int K, int stage
       }
     }
     __syncwarp();
-    if (lane == 0) mbar_arrive(sm.bars + 8u * (sm.rg.ns + slot));  // slot free: the producer may refill it
+    if (SELF) fill_next(sm, p, s_layers, n_phases, pol);  // slot free: request the chunk this warp needs a ring later
+    else if (lane == 0) mbar_arrive(sm.bars + 8u * (sm.rg.ns + slot));  // slot free: the producer may refill it
 #pragma unroll
     for (int m = 0; m < MT; ++m) {
       // diagonals: D1[n][n] sits in c0 / c1 and D2[n+8][n] in c2 / c3 of the lanes with lane/4 == 2 (lane%4) (+1)
@@ -811,8 +869,21 @@ __device__ __forceinline__ void touch_kv_pages(const MegaParams& p, int layer, i
   }
 }
 
-template <int MT, int GQ>
-__global__ void __launch_bounds__(MK_BLOCK, 1)
+__device__ __forceinline__ PhaseW phase_weights(const MegaParams& p, const LlamaLayerPtrs* s_layers, int ph) {
+  const pcy_llama_config& c = p.cfg;
+  const int d = c.d_model, f = c.ffn_dim, H = c.n_heads, KVH = c.n_kv_heads;
+  if (ph == 4 * c.n_layers) return PhaseW{p.lm_head, d, c.vocab, d, EPI_FP32};
+  const LlamaLayerPtrs& y = s_layers[ph >> 2];
+  switch (ph & 3) {
+    case 0: return PhaseW{y.wqkv, d, (H + 2 * KVH) * HD, d, EPI_BF16};
+    case 1: return PhaseW{y.wo, H * HD, d, H * HD, EPI_RESIDUAL};
+    case 2: return PhaseW{y.wgu, d, f, d, EPI_SWIGLU};
+    default: return PhaseW{y.wdown, f, d, f, EPI_RESIDUAL};
+  }
+}
+
+template <int MT, int GQ, bool SELF>
+__global__ void __launch_bounds__(SELF ? MK_THREADS : MK_BLOCK, 1)
 llama_decode_megakernel(const MegaParams p) {
   extern __shared__ __align__(128) uint8_t mk_smem[];
   const pcy_llama_config& c = p.cfg;
@@ -826,7 +897,7 @@ llama_decode_megakernel(const MegaParams p) {
   uint8_t* work = mk_smem + (size_t)ns * SLOT_BYTES + 1024;
   // the per-layer weight pointers, copied once so that no phase starts with a dependent global load
   LlamaLayerPtrs* s_layers = reinterpret_cast<LlamaLayerPtrs*>(mk_smem + p.layers_off);
-  for (int i = threadIdx.x; i < c.n_layers * (int)(sizeof(LlamaLayerPtrs) / 8); i += MK_BLOCK)
+  for (int i = threadIdx.x; i < c.n_layers * (int)(sizeof(LlamaLayerPtrs) / 8); i += blockDim.x)
     reinterpret_cast<uint64_t*>(s_layers)[i] = reinterpret_cast<const uint64_t*>(p.layers)[i];
 
   if (threadIdx.x == 0) {
@@ -838,7 +909,7 @@ llama_decode_megakernel(const MegaParams p) {
   }
   __syncthreads();  // the only CTA-wide barrier: after it the producer warp goes its own way
 
-  if (threadIdx.x >= MK_THREADS) {
+  if (!SELF && threadIdx.x >= MK_THREADS) {
     // ===================== producer warp: every weight byte of this CTA, in phase order =====================
     if (threadIdx.x < MK_THREADS + PL) {
       const RingGeom rg{ns, p.ring_magic};
@@ -868,6 +939,17 @@ llama_decode_megakernel(const MegaParams p) {
   sm.phase_ix = 0;
   sm.skew = p.timing != nullptr && p.timing[4095] == 0x534B4557ull;
   uint8_t* att_smem = work;  // the attention phase reuses the activation staging area
+  const int n_phases = 4 * c.n_layers + 1;
+  const uint64_t fill_pol = l2_evict_first_policy();  // weights are read once per step: keep L2 for KV / activations
+  if (SELF) {
+    // this warp's first chunks: ring positions warp, warp + 12, ... < ring_slots
+    sm.f_ph = 0;
+    sm.f_c = (int)(threadIdx.x >> 5);
+    sm.f_pos = threadIdx.x >> 5;
+    fill_load_phase(sm, p, s_layers);
+    fill_normalise(sm, p, s_layers, n_phases);
+    for (int i = 0; i < ns / MK_WARPS; ++i) fill_next(sm, p, s_layers, n_phases, fill_pol);
+  }
 
   GridBarrier bar{p.barrier, 0u, gridDim.x};
   const int t = p.state[0];
@@ -878,7 +960,6 @@ llama_decode_megakernel(const MegaParams p) {
   // and can be inlined: as out-of-line functions they took the kernel parameters and `sm` by reference, i.e. through
   // per-thread copies in local memory (~500 B x 416 threads against the ~28 KB of L1 left beside the ring), and every
   // phase began with chains of local loads served by L2.
-  const int n_phases = 4 * c.n_layers + 1;
   const int n_att_items = p.rows * KVH * ((p.S + t + ATT_CHUNK - 1) / ATT_CHUNK);
   AttnLoads att_loads;
   att_loads.vmask = 0;
@@ -921,7 +1002,7 @@ llama_decode_megakernel(const MegaParams p) {
       n_out = c.vocab; K = d; stage = STAGE_RMS; A = p.x; lda = d; rms_w = p.norm; epi = EPI_FP32; out = p.logits;
       ldo = c.vocab;
     }
-    gemv_phase<MT>(sm, n_out, K, stage, A, lda, rows, rms_w, c.rms_eps, epi, out, ldo, [&]() {
+    gemv_phase<MT, SELF>(sm, p, s_layers, n_phases, fill_pol, n_out, K, stage, A, lda, rows, rms_w, c.rms_eps, epi, out, ldo, [&]() {
       // the K / V rows of this layer's attention item: requested while the qkv weights stream
       if (kind == 0 && (int)blockIdx.x < n_att_items) att_loads.request(p, l, t, blockIdx.x);
     });
@@ -937,6 +1018,10 @@ llama_decode_megakernel(const MegaParams p) {
 }
 
 unsigned long long* g_timing = nullptr;
+bool g_self_refill = [] {
+  const char* e = getenv("PCY_DECODE_SELF_REFILL");
+  return e && atoi(e) != 0;
+}();
 
 constexpr size_t SMEM_LIMIT = 227 * 1024;
 constexpr double MAX_SHARE = 1.15;
@@ -972,6 +1057,7 @@ int ring_slots_for(const pcy_llama_config& c, int mt) {
 }  // namespace
 
 void decode_megakernel_set_timing(unsigned long long* dev_buf) { g_timing = dev_buf; }
+void decode_megakernel_set_self_refill(int enabled) { g_self_refill = enabled != 0; }
 
 int decode_megakernel_set_shares(const float* shares, int n) {
   if (shares == nullptr || n == 0) {  // back to equal slices
@@ -1065,16 +1151,28 @@ int decode_megakernel(const pcy_llama_config& c, const LlamaLayerPtrs* layers_de
   p.layers_off = (int)((size_t)p.ring_slots * SLOT_BYTES + work_smem_bytes(c, mt));
   const size_t smem = (size_t)p.layers_off + layer_table_bytes(c);
   PCY_REQUIRE(smem <= SMEM_LIMIT, "decode megakernel: needs %zu bytes of shared memory", smem);
+  // pcy_set_decode_self_refill(1) / PCY_DECODE_SELF_REFILL=1: no producer warp (12 warps, 168 registers, no spills; every warp refills its own ring
+  // slots).  Measured on B200: 3.049 ms per token against 3.047 ms with the producer warp - what this kernel loses is
+  // arrival skew at the grid barriers (scripts/profile_decode_phases.py), not local-memory traffic, unlike the beam
+  // kernel, where the same change was worth 9 %.  Kept as an option, parity-tested (tests/test_gpu_llama.py).
+  const bool self_refill = g_self_refill;
   void* fn = nullptr;
-  if (mt == 1) fn = (void*)llama_decode_megakernel<1, 4>;
-  else if (mt == 2) fn = (void*)llama_decode_megakernel<2, 4>;
-  else fn = (void*)llama_decode_megakernel<4, 4>;
-  static SmemOptIn opt[3];
-  const int slot = mt == 1 ? 0 : mt == 2 ? 1 : 2;
+  if (self_refill) {
+    if (mt == 1) fn = (void*)llama_decode_megakernel<1, 4, true>;
+    else if (mt == 2) fn = (void*)llama_decode_megakernel<2, 4, true>;
+    else fn = (void*)llama_decode_megakernel<4, 4, true>;
+  } else {
+    if (mt == 1) fn = (void*)llama_decode_megakernel<1, 4, false>;
+    else if (mt == 2) fn = (void*)llama_decode_megakernel<2, 4, false>;
+    else fn = (void*)llama_decode_megakernel<4, 4, false>;
+  }
+  static SmemOptIn opt[6];
+  const int slot = (mt == 1 ? 0 : mt == 2 ? 1 : 2) + (self_refill ? 3 : 0);
   if (opt[slot].need(smem)) PCY_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   void* args[] = {(void*)&p};
   // cooperative launch: guarantees that all CTAs are co-resident (the grid barrier needs it)
-  PCY_CUDA(cudaLaunchCooperativeKernel(fn, dim3(num_sms()), dim3(MK_BLOCK), args, smem, stream));
+  PCY_CUDA(cudaLaunchCooperativeKernel(fn, dim3(num_sms()), dim3(self_refill ? MK_THREADS : MK_BLOCK), args, smem,
+                                       stream));
   count_launch();
   return 0;
 }

@@ -205,6 +205,7 @@ struct RowsParams {
   int off_misc;
   unsigned long long* timing;
   int timing_cta;
+  int look_ahead;  // weight tiles per warp prefetched into L2 beyond the ring at every phase end (0 = off)
   int align_mask;  // bit k: phases of kind k (0 qkv, 1 o_proj, 2 gate/up, 4 LM head) are cut at row-group boundaries
 };
 
@@ -328,6 +329,9 @@ struct Ctx {
   int depth;            // slots per warp
   uint32_t n_used;      // tiles consumed so far by this warp (tile e lives in slot e % depth, parity (e / depth) & 1)
   Cursor fill;          // the next tile to request
+  Cursor ahead;         // L2 look-ahead: the next tile to PREFETCH (valid while n_ahead > 0)
+  int n_ahead;          // tiles between `fill` and `ahead`
+  int ahead_max;        // look-ahead depth per warp (0 = off)
   int n_phases;
   uint32_t act;        // staged activations: row m at act + m * pitch
   uint32_t pitch;      // kcap * 2 + 16 bytes
@@ -349,6 +353,7 @@ __device__ __forceinline__ void refill(const RowsParams& p, Ctx& cx, uint32_t sl
   int map, row0, k0;
   const int warp = threadIdx.x >> 5;
   if (!cx.fill.next(p, warp, cx.n_phases, map, row0, k0)) return;
+  if (cx.n_ahead > 0) --cx.n_ahead;
   if ((threadIdx.x & 31) == 0) {
     fence_proxy_async_smem();  // the warp's ldmatrix reads of the slot are ordered before the bulk write
     const uint32_t bar = cx.bars + 8u * slot;
@@ -357,6 +362,31 @@ __device__ __forceinline__ void refill(const RowsParams& p, Ctx& cx, uint32_t sl
     const uint64_t pol = l2_evict_first_policy();  // weights are read once per step: keep L2 for KV / activations
 #pragma unroll
     for (int i = 0; i < 4; ++i) tma_load_2d_hint(dst + i * 2048, p.maps + map, bar, k0 + i * 64, row0, pol);
+  }
+}
+
+// L2 look-ahead.  The ring holds 2.9 us of streaming at 10 rows; the bubbles between the streams of two phases
+// (pool / ticket epilogue, grid barrier, staging; the attention phase) are 10-20 us long, and once the ring is full HBM
+// idles through the rest of them.  So when a warp runs out of tiles to consume it asks for the tiles BEYOND its ring
+// slots to be brought into L2 (cp.async.bulk.prefetch.tensor): HBM keeps streaming during the bubble, and the ring
+// refills from L2 - faster than HBM delivers - once consumption resumes.  Only issued at phase ends and inside the
+// attention phase, never alongside a running stream (an always-on prefetch only races the fills for the same lines:
+// measured slower in decode_megakernel.cu).
+__device__ __forceinline__ void tma_prefetch_2d(const void* desc, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(desc), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void look_ahead(const RowsParams& p, Ctx& cx, int upto) {
+  if (cx.ahead_max == 0 || cx.n_ahead >= upto) return;
+  if (cx.n_ahead == 0) cx.ahead = cx.fill;
+  const int warp = threadIdx.x >> 5;
+  while (cx.n_ahead < upto) {
+    int map, row0, k0;
+    if (!cx.ahead.next(p, warp, cx.n_phases, map, row0, k0)) break;
+    ++cx.n_ahead;
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) tma_prefetch_2d(p.maps + map, k0 + i * 64, row0);
+    }
   }
 }
 
@@ -570,6 +600,7 @@ __device__ __forceinline__ void weight_phase(const RowsParams& p, Ctx& cx, const
       refill(p, cx, slot);  // the slot is free: request the tile this warp needs `depth` tiles from now
     }
     if (cur_rg >= 0) flush();
+    look_ahead(p, cx, cx.ahead_max);  // this warp has nothing to consume until the next phase is staged
     consumer_sync();
     cx.stamp();
 
@@ -782,6 +813,7 @@ __device__ __forceinline__ void attention_phase(const RowsParams& p, Ctx& cx, Gr
   cx.stamp();
   bar.sync();
   cx.stamp();
+  look_ahead(p, cx, 2 * cx.ahead_max);  // the attention phase is the longest gap between two weight streams
 
   int cur_pair = -1;
   for (int item = it_lo; item < it_hi; ++item) {
@@ -1114,6 +1146,8 @@ llama_decode_rows_megakernel(const RowsParams p) {
     cx.bars = bars + 8u * (uint32_t)(warp * cx.depth);
     cx.n_used = 0;
     cx.n_phases = n_phases;
+    cx.n_ahead = 0;
+    cx.ahead_max = p.look_ahead;
     cx.fill.ph = 0;
     cx.fill.begin_phase(p, warp);
     for (int i = 0; i < cx.depth; ++i) refill(p, cx, (uint32_t)i);  // the warp's first tiles
@@ -1392,6 +1426,11 @@ int decode_rows_megakernel(const pcy_llama_config& c, const LlamaLayerPtrs* laye
     return e ? atoi(e) : 3;
   }();
   p.align_mask = align_env;
+  static const int ahead_env = [] {
+    const char* e = getenv("PCY_ROWS_LOOKAHEAD");  // tuning knob, see RowsParams::look_ahead
+    return e ? atoi(e) : 0;
+  }();
+  p.look_ahead = std::max(0, ahead_env);
   PCY_CUDA(cudaMemsetAsync(p.barrier, 0, 512, stream));  // grid barrier counter (tickets reset themselves)
   void* fn = pl.nt == 1 ? (void*)llama_decode_rows_megakernel<1> : (void*)llama_decode_rows_megakernel<2>;
   static SmemOptIn opt[2];

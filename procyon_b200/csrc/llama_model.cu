@@ -113,6 +113,11 @@ int pcy_set_decode_timing_buffer(void* dev_u64) {
 
 int pcy_set_decode_sm_shares(const float* shares, int n) { return decode_megakernel_set_shares(shares, n); }
 
+int pcy_set_decode_self_refill(int enabled) {
+  decode_megakernel_set_self_refill(enabled);
+  return 0;
+}
+
 int pcy_set_decode_rows_megakernel(int enabled) {
   g_rows_megakernel = enabled != 0;
   return 0;

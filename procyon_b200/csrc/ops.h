@@ -141,6 +141,7 @@ struct LlamaLayerPtrs {
 #include "../../include/procyon_b200.h"
 namespace pcy {
 void decode_megakernel_set_timing(unsigned long long* dev_buf);
+void decode_megakernel_set_self_refill(int enabled);
 int decode_megakernel_set_shares(const float* shares, int n);
 bool decode_megakernel_supported(const pcy_llama_config& c, int rows);
 int64_t decode_megakernel_scratch_bytes(const pcy_llama_config& c, int rows, int S, int max_gen);

@@ -240,6 +240,31 @@ def test_persistent_and_per_op_decode_match_oracle(cuda_device, kind, rows):
         _assert_argmax_where_clear(got, ref)
 
 
+@pytest.mark.parametrize("kind,rows", [("gq4", 1), ("gq4wide", 2), ("gq4wide", 4)])
+def test_persistent_decode_without_producer_warp_is_bit_identical(cuda_device, kind, rows):
+    """`pcy_set_decode_self_refill(1)`: the greedy persistent kernel with every consumer warp refilling its own ring
+    slots (no producer warp, no empty barriers).  The arithmetic and its order are unchanged, so every step's logits
+    must be bit-identical to the producer-warp form (multi-chunk rows of the wide config included)."""
+    from oracle.llama import random_llama_state_dict
+    from procyon_b200 import _lib
+
+    oc, pc = _cfgs(kind)
+    sd = random_llama_state_dict(oc, seed=3)
+    m = _build(sd, pc)
+    ids, emb, mask = _inputs(oc, sd, rows, 150, seed=7, pad_left=4)
+    forced = torch.randint(0, oc.vocab, (rows, 7), generator=torch.Generator().manual_seed(rows))
+    lib = _lib.load()
+    try:
+        lib.pcy_set_decode_self_refill(0)
+        a = _forced_decode(m, emb, mask, forced, 4)
+        lib.pcy_set_decode_self_refill(1)
+        b = _forced_decode(m, emb, mask, forced, 4)
+    finally:
+        lib.pcy_set_decode_self_refill(0)
+    assert torch.isfinite(a).all()
+    assert torch.equal(a, b)
+
+
 @pytest.mark.parametrize("rows,S", [(1, 1300), (4, 1800)])
 def test_persistent_decode_long_context(cuda_device, rows, S):
     """Long prompts in the single-launch decode step: more than 12 KV splits per head (two-pass merge of the split
