@@ -55,10 +55,12 @@ def main():
         t2 = timeit(ours)
         same = bool(torch.equal(r0, ops.linear(A[0], W[0], force="tc")))
         lib.pcy_set_gemm_pair_mma(1)
+        t1 = timeit(ours)  # the default heuristics (tile width by wave efficiency, pair MMA from three waves)
         tc = timeit(cublas)
         rows.append({"shape": name, "M": M, "N": N, "K": K, "single_cta_tflops": round(fl / t0 / 1e9, 1),
                      "pair_mma_tflops": round(fl / t2 / 1e9, 1), "pair_bit_identical": same,
-                     "cublas_tflops": round(fl / tc / 1e9, 1)})
+                     "default_tflops": round(fl / t1 / 1e9, 1), "cublas_tflops": round(fl / tc / 1e9, 1),
+                     "default_vs_cublas": round(tc / t1, 3)})
         print(json.dumps(rows[-1]), flush=True)
 
 
