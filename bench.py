@@ -397,20 +397,36 @@ def time_retrieval(model, device, world, rank, hbm_peak):
         val, idx = index.topk(out["contrastive_out"]["positive"]["text"][:1].float(), 20)
         return val.cpu(), idx.cpu()
 
-    for _ in range(3):
-        val, idx = query()
-    torch.cuda.synchronize(device)
-    if world > 1:
-        dist.barrier()
-    n = 10
-    t0 = time.perf_counter()
-    for _ in range(n):
-        val, idx = query()
-    torch.cuda.synchronize(device)
-    dt = torch.tensor([(time.perf_counter() - t0) / n], device=device, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-    res["query"] = {"ms_per_query": float(dt) * 1e3, "queries_per_s": 1.0 / float(dt), "prompt_tokens": PROMPT_LEN,
+    from procyon_b200.model.pmc_llama import LlamaPostTokenization
+
+    def timed():
+        for _ in range(3):
+            val, idx = query()
+        torch.cuda.synchronize(device)
+        if world > 1:
+            dist.barrier()
+        n = 10
+        t0 = time.perf_counter()
+        for _ in range(n):
+            val, idx = query()
+        torch.cuda.synchronize(device)
+        dt = torch.tensor([(time.perf_counter() - t0) / n], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        return float(dt), idx
+
+    # forward() pads the prompt to max_text_len like the reference (model_unified.py:1283); by default the positions
+    # after the last valid token are not computed (LlamaPostTokenization.trim_trailing_pads) - both are timed
+    dt, idx = timed()
+    LlamaPostTokenization.trim_trailing_pads = False
+    try:
+        dt_full, idx_full = timed()
+    finally:
+        LlamaPostTokenization.trim_trailing_pads = True
+    res["query"] = {"ms_per_query": dt * 1e3, "queries_per_s": 1.0 / dt, "prompt_tokens": PROMPT_LEN,
+                    "padded_to": int(model.config.max_text_len),
+                    "ms_per_query_all_padded_positions_computed": dt_full * 1e3,
+                    "same_top1": bool(int(idx[0, 0]) == int(idx_full[0, 0])),
                     "d": d, "db_rows_per_rank": index.local.shape[0], "db_sharded_over": world,
                     "exchange": "all-gather of 20 (score, row) candidates per rank" if world > 1 else "none",
                     "top1_row": int(idx[0, 0]),

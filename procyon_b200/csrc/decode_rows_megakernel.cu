@@ -365,13 +365,13 @@ __device__ __forceinline__ void refill(const RowsParams& p, Ctx& cx, uint32_t sl
   }
 }
 
-// L2 look-ahead.  The ring holds 2.9 us of streaming at 10 rows; the bubbles between the streams of two phases
-// (pool / ticket epilogue, grid barrier, staging; the attention phase) are 10-20 us long, and once the ring is full HBM
-// idles through the rest of them.  So when a warp runs out of tiles to consume it asks for the tiles BEYOND its ring
-// slots to be brought into L2 (cp.async.bulk.prefetch.tensor): HBM keeps streaming during the bubble, and the ring
-// refills from L2 - faster than HBM delivers - once consumption resumes.  Only issued at phase ends and inside the
-// attention phase, never alongside a running stream (an always-on prefetch only races the fills for the same lines:
-// measured slower in decode_megakernel.cu).
+// L2 look-ahead (EXPERIMENT, off by default: PCY_ROWS_LOOKAHEAD=n).  The ring holds 2.9 us of streaming at 10 rows; the
+// bubbles between the streams of two phases (pool / ticket epilogue, grid barrier, staging; the attention phase) are
+// 10-20 us long, and once the ring is full HBM idles through the rest of them.  Idea: when a warp runs out of tiles to
+// consume it asks for the n tiles BEYOND its ring slots to be brought into L2 (cp.async.bulk.prefetch.tensor), so that
+// HBM keeps streaming during the bubble and the ring refills from L2 once consumption resumes.  Measured on B200 at
+// 10 beams: 4.20 ms per step without, 4.42 / 4.55 / 4.84 / 5.10 ms with n = 2 / 4 / 8 / 16 - the streams that follow
+// get slower, not faster (the same outcome as the always-on prefetch lanes tried in decode_megakernel.cu).
 __device__ __forceinline__ void tma_prefetch_2d(const void* desc, int32_t c0, int32_t c1) {
   asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(desc), "r"(c0), "r"(c1) : "memory");
 }

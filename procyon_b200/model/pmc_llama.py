@@ -441,13 +441,34 @@ class LlamaPostTokenization(nn.Module):
         _lib.require_cuda(input_embeds)
         dev = input_embeds.device
         self._ensure_packed(dev)
-        B, S, d = input_embeds.shape
+        B, S_full, d = input_embeds.shape
         c = self.model.config
-        self._ensure_rope(S, dev)
-        x = input_embeds.to(torch.bfloat16).contiguous()
         valid = None
         if attn_masks is not None:
             valid = (attn_masks.to(dev) != 0).to(torch.uint8).contiguous()
+        # Trailing padding.  The reference pads every forward() batch to max_text_len (2048 for ProCyon-Full,
+        # model_unified.py:1283) and HF then runs all of those positions through the 32 layers.  Positions after the
+        # last valid token of the longest row are masked as keys and never read as outputs (labels -100, no [PROT] /
+        # answer token there), and with causal attention nothing before them depends on them: they are not computed
+        # here; their hidden states come back as zeros (reference: values derived from pad embeddings).  Only for
+        # forward passes without a KV cache (generation prompts are un-padded or left-padded).
+        S = S_full
+        if valid is not None and not want_cache and self.trim_trailing_pads and S_full > 1:
+            pos = torch.arange(1, S_full + 1, device=dev, dtype=torch.int32)
+            S = max(1, int((valid.to(torch.int32) * pos).amax().item()))
+        self._ensure_rope(S_full, dev)
+        if S < S_full:
+            def remap(rows):  # flat token rows b * S_full + p -> b * S + p
+                rows = rows.to(device=dev, dtype=torch.int64)
+                b, p_ = rows // S_full, rows % S_full
+                assert bool((p_ < S).all()), "a selected row lies in the trailing padding"
+                return (b * S + p_).to(torch.int32)
+
+            sel_rows = remap(sel_rows) if sel_rows is not None and sel_rows.numel() > 0 else sel_rows
+            acc_rows = remap(acc_rows) if acc_rows is not None and acc_rows.numel() > 0 else acc_rows
+            input_embeds = input_embeds[:, :S]
+            valid_full, valid = valid, valid[:, :S].contiguous()
+        x = input_embeds.to(torch.bfloat16).contiguous()
         kvd = c.num_key_value_heads * c.head_dim
         kv = None
         if want_cache:
@@ -473,6 +494,12 @@ class LlamaPostTokenization(nn.Module):
                                        ptr(acc_rows) if n_acc else None, c_int(n_acc), ptr(acc), ptr(ws),
                                        c_i64(ws.numel()), stream_ptr(dev)), "pcy_llama_prefill_ex")
         self.last_hidden_sum = acc
+        if S < S_full:
+            if hidden is not None:
+                full = torch.zeros((B, S_full, d), device=dev, dtype=hidden.dtype)
+                full[:, :S] = hidden
+                hidden = full
+            valid = valid_full
         return kv, hidden, logits, valid
 
     def lm_head_logits(self, hidden_rows: torch.Tensor) -> torch.Tensor:
@@ -595,6 +622,9 @@ class LlamaPostTokenization(nn.Module):
             sess.reset(sel_logits[r0:r1].contiguous())
             out.append(sess)
         return out[0] if len(out) == 1 else SessionGroup(out)
+
+    # compute only up to the last valid position of a padded forward() batch (see prefill); False = every position
+    trim_trailing_pads = True
 
     # ---- reference-facing forward -------------------------------------------------------------------------------
     def forward(self, input_embeds=None, input_ids=None, attn_masks=None, full_labels=None, past_key_values=None,

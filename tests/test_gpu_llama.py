@@ -67,6 +67,52 @@ def test_prefill_hidden_logits_loss(llama):
     assert out.past_key_values is None
 
 
+@pytest.mark.parametrize("S,lens", [(160, (70, 41, 133)), (300, (150, 150)), (64, (64, 10))])
+def test_prefill_skips_trailing_padding(llama, S, lens):
+    """forward() batches arrive right-padded to max_text_len (reference: model_unified.py:1283, 2048 for ProCyon-Full).
+    Positions after the last valid token of the longest row are not computed (`trim_trailing_pads`): hidden states,
+    logits and the LM loss at every VALID position must equal the full computation and the oracle, the [PROT]-style
+    hidden-state sums too, and the skipped positions come back as zeros."""
+    from oracle.llama import llama_forward
+    from procyon_b200.model.pmc_llama import LlamaPostTokenization
+
+    oc, sd, m = llama
+    B = len(lens)
+    ids, emb, _ = _inputs(oc, sd, B, S, seed=S)
+    mask = torch.zeros(B, S)
+    for b, n in enumerate(lens):
+        mask[b, :n] = 1
+    labels = ids.clone()
+    labels[:, :8] = -100
+    labels[mask == 0] = -100
+    pick = torch.zeros(B, S, dtype=torch.bool)
+    for b, n in enumerate(lens):
+        pick[b, n - 1] = True  # the last valid token of every row, like a [PROT] position
+    ref = llama_forward(sd, oc, inputs_embeds=emb.float(), attention_mask=mask, labels=labels, act_round="bf16")
+
+    def run(trim):
+        LlamaPostTokenization.trim_trailing_pads = trim
+        try:
+            return m(input_embeds=emb.cuda(), attn_masks=mask.cuda(), full_labels=labels.cuda(),
+                     sum_hidden_rows=pick.cuda())
+        finally:
+            LlamaPostTokenization.trim_trailing_pads = True
+
+    a, b_ = run(True), run(False)
+    keep = mask.bool()
+    ha, hb = a.hidden_states[-1].float().cpu(), b_.hidden_states[-1].float().cpu()
+    # (300 k elements of O(1) magnitude after two bf16 layers: one or two land a bf16 ulp of an intermediate past 3e-2)
+    torch.testing.assert_close(ha[keep], ref["hidden_states"][-1][keep], rtol=3e-2, atol=5e-2)
+    torch.testing.assert_close(ha[keep], hb[keep], rtol=3e-2, atol=5e-2)
+    torch.testing.assert_close(a.logits.cpu()[keep], ref["logits"][keep], rtol=3e-2, atol=4e-2)
+    assert abs(a.loss.item() - ref["loss"].item()) < 2e-2 and abs(a.loss.item() - b_.loss.item()) < 2e-2
+    torch.testing.assert_close(a.hidden_sum.cpu(), b_.hidden_sum.cpu(), rtol=3e-2, atol=6e-2)
+    n_max = max(lens)
+    if n_max < S:
+        assert float(ha[:, n_max:].abs().max()) == 0.0          # skipped positions: zeros
+        assert float(hb[:, n_max:].abs().max()) > 0.0           # (the full computation fills them)
+
+
 def test_decode_step_matches_oracle_and_prefill(llama):
     from oracle.llama import llama_forward
 
