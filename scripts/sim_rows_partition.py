@@ -7,13 +7,13 @@ from collections import defaultdict
 RW, PW, TR, TK = 8, 3, 16, 256
 
 
-def make_geom(N, K, kcap):
+def make_geom(N, K, kcap, aligned=False):
     n_rg = (N + TR - 1) // TR
     ck = K // TK
     kq0 = (K + kcap - 1) // kcap
     ckq = (ck + kq0 - 1) // kq0
     KQ = (ck + ckq - 1) // ckq
-    return dict(n_rg=n_rg, ck=ck, KQ=KQ, ckq=ckq, per=n_rg * ckq, T=n_rg * ck)
+    return dict(n_rg=n_rg, ck=ck, KQ=KQ, ckq=ckq, per=n_rg * ckq, T=n_rg * ck, unit=ck if (aligned and KQ == 1) else 1)
 
 
 def part_len(g, q):
@@ -32,10 +32,17 @@ def lo_of(T, i, nb):
     return T * i // nb
 
 
+def cta_lo(g, i, nb):
+    """first chunk of CTA i: stream-K cut, or (unit = chunks per row group) at row-group boundaries"""
+    return (g["T"] // g["unit"]) * i // nb * g["unit"]
+
+
 def plan_ok(N, K, kcap, swiglu, nb):
     """the host-side guard of plan_matrix()"""
     g = make_geom(N, K, kcap)
     cmax = (g["T"] + nb - 1) // nb
+    if g["KQ"] == 1:
+        cmax = max(cmax, (g["n_rg"] + nb - 1) // nb * g["ck"])
     span = (cmax + RW - 1) // RW
     len_min = min(part_len(g, q) for q in range(g["KQ"]))
     pieces = 1 if span <= 1 else (span + len_min - 2) // len_min + 1
@@ -44,8 +51,8 @@ def plan_ok(N, K, kcap, swiglu, nb):
     return pieces <= PW
 
 
-def simulate(N, K, kcap, swiglu, nb):
-    g = make_geom(N, K, kcap)
+def simulate(N, K, kcap, swiglu, nb, aligned=False):
+    g = make_geom(N, K, kcap, aligned)
     T = g["T"]
     seen = defaultdict(int)
     tickets = defaultdict(int)
@@ -62,7 +69,7 @@ def simulate(N, K, kcap, swiglu, nb):
     max_np = 0
     ring_positions = 0
     for bid in range(nb):
-        lo, hi = lo_of(T, bid, nb), lo_of(T, bid + 1, nb)
+        lo, hi = cta_lo(g, bid, nb), cta_lo(g, bid + 1, nb)
         a = lo
         while a < hi:
             q = min(a // g["per"], g["KQ"] - 1)
@@ -124,6 +131,7 @@ def simulate(N, K, kcap, swiglu, nb):
                 if g["KQ"] == 1 and og_c0 >= lo and og_c0 + og_total <= hi:
                     finished[og] += 1
                     continue
+                assert g["unit"] == 1, "a group-aligned cut never splits a group between CTAs"
                 for s in range(2 if swiglu else 1):
                     if segn[s] == 0:
                         continue
@@ -174,6 +182,8 @@ if __name__ == "__main__":
                     print(name, label, "not supported on", n, "SMs (per-op path)")
                     continue
                 r = simulate(N, K, kcap, sw, n)
+                if not sw:
+                    simulate(N, K, kcap, sw, n, aligned=True)
                 if n == nb:
                     print(name, label, r)
     print("ok")
