@@ -50,10 +50,11 @@ constexpr int PPB = 144;          // bytes per P row (64 bf16 + 16)
 constexpr int PSTR = HD + 4;      // floats per (split, head) attention partial: 128 outputs, max, sum
 constexpr int MERGE_B = 18;       // splits merged per batch of independent loads (72 registers)
 constexpr int KV_ISSUERS = 2 * SUBK;  // threads that fetch K / V rows of an item (arrival count of its mbarrier)
-// misc block of shared memory: [0, 96) row group of every pool tile | [128, 192) tokens | [256, ...) mbarriers (full /
+// misc block of shared memory: [0, 96) row group of every pool tile | [128, 192) tokens | [192, 232) chunk ranges |
+// [256, ...) mbarriers (full /
 // empty per ring slot + one for the attention tiles) | [MISC_LN, ...) two RMSNorm weight pointers per layer
 constexpr int MAX_SLOTS = 40;
-constexpr int MISC_TOK = 128, MISC_BARS = 256, MISC_LN = MISC_BARS + 8 * (MAX_SLOTS + 1) + 8;
+constexpr int MISC_TOK = 128, MISC_LOHI = 192, MISC_BARS = 256, MISC_LN = MISC_BARS + 8 * (MAX_SLOTS + 1) + 8;
 
 enum : int { EPI_BF16 = 0, EPI_RESIDUAL = 1, EPI_SWIGLU = 2, EPI_FP32 = 3 };
 enum : int { STAGE_PLAIN = 0, STAGE_RMS = 1 };
@@ -109,6 +110,11 @@ __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], 
 }
 __device__ __forceinline__ float ldcg_bf16(const bf16* p) {
   return __bfloat162float(__ushort_as_bfloat16(__ldcg(reinterpret_cast<const unsigned short*>(p))));
+}
+__device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
+  uint4 u;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(addr) : "memory");
+  return u;
 }
 __device__ __forceinline__ void sts_v4(uint32_t addr, uint4 u) {
   asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w) : "memory");
@@ -205,13 +211,14 @@ struct RowsParams {
   int off_misc;
   unsigned long long* timing;
   int timing_cta;
-  int look_ahead;  // weight tiles per warp prefetched into L2 beyond the ring at every phase end (0 = off)
+  Geom geom[5];    // per phase kind (0 qkv, 1 o_proj, 2 gate/up, 3 down, 4 LM head), computed on the host: the kernel
+                   // is ~200 KB of SASS that runs out of a cold instruction cache at every phase boundary, and each
+                   // inlined copy of the geometry arithmetic (five integer divisions) is 150 instructions of it
   int align_mask;  // bit k: phases of kind k (0 qkv, 1 o_proj, 2 gate/up, 4 LM head) are cut at row-group boundaries
 };
 
 struct PhaseDesc {
-  int N, K, stage, epi, map;
-  bool aligned;
+  int N, K, stage, epi, map, kind;
   const bf16* A;
   int64_t lda;
   const bf16* rms_w;
@@ -228,7 +235,7 @@ __device__ __forceinline__ PhaseDesc phase_desc(const RowsParams& p, const bf16*
   PhaseDesc z;
   z.rms_w = nullptr;
   z.map = ph;
-  z.aligned = (p.align_mask >> (ph == n_phases - 1 ? 4 : (ph & 3))) & 1;
+  z.kind = ph == n_phases - 1 ? 4 : (ph & 3);
   if (ph == n_phases - 1) {
     z.N = c.vocab; z.K = d; z.stage = STAGE_RMS; z.epi = EPI_FP32; z.A = p.x; z.lda = d; z.rms_w = p.norm;
     z.out = p.logits; z.ldo = c.vocab;
@@ -260,18 +267,6 @@ __device__ __forceinline__ PhaseDesc phase_desc(const RowsParams& p, const bf16*
 // of the ring and refills a slot itself, right after it has consumed it, with the tile it will need ring-depth tiles
 // later - whatever phase that tile belongs to, so weights keep streaming across grid barriers, staging and attention.
 // The cursor walks the warp's tiles: phases -> runs (the CTA's chunks of one k-part) -> the warp's span of the run.
-__device__ __forceinline__ void phase_shape(const RowsParams& p, int ph, int& N, int& K, bool& aligned) {
-  const pcy_llama_config& c = p.cfg;
-  const int n_phases = 4 * c.n_layers + 1;
-  const int kind = ph == n_phases - 1 ? 4 : (ph & 3);
-  aligned = (p.align_mask >> kind) & 1;
-  if (kind == 4) { N = c.vocab; K = c.d_model; }
-  else if (kind == 0) { N = (c.n_heads + 2 * c.n_kv_heads) * HD; K = c.d_model; }
-  else if (kind == 1) { N = c.d_model; K = c.n_heads * HD; }
-  else if (kind == 2) { N = 2 * c.ffn_dim; K = c.d_model; }
-  else { N = c.d_model; K = c.ffn_dim; }
-}
-
 struct Cursor {
   int ph;              // phase of the next tile (n_phases = exhausted)
   int hi, b;           // end of the CTA's range in the phase, end of the current run
@@ -279,6 +274,7 @@ struct Cursor {
   int q, len, qbase;   // run constants: k-part, chunks per (row group, part), first chunk of the part
   int ckq;
   int n_rg, ck, KQ, per, T;
+  const int* lohi;     // shared memory: [kind][2] first / end chunk of this CTA's range for every phase kind
 
   __device__ __forceinline__ void begin_run(int a, int warp) {
     q = min(a / per, KQ - 1);
@@ -290,14 +286,11 @@ struct Cursor {
     c_hi = a + C * (warp + 1) / RW;
   }
   __device__ __forceinline__ void begin_phase(const RowsParams& p, int warp) {
-    int N, K;
-    bool aligned;
-    phase_shape(p, ph, N, K, aligned);
-    const Geom g = make_geom(N, K, p.kcap, aligned);
+    const int kind = ph == 4 * p.cfg.n_layers ? 4 : (ph & 3);
+    const Geom& g = p.geom[kind];
     n_rg = g.n_rg; ck = g.ck; KQ = g.KQ; ckq = g.ckq; per = g.per; T = g.T;
-    const int lo = cta_lo(g, blockIdx.x, gridDim.x);
-    hi = cta_lo(g, blockIdx.x + 1, gridDim.x);
-    b = lo;
+    hi = lohi[2 * kind + 1];
+    b = lohi[2 * kind];
     c = c_hi = 0;
   }
   // the next tile: tensor map index, first weight row, first k element; false when every phase is exhausted
@@ -329,9 +322,6 @@ struct Ctx {
   int depth;            // slots per warp
   uint32_t n_used;      // tiles consumed so far by this warp (tile e lives in slot e % depth, parity (e / depth) & 1)
   Cursor fill;          // the next tile to request
-  Cursor ahead;         // L2 look-ahead: the next tile to PREFETCH (valid while n_ahead > 0)
-  int n_ahead;          // tiles between `fill` and `ahead`
-  int ahead_max;        // look-ahead depth per warp (0 = off)
   int n_phases;
   uint32_t act;        // staged activations: row m at act + m * pitch
   uint32_t pitch;      // kcap * 2 + 16 bytes
@@ -353,7 +343,6 @@ __device__ __forceinline__ void refill(const RowsParams& p, Ctx& cx, uint32_t sl
   int map, row0, k0;
   const int warp = threadIdx.x >> 5;
   if (!cx.fill.next(p, warp, cx.n_phases, map, row0, k0)) return;
-  if (cx.n_ahead > 0) --cx.n_ahead;
   if ((threadIdx.x & 31) == 0) {
     fence_proxy_async_smem();  // the warp's ldmatrix reads of the slot are ordered before the bulk write
     const uint32_t bar = cx.bars + 8u * slot;
@@ -362,31 +351,6 @@ __device__ __forceinline__ void refill(const RowsParams& p, Ctx& cx, uint32_t sl
     const uint64_t pol = l2_evict_first_policy();  // weights are read once per step: keep L2 for KV / activations
 #pragma unroll
     for (int i = 0; i < 4; ++i) tma_load_2d_hint(dst + i * 2048, p.maps + map, bar, k0 + i * 64, row0, pol);
-  }
-}
-
-// L2 look-ahead (EXPERIMENT, off by default: PCY_ROWS_LOOKAHEAD=n).  The ring holds 2.9 us of streaming at 10 rows; the
-// bubbles between the streams of two phases (pool / ticket epilogue, grid barrier, staging; the attention phase) are
-// 10-20 us long, and once the ring is full HBM idles through the rest of them.  Idea: when a warp runs out of tiles to
-// consume it asks for the n tiles BEYOND its ring slots to be brought into L2 (cp.async.bulk.prefetch.tensor), so that
-// HBM keeps streaming during the bubble and the ring refills from L2 once consumption resumes.  Measured on B200 at
-// 10 beams: 4.20 ms per step without, 4.42 / 4.55 / 4.84 / 5.10 ms with n = 2 / 4 / 8 / 16 - the streams that follow
-// get slower, not faster (the same outcome as the always-on prefetch lanes tried in decode_megakernel.cu).
-__device__ __forceinline__ void tma_prefetch_2d(const void* desc, int32_t c0, int32_t c1) {
-  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(desc), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void look_ahead(const RowsParams& p, Ctx& cx, int upto) {
-  if (cx.ahead_max == 0 || cx.n_ahead >= upto) return;
-  if (cx.n_ahead == 0) cx.ahead = cx.fill;
-  const int warp = threadIdx.x >> 5;
-  while (cx.n_ahead < upto) {
-    int map, row0, k0;
-    if (!cx.ahead.next(p, warp, cx.n_phases, map, row0, k0)) break;
-    ++cx.n_ahead;
-    if ((threadIdx.x & 31) == 0) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) tma_prefetch_2d(p.maps + map, k0 + i * 64, row0);
-    }
   }
 }
 
@@ -416,14 +380,14 @@ __device__ __forceinline__ void mma_tile(uint32_t wt, uint32_t a_lane, float (&a
   }
 }
 
-template <int NT>
-__device__ __forceinline__ void store_out(const PhaseDesc& z, int rows, int n_out, int col, int m, float v) {
+// one output element
+__device__ __forceinline__ void store_out(void* out, int64_t ldo, int epi, int rows, int n_out, int col, int m, float v) {
   if (m >= rows || col >= n_out) return;
-  if (z.epi == EPI_FP32) {
-    reinterpret_cast<float*>(z.out)[(int64_t)m * z.ldo + col] = v;
+  if (epi == EPI_FP32) {
+    reinterpret_cast<float*>(out)[(int64_t)m * ldo + col] = v;
   } else {
-    bf16* op = reinterpret_cast<bf16*>(z.out) + (int64_t)m * z.ldo + col;
-    if (z.epi == EPI_RESIDUAL) v += ldcg_bf16(op);
+    bf16* op = reinterpret_cast<bf16*>(out) + (int64_t)m * ldo + col;
+    if (epi == EPI_RESIDUAL) v += ldcg_bf16(op);
     *op = __float2bfloat16_rn(v);
   }
 }
@@ -438,10 +402,10 @@ __device__ __forceinline__ void weight_phase(const RowsParams& p, Ctx& cx, const
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nb = gridDim.x, bid = blockIdx.x;
   const int rows = p.rows;
-  const Geom g = make_geom(z.N, z.K, p.kcap, z.aligned);
+  const Geom g = p.geom[z.kind];
   const bool swiglu = z.epi == EPI_SWIGLU;
   const int n_out = swiglu ? z.N / 2 : z.N;
-  const int lo = cta_lo(g, bid, nb), hi = cta_lo(g, bid + 1, nb);
+  const int lo = cx.fill.lohi[2 * z.kind], hi = cx.fill.lohi[2 * z.kind + 1];
   const int nseg = swiglu ? 2 : g.KQ;
   const unsigned int og_total = (unsigned int)(swiglu ? 2 * g.ck : g.ck);
 
@@ -455,6 +419,79 @@ __device__ __forceinline__ void weight_phase(const RowsParams& p, Ctx& cx, const
     // Every L2 round trip costs 2-3 us while all SMs stream weights, so the loads of ALL rows are issued before the
     // first use: thread t owns the 16-byte column pieces t and t + 256 of every row (and of the RMSNorm weight).
     if (tid < RW * PW) cx.prg[tid] = -1;
+    if (rows <= 4)
+    {
+      // Up to 4 rows: cp.async (L2 -> shared memory, no registers in between) and rolled loops.  This block runs once
+      // per phase out of a cold instruction cache (the kernel is ~200 KB of SASS), and with few rows the unrolled
+      // register-staged form below costs more in instruction fetch than in data: 3.9 us for 2 rows against 1.7 us for
+      // a plain copy of the same bytes (2 rows: 3.51 -> 3.40 ms per step).  From 5 rows on the three passes over shared
+      // memory (raw copy, sums of squares, in-place normalisation) cost more than they save (10 rows: 7.5 vs 5.8 us).
+      const int pcs = kn >> 3;  // 16-byte pieces per row
+      const bool rms = z.stage == STAGE_RMS;
+      for (int m = 0; m < rows; ++m) {
+        const bf16* src = (tok_rows ? p.embed + (int64_t)tok_rows[m] * z.K : z.A + (int64_t)m * z.lda) + k0;
+        for (int pc = tid; pc < pcs; pc += RT)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(cx.act + m * cx.pitch + pc * 16),
+                       "l"(src + pc * 8) : "memory");
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      uint4 g0 = make_uint4(0, 0, 0, 0), g1 = g0;  // RMSNorm weight of this thread's two column pieces
+      if (rms) {
+        if (tid < pcs) g0 = *reinterpret_cast<const uint4*>(z.rms_w + tid * 8);
+        if (tid + RT < pcs) g1 = *reinterpret_cast<const uint4*>(z.rms_w + (tid + RT) * 8);
+      }
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      if (rms) {
+        // RMSNorm with HF rounding, in place: y = w * bf16(x * rstd), rstd from fp32 sums over the whole row.  Every
+        // thread only touches the pieces it copied itself (t and t + 256 of every row: K <= 4096, checked on the host).
+        float* red = cx.pool;  // [16][RW] sums of squares (the pool is idle while staging)
+        for (int m = 0; m < rows; ++m) {
+          float ss = 0.f;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int pc = tid + h * RT;
+            if (pc < pcs) {
+              const uint4 u = lds_v4(cx.act + m * cx.pitch + pc * 16);
+              const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
+              ss += a0.x * a0.x + a0.y * a0.y + a1.x * a1.x + a1.y * a1.y + a2.x * a2.x + a2.y * a2.y + a3.x * a3.x +
+                    a3.y * a3.y;
+            }
+          }
+          ss = warp_sum(ss);
+          if (lane == 0) red[m * RW + warp] = ss;
+        }
+        consumer_sync();
+        for (int m = 0; m < rows; ++m) {
+          float tot = 0.f;
+#pragma unroll
+          for (int w = 0; w < RW; ++w) tot += red[m * RW + w];
+          const float rstd = rsqrtf(tot / (float)z.K + p.cfg.rms_eps);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int pc = tid + h * RT;
+            if (pc < pcs) {
+              const uint32_t addr = cx.act + m * cx.pitch + pc * 16;
+              const uint4 u = lds_v4(addr);
+              const uint4 gw = h == 0 ? g0 : g1;
+              const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+              const uint32_t gg[4] = {gw.x, gw.y, gw.z, gw.w};
+              uint32_t oo[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                // two elements at a time: bf16(x * rstd) by one packed conversion, times the weight by one packed
+                // bf16 multiply (the product of two bf16 is exact in fp32, so rounding it once is what the fp32 form
+                // w * bf16_round(x * rstd) -> bf16 gives)
+                const float2 xv = unpack_bf16x2(uu[e]);
+                const uint32_t t2 = pack_bf16x2(xv.x * rstd, xv.y * rstd);
+                asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(oo[e]) : "r"(gg[e]), "r"(t2));
+              }
+              sts_v4(addr, make_uint4(oo[0], oo[1], oo[2], oo[3]));
+            }
+          }
+        }
+      }
+    }
+    else
     {
       constexpr int RBATCH = 10;  // rows per batch of loads (2 pieces per thread and row: 80 registers)
       const int pcs = kn >> 3;    // 16-byte pieces per row
@@ -559,10 +596,10 @@ __device__ __forceinline__ void weight_phase(const RowsParams& p, Ctx& cx, const
         const int wr = lane >> 2, mc = (lane & 3) * 2;
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) {
-          store_out<NT>(z, rows, n_out, cur_rg * TR + wr, nt * 8 + mc, acc[nt][0]);
-          store_out<NT>(z, rows, n_out, cur_rg * TR + wr, nt * 8 + mc + 1, acc[nt][1]);
-          store_out<NT>(z, rows, n_out, cur_rg * TR + wr + 8, nt * 8 + mc, acc[nt][2]);
-          store_out<NT>(z, rows, n_out, cur_rg * TR + wr + 8, nt * 8 + mc + 1, acc[nt][3]);
+          store_out(z.out, z.ldo, z.epi, rows, n_out, cur_rg * TR + wr, nt * 8 + mc, acc[nt][0]);
+          store_out(z.out, z.ldo, z.epi, rows, n_out, cur_rg * TR + wr, nt * 8 + mc + 1, acc[nt][1]);
+          store_out(z.out, z.ldo, z.epi, rows, n_out, cur_rg * TR + wr + 8, nt * 8 + mc, acc[nt][2]);
+          store_out(z.out, z.ldo, z.epi, rows, n_out, cur_rg * TR + wr + 8, nt * 8 + mc + 1, acc[nt][3]);
         }
       } else {
         if (np >= PW) __trap();  // the host-side sizing guarantees this never happens
@@ -600,7 +637,6 @@ __device__ __forceinline__ void weight_phase(const RowsParams& p, Ctx& cx, const
       refill(p, cx, slot);  // the slot is free: request the tile this warp needs `depth` tiles from now
     }
     if (cur_rg >= 0) flush();
-    look_ahead(p, cx, cx.ahead_max);  // this warp has nothing to consume until the next phase is staged
     consumer_sync();
     cx.stamp();
 
@@ -647,7 +683,7 @@ __device__ __forceinline__ void weight_phase(const RowsParams& p, Ctx& cx, const
             if (m < rows && col < n_out)
               reinterpret_cast<bf16*>(z.out)[(int64_t)m * z.ldo + col] = __float2bfloat16_rn(silu(sum[0][i]) * sum[1][i]);
           } else {
-            store_out<NT>(z, rows, n_out, col, m, sum[0][i]);
+            store_out(z.out, z.ldo, z.epi, rows, n_out, col, m, sum[0][i]);
           }
         }
       };
@@ -813,7 +849,6 @@ __device__ __forceinline__ void attention_phase(const RowsParams& p, Ctx& cx, Gr
   cx.stamp();
   bar.sync();
   cx.stamp();
-  look_ahead(p, cx, 2 * cx.ahead_max);  // the attention phase is the longest gap between two weight streams
 
   int cur_pair = -1;
   for (int item = it_lo; item < it_hi; ++item) {
@@ -1129,6 +1164,12 @@ llama_decode_rows_megakernel(const RowsParams p) {
   const bf16** s_ln = reinterpret_cast<const bf16**>(misc + MISC_LN);
   for (int i = threadIdx.x; i < 2 * c.n_layers; i += RBLOCK)
     s_ln[i] = (i & 1) ? p.layers[i >> 1].ln2 : p.layers[i >> 1].ln1;
+  // this CTA's chunk range of every phase kind (the cut itself: cta_lo)
+  int* s_lohi = reinterpret_cast<int*>(misc + MISC_LOHI);
+  if (threadIdx.x < 5) {
+    s_lohi[2 * threadIdx.x] = cta_lo(p.geom[threadIdx.x], blockIdx.x, gridDim.x);
+    s_lohi[2 * threadIdx.x + 1] = cta_lo(p.geom[threadIdx.x], blockIdx.x + 1, gridDim.x);
+  }
   if (threadIdx.x == 0) {
     for (int i = 0; i < ns; ++i) mbar_init(bars + 8u * i, 1);  // one arrive.expect_tx by the refilling warp + the bytes
     mbar_init(kvbar, KV_ISSUERS);
@@ -1146,9 +1187,8 @@ llama_decode_rows_megakernel(const RowsParams p) {
     cx.bars = bars + 8u * (uint32_t)(warp * cx.depth);
     cx.n_used = 0;
     cx.n_phases = n_phases;
-    cx.n_ahead = 0;
-    cx.ahead_max = p.look_ahead;
     cx.fill.ph = 0;
+    cx.fill.lohi = s_lohi;
     cx.fill.begin_phase(p, warp);
     for (int i = 0; i < cx.depth; ++i) refill(p, cx, (uint32_t)i);  // the warp's first tiles
   }
@@ -1426,11 +1466,11 @@ int decode_rows_megakernel(const pcy_llama_config& c, const LlamaLayerPtrs* laye
     return e ? atoi(e) : 3;
   }();
   p.align_mask = align_env;
-  static const int ahead_env = [] {
-    const char* e = getenv("PCY_ROWS_LOOKAHEAD");  // tuning knob, see RowsParams::look_ahead
-    return e ? atoi(e) : 0;
-  }();
-  p.look_ahead = std::max(0, ahead_env);
+  {
+    const int d = c.d_model, f = c.ffn_dim, H = c.n_heads, KVH = c.n_kv_heads;
+    const int Ns[5] = {(H + 2 * KVH) * HD, d, 2 * f, d, c.vocab}, Ks[5] = {d, H * HD, d, f, d};
+    for (int k = 0; k < 5; ++k) p.geom[k] = make_geom(Ns[k], Ks[k], pl.kcap, (p.align_mask >> k) & 1);
+  }
   PCY_CUDA(cudaMemsetAsync(p.barrier, 0, 512, stream));  // grid barrier counter (tickets reset themselves)
   void* fn = pl.nt == 1 ? (void*)llama_decode_rows_megakernel<1> : (void*)llama_decode_rows_megakernel<2>;
   static SmemOptIn opt[2];

@@ -100,7 +100,7 @@ static int g_rows_megakernel = 1;
 static bool use_rows_megakernel(const LlamaModel* m, int rows, int beams) {
   static const bool force_multi = getenv("PCY_DECODE_MULTIKERNEL") != nullptr;
   // (pcy_set_decode_megakernel(0) selects the per-op path for EVERY row count, as documented)
-  return !force_multi && g_rows_megakernel != 0 && g_megakernel_max_rows > 0 && rows > g_megakernel_max_rows &&
+  return !force_multi && g_rows_megakernel != 0 && g_megakernel_max_rows != 0 && rows > g_megakernel_max_rows &&
          m->rows_maps != nullptr && decode_rows_megakernel_supported(m->cfg, rows, beams);
 }
 
@@ -129,7 +129,8 @@ int pcy_set_decode_rows_timing_buffer(void* dev_u64) {
 }
 
 int pcy_set_decode_megakernel(int max_rows) {
-  g_megakernel_max_rows = max_rows < 0 ? 0 : (max_rows > 4 ? 4 : max_rows);
+  // (-1: experiment - the tile-streaming kernel for every row count, 1 included)
+  g_megakernel_max_rows = max_rows < 0 ? -1 : (max_rows > 4 ? 4 : max_rows);
   return 0;
 }
 
