@@ -393,8 +393,11 @@ __device__ __forceinline__ void store_out(void* out, int64_t ldo, int epi, int r
 }
 
 // Weight phase: out = epi(W . A) for this CTA's chunk range.
-template <int NT>
-__device__ __forceinline__ void weight_phase(const RowsParams& p, Ctx& cx, const PhaseDesc& z, const int32_t* tok_rows) {
+// `after_consume` runs right after the CTA has consumed its last tile of a run (the staging area is free from then on):
+// the qkv phase uses it to request the K / V rows of its first attention item before it turns to its epilogue.
+template <int NT, class AfterConsume>
+__device__ __forceinline__ void weight_phase(const RowsParams& p, Ctx& cx, const PhaseDesc& z, const int32_t* tok_rows,
+                                             AfterConsume&& after_consume) {
   // partial tile: [16 weight rows][rs activation rows] fp32; when tiles are added, lane l owns weight row l / 2 and
   // the activation rows (l & 1) * rs / 2 ... of it
   constexpr int EPL = 4 * NT;       // upper bound of rs / 2
@@ -638,6 +641,7 @@ __device__ __forceinline__ void weight_phase(const RowsParams& p, Ctx& cx, const
     }
     if (cur_rg >= 0) flush();
     consumer_sync();
+    after_consume();
     cx.stamp();
 
     // ---- per output group: add the warps' pieces; finish here or through the global ticket ----
@@ -827,9 +831,38 @@ __device__ __forceinline__ void att_request(const RowsParams& p, const AttLayout
   }
 }
 
+// Beams allowed to see key `threadIdx.x` of an item (threads 0..63): prompt keys by the left-pad mask, generated
+// (step, physical row) entries by the ancestry table - all 16 loads of it issued together.
+__device__ __forceinline__ uint32_t att_key_bits(const RowsParams& p, const AttGeom& ag, int item, uint32_t all_beams) {
+  const int tid = threadIdx.x;
+  uint32_t bits = 0;
+  if (tid >= SUBK) return bits;
+  const int KVH = p.cfg.n_kv_heads;
+  const int pair = item / ag.n_splits, split = item - pair * ag.n_splits;
+  const int input = pair / KVH;
+  const int key = split * SUBK + tid;
+  if (key < p.S) {
+    bits = (p.prompt_valid == nullptr || p.prompt_valid[(int64_t)input * p.S + key] != 0) ? all_beams : 0u;
+  } else if (key < ag.Nk) {
+    const int jj = key - p.S, gi = jj / p.beams, r = jj - gi * p.beams;
+    if (gi == ag.g_cur) {
+      bits = 1u << r;
+    } else {
+      int sl[16];
+#pragma unroll
+      for (int bb = 0; bb < 16; ++bb)
+        sl[bb] = bb < p.beams ? p.slots[(int64_t)(input * p.beams + bb) * p.max_gen + gi] : -1;
+#pragma unroll
+      for (int bb = 0; bb < 16; ++bb)
+        if (sl[bb] == input * p.beams + r) bits |= 1u << bb;
+    }
+  }
+  return bits;
+}
+
 template <int NT>
 __device__ __forceinline__ void attention_phase(const RowsParams& p, Ctx& cx, GridBarrier& bar, const AttLayout& s,
-                                                uint32_t kvbar, uint32_t& kv_par, int layer, int t) {
+                                                uint32_t kvbar, uint32_t& kv_par, int layer, int t, bool requested) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nb = gridDim.x, bid = blockIdx.x;
   const int H = p.cfg.n_heads, KVH = p.cfg.n_kv_heads, kvd = KVH * HD, qkv_dim = (H + 2 * KVH) * HD;
@@ -842,10 +875,20 @@ __device__ __forceinline__ void attention_phase(const RowsParams& p, Ctx& cx, Gr
   const float2* cs = reinterpret_cast<const float2*>(p.rope) + (int64_t)ag.pos_cur * (HD / 2);
   const uint32_t all_beams = (1u << p.beams) - 1u;
 
-  // the first item's cached rows are requested before the grid barrier that completes qkv
-  consumer_sync();  // everybody is done with the staging area / pool of the qkv phase
-  fence_proxy_async_smem();
-  if (it_lo < it_hi) att_request(p, s, ag, layer, it_lo, kvbar);
+  // the first item's cached rows are requested before the grid barrier that completes qkv (normally right after the
+  // qkv phase's last tile, see weight_phase's after_consume)
+  if (!requested) {
+    consumer_sync();  // everybody is done with the staging area of the qkv phase
+    fence_proxy_async_smem();
+    if (it_lo < it_hi) att_request(p, s, ag, layer, it_lo, kvbar);
+  }
+  // ... and so is everything else that does not depend on this step's qkv: the RoPE factors of this thread's column
+  // pieces (pieces pp = tid & 7 and pp + 8 of every row it rotates) and the per-key beam masks of the first item
+  float2 csr[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) csr[e] = cs[(tid & 7) * 8 + e];
+  uint32_t bits_first = 0;
+  if (it_lo < it_hi) bits_first = att_key_bits(p, ag, it_lo, all_beams);
   cx.stamp();
   bar.sync();
   cx.stamp();
@@ -895,27 +938,8 @@ __device__ __forceinline__ void attention_phase(const RowsParams& p, Ctx& cx, Gr
                                                        (H + KVH + kvh) * HD + pc * 8));
       }
     }
-    // which beams may see each key (threads 0..63, one key each)
-    uint32_t bits = 0;
-    if (tid < SUBK) {
-      const int key = key0 + tid;
-      if (key < p.S) {
-        bits = (p.prompt_valid == nullptr || p.prompt_valid[(int64_t)input * p.S + key] != 0) ? all_beams : 0u;
-      } else if (key < ag.Nk) {
-        const int jj = key - p.S, gi = jj / p.beams, r = jj - gi * p.beams;
-        if (gi == ag.g_cur) {
-          bits = 1u << r;
-        } else {
-          int sl[16];
-#pragma unroll
-          for (int bb = 0; bb < 16; ++bb)
-            sl[bb] = bb < p.beams ? p.slots[(int64_t)(input * p.beams + bb) * p.max_gen + gi] : -1;
-#pragma unroll
-          for (int bb = 0; bb < 16; ++bb)
-            if (sl[bb] == input * p.beams + r) bits |= 1u << bb;
-        }
-      }
-    }
+    // which beams may see each key (threads 0..63, one key each; the first item's were fetched before the barrier)
+    const uint32_t bits = item == it_lo ? bits_first : att_key_bits(p, ag, item, all_beams);
     // rotate-half RoPE of a pair of pieces: out_lo = lo c - hi s, out_hi = hi c + lo s, rounded to bf16
     auto rope_pair = [&](const uint4& lo4, const uint4& hi4, int pp, uint4& o_lo, uint4& o_hi) {
       const uint32_t l[4] = {lo4.x, lo4.y, lo4.z, lo4.w}, h[4] = {hi4.x, hi4.y, hi4.z, hi4.w};
@@ -923,7 +947,7 @@ __device__ __forceinline__ void attention_phase(const RowsParams& p, Ctx& cx, Gr
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const float2 lv = unpack_bf16x2(l[e]), hv = unpack_bf16x2(h[e]);
-        const float2 c0 = cs[pp * 8 + e * 2], c1 = cs[pp * 8 + e * 2 + 1];
+        const float2 c0 = csr[e * 2], c1 = csr[e * 2 + 1];  // (pp == tid & 7 for every unit of this thread)
         ol[e] = pack_bf16x2(lv.x * c0.x - hv.x * c0.y, lv.y * c1.x - hv.y * c1.y);
         oh[e] = pack_bf16x2(hv.x * c0.x + lv.x * c0.y, hv.y * c1.x + lv.y * c1.y);
       }
@@ -1232,16 +1256,27 @@ llama_decode_rows_megakernel(const RowsParams p) {
     }
   }
 
+  bool kv_requested = false;
   for (int ph = 0; ph < n_phases; ++ph) {
     const int kind = ph == n_phases - 1 ? 4 : (ph & 3);
     const PhaseDesc z = phase_desc(p, s_ln, ph);
     if (kind == 1) {
-      attention_phase<NT>(p, cx, bar, al, kvbar, kv_par, ph >> 2, t);
+      attention_phase<NT>(p, cx, bar, al, kvbar, kv_par, ph >> 2, t, kv_requested);
+      kv_requested = false;
       cx.stamp();
       bar.sync();
       cx.stamp();
     }
-    weight_phase<NT>(p, cx, z, ph == 0 ? s_tok : nullptr);
+    weight_phase<NT>(p, cx, z, ph == 0 ? s_tok : nullptr, [&]() {
+      if (kind != 0) return;
+      kv_requested = true;  // (a CTA without qkv tiles never gets here: attention_phase then asks itself)
+      // the attention phase of this layer follows: the staging area is free, ask for the K / V rows of this CTA's
+      // first item now - they travel while the qkv epilogue and the grid barrier run
+      const AttGeom ag = att_geom(p, t);
+      const int it_lo = range_lo(ag.n_items, blockIdx.x, gridDim.x), it_hi = range_lo(ag.n_items, blockIdx.x + 1, gridDim.x);
+      fence_proxy_async_smem();
+      if (it_lo < it_hi) att_request(p, al, ag, ph >> 2, it_lo, kvbar);
+    });
     cx.stamp();
     if (kind != 0 && kind != 4) {  // (the barrier after the qkv phase is inside attention_phase)
       bar.sync();
