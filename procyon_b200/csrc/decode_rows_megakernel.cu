@@ -1,4 +1,4 @@
-// One persistent kernel per Llama decode step for 3..16 rows (inputs x beams): the beam-search path, which is what
+// One persistent kernel per Llama decode step for 2..16 rows (inputs x beams): the beam-search path, which is what
 // every shipped caller of the reference runs (procyon/evaluate/framework/procyon.py:71-76, beam_size = 2 x captions).
 //
 // Same skeleton as decode_megakernel.cu (one CTA per SM, the CTA's share of all 4 L + 1 weight matrices streamed through
@@ -8,7 +8,8 @@
 //   * a ring slot is a TILE of 16 weight rows x 256 k (4 TMA boxes of 16 x 64, 128-byte swizzle), so that one
 //     ldmatrix.x4 of weights (A) and one of activations (B) feed two real mma.sync.m16n8k16 (16 weight rows x 16 rows);
 //   * work is cut stream-K style: the chunk sequence (k-part, row group, k-chunk) of a matrix is split evenly over the
-//     CTAs and, inside a CTA, over the 8 consumer warps, whatever the row count of the matrix.  A warp keeps the
+//     CTAs and, inside a CTA, over the 8 warps, whatever the row count of the matrix (the two short matrices, qkv and
+//     o_proj, are cut at row-group boundaries instead: a split group costs two L2 round trips at phase end).  A warp keeps the
 //     16 x 16 accumulator of its current row group in registers; pieces of a row group that end up in different warps
 //     meet in a shared-memory pool, pieces in different CTAs in a global scratch with a ticket per output group - the
 //     last contributor adds them in a fixed order (bit-reproducible) and runs the epilogue;
