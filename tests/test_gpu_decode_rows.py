@@ -81,7 +81,12 @@ def test_rows_kernel_single_row(cuda_device):
 
 
 @pytest.mark.parametrize("n,beams,S,pad,steps", [(1, 10, 300, 0, 7), (2, 6, 260, 9, 6), (1, 16, 129, 0, 5), (1, 5, 64, 0, 14),
-                                                 (3, 4, 100, 11, 6), (1, 3, 1100, 0, 4)])
+                                                 (3, 4, 100, 11, 6), (1, 3, 1100, 0, 4),
+                                                 # 4 inputs x 2 kv heads x 19 key splits = 152 attention items on 148 SMs:
+                                                 # some CTAs take two items (a second Q staging, tile reuse)
+                                                 (4, 4, 1200, 0, 3),
+                                                 # 40 steps: the generated entries (10 x t keys) outgrow the prompt
+                                                 (1, 10, 70, 0, 40)])
 def test_rows_kernel_beam_steps_match_per_op_on_identical_state(cuda_device, n, beams, S, pad, steps):
     """Real beam-search state (ancestry through `slots`, keys shared between beams, this step's rows appended inside the
     kernel): after every selection step both paths run on the SAME session state - logits of every beam row must agree,
@@ -96,7 +101,7 @@ def test_rows_kernel_beam_steps_match_per_op_on_identical_state(cuda_device, n, 
     ids, emb, mask = _inputs(oc, sd, n, S, seed=beams + S, pad_left=pad)
     am = mask.cuda() if pad else None
     lib = _lib.load()
-    sess = m.get_session(n, beams, S, 16, torch.device("cuda"), pad > 0, False)
+    sess = m.get_session(n, beams, S, max(16, steps + 2), torch.device("cuda"), pad > 0, False)
     sel = torch.tensor([(i + 1) * S - 1 for i in range(n)], device="cuda", dtype=torch.int32)
     _, _, logits, valid = m.prefill(emb.cuda(), am, want_cache=True, want_hidden=False, sel_rows=sel,
                                     kv_out=sess.kv_prompt)
