@@ -104,6 +104,10 @@ int pcy_set_esm_tc_attention(int enabled);
    2 with the bf16 pairs of P built on the ALU pipe (round half up) instead of the XU pipe's F2FP; 4 = as 2 with one
    64-thread named barrier per step between the two warps of a row pair instead of two CTA-wide bar.sync */
 int pcy_set_esm_attention_kernel(int kernel);
+/* rows: when the sequence length leaves at most `rows` query rows beyond the last full 128-row tile (512 residues +
+   BOS + EOS = 4 tiles + 2 rows), the mma.sync kernel takes those rows instead of one more tcgen05 CTA per (protein,
+   head) that streams all keys for them; 0: every row on the tcgen05 kernel */
+int pcy_set_esm_attention_tail_rows(int rows);
 /* 1: attention kernels 2 / 3 / 4 apply RoPE to Q while they move it into TMEM and the RoPE pass only rotates K;
    0 (default; measured faster overall on B200): the RoPE pass rotates Q and K in place before the attention kernel */
 int pcy_set_esm_attention_q_rope(int enabled);

@@ -18,6 +18,10 @@ namespace pcy {
 // S / P / P.V (esm_attention_tc64_kernel), 2 = 64-key steps with Q and P in TMEM (esm_attention_ts_kernel), 3 = the
 // same with P packed on the ALU pipe, 4 = kernel 2 with pair barriers instead of CTA-wide bar.sync
 int g_esm_attention_kernel = 4;
+// pcy_set_esm_attention_tail_rows(n): when T leaves at most n query rows beyond the last full 128-row tile (ESM2 adds
+// BOS + EOS: 512 residues are T = 514 = 4 tiles + 2 rows), those rows go to the mma.sync kernel of attention.cu instead
+// of a fifth tcgen05 CTA that streams all of K / V for two live rows.  0 = every row on the tcgen05 kernel.
+int g_esm_attention_tail_rows = 0;
 // pcy_set_esm_attention_q_rope(1): kernels 2 / 3 / 4 rotate Q on its way into TMEM and the RoPE pass only covers K.
 // Measured on B200 (profiles/r02_esm_breakdown.log): the RoPE pass drops 8.3 -> 4.3 ms per 256-protein step, but the
 // attention kernel's prologue (cos / sin loads + 4 FMAs per element in front of the first MMA, on the critical path of
@@ -795,6 +799,31 @@ esm_attention_ts_kernel(const __grid_constant__ CUtensorMap tmap, const TcAttnPa
         else publish_valid(j);
         mbar_wait(s_full0 + 8 * (j & 1), (j >> 1) & 1);
         tc_fence_after();
+        if (PAIR && mw == 0u) {
+          // None of this warp's 32 keys is valid (the upper half of the last step when T % 64 <= 32 — 512 residues +
+          // BOS + EOS leave 2 keys for step 9 — or a block of padding): no scores to read, no exponentials; only the
+          // row maximum of the partner warp (for the rescale of this thread's O columns) and the appointments.
+          const int xo = (j & 1) * 2 * TBM;
+          xchg[xo + half * TBM + r] = __float2bfloat16_ru(-INFINITY);
+          pair_sync();
+          const float mx = __bfloat162float(xchg[xo + (half ^ 1) * TBM + r]);
+          const float m_new = fmaxf(m_run, mx);
+          const float corr = (m_new == -INFINITY) ? 1.f : exp2f((m_run - m_new) * p.scale_log2);
+          if (j * TBN2 + half * 32 < p.T) {  // P.V(j) reads this warp's P columns (K = keys of the step up to T): zeros
+            uint32_t zeros[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) zeros[i] = 0u;
+            tmem_st_32x32b_x16(t_lane + (uint32_t)((j & 1) * TBN2 + half * 16), zeros);
+          }
+          l_run *= corr;
+          m_run = m_new;
+          if (j > 0) fold_o(j - 1, corr_prev);
+          corr_prev = corr;
+          tc_wait_st();
+          tc_fence_before();
+          mbar_arrive(p_ready0 + 8 * (j & 1));
+          continue;
+        }
         uint32_t v[32];  // this thread's 32 scores of the step stay in registers for both passes
         tmem_ld_32x32b_x32(t_lane + (uint32_t)((j & 1) * TBN2 + half * 32), v);
         tc_wait_ld();
@@ -933,7 +962,12 @@ int esm_attention_tc(const bf16* qkv, const uint8_t* key_valid, bf16* out, int B
                      float scale, const float* q_rope, int* rows_done, cudaStream_t stream) {
   *rows_done = 0;
   if (T < TBM || d / n_heads != THD) return 0;
-  const int n_q_tiles = (T + TBM - 1) / TBM;
+  int n_q_tiles = (T + TBM - 1) / TBM;
+  int covered = T;
+  if (T % TBM != 0 && T % TBM <= g_esm_attention_tail_rows) {  // the caller runs the few rows left (rows_done < T)
+    n_q_tiles = T / TBM;
+    covered = n_q_tiles * TBM;
+  }
   static SmemOptIn opt;
   if (opt.need(1)) {
     PCY_CUDA(cudaFuncSetAttribute(esm_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
@@ -959,7 +993,7 @@ int esm_attention_tc(const bf16* qkv, const uint8_t* key_valid, bf16* out, int B
   else if (kern == 1) esm_attention_tc64_kernel<<<grid, TC_THREADS, TC2_SMEM, stream>>>(tmap, p);
   else esm_attention_tc_kernel<<<grid, TC_THREADS, TC_SMEM, stream>>>(tmap, p);
   PCY_LAUNCH_CHECK();
-  *rows_done = T;
+  *rows_done = covered;
   return 0;
 }
 

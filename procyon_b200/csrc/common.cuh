@@ -43,6 +43,7 @@ extern bool g_gemm_cluster;
 extern int g_gemm_pair_mma;
 extern int g_gemm_force_tile;
 extern int g_esm_attention_kernel;
+extern int g_esm_attention_tail_rows;
 extern bool g_esm_attention_q_rope;
 extern bool g_skinny_mma;
 extern bool g_pdl;  // pcy_set_pdl: programmatic dependent launch for the one-launch-per-op decode chain (default on)
@@ -143,26 +144,79 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
 }
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
-// erf GELU, as torch.nn.GELU() / fair-esm `gelu`:  gelu(x) = x * Phi(x),  Phi(x) = 1 - erfc(t)/2 for x >= 0 and
-// erfc(t)/2 for x < 0 with t = |x|/sqrt(2), and erfc(t) = 2^(t*Q(t)) where Q is the degree-6 near-minimax fit of
-// log2(erfc(t))/t on [0, 4] (t is clamped there: erfc(4) = 1.5e-8).  Measured against the fp64 erf form over
-// [-8, 8] in fp32 arithmetic: |error| <= 1.4e-6 absolute, <= 2.3e-5 relative for |x| < 5.5 — 170x below one bf16 ulp,
-// the precision every caller stores the result in.  14 instructions with one MUFU.EX2, where erff() costs 27 (two
-// coefficient sets picked by 9 FSELs): the fc1 epilogue of the ESM2 encoder was issue-bound on it (1028 TFLOP/s in
-// situ next to 1340-1470 for the other three GEMMs of the layer).  (An Abramowitz-Stegun erf with rcp + ex2 was
-// measured SLOWER than erff: two quarter-rate MUFU ops.)
+// ---- packed fp32 pairs (sm_100: FFMA2 / FMUL2 / FADD2 process two fp32 lanes per issued instruction) ----
+__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t r, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(r));
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t f2_bcast(float v) { return f2_pack(v, v); }
+
+// erf GELU, as torch.nn.GELU() / fair-esm `gelu`:  gelu(x) = x * Phi(x) = max(x, 0) - |x| * erfc(t)/2 with
+// t = |x|/sqrt(2) (for x >= 0 that is x - x * erfc/2, for x < 0 it is x * erfc/2), and erfc(t) = 2^(t*Q(t)) where Q is
+// the degree-6 near-minimax fit of log2(erfc(t))/t on [0, 4]; beyond 4 the exponent t*Q(t) - 1 stays below -26.9 and
+// falls monotonically (checked up to the fp32 overflow of t^7, where ex2(-inf) = 0), so no clamp is needed.
+// Measured against the fp64 erf form over [-8, 8] in fp32 arithmetic: |error| <= 1.3e-6 absolute — 170x below one
+// bf16 ulp, the precision every caller stores the result in.  12 instructions with one MUFU.EX2, where erff() costs
+// 27 (two coefficient sets picked by 9 FSELs).  The fc1 epilogue of the ESM2 encoder is bound by the FMA pipe on this
+// function (round 2: one more FFMA per element cost 4.5 ms of a 51 ms GEMM), hence gelu_erf2: the same arithmetic on
+// PAIRS of values with FFMA2 / FMUL2 — bit-identical results, half the FMA-pipe instructions (fc1 51.3 -> 47.5 ms).  (An Abramowitz-Stegun
+// erf with rcp + ex2 was measured SLOWER than erff: two quarter-rate MUFU ops.)
+#define PCY_GELU_C0 -1.2784041246050037e-05f
+#define PCY_GELU_C1 0.00038682681042701006f
+#define PCY_GELU_C2 -0.004717740695923567f
+#define PCY_GELU_C3 0.03266161307692528f
+#define PCY_GELU_C4 -0.1509079933166504f
+#define PCY_GELU_C5 -0.9179017543792725f
+#define PCY_GELU_C6 -1.6279263496398926f
 __device__ __forceinline__ float gelu_erf(float x) {
-  const float t = fminf(fabsf(x) * 0.70710678118654752440f, 4.0f);
-  float q = -1.2784041246050037e-05f;
-  q = fmaf(q, t, 0.00038682681042701006f);
-  q = fmaf(q, t, -0.004717740695923567f);
-  q = fmaf(q, t, 0.03266161307692528f);
-  q = fmaf(q, t, -0.1509079933166504f);
-  q = fmaf(q, t, -0.9179017543792725f);
-  q = fmaf(q, t, -1.6279263496398926f);
+  const float na = -fabsf(x);
+  const float t = na * -0.70710678118654752440f;
+  float q = PCY_GELU_C0;
+  q = fmaf(q, t, PCY_GELU_C1);
+  q = fmaf(q, t, PCY_GELU_C2);
+  q = fmaf(q, t, PCY_GELU_C3);
+  q = fmaf(q, t, PCY_GELU_C4);
+  q = fmaf(q, t, PCY_GELU_C5);
+  q = fmaf(q, t, PCY_GELU_C6);
   float h;  // erfc(t) / 2
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(h) : "f"(fmaf(t, q, -1.0f)));
-  return x * (x >= 0.f ? 1.0f - h : h);
+  return fmaf(na, h, fmaxf(x, 0.f));
+}
+__device__ __forceinline__ uint64_t gelu_erf2(uint64_t x) {
+  const uint64_t na = x | 0x8000000080000000ull;  // -|x| in both lanes
+  const uint64_t t = f2_mul(na, f2_bcast(-0.70710678118654752440f));
+  uint64_t q = f2_fma(f2_bcast(PCY_GELU_C0), t, f2_bcast(PCY_GELU_C1));
+  q = f2_fma(q, t, f2_bcast(PCY_GELU_C2));
+  q = f2_fma(q, t, f2_bcast(PCY_GELU_C3));
+  q = f2_fma(q, t, f2_bcast(PCY_GELU_C4));
+  q = f2_fma(q, t, f2_bcast(PCY_GELU_C5));
+  q = f2_fma(q, t, f2_bcast(PCY_GELU_C6));
+  const uint64_t e = f2_fma(t, q, f2_bcast(-1.0f));
+  float e0, e1, h0, h1, x0, x1;
+  f2_unpack(e, e0, e1);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(h0) : "f"(e0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(h1) : "f"(e1));
+  f2_unpack(x, x0, x1);
+  return f2_fma(na, f2_pack(h0, h1), f2_pack(fmaxf(x0, 0.f), fmaxf(x1, 0.f)));
 }
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
 

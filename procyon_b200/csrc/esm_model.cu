@@ -87,6 +87,12 @@ int pcy_set_esm_attention_kernel(int kernel) {
   return 0;
 }
 
+int pcy_set_esm_attention_tail_rows(int rows) {
+  PCY_REQUIRE(rows >= 0 && rows < 128, "set_esm_attention_tail_rows: %d not in [0, 128)", rows);
+  pcy::g_esm_attention_tail_rows = rows;
+  return 0;
+}
+
 int pcy_set_esm_attention_q_rope(int enabled) {
   pcy::g_esm_attention_q_rope = enabled != 0;
   return 0;

@@ -91,6 +91,33 @@ __device__ __forceinline__ void epi_bias_scale(float (&v)[32], int col0, const E
   }
 }
 
+// The same step on PAIRS of columns (FADD2 / FMUL2), for the coalesced store path, whose 32-column chunks are always
+// complete (col0 + 32 <= N).  Bit-identical to epi_bias_scale lane by lane.
+__device__ __forceinline__ void epi_bias_scale2(uint64_t (&v)[16], int col0, const EpiParams& p) {
+  if (p.bias != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 16; j += 2) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + 2 * j));
+      v[j] = f2_add(v[j], f2_pack(b.x, b.y));
+      v[j + 1] = f2_add(v[j + 1], f2_pack(b.z, b.w));
+    }
+  }
+  if (col0 + 32 <= p.scale_ncols) {
+    const uint64_t sc = f2_bcast(p.scale);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = f2_mul(v[j], sc);
+  } else if (col0 < p.scale_ncols) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      float a, b;
+      f2_unpack(v[j], a, b);
+      if (col0 + 2 * j < p.scale_ncols) a *= p.scale;
+      if (col0 + 2 * j + 1 < p.scale_ncols) b *= p.scale;
+      v[j] = f2_pack(a, b);
+    }
+  }
+}
+
 __device__ __forceinline__ void epi_store_bf16(const float (&v)[32], int row, int col0, const EpiParams& p) {
   bf16* cp = reinterpret_cast<bf16*>(p.C) + (int64_t)row * p.ldc + col0;
   if ((col0 + 32 <= p.N) && ((reinterpret_cast<uintptr_t>(cp) & 15) == 0)) {
@@ -361,14 +388,19 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             uint32_t r2[32];
             tmem_ld_32x32b_x32(t_addr + (uint32_t)((c + hf) * 32), r2);
             tc_wait_ld();
-            float v2[32];
+            // bias, scale and GELU on 16 PAIRS of columns: two fp32 lanes per FMA-pipe instruction (FFMA2), on which this
+            // epilogue is bound under the fc1 GEMM of the ESM2 encoder
+            uint64_t vp[16];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v2[j] = __uint_as_float(r2[j]);
-            epi_bias_scale(v2, col0 + hf * 32, p);
+            for (int j = 0; j < 16; ++j) vp[j] = f2_pack(__uint_as_float(r2[2 * j]), __uint_as_float(r2[2 * j + 1]));
+            epi_bias_scale2(vp, col0 + hf * 32, p);
             if (p.act == ACT_GELU) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v2[j] = gelu_erf(v2[j]);
+              for (int j = 0; j < 16; ++j) vp[j] = gelu_erf2(vp[j]);
             }
+            float v2[32];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f2_unpack(vp[j], v2[2 * j], v2[2 * j + 1]);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               const uint32_t addr = stg + lane * 128 + (((hf * 4 + q) ^ (lane & 7)) << 4);

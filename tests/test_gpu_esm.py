@@ -115,16 +115,23 @@ def test_esm_tcgen05_attention_matches_mma_sync_and_oracle(cuda_device, lengths)
                 lib.pcy_set_esm_attention_q_rope(0)
                 torch.testing.assert_close(outs[steps64][toks != O.PAD_IDX], inside[toks != O.PAD_IDX], rtol=1e-2,
                                            atol=1e-2)
+        # the rows beyond the last full 128-row tile on the mma.sync kernel instead of one more tcgen05 CTA
+        lib.pcy_set_esm_attention_kernel(4)
+        lib.pcy_set_esm_attention_tail_rows(16)
+        tail = m.encode_tokens(toks.cuda()).float().cpu()
+        lib.pcy_set_esm_attention_tail_rows(0)
         lib.pcy_set_esm_tc_attention(0)
         lib.pcy_set_fused_rope(0)
         b = m.encode_tokens(toks.cuda()).float().cpu()
     finally:
+        lib.pcy_set_esm_attention_tail_rows(0)
         lib.pcy_set_esm_tc_attention(1)
         lib.pcy_set_esm_attention_kernel(4)  # the default
         lib.pcy_set_esm_attention_q_rope(0)  # the default
         lib.pcy_set_fused_rope(0)
     nonpad = toks != O.PAD_IDX
     ref = O.esm2_forward(sd, toks, L, H, act_round="bf16")
+    outs["tail"] = tail
     for steps64, a in outs.items():
         torch.testing.assert_close(a[nonpad], b[nonpad], rtol=2e-2, atol=2e-2)
         torch.testing.assert_close(a[nonpad], ref[nonpad], rtol=3e-2, atol=3e-2)
