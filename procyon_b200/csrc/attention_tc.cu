@@ -697,6 +697,7 @@ esm_attention_ts_kernel(const __grid_constant__ CUtensorMap tmap, const TcAttnPa
     const int r = quad * 32 + lane;  // query row within the tile = TMEM lane
     const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
     constexpr int OH = THD / 2;  // output columns per thread
+    uint32_t step_masks = 0;     // PAIR: lane j holds the validity word of this warp's keys of step j
     {
       // this thread's half of its query row (32 bf16 = 16 packed columns) -> TMEM: the A operand of every S = Q K^T
       const bf16* qrow_p = qkv + (int64_t)(row_base + q0 + r) * (3 * p.d) + h * THD;
@@ -730,6 +731,20 @@ esm_attention_ts_kernel(const __grid_constant__ CUtensorMap tmap, const TcAttnPa
           }
           const uint4 u = pack8(out);
           qr[4 * c] = u.x; qr[4 * c + 1] = u.y; qr[4 * c + 2] = u.z; qr[4 * c + 3] = u.w;
+        }
+      }
+      if (PAIR && n_kv <= 32) {
+        // Validity bits of this warp's 32 keys of EVERY step, taken here, under the latency of the Q loads above: lane j
+        // keeps the word of step j.  (ncu: as one byte load + ballot per step, the compare behind the load was the
+        // single hottest stall of the step loop, 8 % of the kernel's warp samples.)
+        const uint8_t* vg = p.key_valid ? p.key_valid + (int64_t)b * p.T : nullptr;
+#pragma unroll 4
+        for (int j = 0; j < n_kv; ++j) {
+          const int kidx = j * TBN2 + half * 32 + lane;
+          bool ok = kidx < p.T;
+          if (ok && vg) ok = vg[kidx] != 0;
+          const uint32_t word = __ballot_sync(0xffffffffu, ok);
+          if (lane == j) step_masks = word;
         }
       }
       tmem_st_32x32b_x16(t_lane + COL_Q + half * 16, qr);
@@ -780,9 +795,10 @@ esm_attention_ts_kernel(const __grid_constant__ CUtensorMap tmap, const TcAttnPa
         asm volatile("bar.sync 1, 256;" ::: "memory");
       }
     } else {
-      float o[OH];
+      // the running output row as 16 fp32 PAIRS: rescale + accumulate is one FFMA2 per two columns
+      uint64_t o2[OH / 2];
 #pragma unroll
-      for (int i = 0; i < OH; ++i) o[i] = 0.f;
+      for (int i = 0; i < OH / 2; ++i) o2[i] = 0ull;
       float m_run = -INFINITY, l_run = 0.f, corr_prev = 1.f;
       auto fold_o = [&](int jj, float corr) {  // o = o * corr + P.V tile of step jj (this thread's 32 columns)
         mbar_wait(o_full, jj & 1);
@@ -790,12 +806,14 @@ esm_attention_ts_kernel(const __grid_constant__ CUtensorMap tmap, const TcAttnPa
         uint32_t v[32];
         tmem_ld_32x32b_x32(t_lane + COL_O + half * OH, v);
         tc_wait_ld();
+        const uint64_t c2 = f2_bcast(corr);
 #pragma unroll
-        for (int i = 0; i < OH; ++i) o[i] = fmaf(o[i], corr, __uint_as_float(v[i]));
+        for (int i = 0; i < OH / 2; ++i)
+          o2[i] = f2_fma(o2[i], c2, f2_pack(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])));
       };
       for (int j = 0; j < n_kv; ++j) {
         uint32_t mw;
-        if (PAIR) mw = own_mask(j);
+        if (PAIR) mw = (n_kv <= 32) ? __shfl_sync(0xffffffffu, step_masks, j) : own_mask(j);
         else publish_valid(j);
         mbar_wait(s_full0 + 8 * (j & 1), (j >> 1) & 1);
         tc_fence_after();
@@ -857,14 +875,21 @@ esm_attention_ts_kernel(const __grid_constant__ CUtensorMap tmap, const TcAttnPa
         float ls4[4] = {0.f, 0.f, 0.f, 0.f};
         uint32_t packed[16];
         if (PAIR && mw == 0xffffffffu) {  // every key of this warp's 32 is valid: no select per score
+          // exponent and row sum on pairs of scores (FFMA2 / FADD2: half the FMA-pipe instructions)
+          const uint64_t sc2 = f2_bcast(p.scale_log2), nm2 = f2_bcast(-moff);
+          uint64_t ls2[4] = {0ull, 0ull, 0ull, 0ull};
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
-            float p0, p1;
-            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(fmaf(__uint_as_float(v[i]), p.scale_log2, -moff)));
-            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(fmaf(__uint_as_float(v[i + 1]), p.scale_log2, -moff)));
-            ls4[(i >> 1) & 3] += p0 + p1;
+            float e0, e1, p0, p1;
+            f2_unpack(f2_fma(f2_pack(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), sc2, nm2), e0, e1);
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(e0));
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(e1));
+            ls2[(i >> 1) & 3] = f2_add(ls2[(i >> 1) & 3], f2_pack(p0, p1));
             packed[i >> 1] = pack_bf16x2(p0, p1);
           }
+          float a0, a1;
+          f2_unpack(f2_add(f2_add(ls2[0], ls2[1]), f2_add(ls2[2], ls2[3])), a0, a1);
+          ls4[0] = a0 + a1;
         } else
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
@@ -904,6 +929,9 @@ esm_attention_ts_kernel(const __grid_constant__ CUtensorMap tmap, const TcAttnPa
       if (qrow < p.T && qrow >= q_tile * TBM) {  // rows below q_tile*TBM belong to the previous tile
         const float inv = l_tot > 0.f ? 1.f / l_tot : 0.f;
         bf16* op = p.o + (int64_t)(row_base + qrow) * p.o_rs + h * THD + half * OH;
+        float o[OH];
+#pragma unroll
+        for (int i = 0; i < OH / 2; ++i) f2_unpack(o2[i], o[2 * i], o[2 * i + 1]);
 #pragma unroll
         for (int c = 0; c < OH; c += 8) {
           uint4 u;
