@@ -134,9 +134,13 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// two floats -> one register of two bf16 (round to nearest even), `lo` in bits 0..15.  As one cvt: through
+// __floats2bfloat162_rn + a reinterpret_cast the compiler rebuilt the word from its halves with two PRMTs per pair
+// (ncu of the fc1 epilogue: 64 PRMT per 64 columns).
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
-  return *reinterpret_cast<uint32_t*>(&h);
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
 }
 __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   __nv_bfloat162 h = *reinterpret_cast<__nv_bfloat162*>(&u);
