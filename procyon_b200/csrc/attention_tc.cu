@@ -16,8 +16,9 @@ namespace pcy {
 
 // pcy_set_esm_attention_kernel: 0 = 128-key steps (esm_attention_tc_kernel), 1 = 64-key steps with double-buffered
 // S / P / P.V (esm_attention_tc64_kernel), 2 = 64-key steps with Q and P in TMEM (esm_attention_ts_kernel), 3 = the
-// same with P packed on the ALU pipe, 4 = kernel 2 with pair barriers instead of CTA-wide bar.sync
-int g_esm_attention_kernel = 4;
+// same with P packed on the ALU pipe, 4 = kernel 2 with pair barriers instead of CTA-wide bar.sync, 5 (default) =
+// kernel 4 with the output tile accumulated in TMEM
+int g_esm_attention_kernel = 5;
 // pcy_set_esm_attention_tail_rows(n): when T leaves at most n query rows beyond the last full 128-row tile (ESM2 adds
 // BOS + EOS: 512 residues are T = 514 = 4 tiles + 2 rows), those rows go to the mma.sync kernel of attention.cu instead
 // of a fifth tcgen05 CTA that streams all of K / V for two live rows.  0 = every row on the tcgen05 kernel.
@@ -592,7 +593,16 @@ constexpr int TS_SMEM = 2 * KV2_STAGES * KV2_BYTES + 4 * TBM * 2 /*row max excha
 // validity bits of its own 32 keys with one ballot, the pair meets at ONE 64-thread named barrier per step (row-max
 // slots double-buffered by step parity), and the masked / unmasked forms of the exponential pass are separate loops
 // (as one loop the compiler predicates 66 LOP3 / FSEL into every step, masked or not).
-template <bool ALU_PACK, bool PAIR = false>
+// OACC (kernel 5): the output tile is not carried in registers and folded in step by step (a TMEM read of the P.V
+// tile + a wait for its MMAs in EVERY step of the softmax threads' serial chain) but accumulates in TMEM across all
+// steps (use_acc), like the causal prefill kernel's.  The running maximum is then only raised when a step's maximum
+// exceeds it by more than 2^8 (the exponentials stay <= 256, exact in the fp32 row sum and well inside bf16's range for
+// P; both threads of a row take the same decision from the same two numbers), and only such steps rescale O in TMEM
+// (tcgen05.ld -> scale -> tcgen05.st between the completion of P.V(j-1) and the release of P(j)).
+// 256-protein step of ESM2-650M on B200: 51.4 -> 49.7 ms.  (Requesting the scores of step j + 1 from TMEM at the end of
+// step j — they are complete a step ahead — was measured slower, 49.7 -> 53.8 ms: with v[] live across the loop edge
+// the 96-register budget of two CTAs per SM spills.)
+template <bool ALU_PACK, bool PAIR = false, bool OACC = false>
 __global__ void __launch_bounds__(TC_THREADS, 2)
 esm_attention_ts_kernel(const __grid_constant__ CUtensorMap tmap, const TcAttnParams p, const bf16* __restrict__ qkv) {
   extern __shared__ uint8_t smem_raw[];
@@ -685,7 +695,8 @@ esm_attention_ts_kernel(const __grid_constant__ CUtensorMap tmap, const TcAttnPa
         const int n_mma = (min(TBN2, p.T - j * TBN2) + 15) & ~15;
         for (int k = 0; k < n_mma / 16; ++k) {
           const uint64_t vd = make_desc_mnmajor_sw128(sV + st * KV2_BYTES + k * 2048, 1024);
-          tc_mma_bf16_ts(tmem_base + COL_O, tmem_base + (uint32_t)((j & 1) * TBN2 + 8 * k), vd, idesc_o, k > 0 ? 1u : 0u);
+          tc_mma_bf16_ts(tmem_base + COL_O, tmem_base + (uint32_t)((j & 1) * TBN2 + 8 * k), vd, idesc_o,
+                         (k > 0 || (OACC && j > 0)) ? 1u : 0u);
         }
         tc_commit(kv_empty0 + 8 * st);
         tc_commit(o_full);
@@ -811,6 +822,49 @@ esm_attention_ts_kernel(const __grid_constant__ CUtensorMap tmap, const TcAttnPa
         for (int i = 0; i < OH / 2; ++i)
           o2[i] = f2_fma(o2[i], c2, f2_pack(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])));
       };
+      // new running maximum and the factor that brings the row sum (and O) from the old offset to the new one
+      auto raise_max = [&](float mx, float& m_new, float& corr) {
+        const float m_cand = fmaxf(m_run, mx);
+        if (OACC) {
+          const bool first = (m_run == -INFINITY);
+          const float d = first ? 0.f : (m_cand - m_run) * p.scale_log2;
+          const bool grow = (m_cand != -INFINITY) && (first || d > 8.f);
+          m_new = grow ? m_cand : m_run;
+          corr = (grow && !first) ? exp2f(-d) : 1.f;
+        } else {
+          m_new = m_cand;
+          corr = (m_new == -INFINITY) ? 1.f : exp2f((m_run - m_new) * p.scale_log2);
+        }
+      };
+      // what has to happen to O between the P store of step j and the release of P(j) to the MMA thread
+      auto settle_o = [&](int j, float corr) {
+        if (OACC) {
+          // Every thread passes EVERY phase of o_full in order, needed or not: a parity wait can only tell the current
+          // phase from the one before it, and a thread that skipped phases would, at the end, take "P.V(n-2) still
+          // running" for "P.V(n-1) done" (seen on B200 as run-to-run differences in rows whose last step is a fast one).
+          // P.V(j-1) has had a whole step to finish, so this wait is almost always a single successful poll.
+          if (j > 0) mbar_wait(o_full, (j - 1) & 1);
+          if (j > 0 && __any_sync(0xffffffffu, corr != 1.f)) {
+            tc_fence_after();
+            uint32_t ov[32];
+            tmem_ld_32x32b_x32(t_lane + COL_O + half * OH, ov);
+            tc_wait_ld();
+            uint32_t lo[16], hi[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              lo[i] = __float_as_uint(__uint_as_float(ov[i]) * corr);
+              hi[i] = __float_as_uint(__uint_as_float(ov[16 + i]) * corr);
+            }
+            tmem_st_32x32b_x16(t_lane + COL_O + half * OH, lo);
+            tmem_st_32x32b_x16(t_lane + COL_O + half * OH + 16, hi);
+          }
+        } else {
+          // the P.V tile of the previous step (complete for about a step by now) must be folded in before P.V(j),
+          // which overwrites it, can be released
+          if (j > 0) fold_o(j - 1, corr_prev);
+          corr_prev = corr;
+        }
+      };
       for (int j = 0; j < n_kv; ++j) {
         uint32_t mw;
         if (PAIR) mw = (n_kv <= 32) ? __shfl_sync(0xffffffffu, step_masks, j) : own_mask(j);
@@ -825,8 +879,8 @@ esm_attention_ts_kernel(const __grid_constant__ CUtensorMap tmap, const TcAttnPa
           xchg[xo + half * TBM + r] = __float2bfloat16_ru(-INFINITY);
           pair_sync();
           const float mx = __bfloat162float(xchg[xo + (half ^ 1) * TBM + r]);
-          const float m_new = fmaxf(m_run, mx);
-          const float corr = (m_new == -INFINITY) ? 1.f : exp2f((m_run - m_new) * p.scale_log2);
+          float m_new, corr;
+          raise_max(mx, m_new, corr);
           if (j * TBN2 + half * 32 < p.T) {  // P.V(j) reads this warp's P columns (K = keys of the step up to T): zeros
             uint32_t zeros[16];
 #pragma unroll
@@ -835,8 +889,7 @@ esm_attention_ts_kernel(const __grid_constant__ CUtensorMap tmap, const TcAttnPa
           }
           l_run *= corr;
           m_run = m_new;
-          if (j > 0) fold_o(j - 1, corr_prev);
-          corr_prev = corr;
+          settle_o(j, corr);
           tc_wait_st();
           tc_fence_before();
           mbar_arrive(p_ready0 + 8 * (j & 1));
@@ -867,8 +920,8 @@ esm_attention_ts_kernel(const __grid_constant__ CUtensorMap tmap, const TcAttnPa
         if (PAIR) pair_sync();
         else asm volatile("bar.sync 1, 256;" ::: "memory");
         const float mx = fmaxf(__bfloat162float(mx_own_b), __bfloat162float(xchg[xo + (half ^ 1) * TBM + r]));
-        const float m_new = fmaxf(m_run, mx);
-        const float corr = (m_new == -INFINITY) ? 1.f : exp2f((m_run - m_new) * p.scale_log2);
+        float m_new, corr;
+        raise_max(mx, m_new, corr);
         const float moff = (m_new == -INFINITY) ? 0.f : m_new * p.scale_log2;
         // p = exp2(s*scale - moff) -> bf16 pairs -> TMEM columns [16*half, 16*half + 16) of this step's S buffer
         // (all 256 threads passed the first bar.sync with their scores in registers, so the buffer is free to reuse)
@@ -909,15 +962,25 @@ esm_attention_ts_kernel(const __grid_constant__ CUtensorMap tmap, const TcAttnPa
         tmem_st_32x32b_x16(t_lane + (uint32_t)((j & 1) * TBN2 + half * 16), packed);
         l_run = l_run * corr + ((ls4[0] + ls4[1]) + (ls4[2] + ls4[3]));
         m_run = m_new;
-        // the P.V tile of the previous step (complete for about a step by now) must be folded in before P.V(j), which
-        // overwrites it, can be released
-        if (j > 0) fold_o(j - 1, corr_prev);
-        corr_prev = corr;
+        settle_o(j, corr);
         tc_wait_st();
         tc_fence_before();
         mbar_arrive(p_ready0 + 8 * (j & 1));
       }
-      fold_o(n_kv - 1, corr_prev);
+      float o[OH];
+      if (OACC) {
+        mbar_wait(o_full, (n_kv - 1) & 1);
+        tc_fence_after();
+        uint32_t ov[32];
+        tmem_ld_32x32b_x32(t_lane + COL_O + half * OH, ov);
+        tc_wait_ld();
+#pragma unroll
+        for (int i = 0; i < OH; ++i) o[i] = __uint_as_float(ov[i]);
+      } else {
+        fold_o(n_kv - 1, corr_prev);
+#pragma unroll
+        for (int i = 0; i < OH / 2; ++i) f2_unpack(o2[i], o[2 * i], o[2 * i + 1]);
+      }
       // ---- finalize: row sum = both halves ----
       if (PAIR) pair_sync();
       else asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -929,9 +992,6 @@ esm_attention_ts_kernel(const __grid_constant__ CUtensorMap tmap, const TcAttnPa
       if (qrow < p.T && qrow >= q_tile * TBM) {  // rows below q_tile*TBM belong to the previous tile
         const float inv = l_tot > 0.f ? 1.f / l_tot : 0.f;
         bf16* op = p.o + (int64_t)(row_base + qrow) * p.o_rs + h * THD + half * OH;
-        float o[OH];
-#pragma unroll
-        for (int i = 0; i < OH / 2; ++i) f2_unpack(o2[i], o[2 * i], o[2 * i + 1]);
 #pragma unroll
         for (int c = 0; c < OH; c += 8) {
           uint4 u;
@@ -1004,6 +1064,8 @@ int esm_attention_tc(const bf16* qkv, const uint8_t* key_valid, bf16* out, int B
     PCY_CUDA(cudaFuncSetAttribute(esm_attention_ts_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM));
     PCY_CUDA(cudaFuncSetAttribute(esm_attention_ts_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   TS_SMEM));
+    PCY_CUDA(cudaFuncSetAttribute(esm_attention_ts_kernel<false, true, true>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM));
   }
   const int kern = g_esm_attention_kernel;
   const bool steps64 = kern != 0;
@@ -1015,7 +1077,8 @@ int esm_attention_tc(const bf16* qkv, const uint8_t* key_valid, bf16* out, int B
   p.q_rope = q_rope;
   PCY_REQUIRE(q_rope == nullptr || kern >= 2, "esm_attention_tc: only the TMEM-operand kernels rotate Q themselves");
   dim3 grid(n_q_tiles, n_heads, B);
-  if (kern == 4) esm_attention_ts_kernel<false, true><<<grid, TC_THREADS, TS_SMEM, stream>>>(tmap, p, qkv);
+  if (kern == 5) esm_attention_ts_kernel<false, true, true><<<grid, TC_THREADS, TS_SMEM, stream>>>(tmap, p, qkv);
+  else if (kern == 4) esm_attention_ts_kernel<false, true><<<grid, TC_THREADS, TS_SMEM, stream>>>(tmap, p, qkv);
   else if (kern == 3) esm_attention_ts_kernel<true><<<grid, TC_THREADS, TS_SMEM, stream>>>(tmap, p, qkv);
   else if (kern == 2) esm_attention_ts_kernel<false><<<grid, TC_THREADS, TS_SMEM, stream>>>(tmap, p, qkv);
   else if (kern == 1) esm_attention_tc64_kernel<<<grid, TC_THREADS, TC2_SMEM, stream>>>(tmap, p);

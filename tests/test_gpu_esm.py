@@ -102,21 +102,24 @@ def test_esm_tcgen05_attention_matches_mma_sync_and_oracle(cuda_device, lengths)
     lib = _lib.load()
     outs = {}
     try:
-        for steps64 in (4, 3, 2, 1, 0):
+        for steps64 in (5, 4, 3, 2, 1, 0):
             lib.pcy_set_esm_tc_attention(1)
             lib.pcy_set_esm_attention_kernel(steps64)
             lib.pcy_set_fused_rope(1 if steps64 == 0 else 0)
             outs[steps64] = m.encode_tokens(toks.cuda()).float().cpu()
-            again = m.encode_tokens(toks.cuda()).float().cpu()
-            assert torch.equal(outs[steps64], again)  # deterministic
-            if steps64 in (2, 4):  # Q rotated inside the attention kernel vs by the RoPE pass (default): same arithmetic
+            # deterministic (kernel 5 first failed exactly here: a softmax thread that skipped phases of the P.V barrier
+            # took "P.V(n-2) still running" for "P.V(n-1) done" in rows whose last key step is a fast, fully masked one)
+            for _ in range(3 if steps64 == 5 else 1):
+                again = m.encode_tokens(toks.cuda()).float().cpu()
+                assert torch.equal(outs[steps64], again)
+            if steps64 in (2, 4, 5):  # Q rotated inside the attention kernel vs by the RoPE pass (default): same arithmetic
                 lib.pcy_set_esm_attention_q_rope(1)
                 inside = m.encode_tokens(toks.cuda()).float().cpu()
                 lib.pcy_set_esm_attention_q_rope(0)
                 torch.testing.assert_close(outs[steps64][toks != O.PAD_IDX], inside[toks != O.PAD_IDX], rtol=1e-2,
                                            atol=1e-2)
         # the rows beyond the last full 128-row tile on the mma.sync kernel instead of one more tcgen05 CTA
-        lib.pcy_set_esm_attention_kernel(4)
+        lib.pcy_set_esm_attention_kernel(5)
         lib.pcy_set_esm_attention_tail_rows(16)
         tail = m.encode_tokens(toks.cuda()).float().cpu()
         lib.pcy_set_esm_attention_tail_rows(0)
@@ -126,7 +129,7 @@ def test_esm_tcgen05_attention_matches_mma_sync_and_oracle(cuda_device, lengths)
     finally:
         lib.pcy_set_esm_attention_tail_rows(0)
         lib.pcy_set_esm_tc_attention(1)
-        lib.pcy_set_esm_attention_kernel(4)  # the default
+        lib.pcy_set_esm_attention_kernel(5)  # the default
         lib.pcy_set_esm_attention_q_rope(0)  # the default
         lib.pcy_set_fused_rope(0)
     nonpad = toks != O.PAD_IDX
