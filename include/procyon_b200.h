@@ -104,7 +104,9 @@ int pcy_set_esm_tc_attention(int enabled);
    2 with the bf16 pairs of P built on the ALU pipe (round half up) instead of the XU pipe's F2FP; 4 = as 2 with one
    64-thread named barrier per step between the two warps of a row pair instead of two CTA-wide bar.sync; 5 = as 4 with
    the output tile accumulated in TMEM across the steps (use_acc) and rescaled there only when a row's running maximum
-   grows by more than 2^8, instead of a TMEM read + register fold of the P.V tile in every step */
+   grows by more than 2^8, instead of a TMEM read + register fold of the P.V tile in every step (default); 6 = ONE thread
+   per query row (four softmax warps, 64 scores per thread and step, no row-maximum exchange, no barrier between
+   softmax warps; otherwise as 5): half the instructions of 5 at the same speed on B200 */
 int pcy_set_esm_attention_kernel(int kernel);
 /* rows: when the sequence length leaves at most `rows` query rows beyond the last full 128-row tile (512 residues +
    BOS + EOS = 4 tiles + 2 rows), the mma.sync kernel takes those rows instead of one more tcgen05 CTA per (protein,

@@ -1012,6 +1012,302 @@ esm_attention_ts_kernel(const __grid_constant__ CUtensorMap tmap, const TcAttnPa
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Kernel 6: ONE thread per query row.
+//
+// In kernels 2-5 a row's 64 scores of a step are split over two threads in two warps, which then have to agree on the
+// row maximum (shared-memory exchange + a named barrier in every step), and eight softmax warps per CTA each pay the
+// fixed cost of a step (waits, fences, mask word, rescale factor, loop) for 32 scores per thread.  ncu of kernel 4 / 5
+// (profiles/r02_ncu_esm_attention_pair.txt): 40 % of the issue slots used, no pipe saturated, the softmax threads'
+// serial chain per step is what the CTA waits for.  Here four softmax warps own one TMEM lane quadrant each and a thread
+// does its row's whole step: 64 scores in registers (two tcgen05.ld), the maximum without any exchange (and exact in
+// fp32: no bf16 rounding of an exchanged value), 64 exponentials, one P store of 32 packed columns, and — as in kernel
+// 5 — O accumulated in TMEM and rescaled only when the maximum grows by more than 2^8.  No thread ever touches another
+// thread's TMEM lane, so the only synchronisation left is with the MMA thread (s_full / p_ready / o_full).  Five warps per
+// CTA leave 204 registers per thread at two CTAs per SM.  The MMA / TMA thread is kernel 5's.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int RW_WARPS = 4;
+constexpr int RW_THREADS = (RW_WARPS + 1) * 32;
+
+__global__ void __launch_bounds__(RW_THREADS, 2)
+esm_attention_row_kernel(const __grid_constant__ CUtensorMap tmap, const TcAttnParams p, const bf16* __restrict__ qkv) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = smem_u32(smem_raw);
+  if ((base & 1023u) != 0u) __trap();
+  const uint32_t sK = base;                             // KV2_STAGES stages
+  const uint32_t sV = sK + KV2_STAGES * KV2_BYTES;      // KV2_STAGES stages
+  const uint32_t bars = sV + KV2_STAGES * KV2_BYTES;
+  const uint32_t q_full = bars, kv_full0 = bars + 8, kv_empty0 = kv_full0 + 8 * KV2_STAGES,
+                 s_full0 = kv_empty0 + 8 * KV2_STAGES, p_ready0 = s_full0 + 16, o_full = p_ready0 + 16,
+                 tmem_slot = o_full + 8;
+  constexpr uint32_t COL_O = 2 * TBN2, COL_Q = 2 * TBN2 + THD;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q_tile = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int q0 = min(q_tile * TBM, p.T - TBM);  // shifted last tile, see the first kernel
+  const int row_base = b * p.T;
+  const int n_kv = (p.T + TBN2 - 1) / TBN2;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmap);
+    mbar_init(q_full, RW_WARPS * 32);
+    for (int s = 0; s < KV2_STAGES; ++s) {
+      mbar_init(kv_full0 + 8 * s, 1);
+      mbar_init(kv_empty0 + 8 * s, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(s_full0 + 8 * s, 1);
+      mbar_init(p_ready0 + 8 * s, RW_WARPS * 32);
+    }
+    mbar_init(o_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == RW_WARPS) {
+    tmem_alloc(tmem_slot, TMEM_COLS_ATT);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == RW_WARPS) {
+    if (lane == 0) {
+      // ---------------- TMA producer + MMA issuer (one thread), as in kernel 5 ----------------
+      auto load_kv = [&](int t) {
+        const int st = t & (KV2_STAGES - 1);
+        mbar_arrive_expect_tx(kv_full0 + 8 * st, 2 * KV2_BYTES);
+        tma_load_2d(sK + st * KV2_BYTES, &tmap, kv_full0 + 8 * st, p.d + h * THD, row_base + t * TBN2);
+        tma_load_2d(sV + st * KV2_BYTES, &tmap, kv_full0 + 8 * st, 2 * p.d + h * THD, row_base + t * TBN2);
+      };
+      auto issue_s = [&](int t) {  // S(t) = Q K(t)^T into S buffer t & 1; A = Q in TMEM
+        const int st = t & (KV2_STAGES - 1);
+        mbar_wait(kv_full0 + 8 * st, (t / KV2_STAGES) & 1);
+        tc_fence_after();
+        const int keys = min(TBN2, p.T - t * TBN2);
+        const uint32_t idesc_s = make_idesc_bf16(TBM, (keys + 15) & ~15);
+        const uint64_t kd = make_desc_kmajor_sw128(sK + st * KV2_BYTES);
+#pragma unroll
+        for (int k = 0; k < THD / 16; ++k)
+          tc_mma_bf16_ts(tmem_base + (uint32_t)((t & 1) * TBN2), tmem_base + COL_Q + 8 * k, kd + 2 * k, idesc_s,
+                         k > 0 ? 1u : 0u);
+        tc_commit(s_full0 + 8 * (t & 1));
+      };
+      for (int t = 0; t < min(KV2_STAGES - 1, n_kv); ++t) load_kv(t);
+      mbar_wait(q_full, 0);
+      tc_fence_after();
+      issue_s(0);
+      const uint32_t idesc_o = make_idesc_bf16(TBM, THD, 0, 1);
+      for (int j = 0; j < n_kv; ++j) {
+        if (j + 1 < n_kv) issue_s(j + 1);
+        const int t = j + KV2_STAGES - 1;  // refill the stage tile j-1 used, once P.V(j-1) has retired
+        if (t < n_kv) {
+          if (t >= KV2_STAGES) mbar_wait(kv_empty0 + 8 * (t & (KV2_STAGES - 1)), ((t / KV2_STAGES) - 1) & 1);
+          load_kv(t);
+        }
+        // O += P(j) V(j) : M=128, N=64, K = keys of this step rounded up to 16; A = P in TMEM, B = V (MN-major)
+        mbar_wait(p_ready0 + 8 * (j & 1), (j >> 1) & 1);
+        tc_fence_after();
+        const int st = j & (KV2_STAGES - 1);
+        const int n_mma = (min(TBN2, p.T - j * TBN2) + 15) & ~15;
+        for (int k = 0; k < n_mma / 16; ++k) {
+          const uint64_t vd = make_desc_mnmajor_sw128(sV + st * KV2_BYTES + k * 2048, 1024);
+          tc_mma_bf16_ts(tmem_base + COL_O, tmem_base + (uint32_t)((j & 1) * TBN2 + 8 * k), vd, idesc_o,
+                         (k > 0 || j > 0) ? 1u : 0u);
+        }
+        tc_commit(kv_empty0 + 8 * st);
+        tc_commit(o_full);
+      }
+    }
+  } else {
+    // ---------------- softmax: one thread per query row, all 64 keys of a step ----------------
+    const int r = warp * 32 + lane;  // query row within the tile = TMEM lane (warp w may touch lanes 32 w .. 32 w + 31)
+    const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
+    uint32_t masks_lo = 0, masks_hi = 0;  // lane j: validity words of keys [64 j, 64 j + 32) and [64 j + 32, 64 j + 64)
+    {
+      // the query row (64 bf16 = 32 packed columns) -> TMEM: the A operand of every S = Q K^T
+      const uint4* qp = reinterpret_cast<const uint4*>(qkv + (int64_t)(row_base + q0 + r) * (3 * p.d) + h * THD);
+      uint32_t qa[16], qb[16];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint4 u = __ldg(qp + i), w = __ldg(qp + 4 + i);
+        qa[4 * i] = u.x; qa[4 * i + 1] = u.y; qa[4 * i + 2] = u.z; qa[4 * i + 3] = u.w;
+        qb[4 * i] = w.x; qb[4 * i + 1] = w.y; qb[4 * i + 2] = w.z; qb[4 * i + 3] = w.w;
+      }
+      // validity bits of every step's keys, under the latency of the loads above (n_kv <= 32 is checked on the host)
+      const uint8_t* vg = p.key_valid ? p.key_valid + (int64_t)b * p.T : nullptr;
+#pragma unroll 2
+      for (int j = 0; j < n_kv; ++j) {
+        const int k0 = j * TBN2 + lane, k1 = k0 + 32;
+        bool ok0 = k0 < p.T, ok1 = k1 < p.T;
+        if (ok0 && vg) ok0 = vg[k0] != 0;
+        if (ok1 && vg) ok1 = vg[k1] != 0;
+        const uint32_t w0 = __ballot_sync(0xffffffffu, ok0), w1 = __ballot_sync(0xffffffffu, ok1);
+        if (lane == j) { masks_lo = w0; masks_hi = w1; }
+      }
+      tmem_st_32x32b_x16(t_lane + COL_Q, qa);
+      tmem_st_32x32b_x16(t_lane + COL_Q + 16, qb);
+      tc_wait_st();
+      tc_fence_before();
+      mbar_arrive(q_full);
+    }
+    const bool live = q0 + warp * 32 + 31 >= q_tile * TBM;  // see the first kernel
+    if (!live) {
+      for (int j = 0; j < n_kv; ++j) {
+        mbar_wait(s_full0 + 8 * (j & 1), (j >> 1) & 1);
+        if (j > 0) mbar_wait(o_full, (j - 1) & 1);
+        mbar_arrive(p_ready0 + 8 * (j & 1));
+      }
+      mbar_wait(o_full, (n_kv - 1) & 1);
+    } else {
+      float m_run = -INFINITY, l_run = 0.f;
+      // row maximum of 32 scores (invalid keys and the stale columns past the step's keys count as -inf)
+      auto max32 = [&](const uint32_t (&v)[32], uint32_t mw) -> float {
+        float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        if (mw == 0xffffffffu) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(v[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            mx4[i & 3] = fmaxf(mx4[i & 3], ((mw >> i) & 1u) ? __uint_as_float(v[i]) : -INFINITY);
+        }
+        return fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+      };
+      // p = exp2(s * scale - moff) of 32 scores -> 16 packed bf16 pairs; returns their sum
+      auto exp32 = [&](const uint32_t (&v)[32], uint32_t mw, float moff, uint32_t (&packed)[16]) -> float {
+        const uint64_t sc2 = f2_bcast(p.scale_log2), nm2 = f2_bcast(-moff);
+        uint64_t ls2[4] = {0ull, 0ull, 0ull, 0ull};
+        if (mw == 0xffffffffu) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            float e0, e1, p0, p1;
+            f2_unpack(f2_fma(f2_pack(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), sc2, nm2), e0, e1);
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(e0));
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(e1));
+            ls2[(i >> 1) & 3] = f2_add(ls2[(i >> 1) & 3], f2_pack(p0, p1));
+            packed[i >> 1] = pack_bf16x2(p0, p1);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            float e0, e1, p0, p1;
+            f2_unpack(f2_fma(f2_pack(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), sc2, nm2), e0, e1);
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(e0));
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(e1));
+            p0 = ((mw >> i) & 1u) ? p0 : 0.f;  // select, not multiply: a stale column may hold anything
+            p1 = ((mw >> (i + 1)) & 1u) ? p1 : 0.f;
+            ls2[(i >> 1) & 3] = f2_add(ls2[(i >> 1) & 3], f2_pack(p0, p1));
+            packed[i >> 1] = pack_bf16x2(p0, p1);
+          }
+        }
+        float a0, a1;
+        f2_unpack(f2_add(f2_add(ls2[0], ls2[1]), f2_add(ls2[2], ls2[3])), a0, a1);
+        return a0 + a1;
+      };
+      for (int j = 0; j < n_kv; ++j) {
+        const uint32_t mlo = __shfl_sync(0xffffffffu, masks_lo, j), mhi = __shfl_sync(0xffffffffu, masks_hi, j);
+        const bool hi_read = j * TBN2 + 32 < p.T;  // P.V(j) reads the P columns of keys 32..63 (K = keys up to T)
+        mbar_wait(s_full0 + 8 * (j & 1), (j >> 1) & 1);
+        tc_fence_after();
+        const uint32_t s_col = t_lane + (uint32_t)((j & 1) * TBN2);
+        uint32_t va[32], vb[32];
+        if (mlo != 0u) tmem_ld_32x32b_x32(s_col, va);
+        if (mhi != 0u) tmem_ld_32x32b_x32(s_col + 32, vb);
+        tc_wait_ld();
+        float mx = -INFINITY;
+        if (mlo != 0u) mx = max32(va, mlo);
+        if (mhi != 0u) mx = fmaxf(mx, max32(vb, mhi));
+        // running maximum: raised only by more than 2^8 (see kernel 5); corr brings l and O to the new offset
+        const float m_cand = fmaxf(m_run, mx);
+        const bool first = (m_run == -INFINITY);
+        const float dlt = first ? 0.f : (m_cand - m_run) * p.scale_log2;
+        const bool grow = (m_cand != -INFINITY) && (first || dlt > 8.f);
+        const float m_new = grow ? m_cand : m_run;
+        const float corr = (grow && !first) ? exp2f(-dlt) : 1.f;
+        const float moff = (m_new == -INFINITY) ? 0.f : m_new * p.scale_log2;
+        // P(j) over this row's own scores: columns [0, 16) = keys 0..31, [16, 32) = keys 32..63 of S buffer j & 1
+        float lsum = 0.f;
+        {
+          uint32_t packed[16];
+          if (mlo != 0u) {
+            lsum = exp32(va, mlo, moff, packed);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) packed[i] = 0u;
+          }
+          tmem_st_32x32b_x16(s_col, packed);
+        }
+        if (hi_read) {
+          uint32_t packed[16];
+          if (mhi != 0u) {
+            lsum += exp32(vb, mhi, moff, packed);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) packed[i] = 0u;
+          }
+          tmem_st_32x32b_x16(s_col + 16, packed);
+        }
+        l_run = l_run * corr + lsum;
+        m_run = m_new;
+        // every phase of o_full is passed in order (see kernel 5); O is rescaled in TMEM only when a maximum was raised
+        if (j > 0) mbar_wait(o_full, (j - 1) & 1);
+        if (j > 0 && __any_sync(0xffffffffu, corr != 1.f)) {
+          tc_fence_after();
+#pragma unroll
+          for (int c = 0; c < THD; c += 32) {
+            uint32_t ov[32];
+            tmem_ld_32x32b_x32(t_lane + COL_O + c, ov);
+            tc_wait_ld();
+            uint32_t lo[16], hi[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              lo[i] = __float_as_uint(__uint_as_float(ov[i]) * corr);
+              hi[i] = __float_as_uint(__uint_as_float(ov[16 + i]) * corr);
+            }
+            tmem_st_32x32b_x16(t_lane + COL_O + c, lo);
+            tmem_st_32x32b_x16(t_lane + COL_O + c + 16, hi);
+          }
+        }
+        tc_wait_st();
+        tc_fence_before();
+        mbar_arrive(p_ready0 + 8 * (j & 1));
+      }
+      // ---- finalize: O / row sum ----
+      mbar_wait(o_full, (n_kv - 1) & 1);
+      tc_fence_after();
+      const int qrow = q0 + r;
+      const bool write = qrow < p.T && qrow >= q_tile * TBM;  // rows below q_tile*TBM belong to the previous tile
+      const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+      bf16* op = p.o + (int64_t)(row_base + qrow) * p.o_rs + h * THD;
+#pragma unroll
+      for (int c = 0; c < THD; c += 32) {
+        uint32_t ov[32];
+        tmem_ld_32x32b_x32(t_lane + COL_O + c, ov);
+        tc_wait_ld();
+        if (write) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            uint4 u;
+            u.x = pack_bf16x2(__uint_as_float(ov[i]) * inv, __uint_as_float(ov[i + 1]) * inv);
+            u.y = pack_bf16x2(__uint_as_float(ov[i + 2]) * inv, __uint_as_float(ov[i + 3]) * inv);
+            u.z = pack_bf16x2(__uint_as_float(ov[i + 4]) * inv, __uint_as_float(ov[i + 5]) * inv);
+            u.w = pack_bf16x2(__uint_as_float(ov[i + 6]) * inv, __uint_as_float(ov[i + 7]) * inv);
+            *reinterpret_cast<uint4*>(op + c + i) = u;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == RW_WARPS) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS_ATT);
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -1042,7 +1338,8 @@ int make_qkv_map(const bf16* qkv, int64_t rows, int64_t cols, int64_t ld, int bo
 // qkv bf16 [B*T, 3d] (q pre-scaled, RoPE applied), out bf16 [B*T, d]; covers all T query rows of every sequence when
 // T >= 128 and head_dim == 64 (*rows_done = T), otherwise does nothing (*rows_done = 0).
 bool esm_attention_tc_ropes_q(int T, int n_heads, int d) {
-  return g_esm_attention_kernel >= 2 && g_esm_attention_q_rope && T >= TBM && d / n_heads == THD;
+  return g_esm_attention_kernel >= 2 && g_esm_attention_kernel <= 5 && g_esm_attention_q_rope && T >= TBM &&
+         d / n_heads == THD;
 }
 
 // q_rope: RoPE table for Q when the caller left Q un-rotated (only if esm_attention_tc_ropes_q() said so), else null
@@ -1066,8 +1363,10 @@ int esm_attention_tc(const bf16* qkv, const uint8_t* key_valid, bf16* out, int B
                                   TS_SMEM));
     PCY_CUDA(cudaFuncSetAttribute(esm_attention_ts_kernel<false, true, true>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM));
+    PCY_CUDA(cudaFuncSetAttribute(esm_attention_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM));
   }
-  const int kern = g_esm_attention_kernel;
+  int kern = g_esm_attention_kernel;
+  if (kern == 6 && (T + TBN2 - 1) / TBN2 > 32) kern = 5;  // kernel 6 keeps a step's validity words in one lane each
   const bool steps64 = kern != 0;
   CUtensorMap tmap;
   PCY_TRY(make_qkv_map(qkv, (int64_t)B * T, 3 * d, 3 * d, steps64 ? TBN2 : TBN, &tmap));
@@ -1075,9 +1374,11 @@ int esm_attention_tc(const bf16* qkv, const uint8_t* key_valid, bf16* out, int B
   p.o = out; p.o_rs = d; p.key_valid = key_valid; p.B = B; p.H = n_heads; p.T = T; p.d = d; p.n_q_tiles = n_q_tiles;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.q_rope = q_rope;
-  PCY_REQUIRE(q_rope == nullptr || kern >= 2, "esm_attention_tc: only the TMEM-operand kernels rotate Q themselves");
+  PCY_REQUIRE(q_rope == nullptr || (kern >= 2 && kern <= 5),
+              "esm_attention_tc: only the TMEM-operand kernels 2-5 rotate Q themselves");
   dim3 grid(n_q_tiles, n_heads, B);
-  if (kern == 5) esm_attention_ts_kernel<false, true, true><<<grid, TC_THREADS, TS_SMEM, stream>>>(tmap, p, qkv);
+  if (kern == 6) esm_attention_row_kernel<<<grid, RW_THREADS, TS_SMEM, stream>>>(tmap, p, qkv);
+  else if (kern == 5) esm_attention_ts_kernel<false, true, true><<<grid, TC_THREADS, TS_SMEM, stream>>>(tmap, p, qkv);
   else if (kern == 4) esm_attention_ts_kernel<false, true><<<grid, TC_THREADS, TS_SMEM, stream>>>(tmap, p, qkv);
   else if (kern == 3) esm_attention_ts_kernel<true><<<grid, TC_THREADS, TS_SMEM, stream>>>(tmap, p, qkv);
   else if (kern == 2) esm_attention_ts_kernel<false><<<grid, TC_THREADS, TS_SMEM, stream>>>(tmap, p, qkv);

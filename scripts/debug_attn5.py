@@ -16,7 +16,7 @@ for lengths in ([298, 131, 260], [512, 300, 130, 64], [126, 126]):
     lib = _lib.load()
     lib.pcy_set_esm_attention_kernel(4)
     ref = m.encode_tokens(toks.cuda()).float().cpu()
-    lib.pcy_set_esm_attention_kernel(5)
+    lib.pcy_set_esm_attention_kernel(int(sys.argv[1]) if len(sys.argv) > 1 else 5)
     outs = [m.encode_tokens(toks.cuda()).float().cpu() for _ in range(12)]
     lib.pcy_set_esm_attention_kernel(4)
     nonpad = toks != O.PAD_IDX

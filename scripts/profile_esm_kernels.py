@@ -25,6 +25,10 @@ def main():
     toks[:, 0] = 0
     toks[:, 1:513] = torch.randint(4, 24, (n, 512), generator=g)
     toks[:, 513] = 2
+    import os
+    if os.environ.get("PCY_ESM_ATTN") is not None:
+        from procyon_b200 import _lib
+        _lib.load().pcy_set_esm_attention_kernel(int(os.environ["PCY_ESM_ATTN"]))
     out, _ = m(toks.to(dev))
     torch.cuda.synchronize()
     print("done", tuple(out.shape))
