@@ -56,6 +56,9 @@ struct TcAttnParams {
   bf16* o;
   int64_t o_rs;  // output row stride (elements)
   const uint8_t* key_valid;  // [B][T] or null
+  // the same as bits: word w of a sequence covers keys [32 w, 32 w + 32) (bits past T are 0), 2 * ceil(T / 64) words per
+  // sequence; null: kernels that want the words of every step up front build them from the bytes with ballots
+  const uint32_t* valid_words;
   int B, H, T, d;
   int n_q_tiles;
   float scale_log2;
@@ -744,7 +747,11 @@ esm_attention_ts_kernel(const __grid_constant__ CUtensorMap tmap, const TcAttnPa
           qr[4 * c] = u.x; qr[4 * c + 1] = u.y; qr[4 * c + 2] = u.z; qr[4 * c + 3] = u.w;
         }
       }
-      if (PAIR && n_kv <= 32) {
+      if (PAIR && n_kv <= 32 && p.valid_words != nullptr) {
+        // one load per lane, issued with the Q loads: a single global round trip in the CTA's prologue (as bytes +
+        // ballots the loop below makes one round trip per four steps, ncu: 11 % of the warp samples of kernel 6)
+        if (lane < n_kv) step_masks = __ldg(p.valid_words + (int64_t)b * (2 * n_kv) + 2 * lane + half);
+      } else if (PAIR && n_kv <= 32) {
         // Validity bits of this warp's 32 keys of EVERY step, taken here, under the latency of the Q loads above: lane j
         // keeps the word of step j.  (ncu: as one byte load + ballot per step, the compare behind the load was the
         // single hottest stall of the step loop, 8 % of the kernel's warp samples.)
@@ -1137,6 +1144,13 @@ esm_attention_row_kernel(const __grid_constant__ CUtensorMap tmap, const TcAttnP
       }
       // validity bits of every step's keys, under the latency of the loads above (n_kv <= 32 is checked on the host)
       const uint8_t* vg = p.key_valid ? p.key_valid + (int64_t)b * p.T : nullptr;
+      if (p.valid_words != nullptr) {
+        if (lane < n_kv) {
+          const uint2 w = __ldg(reinterpret_cast<const uint2*>(p.valid_words + (int64_t)b * (2 * n_kv)) + lane);
+          masks_lo = w.x;
+          masks_hi = w.y;
+        }
+      } else
 #pragma unroll 2
       for (int j = 0; j < n_kv; ++j) {
         const int k0 = j * TBN2 + lane, k1 = k0 + 32;
@@ -1335,6 +1349,19 @@ int make_qkv_map(const bf16* qkv, int64_t rows, int64_t cols, int64_t ld, int bo
 
 }  // namespace
 
+// validity bytes [B][T] -> bits: one warp per 32-key word, 2 * ceil(T / 64) words per sequence (an even count, so that the
+// two words of a 64-key step are one aligned 8-byte load)
+__global__ void pack_key_valid_kernel(const uint8_t* __restrict__ valid, uint32_t* __restrict__ words, int T, int nw,
+                                      int total) {
+  const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (w >= total) return;
+  const int b = w / nw, k = (w - b * nw) * 32 + lane;
+  const bool ok = k < T && valid[(int64_t)b * T + k] != 0;
+  const uint32_t word = __ballot_sync(0xffffffffu, ok);
+  if (lane == 0) words[w] = word;
+}
+
 // qkv bf16 [B*T, 3d] (q pre-scaled, RoPE applied), out bf16 [B*T, d]; covers all T query rows of every sequence when
 // T >= 128 and head_dim == 64 (*rows_done = T), otherwise does nothing (*rows_done = 0).
 bool esm_attention_tc_ropes_q(int T, int n_heads, int d) {
@@ -1343,8 +1370,17 @@ bool esm_attention_tc_ropes_q(int T, int n_heads, int d) {
 }
 
 // q_rope: RoPE table for Q when the caller left Q un-rotated (only if esm_attention_tc_ropes_q() said so), else null
-int esm_attention_tc(const bf16* qkv, const uint8_t* key_valid, bf16* out, int B, int T, int n_heads, int d,
-                     float scale, const float* q_rope, int* rows_done, cudaStream_t stream) {
+int esm_pack_key_valid(const uint8_t* key_valid, uint32_t* words, int B, int T, cudaStream_t stream) {
+  PCY_REQUIRE(key_valid && words, "esm_pack_key_valid: null argument");
+  const int nw = esm_key_valid_words(T), total = B * nw;
+  if (total == 0) return 0;
+  pack_key_valid_kernel<<<ceil_div(total, 8), 256, 0, stream>>>(key_valid, words, T, nw, total);
+  PCY_LAUNCH_CHECK();
+  return 0;
+}
+
+int esm_attention_tc(const bf16* qkv, const uint8_t* key_valid, const uint32_t* key_valid_words, bf16* out, int B, int T,
+                     int n_heads, int d, float scale, const float* q_rope, int* rows_done, cudaStream_t stream) {
   *rows_done = 0;
   if (T < TBM || d / n_heads != THD) return 0;
   int n_q_tiles = (T + TBM - 1) / TBM;
@@ -1371,7 +1407,8 @@ int esm_attention_tc(const bf16* qkv, const uint8_t* key_valid, bf16* out, int B
   CUtensorMap tmap;
   PCY_TRY(make_qkv_map(qkv, (int64_t)B * T, 3 * d, 3 * d, steps64 ? TBN2 : TBN, &tmap));
   TcAttnParams p;
-  p.o = out; p.o_rs = d; p.key_valid = key_valid; p.B = B; p.H = n_heads; p.T = T; p.d = d; p.n_q_tiles = n_q_tiles;
+  p.o = out; p.o_rs = d; p.key_valid = key_valid; p.valid_words = key_valid ? key_valid_words : nullptr;
+  p.B = B; p.H = n_heads; p.T = T; p.d = d; p.n_q_tiles = n_q_tiles;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.q_rope = q_rope;
   PCY_REQUIRE(q_rope == nullptr || (kern >= 2 && kern <= 5),

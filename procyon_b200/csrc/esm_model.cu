@@ -244,7 +244,8 @@ int64_t pcy_esm_workspace_bytes(void* handle, int B, int T) {
   EsmModel* m = reinterpret_cast<EsmModel*>(handle);
   const int64_t n = (int64_t)B * T, d = m->cfg.d_model;
   const int64_t wide = std::max<int64_t>(3 * d, m->cfg.ffn_dim);
-  return round_up(n * d * 2, 256) * 2 + round_up(n * wide * 2, 256) + round_up(n, 256) + 1024;
+  return round_up(n * d * 2, 256) * 2 + round_up(n * wide * 2, 256) + round_up(n, 256) +
+         round_up((int64_t)B * esm_key_valid_words(T) * 4, 256) + 1024;
 }
 
 int pcy_esm_encode(void* handle, const int32_t* tokens, int B, int T, void* out_states, void* workspace,
@@ -269,10 +270,12 @@ int pcy_esm_encode(void* handle, const int32_t* tokens, int B, int T, void* out_
   const int64_t wide = std::max<int64_t>(3 * d, f);
   bf16* big = carve<bf16>(p, n * wide);
   uint8_t* valid = carve<uint8_t>(p, n);
+  uint32_t* valid_words = carve<uint32_t>(p, (int64_t)B * esm_key_valid_words(T));
 
   g_prof.mark(-1, stream);
   PCY_TRY(esm_embed(tokens, m->embed, x, B, T, d, c.pad_idx, c.mask_idx, c.token_dropout, stream));
   PCY_TRY(make_key_valid(tokens, valid, n, c.pad_idx, stream));
+  PCY_TRY(esm_pack_key_valid(valid, valid_words, B, T, stream));  // the same as bits, for the attention prologue
   g_prof.mark(PC_EMBED, stream);
   const float q_scale = 1.0f / sqrtf((float)hd);
 
@@ -295,7 +298,7 @@ int pcy_esm_encode(void* handle, const int32_t* tokens, int B, int T, void* out_
     g_prof.mark(PC_ROPE, stream);
     int rows_done = 0;
     if (g_esm_tc_attention)
-      PCY_TRY(esm_attention_tc(big, valid, h, B, T, H, d, 1.0f, q_in_attn ? m->rope : nullptr, &rows_done, stream));
+      PCY_TRY(esm_attention_tc(big, valid, valid_words, h, B, T, H, d, 1.0f, q_in_attn ? m->rope : nullptr, &rows_done, stream));
     AttnArgs a;
     a.q = big + (int64_t)rows_done * 3 * d; a.k = big + d; a.v = big + 2 * d; a.o = h + (int64_t)rows_done * d;
     a.q_bs = a.k_bs = a.v_bs = (int64_t)T * 3 * d; a.q_rs = a.k_rs = a.v_rs = 3 * d;

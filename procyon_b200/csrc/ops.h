@@ -87,8 +87,11 @@ int flash_attention(const AttnArgs& a, cudaStream_t stream);
 // tcgen05 bidirectional attention for head_dim 64 on a fused [B*T, 3d] qkv buffer; covers the full 128-row query
 // tiles of every sequence (rows_done = floor(T/128)*128, 0 if the shape is unsupported)
 bool esm_attention_tc_ropes_q(int T, int n_heads, int d);
-int esm_attention_tc(const bf16* qkv, const uint8_t* key_valid, bf16* out, int B, int T, int n_heads, int d,
-                     float scale, const float* q_rope, int* rows_done, cudaStream_t stream);
+// key_valid_words: the same validity as bits, 2 * ceil(T / 64) words per sequence (esm_pack_key_valid), or null
+int esm_attention_tc(const bf16* qkv, const uint8_t* key_valid, const uint32_t* key_valid_words, bf16* out, int B, int T,
+                     int n_heads, int d, float scale, const float* q_rope, int* rows_done, cudaStream_t stream);
+inline int esm_key_valid_words(int T) { return 2 * ((T + 63) / 64); }
+int esm_pack_key_valid(const uint8_t* key_valid, uint32_t* words, int B, int T, cudaStream_t stream);
 
 // ---- decode-step attention (RoPE + KV append + split-KV attention + combine, one launch) ------------
 struct DecodeAttnArgs {
