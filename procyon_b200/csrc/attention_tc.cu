@@ -631,6 +631,25 @@ esm_attention_ts_kernel(const __grid_constant__ CUtensorMap tmap, const TcAttnPa
   const int row_base = b * p.T;
   const int n_kv = (p.T + TBN2 - 1) / TBN2;
 
+  // The softmax threads' first global loads — their half of the query row and the validity words — are issued BEFORE
+  // the CTA's setup (barrier init, TMEM allocation, __syncthreads): a CTA lives for nine key steps and these loads head
+  // the critical path of its first one.
+  uint32_t qr[16];
+  uint32_t step_masks = 0;  // PAIR: lane j holds the validity word of this warp's keys of step j
+  const bool early_q = warp < SM_WARPS && p.q_rope == nullptr;
+  if (early_q) {
+    const int e_quad = warp & 3, e_half = warp >> 2;
+    const uint4* qp = reinterpret_cast<const uint4*>(
+        qkv + (int64_t)(row_base + q0 + e_quad * 32 + lane) * (3 * p.d) + h * THD + e_half * 32);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint4 u = __ldg(qp + i);
+      qr[4 * i] = u.x; qr[4 * i + 1] = u.y; qr[4 * i + 2] = u.z; qr[4 * i + 3] = u.w;
+    }
+    if (PAIR && n_kv <= 32 && p.valid_words != nullptr && lane < n_kv)
+      step_masks = __ldg(p.valid_words + (int64_t)b * (2 * n_kv) + 2 * lane + e_half);
+  }
+
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmap);
     mbar_init(q_full, SM_WARPS * 32);
@@ -711,18 +730,11 @@ esm_attention_ts_kernel(const __grid_constant__ CUtensorMap tmap, const TcAttnPa
     const int r = quad * 32 + lane;  // query row within the tile = TMEM lane
     const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
     constexpr int OH = THD / 2;  // output columns per thread
-    uint32_t step_masks = 0;     // PAIR: lane j holds the validity word of this warp's keys of step j
     {
       // this thread's half of its query row (32 bf16 = 16 packed columns) -> TMEM: the A operand of every S = Q K^T
       const bf16* qrow_p = qkv + (int64_t)(row_base + q0 + r) * (3 * p.d) + h * THD;
-      uint32_t qr[16];
       if (p.q_rope == nullptr) {
-        const uint4* qp = reinterpret_cast<const uint4*>(qrow_p + half * 32);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const uint4 u = __ldg(qp + i);
-          qr[4 * i] = u.x; qr[4 * i + 1] = u.y; qr[4 * i + 2] = u.z; qr[4 * i + 3] = u.w;
-        }
+        // (loaded before the CTA's setup)
       } else {
         // Q arrives un-rotated (the RoPE pass then only touches K: a third less HBM traffic for it); same arithmetic
         // as rope_kernel: out[i] = x[i] cos_i - x[i+32] sin_i, out[i+32] = x[i+32] cos_i + x[i] sin_i, one rounding
@@ -750,7 +762,7 @@ esm_attention_ts_kernel(const __grid_constant__ CUtensorMap tmap, const TcAttnPa
       if (PAIR && n_kv <= 32 && p.valid_words != nullptr) {
         // one load per lane, issued with the Q loads: a single global round trip in the CTA's prologue (as bytes +
         // ballots the loop below makes one round trip per four steps, ncu: 11 % of the warp samples of kernel 6)
-        if (lane < n_kv) step_masks = __ldg(p.valid_words + (int64_t)b * (2 * n_kv) + 2 * lane + half);
+        if (!early_q && lane < n_kv) step_masks = __ldg(p.valid_words + (int64_t)b * (2 * n_kv) + 2 * lane + half);
       } else if (PAIR && n_kv <= 32) {
         // Validity bits of this warp's 32 keys of EVERY step, taken here, under the latency of the Q loads above: lane j
         // keeps the word of step j.  (ncu: as one byte load + ballot per step, the compare behind the load was the
@@ -1055,6 +1067,24 @@ esm_attention_row_kernel(const __grid_constant__ CUtensorMap tmap, const TcAttnP
   const int row_base = b * p.T;
   const int n_kv = (p.T + TBN2 - 1) / TBN2;
 
+  // first global loads (query row, validity words) before the CTA's setup, see esm_attention_ts_kernel
+  uint32_t qa[16], qb[16];
+  uint32_t masks_lo = 0, masks_hi = 0;  // lane j: validity words of keys [64 j, 64 j + 32) and [64 j + 32, 64 j + 64)
+  if (warp < RW_WARPS) {
+    const uint4* qp = reinterpret_cast<const uint4*>(qkv + (int64_t)(row_base + q0 + warp * 32 + lane) * (3 * p.d) + h * THD);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint4 u = __ldg(qp + i), w = __ldg(qp + 4 + i);
+      qa[4 * i] = u.x; qa[4 * i + 1] = u.y; qa[4 * i + 2] = u.z; qa[4 * i + 3] = u.w;
+      qb[4 * i] = w.x; qb[4 * i + 1] = w.y; qb[4 * i + 2] = w.z; qb[4 * i + 3] = w.w;
+    }
+    if (p.valid_words != nullptr && lane < n_kv) {
+      const uint2 w = __ldg(reinterpret_cast<const uint2*>(p.valid_words + (int64_t)b * (2 * n_kv)) + lane);
+      masks_lo = w.x;
+      masks_hi = w.y;
+    }
+  }
+
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmap);
     mbar_init(q_full, RW_WARPS * 32);
@@ -1131,26 +1161,11 @@ esm_attention_row_kernel(const __grid_constant__ CUtensorMap tmap, const TcAttnP
     // ---------------- softmax: one thread per query row, all 64 keys of a step ----------------
     const int r = warp * 32 + lane;  // query row within the tile = TMEM lane (warp w may touch lanes 32 w .. 32 w + 31)
     const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
-    uint32_t masks_lo = 0, masks_hi = 0;  // lane j: validity words of keys [64 j, 64 j + 32) and [64 j + 32, 64 j + 64)
     {
-      // the query row (64 bf16 = 32 packed columns) -> TMEM: the A operand of every S = Q K^T
-      const uint4* qp = reinterpret_cast<const uint4*>(qkv + (int64_t)(row_base + q0 + r) * (3 * p.d) + h * THD);
-      uint32_t qa[16], qb[16];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const uint4 u = __ldg(qp + i), w = __ldg(qp + 4 + i);
-        qa[4 * i] = u.x; qa[4 * i + 1] = u.y; qa[4 * i + 2] = u.z; qa[4 * i + 3] = u.w;
-        qb[4 * i] = w.x; qb[4 * i + 1] = w.y; qb[4 * i + 2] = w.z; qb[4 * i + 3] = w.w;
-      }
-      // validity bits of every step's keys, under the latency of the loads above (n_kv <= 32 is checked on the host)
+      // the query row (64 bf16 = 32 packed columns, loaded before the setup) -> TMEM: the A operand of every S = Q K^T;
+      // without packed validity words: the bits of every step's keys from the bytes (n_kv <= 32 is checked on the host)
       const uint8_t* vg = p.key_valid ? p.key_valid + (int64_t)b * p.T : nullptr;
-      if (p.valid_words != nullptr) {
-        if (lane < n_kv) {
-          const uint2 w = __ldg(reinterpret_cast<const uint2*>(p.valid_words + (int64_t)b * (2 * n_kv)) + lane);
-          masks_lo = w.x;
-          masks_hi = w.y;
-        }
-      } else
+      if (p.valid_words == nullptr)
 #pragma unroll 2
       for (int j = 0; j < n_kv; ++j) {
         const int k0 = j * TBN2 + lane, k1 = k0 + 32;
