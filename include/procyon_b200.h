@@ -106,7 +106,9 @@ int pcy_set_esm_tc_attention(int enabled);
    the output tile accumulated in TMEM across the steps (use_acc) and rescaled there only when a row's running maximum
    grows by more than 2^8, instead of a TMEM read + register fold of the P.V tile in every step (default); 6 = ONE thread
    per query row (four softmax warps, 64 scores per thread and step, no row-maximum exchange, no barrier between
-   softmax warps; otherwise as 5): half the instructions of 5 at the same speed on B200 */
+   softmax warps; otherwise as 5): 21 % fewer instructions than 5 at the same speed on B200; 7 = kernel 6 as persistent
+   CTAs (2 x #SM CTAs walk the (protein, head, query tile) items; barriers keep running phases, TMEM is allocated once,
+   the next item's Q and K / V are requested under the current item's last steps): same speed again */
 int pcy_set_esm_attention_kernel(int kernel);
 /* rows: when the sequence length leaves at most `rows` query rows beyond the last full 128-row tile (512 residues +
    BOS + EOS = 4 tiles + 2 rows), the mma.sync kernel takes those rows instead of one more tcgen05 CTA per (protein,

@@ -1337,6 +1337,330 @@ esm_attention_row_kernel(const __grid_constant__ CUtensorMap tmap, const TcAttnP
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Kernel 7: kernel 6 as a PERSISTENT CTA.
+//
+// A (protein, head, query tile) item is nine key steps: with one CTA per item, launching the CTA, initialising its
+// barriers, allocating TMEM, the first global round trip for Q and draining the pipeline at the end are a large part
+// of its life (ncu of kernel 6: 11 % of the warp samples in the prologue, 6 % at the final barrier).  Here 2 x #SM CTAs
+// walk the items round-robin.  All mbarriers keep running phase counters (global step g, global K/V tile count), TMEM
+// is allocated once, the MMA thread runs ahead into the next item (its K/V tiles stream in while the softmax threads
+// still finish the current one), and the softmax threads request the next item's query row and validity words before
+// they read out the current item's O.  One more barrier, o_free: the first P.V of an item overwrites O (use_acc = 0), so
+// it waits until every softmax thread has read the previous item's result.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(RW_THREADS, 2)
+esm_attention_row_persistent_kernel(const __grid_constant__ CUtensorMap tmap, const TcAttnParams p,
+                                    const bf16* __restrict__ qkv, int n_items) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = smem_u32(smem_raw);
+  if ((base & 1023u) != 0u) __trap();
+  const uint32_t sK = base;                             // KV2_STAGES stages
+  const uint32_t sV = sK + KV2_STAGES * KV2_BYTES;      // KV2_STAGES stages
+  const uint32_t bars = sV + KV2_STAGES * KV2_BYTES;
+  const uint32_t q_full = bars, kv_full0 = bars + 8, kv_empty0 = kv_full0 + 8 * KV2_STAGES,
+                 s_full0 = kv_empty0 + 8 * KV2_STAGES, p_ready0 = s_full0 + 16, o_full = p_ready0 + 16,
+                 o_free = o_full + 8, tmem_slot = o_free + 8;
+  constexpr uint32_t COL_O = 2 * TBN2, COL_Q = 2 * TBN2 + THD;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_kv = (p.T + TBN2 - 1) / TBN2;
+  auto decode = [&](int it, int& q_tile, int& h, int& b) {  // query tile fastest: neighbours share K / V in L2
+    q_tile = it % p.n_q_tiles;
+    const int t = it / p.n_q_tiles;
+    h = t % p.H;
+    b = t / p.H;
+  };
+  // this thread's query row (64 bf16) and the validity words of the item's sequence (lane j: step j)
+  uint32_t qa[16], qb[16];
+  uint32_t masks_lo = 0, masks_hi = 0;
+  auto request_item = [&](int it) {
+    int q_tile, h, b;
+    decode(it, q_tile, h, b);
+    const int q0 = min(q_tile * TBM, p.T - TBM);
+    const uint4* qp =
+        reinterpret_cast<const uint4*>(qkv + (int64_t)(b * p.T + q0 + warp * 32 + lane) * (3 * p.d) + h * THD);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint4 u = __ldg(qp + i), w = __ldg(qp + 4 + i);
+      qa[4 * i] = u.x; qa[4 * i + 1] = u.y; qa[4 * i + 2] = u.z; qa[4 * i + 3] = u.w;
+      qb[4 * i] = w.x; qb[4 * i + 1] = w.y; qb[4 * i + 2] = w.z; qb[4 * i + 3] = w.w;
+    }
+    masks_lo = masks_hi = 0;
+    if (lane < n_kv) {
+      const uint2 w = __ldg(reinterpret_cast<const uint2*>(p.valid_words + (int64_t)b * (2 * n_kv)) + lane);
+      masks_lo = w.x;
+      masks_hi = w.y;
+    }
+  };
+  if (warp < RW_WARPS && (int)blockIdx.x < n_items) request_item(blockIdx.x);  // before the setup, see kernel 6
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmap);
+    mbar_init(q_full, RW_WARPS * 32);
+    for (int s = 0; s < KV2_STAGES; ++s) {
+      mbar_init(kv_full0 + 8 * s, 1);
+      mbar_init(kv_empty0 + 8 * s, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(s_full0 + 8 * s, 1);
+      mbar_init(p_ready0 + 8 * s, RW_WARPS * 32);
+    }
+    mbar_init(o_full, 1);
+    mbar_init(o_free, RW_WARPS * 32);
+    fence_barrier_init();
+  }
+  if (warp == RW_WARPS) {
+    tmem_alloc(tmem_slot, TMEM_COLS_ATT);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == RW_WARPS) {
+    if (lane == 0) {
+      // ---------------- TMA producer + MMA issuer (one thread) ----------------
+      uint32_t g0 = 0;  // global step of the item's step 0 (S / P buffer and barrier parities run across items)
+      uint32_t kl = 0;  // K / V tiles requested so far (stage = count & 3)
+      uint32_t ks = 0;  // K / V tiles consumed by an S = Q K^T so far
+      int n = 0;        // items done by this CTA
+      for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++n) {
+        int q_tile, h, b;
+        decode(it, q_tile, h, b);
+        const int row_base = b * p.T;
+        auto load_kv = [&](int t) {  // tile t of this item
+          const uint32_t st = kl & (KV2_STAGES - 1);
+          if (kl >= KV2_STAGES) mbar_wait(kv_empty0 + 8 * st, ((kl / KV2_STAGES) - 1) & 1);  // its last user's P.V retired
+          mbar_arrive_expect_tx(kv_full0 + 8 * st, 2 * KV2_BYTES);
+          tma_load_2d(sK + st * KV2_BYTES, &tmap, kv_full0 + 8 * st, p.d + h * THD, row_base + t * TBN2);
+          tma_load_2d(sV + st * KV2_BYTES, &tmap, kv_full0 + 8 * st, 2 * p.d + h * THD, row_base + t * TBN2);
+          ++kl;
+        };
+        const uint32_t k0 = ks;  // global count of this item's tile 0
+        auto issue_s = [&](int t) {  // S(t) = Q K(t)^T into S buffer (g0 + t) & 1; A = Q in TMEM
+          const uint32_t st = ks & (KV2_STAGES - 1);
+          mbar_wait(kv_full0 + 8 * st, (ks / KV2_STAGES) & 1);
+          tc_fence_after();
+          const int keys = min(TBN2, p.T - t * TBN2);
+          const uint32_t idesc_s = make_idesc_bf16(TBM, (keys + 15) & ~15);
+          const uint64_t kd = make_desc_kmajor_sw128(sK + st * KV2_BYTES);
+          const uint32_t gs = g0 + (uint32_t)t;
+#pragma unroll
+          for (int k = 0; k < THD / 16; ++k)
+            tc_mma_bf16_ts(tmem_base + (gs & 1u) * TBN2, tmem_base + COL_Q + 8 * k, kd + 2 * k, idesc_s, k > 0 ? 1u : 0u);
+          tc_commit(s_full0 + 8 * (gs & 1u));
+          ++ks;
+        };
+        for (int t = 0; t < min(KV2_STAGES - 1, n_kv); ++t) load_kv(t);
+        mbar_wait(q_full, n & 1);
+        tc_fence_after();
+        issue_s(0);
+        const uint32_t idesc_o = make_idesc_bf16(TBM, THD, 0, 1);
+        for (int j = 0; j < n_kv; ++j) {
+          if (j + 1 < n_kv) issue_s(j + 1);
+          const int t = j + KV2_STAGES - 1;
+          if (t < n_kv) load_kv(t);
+          const uint32_t gj = g0 + (uint32_t)j;
+          mbar_wait(p_ready0 + 8 * (gj & 1u), (gj >> 1) & 1u);
+          if (j == 0 && n > 0) mbar_wait(o_free, (n - 1) & 1);  // the previous item's O has been read out
+          tc_fence_after();
+          const uint32_t st = (k0 + (uint32_t)j) & (KV2_STAGES - 1);
+          const int n_mma = (min(TBN2, p.T - j * TBN2) + 15) & ~15;
+          for (int k = 0; k < n_mma / 16; ++k) {
+            const uint64_t vd = make_desc_mnmajor_sw128(sV + st * KV2_BYTES + k * 2048, 1024);
+            tc_mma_bf16_ts(tmem_base + COL_O, tmem_base + (gj & 1u) * TBN2 + 8 * k, vd, idesc_o,
+                           (k > 0 || j > 0) ? 1u : 0u);
+          }
+          tc_commit(kv_empty0 + 8 * st);
+          tc_commit(o_full);
+        }
+        g0 += (uint32_t)n_kv;
+      }
+    }
+  } else {
+    // ---------------- softmax: one thread per query row, all 64 keys of a step ----------------
+    const int r = warp * 32 + lane;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
+    auto max32 = [&](const uint32_t (&v)[32], uint32_t mw) -> float {
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+      if (mw == 0xffffffffu) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(v[i]));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          mx4[i & 3] = fmaxf(mx4[i & 3], ((mw >> i) & 1u) ? __uint_as_float(v[i]) : -INFINITY);
+      }
+      return fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+    };
+    auto exp32 = [&](const uint32_t (&v)[32], uint32_t mw, float moff, uint32_t (&packed)[16]) -> float {
+      const uint64_t sc2 = f2_bcast(p.scale_log2), nm2 = f2_bcast(-moff);
+      uint64_t ls2[4] = {0ull, 0ull, 0ull, 0ull};
+      if (mw == 0xffffffffu) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float e0, e1, p0, p1;
+          f2_unpack(f2_fma(f2_pack(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), sc2, nm2), e0, e1);
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(e0));
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(e1));
+          ls2[(i >> 1) & 3] = f2_add(ls2[(i >> 1) & 3], f2_pack(p0, p1));
+          packed[i >> 1] = pack_bf16x2(p0, p1);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float e0, e1, p0, p1;
+          f2_unpack(f2_fma(f2_pack(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), sc2, nm2), e0, e1);
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(e0));
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(e1));
+          p0 = ((mw >> i) & 1u) ? p0 : 0.f;
+          p1 = ((mw >> (i + 1)) & 1u) ? p1 : 0.f;
+          ls2[(i >> 1) & 3] = f2_add(ls2[(i >> 1) & 3], f2_pack(p0, p1));
+          packed[i >> 1] = pack_bf16x2(p0, p1);
+        }
+      }
+      float a0, a1;
+      f2_unpack(f2_add(f2_add(ls2[0], ls2[1]), f2_add(ls2[2], ls2[3])), a0, a1);
+      return a0 + a1;
+    };
+    uint32_t g0 = 0;
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+      int q_tile, h, b;
+      decode(it, q_tile, h, b);
+      const int q0 = min(q_tile * TBM, p.T - TBM);
+      const int row_base = b * p.T;
+      const uint32_t mlo_all = masks_lo, mhi_all = masks_hi;  // (the registers are reloaded for the next item below)
+      // the query row -> TMEM (every S MMA of the previous item has completed: this thread passed its last s_full)
+      tmem_st_32x32b_x16(t_lane + COL_Q, qa);
+      tmem_st_32x32b_x16(t_lane + COL_Q + 16, qb);
+      tc_wait_st();
+      tc_fence_before();
+      mbar_arrive(q_full);
+      const int it_next = it + (int)gridDim.x;
+      const uint32_t g_last = g0 + (uint32_t)n_kv - 1u;
+      const bool live = q0 + warp * 32 + 31 >= q_tile * TBM;
+      if (!live) {
+        for (int j = 0; j < n_kv; ++j) {
+          const uint32_t gj = g0 + (uint32_t)j;
+          mbar_wait(s_full0 + 8 * (gj & 1u), (gj >> 1) & 1u);
+          if (j > 0) mbar_wait(o_full, (gj - 1u) & 1u);
+          mbar_arrive(p_ready0 + 8 * (gj & 1u));
+        }
+        if (it_next < n_items) request_item(it_next);
+        mbar_wait(o_full, g_last & 1u);
+        mbar_arrive(o_free);
+      } else {
+        float m_run = -INFINITY, l_run = 0.f;
+        for (int j = 0; j < n_kv; ++j) {
+          const uint32_t gj = g0 + (uint32_t)j;
+          const uint32_t mlo = __shfl_sync(0xffffffffu, mlo_all, j), mhi = __shfl_sync(0xffffffffu, mhi_all, j);
+          const bool hi_read = j * TBN2 + 32 < p.T;
+          mbar_wait(s_full0 + 8 * (gj & 1u), (gj >> 1) & 1u);
+          tc_fence_after();
+          const uint32_t s_col = t_lane + (gj & 1u) * TBN2;
+          uint32_t va[32], vb[32];
+          if (mlo != 0u) tmem_ld_32x32b_x32(s_col, va);
+          if (mhi != 0u) tmem_ld_32x32b_x32(s_col + 32, vb);
+          tc_wait_ld();
+          float mx = -INFINITY;
+          if (mlo != 0u) mx = max32(va, mlo);
+          if (mhi != 0u) mx = fmaxf(mx, max32(vb, mhi));
+          const float m_cand = fmaxf(m_run, mx);
+          const bool first = (m_run == -INFINITY);
+          const float dlt = first ? 0.f : (m_cand - m_run) * p.scale_log2;
+          const bool grow = (m_cand != -INFINITY) && (first || dlt > 8.f);
+          const float m_new = grow ? m_cand : m_run;
+          const float corr = (grow && !first) ? exp2f(-dlt) : 1.f;
+          const float moff = (m_new == -INFINITY) ? 0.f : m_new * p.scale_log2;
+          float lsum = 0.f;
+          {
+            uint32_t packed[16];
+            if (mlo != 0u) {
+              lsum = exp32(va, mlo, moff, packed);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) packed[i] = 0u;
+            }
+            tmem_st_32x32b_x16(s_col, packed);
+          }
+          if (hi_read) {
+            uint32_t packed[16];
+            if (mhi != 0u) {
+              lsum += exp32(vb, mhi, moff, packed);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) packed[i] = 0u;
+            }
+            tmem_st_32x32b_x16(s_col + 16, packed);
+          }
+          l_run = l_run * corr + lsum;
+          m_run = m_new;
+          if (j > 0) mbar_wait(o_full, (gj - 1u) & 1u);  // every phase, in order (see kernel 5)
+          if (j > 0 && __any_sync(0xffffffffu, corr != 1.f)) {
+            tc_fence_after();
+#pragma unroll
+            for (int c = 0; c < THD; c += 32) {
+              uint32_t ov[32];
+              tmem_ld_32x32b_x32(t_lane + COL_O + c, ov);
+              tc_wait_ld();
+              uint32_t lo[16], hi[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                lo[i] = __float_as_uint(__uint_as_float(ov[i]) * corr);
+                hi[i] = __float_as_uint(__uint_as_float(ov[16 + i]) * corr);
+              }
+              tmem_st_32x32b_x16(t_lane + COL_O + c, lo);
+              tmem_st_32x32b_x16(t_lane + COL_O + c + 16, hi);
+            }
+          }
+          tc_wait_st();
+          tc_fence_before();
+          mbar_arrive(p_ready0 + 8 * (gj & 1u));
+        }
+        // the next item's query row and validity words are on their way while this item's result is read out
+        if (it_next < n_items) request_item(it_next);
+        mbar_wait(o_full, g_last & 1u);
+        tc_fence_after();
+        const int qrow = q0 + r;
+        const bool write = qrow < p.T && qrow >= q_tile * TBM;  // rows below q_tile*TBM belong to the previous tile
+        const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+        bf16* op = p.o + (int64_t)(row_base + qrow) * p.o_rs + h * THD;
+#pragma unroll
+        for (int c = 0; c < THD; c += 32) {
+          uint32_t ov[32];
+          tmem_ld_32x32b_x32(t_lane + COL_O + c, ov);
+          tc_wait_ld();
+          if (c + 32 == THD) {  // all of O is in registers: the next item's first P.V may overwrite it
+            tc_fence_before();
+            mbar_arrive(o_free);
+          }
+          if (write) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+              uint4 u;
+              u.x = pack_bf16x2(__uint_as_float(ov[i]) * inv, __uint_as_float(ov[i + 1]) * inv);
+              u.y = pack_bf16x2(__uint_as_float(ov[i + 2]) * inv, __uint_as_float(ov[i + 3]) * inv);
+              u.z = pack_bf16x2(__uint_as_float(ov[i + 4]) * inv, __uint_as_float(ov[i + 5]) * inv);
+              u.w = pack_bf16x2(__uint_as_float(ov[i + 6]) * inv, __uint_as_float(ov[i + 7]) * inv);
+              *reinterpret_cast<uint4*>(op + c + i) = u;
+            }
+          }
+        }
+      }
+      g0 += (uint32_t)n_kv;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == RW_WARPS) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS_ATT);
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -1415,9 +1739,12 @@ int esm_attention_tc(const bf16* qkv, const uint8_t* key_valid, const uint32_t* 
     PCY_CUDA(cudaFuncSetAttribute(esm_attention_ts_kernel<false, true, true>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM));
     PCY_CUDA(cudaFuncSetAttribute(esm_attention_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM));
+    PCY_CUDA(cudaFuncSetAttribute(esm_attention_row_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  TS_SMEM));
   }
   int kern = g_esm_attention_kernel;
-  if (kern == 6 && (T + TBN2 - 1) / TBN2 > 32) kern = 5;  // kernel 6 keeps a step's validity words in one lane each
+  if (kern >= 6 && (T + TBN2 - 1) / TBN2 > 32) kern = 5;  // kernels 6 / 7 keep a step's validity words in one lane each
+  if (kern == 7 && (key_valid == nullptr || key_valid_words == nullptr)) kern = 6;  // the persistent kernel reads words
   const bool steps64 = kern != 0;
   CUtensorMap tmap;
   PCY_TRY(make_qkv_map(qkv, (int64_t)B * T, 3 * d, 3 * d, steps64 ? TBN2 : TBN, &tmap));
@@ -1429,7 +1756,11 @@ int esm_attention_tc(const bf16* qkv, const uint8_t* key_valid, const uint32_t* 
   PCY_REQUIRE(q_rope == nullptr || (kern >= 2 && kern <= 5),
               "esm_attention_tc: only the TMEM-operand kernels 2-5 rotate Q themselves");
   dim3 grid(n_q_tiles, n_heads, B);
-  if (kern == 6) esm_attention_row_kernel<<<grid, RW_THREADS, TS_SMEM, stream>>>(tmap, p, qkv);
+  if (kern == 7) {
+    const int n_items = n_q_tiles * n_heads * B;
+    esm_attention_row_persistent_kernel<<<std::min(n_items, 2 * num_sms()), RW_THREADS, TS_SMEM, stream>>>(tmap, p, qkv,
+                                                                                                          n_items);
+  } else if (kern == 6) esm_attention_row_kernel<<<grid, RW_THREADS, TS_SMEM, stream>>>(tmap, p, qkv);
   else if (kern == 5) esm_attention_ts_kernel<false, true, true><<<grid, TC_THREADS, TS_SMEM, stream>>>(tmap, p, qkv);
   else if (kern == 4) esm_attention_ts_kernel<false, true><<<grid, TC_THREADS, TS_SMEM, stream>>>(tmap, p, qkv);
   else if (kern == 3) esm_attention_ts_kernel<true><<<grid, TC_THREADS, TS_SMEM, stream>>>(tmap, p, qkv);

@@ -82,7 +82,7 @@ int pcy_set_esm_tc_attention(int enabled) {
 }
 
 int pcy_set_esm_attention_kernel(int kernel) {
-  PCY_REQUIRE(kernel >= 0 && kernel <= 6, "set_esm_attention_kernel: %d not in {0, ..., 6}", kernel);
+  PCY_REQUIRE(kernel >= 0 && kernel <= 7, "set_esm_attention_kernel: %d not in {0, ..., 7}", kernel);
   pcy::g_esm_attention_kernel = kernel;
   return 0;
 }

@@ -7,7 +7,7 @@ from procyon_b200 import _lib  # noqa: E402
 from procyon_b200.model.esm import ESM_PLM  # noqa: E402
 
 L, d, H = 1, 256, 4
-for lengths in ([298, 131, 260], [512, 300, 130, 64], [126, 126]):
+for lengths in ([298, 131, 260], [512, 300, 130, 64], [126, 126], [512, 300, 130, 64, 257, 511, 129, 40] * 6):
     sd = O.random_esm_state_dict(L, d, seed=21)
     toks = O.random_protein_tokens(len(lengths), 0, seed=9, lengths=lengths)
     m = ESM_PLM(num_params="custom", pooling_method="mean", protein_pooling_correction_option=False, custom_config=(L, d, H), max_protein_len=1024)

@@ -91,7 +91,7 @@ def main():
     import os
     full = os.environ.get("PCY_ESM_BREAKDOWN_ALL", "0") == "1"
     # (attention kernel, Q roped inside it, rows beyond the last full query tile sent to the mma.sync kernel)
-    variants = [(5, False, 0), (6, False, 0)]
+    variants = [(5, False, 0), (7, False, 0), (6, False, 0), (7, False, 0)]
     if full:
         variants += [(4, True, 0), (2, True, 0), (1, False, 0), (0, False, 0)]
     for steps64, qr, tail in variants:
@@ -111,7 +111,7 @@ def main():
         gemm_fl = {"qkv": 6, "out_proj": 2, "fc1": 8, "fc2": 8}
         tf = {k: round(N * T * layers * v * d * d / per[k] / 1e9, 1) for k, v in gemm_fl.items() if per[k] > 0}
         tf["attention"] = round(N * T * layers * 4 * T * d / per["attention"] / 1e9, 1) if per["attention"] > 0 else None
-        print(json.dumps({"tail_rows_to_mma_sync": tail, "q_rope_in_attention": bool(steps64 >= 2 and qr), "attention_kernel": ["128-key steps", "64-key steps, double-buffered", "64-key steps, Q and P in TMEM", "64-key steps, Q and P in TMEM, ALU pack", "64-key steps, Q and P in TMEM, pair barriers", "64-key steps, Q and P in TMEM, pair barriers, O accumulated in TMEM", "64-key steps, one thread per query row, Q / P / O in TMEM"][steps64],
+        print(json.dumps({"tail_rows_to_mma_sync": tail, "q_rope_in_attention": bool(steps64 >= 2 and qr), "attention_kernel": ["128-key steps", "64-key steps, double-buffered", "64-key steps, Q and P in TMEM", "64-key steps, Q and P in TMEM, ALU pack", "64-key steps, Q and P in TMEM, pair barriers", "64-key steps, Q and P in TMEM, pair barriers, O accumulated in TMEM", "64-key steps, one thread per query row, Q / P / O in TMEM", "64-key steps, one thread per query row, persistent CTAs"][steps64],
                           "ms_untraced": round(ms, 2), "proteins_per_s": round(N / ms * 1e3, 1), "ms_per_class": per,
                           "sum_ms": round(tot, 2), "share": {k: round(v / tot, 3) for k, v in per.items()},
                           "tflops_per_class": tf}), flush=True)

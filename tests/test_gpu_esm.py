@@ -102,7 +102,7 @@ def test_esm_tcgen05_attention_matches_mma_sync_and_oracle(cuda_device, lengths)
     lib = _lib.load()
     outs = {}
     try:
-        for steps64 in (6, 5, 4, 3, 2, 1, 0):
+        for steps64 in (7, 6, 5, 4, 3, 2, 1, 0):
             lib.pcy_set_esm_tc_attention(1)
             lib.pcy_set_esm_attention_kernel(steps64)
             lib.pcy_set_fused_rope(1 if steps64 == 0 else 0)
