@@ -196,20 +196,23 @@ llama_embed_splice_kernel(const int32_t* __restrict__ ids, const bf16* __restric
 // Applied in place to `n_heads` heads starting at column col0 of every row; position = pos0 + (row % T).
 // cos_sin: fp32 [P][h][2].  One warp per (row, head).
 // ---------------------------------------------------------------------------------------------
+// IdxT: uint32_t whenever rows * threads-per-row fits (the two divisions per unit are 64-bit otherwise: ~200
+// instructions in front of 32 bytes of traffic)
+template <typename IdxT>
 __global__ void __launch_bounds__(ROW_THREADS)
 rope_kernel(bf16* __restrict__ x, int64_t rows, int T, int n_heads, int head_dim, int64_t ld, int col0,
             const float* __restrict__ cos_sin, const int32_t* __restrict__ pos_ptr, int pos0) {
   // one thread = 8 consecutive columns of the low half of a head and their partners in the high half
   const int half = head_dim >> 1;
   const int per_head = half >> 3;  // threads per head (head_dim % 16 == 0 on this path)
-  const int64_t per_row = (int64_t)n_heads * per_head;
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < rows * per_row;
-       idx += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t row = idx / per_row;
+  const IdxT per_row = (IdxT)n_heads * (IdxT)per_head;
+  const IdxT total = (IdxT)rows * per_row;
+  for (IdxT idx = (IdxT)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (IdxT)gridDim.x * blockDim.x) {
+    const IdxT row = idx / per_row;
     const int rem = (int)(idx - row * per_row);
     const int h = rem / per_head, i = (rem - h * per_head) * 8;
-    const int pos = (pos_ptr ? pos_ptr[0] : pos0) + (int)(row % T);
-    bf16* p = x + row * ld + col0 + h * head_dim + i;
+    const int pos = (pos_ptr ? pos_ptr[0] : pos0) + (int)(row % (IdxT)T);
+    bf16* p = x + (int64_t)row * ld + col0 + h * head_dim + i;
     const float4* cs = reinterpret_cast<const float4*>(cos_sin + ((int64_t)pos * half + i) * 2);
     float lo[8], hi[8];
     unpack8(*reinterpret_cast<const uint4*>(p), lo);
@@ -390,7 +393,12 @@ int rope_inplace(bf16* x, int64_t rows, int T, int n_heads, int head_dim, int64_
     const int64_t threads = units * (head_dim / 16);
     int64_t grid = (threads + ROW_THREADS - 1) / ROW_THREADS;
     if (grid > (int64_t)num_sms() * 32) grid = (int64_t)num_sms() * 32;
-    rope_kernel<<<(int)grid, ROW_THREADS, 0, stream>>>(x, rows, T, n_heads, head_dim, ld, col0, cos_sin, pos_ptr, pos0);
+    if (threads + grid * ROW_THREADS < (int64_t)1 << 31)  // (the grid-stride increment must not wrap either)
+      rope_kernel<uint32_t><<<(int)grid, ROW_THREADS, 0, stream>>>(x, rows, T, n_heads, head_dim, ld, col0, cos_sin,
+                                                                  pos_ptr, pos0);
+    else
+      rope_kernel<int64_t><<<(int)grid, ROW_THREADS, 0, stream>>>(x, rows, T, n_heads, head_dim, ld, col0, cos_sin,
+                                                                 pos_ptr, pos0);
   } else {
     rope_kernel_generic<<<ceil_div(units, ROW_WARPS), ROW_THREADS, 0, stream>>>(x, rows, T, n_heads, head_dim, ld,
                                                                                 col0, cos_sin, pos_ptr, pos0);

@@ -91,7 +91,7 @@ def main():
     import os
     full = os.environ.get("PCY_ESM_BREAKDOWN_ALL", "0") == "1"
     # (attention kernel, Q roped inside it, rows beyond the last full query tile sent to the mma.sync kernel)
-    variants = [(5, False, 0), (7, False, 0), (6, False, 0), (7, False, 0)]
+    variants = [(5, False, 0), (6, False, 0)]
     if full:
         variants += [(4, True, 0), (2, True, 0), (1, False, 0), (0, False, 0)]
     for steps64, qr, tail in variants:
