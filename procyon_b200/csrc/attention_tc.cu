@@ -585,6 +585,16 @@ esm_attention_tc64_kernel(const __grid_constant__ CUtensorMap tmap, const TcAttn
 // tcgen05.st per thread) and consumed from there by P.V — no P tile in shared memory, no async-proxy fence.
 // TMEM columns: S/P buffers at 0 and 64, the P.V tile at 128, Q at 192 (32 columns).
 // ---------------------------------------------------------------------------------------------------------------
+// K / V tiles requested ahead of the S = Q K^T that consumes them, for kernels 2-7.  With KV2_STAGES - 1 = 3 the tile
+// requested in iteration j goes into the stage of tile j - 1, whose P.V was issued a moment ago: the MMA thread sits
+// ~280 cycles at kv_empty in every step (clock64 stamps of the thread, profiles/r02_attention_step_stamps.log: issue of
+// S 430 + this wait 280 + wait for the softmax threads 500-680 + issue of P.V 525 cycles per step).  With 2 it goes into
+// the stage of tile j - 2, free for a whole step, and the tile still has a step (~2 000 cycles) to arrive: parity-green
+// on B200 and measured at the end of round 2 — no faster (47.4 / 46.2 ms for kernels 5 / 6 against 46.4 / 45.6-46.1:
+// the thread then waits that much longer for the softmax threads), so the value every validation run of the round used
+// stays.  1 would dead-lock (S(j+1) is issued before the iteration's load); scripts/sim_attention_phases.py replays all
+// three.
+constexpr int KV2_AHEAD = KV2_STAGES - 1;
 constexpr int TS_SMEM = 2 * KV2_STAGES * KV2_BYTES + 4 * TBM * 2 /*row max exchange, 2 parities*/ + 2 * TBM * 4 /*row sums*/ +
                         16 /*valid words*/ + 144 /*barriers*/;
 
@@ -696,7 +706,7 @@ esm_attention_ts_kernel(const __grid_constant__ CUtensorMap tmap, const TcAttnPa
                          k > 0 ? 1u : 0u);
         tc_commit(s_full0 + 8 * (t & 1));
       };
-      for (int t = 0; t < min(KV2_STAGES - 1, n_kv); ++t) load_kv(t);
+      for (int t = 0; t < min(KV2_AHEAD, n_kv); ++t) load_kv(t);
       mbar_wait(q_full, 0);
       tc_fence_after();
       issue_s(0);
@@ -705,7 +715,7 @@ esm_attention_ts_kernel(const __grid_constant__ CUtensorMap tmap, const TcAttnPa
         // S(j+1) overwrites the buffer that held S(j-1) and P(j-1): the tensor core runs this thread's MMAs in issue
         // order, so it follows P.V(j-1), and the readers of S(j-1) arrived on p_ready(j-1) before that was issued
         if (j + 1 < n_kv) issue_s(j + 1);
-        const int t = j + KV2_STAGES - 1;  // refill the stage tile j-1 used, once P.V(j-1) has retired
+        const int t = j + KV2_AHEAD;  // refill the stage tile j-1 used, once P.V(j-1) has retired (see KV2_AHEAD)
         if (t < n_kv) {
           if (t >= KV2_STAGES) mbar_wait(kv_empty0 + 8 * (t & (KV2_STAGES - 1)), ((t / KV2_STAGES) - 1) & 1);
           load_kv(t);
@@ -1131,14 +1141,14 @@ esm_attention_row_kernel(const __grid_constant__ CUtensorMap tmap, const TcAttnP
                          k > 0 ? 1u : 0u);
         tc_commit(s_full0 + 8 * (t & 1));
       };
-      for (int t = 0; t < min(KV2_STAGES - 1, n_kv); ++t) load_kv(t);
+      for (int t = 0; t < min(KV2_AHEAD, n_kv); ++t) load_kv(t);
       mbar_wait(q_full, 0);
       tc_fence_after();
       issue_s(0);
       const uint32_t idesc_o = make_idesc_bf16(TBM, THD, 0, 1);
       for (int j = 0; j < n_kv; ++j) {
         if (j + 1 < n_kv) issue_s(j + 1);
-        const int t = j + KV2_STAGES - 1;  // refill the stage tile j-1 used, once P.V(j-1) has retired
+        const int t = j + KV2_AHEAD;  // refill the stage tile j-1 used, once P.V(j-1) has retired (see KV2_AHEAD)
         if (t < n_kv) {
           if (t >= KV2_STAGES) mbar_wait(kv_empty0 + 8 * (t & (KV2_STAGES - 1)), ((t / KV2_STAGES) - 1) & 1);
           load_kv(t);
@@ -1454,14 +1464,14 @@ esm_attention_row_persistent_kernel(const __grid_constant__ CUtensorMap tmap, co
           tc_commit(s_full0 + 8 * (gs & 1u));
           ++ks;
         };
-        for (int t = 0; t < min(KV2_STAGES - 1, n_kv); ++t) load_kv(t);
+        for (int t = 0; t < min(KV2_AHEAD, n_kv); ++t) load_kv(t);
         mbar_wait(q_full, n & 1);
         tc_fence_after();
         issue_s(0);
         const uint32_t idesc_o = make_idesc_bf16(TBM, THD, 0, 1);
         for (int j = 0; j < n_kv; ++j) {
           if (j + 1 < n_kv) issue_s(j + 1);
-          const int t = j + KV2_STAGES - 1;
+          const int t = j + KV2_AHEAD;
           if (t < n_kv) load_kv(t);
           const uint32_t gj = g0 + (uint32_t)j;
           mbar_wait(p_ready0 + 8 * (gj & 1u), (gj >> 1) & 1u);

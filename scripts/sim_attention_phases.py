@@ -50,6 +50,8 @@ class Cta:
     wait_every_o_phase: bool
     persistent: bool
     rng: random.Random
+    ahead: int = STAGES - 1  # K / V tiles requested ahead of the S = Q K^T that consumes them
+    stage_tile: dict = field(default_factory=dict)  # ring stage -> global tile it holds
     bars: dict = field(default_factory=dict)
     pipe: list = field(default_factory=list)  # in-order tensor pipe: (kind, payload)
     # TMEM bookkeeping: who still has to read what
@@ -108,12 +110,16 @@ class Cta:
                     raise ProtocolError(f"hazard: S({g}) overwrites P({g - 2}) before P.V({g - 2}) retired")
             if self.q_item != item:
                 raise ProtocolError(f"hazard: S({g}) of item {item} reads Q of item {self.q_item}")
+            if self.stage_tile.get(g % STAGES) != g:
+                raise ProtocolError(f"hazard: S({g}) reads K of tile {self.stage_tile.get(g % STAGES)}")
             self.s_readers[g] = set(range(self.n_soft))
             self.s_done += 1
         elif kind == "PV":
             g, item, first = payload
             if len(self.p_written.get(g, ())) != self.n_soft:
                 raise ProtocolError(f"hazard: P.V({g}) reads P before all threads stored it")
+            if self.stage_tile.get(g % STAGES) != g:
+                raise ProtocolError(f"hazard: P.V({g}) reads V of tile {self.stage_tile.get(g % STAGES)}")
             if first and item > 0 and self.o_item_readers.get(item - 1):
                 raise ProtocolError(f"hazard: first P.V of item {item} overwrites O of item {item - 1} before "
                                     f"{self.o_item_readers[item - 1]} read it")
@@ -132,6 +138,9 @@ class Cta:
                 st = kl % STAGES
                 if kl >= STAGES:
                     yield from self.wait(f"kv_empty{st}", (kl // STAGES - 1) & 1, kl // STAGES - 1, "mma")
+                    if self.o_steps_done < kl - STAGES + 1:
+                        raise ProtocolError(f"hazard: tile {kl} overwrites tile {kl - STAGES} before its P.V retired")
+                self.stage_tile[st] = kl
                 self.bars[f"kv_full{st}"].arrive()  # TMA completes the transaction count
                 kl += 1
 
@@ -144,14 +153,14 @@ class Cta:
                 self.issue("commit", f"s_full{g & 1}")
                 ks += 1
 
-            for t in range(min(STAGES - 1, self.n_kv)):
+            for t in range(min(self.ahead, self.n_kv)):
                 yield from load_kv()
             yield from self.wait("q_full", item & 1, item, "mma")
             yield from issue_s(0)
             for j in range(self.n_kv):
                 if j + 1 < self.n_kv:
                     yield from issue_s(j + 1)
-                if j + STAGES - 1 < self.n_kv:
+                if j + self.ahead < self.n_kv:
                     yield from load_kv()
                 g = g0 + j
                 yield from self.wait(f"p_ready{g & 1}", (g >> 1) & 1, g >> 1, "mma")
@@ -201,11 +210,11 @@ class Cta:
 
 
 def run(n_kv: int, n_items: int, n_soft: int = 4, wait_every_o_phase: bool = True, persistent: bool = True,
-        seed: int = 0, max_ticks: int = 2_000_000) -> None:
+        seed: int = 0, max_ticks: int = 2_000_000, ahead: int = STAGES - 1) -> None:
     """Replays one CTA; raises ProtocolError on aliasing / deadlock / hazard."""
     rng = random.Random(seed)
     cta = Cta(n_kv=n_kv, n_items=n_items, n_soft=n_soft, wait_every_o_phase=wait_every_o_phase, persistent=persistent,
-              rng=rng)
+              rng=rng, ahead=ahead)
     threads = [cta.mma_thread()] + [cta.softmax_thread(t) for t in range(n_soft)]
     alive = list(range(len(threads)))
     for _ in range(max_ticks):
