@@ -51,3 +51,17 @@ def test_parity_wait_semantics():
     assert b.parity_passes(0) and not b.parity_passes(1)
     b.arrive(); b.arrive()  # two phases on: a waiter for phase 0 would now block (same parity as phase 2)
     assert not b.parity_passes(0)
+
+
+@pytest.mark.parametrize("persistent,n_items", [(False, 1), (True, 4)])
+def test_kv_ring_refill_distance(persistent, n_items):
+    """KV2_AHEAD: tiles requested 3 (shipped) or 2 steps ahead of the S = Q K^T that consumes them never overwrite a
+    stage under a pending P.V and always find the right tile; 1 dead-locks, because S(j+1) is issued before the
+    iteration's load; 4 = the ring depth waits for a P.V that cannot have been issued yet."""
+    for ahead in (3, 2):
+        for n_kv in (1, 2, 3, 4, 5, 9, 17):
+            for seed in range(6):
+                sim.run(n_kv=n_kv, n_items=n_items, persistent=persistent, seed=seed, ahead=ahead)
+    for ahead in (1, 4):
+        with pytest.raises(sim.ProtocolError):
+            sim.run(n_kv=9, n_items=n_items, persistent=persistent, seed=0, ahead=ahead)
